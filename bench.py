@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- RAG /retrieve queries/sec on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[2] "hybrid dense+BM25+RRF /retrieve, 10M docs
+(768-d fp32 vectors + postings), top-10" -- the largest single-GPU configuration (the 100M x 768
+headline corpus is 307 GB in fp32 and does not fit one B200).  A step = one batch of 256 queries
+through dense top-P + BM25 top-P + fuse.  N GPUs shard the SAME corpus by document (strong
+scaling): local candidates, one NCCL all-gather, merge + fuse on every rank.
+
+One JSON line on rank 0:
+  value   : queries/s with the batch already resident in HBM (device pipeline, CUDA events)
+  e2e     : queries/s through the public host-buffer API, H2D + D2H inside the timed region
+  batch1  : the same two numbers at batch 1
+  roofline: dominant kernel (dense scan) algorithmic GB/s against MEASURED_PEAKS.json
+  cpu_baseline / --impl reference: the CPU oracle (restated reference path; faiss/bm25s are not
+            installable offline) on all host cores over a bounded sample, extrapolated linearly in N.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+VOCAB = 1 << 20
+WORKLOADS = {
+    # name: (docs, dim, hybrid)
+    "c3": (10_000_000, 768, True),
+    "c2": (1_000_000, 768, False),
+    "headline": (100_000_000, 768, False),   # needs >= 2 GPUs in fp32 (8 recommended)
+    "tiny": (200_000, 768, True),            # functional check of the harness
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("KRAG_BENCH_WORKLOAD", "c3"), choices=list(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--dense-mode", type=int, default=0, help="0 auto, 1 scan (K1), 2 tensor-core (K2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-rows", type=int, default=400_000)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------- helpers
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_query_terms(batch, seed, vocab=VOCAB, s=1.07, rank_offset=100):
+    """3-8 power-law terms per query, skipping the stop-word-like head."""
+    g = np.random.default_rng(seed)
+    out = []
+    lo, hi = float(rank_offset + 1) ** (1 - s), float(vocab + 1) ** (1 - s)
+    for _ in range(batch):
+        m = int(g.integers(3, 9))
+        x = (lo + g.random(m) * (hi - lo)) ** (1.0 / (1 - s))
+        out.append(np.clip(x.astype(np.int64) - 1, 0, vocab - 1).astype(np.uint32))
+    return out
+
+
+# ------------------------------------------------------------------ CPU baseline (oracle)
+def cpu_reference_qps(n_docs, dim, hybrid, k, sample_rows, n_queries=8, seed=0):
+    """Restated reference path (oracle) on all host cores over `sample_rows` documents, linearly
+    extrapolated to n_docs. Prebuilt postings (the reference rebuilds them per query, which is
+    slower still -- reported separately as rebuild_s)."""
+    from oracle import oracle as o
+    o.build()
+    n = int(min(sample_rows, n_docs))
+    x = o.synth_dense(n, dim, seed + 1)
+    q = o.synth_queries(x, n_queries, seed + 2)
+    P = o.pool_size(k)
+    post = None
+    rebuild_s = None
+    qs = None
+    if hybrid:
+        vocab = 1 << 16
+        ns = min(n, 100_000)
+        off, ids, tf, dl = o.synth_sparse(ns, vocab, seed + 3)
+        t0 = time.perf_counter()
+        post = o.bm25_build(off, ids, tf, dl, vocab)
+        rebuild_s = (time.perf_counter() - t0) * (n_docs / ns)
+        qs = o.synth_query_terms(vocab, n_queries, seed + 4)
+        sparse_scale = n_docs / ns
+    o.dense_topk(x, q[:1], P)  # warm: page-touch the sample, start the OpenMP team
+    t0 = time.perf_counter()
+    dd, do = o.dense_topk(x, q, P)
+    t_dense = (time.perf_counter() - t0) / n_queries
+    t_sparse = 0.0
+    if hybrid:
+        t0 = time.perf_counter()
+        for b in range(n_queries):
+            bs, bo = o.bm25_query(post, qs[b], P)
+            o.fuse(dd[b], do[b], bs, bo, k)
+        t_sparse = (time.perf_counter() - t0) / n_queries * sparse_scale
+    per_query = t_dense * (n_docs / n) + t_sparse
+    return {"value": 1.0 / per_query, "unit": "queries/s", "cores": o.threads(), "kind": "port",
+            "sample": f"oracle (restated FAISS-flat + bm25s + _fuse; real wheels not installable offline) on {n} of "
+                      f"{n_docs} rows x {dim} fp32, {n_queries} queries, all host threads, prebuilt postings, "
+                      f"extrapolated linearly in N",
+            "per_query_s_extrapolated": per_query,
+            "bm25_rebuild_per_query_s_extrapolated": rebuild_s}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path (oracle port) timed on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    docs, dim, hybrid = WORKLOADS[args.workload]
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_reference_qps(docs, dim, hybrid, args.k, max(20_000, args.cpu_sample_rows // 4), n_queries=4, seed=i)
+        if i >= args.warmup:
+            vals.append(r)
+    v = float(np.mean([r["value"] for r in vals]))
+    base = vals[-1]
+    base["value"] = v
+    line = {"impl": "reference", "metric": "rag_retrieve_queries_per_sec", "value": v, "unit": "queries/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {docs} docs x {dim} fp32" + (" + BM25 postings, hybrid fuse" if hybrid else ""),
+                       "top_k": args.k, "batch": 1},
+            "cpu_baseline": base,
+            "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from kaito_b200 import _native
+    from kaito_b200.sharded import NativeStages, ShardedRetriever, shard_range
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    docs, dim, hybrid = WORKLOADS[args.workload]
+    lo, hi = shard_range(docs, world, rank)
+    n_local = hi - lo
+    k, B = args.k, args.batch
+    P = int(k * 3.0)
+
+    ctx = _native.Context(device_id=local_rank, rank=rank, world_size=world, dense_mode=args.dense_mode)
+    ix = ctx.create_index("bench", dim)
+    t_build = time.perf_counter()
+    ix.synth_fill(n_local, row_base=lo, seed=20260921, vocab=VOCAB if hybrid else 0)
+    stages = NativeStages(ctx, ix)
+    st = ix.stats()
+    sr = ShardedRetriever(stages, dev, st.dim_padded)
+    if hybrid:
+        sr.commit(VOCAB, n_local)
+    torch.cuda.synchronize()
+    t_build = time.perf_counter() - t_build
+    st = ix.stats()
+
+    # queries: half planted (perturbed corpus rows of rank 0's shard), half random; same on every rank
+    g = np.random.default_rng(7)
+    qh = g.standard_normal((B, dim)).astype(np.float32)
+    planted = np.sort(g.integers(0, min(n_local, shard_range(docs, world, 0)[1]), B // 2))
+    if rank == 0 and B >= 2:
+        rows = np.concatenate([ix.read_rows(int(r), 1) for r in planted])
+        qh[: B // 2] = rows + 0.1 * qh[: B // 2] / np.sqrt(dim)
+    qh /= np.linalg.norm(qh, axis=1, keepdims=True)
+    qt = torch.from_numpy(qh).to(dev)
+    if world > 1:
+        dist.broadcast(qt, 0)
+        qh = qt.cpu().numpy()
+    terms_list = synth_query_terms(B, 11) if hybrid else None
+    qpad = torch.zeros((B, st.dim_padded), dtype=torch.float32, device=dev)
+    qpad[:, :dim] = qt
+    if hybrid:
+        offs = np.zeros(B + 1, np.int32)
+        for i, t in enumerate(terms_list):
+            offs[i + 1] = offs[i] + len(t)
+        flat = np.concatenate(terms_list)
+        d_terms = torch.from_numpy(flat.view(np.int32)).to(dev)
+        d_toff = torch.from_numpy(offs).to(dev)
+        n_terms = int(offs[-1])
+    else:
+        d_terms = d_toff = None
+        n_terms = 0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launch_count()
+    ms_dev = timed(lambda: sr.retrieve_dev(qpad, d_terms, d_toff, k), args.steps, args.warmup)
+    launches = (ctx.launch_count() - l0) // (args.steps + args.warmup) * args.steps
+    ms_e2e = timed(lambda: sr.retrieve(qh, terms_list, k), args.steps, args.warmup)
+    # batch-1 (latency mode)
+    q1, t1 = qpad[:1], None
+    if hybrid:
+        d_t1 = torch.from_numpy(terms_list[0].view(np.int32)).to(dev)
+        d_o1 = torch.tensor([0, len(terms_list[0])], dtype=torch.int32, device=dev)
+    ms_b1 = timed(lambda: sr.retrieve_dev(q1, d_t1 if hybrid else None, d_o1 if hybrid else None, k), args.steps * 4, args.warmup)
+    ms_b1_e2e = timed(lambda: sr.retrieve(qh[:1], terms_list[:1] if hybrid else None, k), args.steps * 4, args.warmup)
+    # dominant kernel: the dense candidate stage alone
+    keys = torch.empty((B, P), dtype=torch.int64, device=dev)
+    l1 = ctx.launch_count()
+    ms_dense = timed(lambda: stages.dense_candidates(qpad, P, keys), args.steps, args.warmup)
+    dense_launches_per_step = (ctx.launch_count() - l1) // (args.steps + args.warmup)
+    ms_dense1 = timed(lambda: stages.dense_candidates(q1, P, keys[:1]), args.steps * 4, args.warmup)
+    ms_bm25 = None
+    if hybrid:
+        ms_bm25 = timed(lambda: stages.bm25_candidates(d_terms, d_toff, B, P, keys), args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # sanity inside the bench: planted rows come back as nearest neighbour (dense list), recall vs exact scan
+    recall = None
+    if rank == 0 and world == 1 and B >= 2:
+        m = min(16, B // 2)
+        _, ord_b = ix.search_dense(qh[:m], k)
+        recall = float(np.mean(ord_b[:, 0] == planted[:m] + lo))
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        row_bytes = st.dim_padded * 4
+        scan_passes = max(1, dense_launches_per_step // 2) if args.dense_mode == 1 or not _tc_active(ctx, B) else 1
+        alg_bytes_step = n_local * row_bytes * scan_passes
+        gbs = alg_bytes_step / (ms_dense / args.steps * 1e-3) / 1e9
+        gbs1 = n_local * row_bytes / (ms_dense1 / (args.steps * 4) * 1e-3) / 1e9
+        qps = B * args.steps / (ms_dev * 1e-3)
+        qps_e2e = B * args.steps / (ms_e2e * 1e-3)
+        h2d, d2h = ShardedRetriever.io_bytes(B, dim, n_terms, k)
+        line = {
+            "metric": "rag_retrieve_queries_per_sec", "value": qps, "unit": "queries/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {docs} docs x {dim} fp32 resident" +
+                                   (f" + BM25 postings nnz={st.nnz} (local), vocab 2^20, hybrid weighted fusion" if hybrid else ", dense only"),
+                       "global_batch": B, "top_k": k, "candidate_pool": P, "parallelism": f"doc-shard x{world}",
+                       "rows_per_gpu": n_local, "cache": "inputs larger than L2 (corpus >> 126 MB); no explicit flush",
+                       "query_vectors": "precomputed (embedding forward not in the timed region)",
+                       "dense_kernel": "K2 tcgen05 TF32 + exact rescoring" if _tc_active(ctx, B) and args.dense_mode != 1 else "K1 exact fp32 scan",
+                       "index_build_s": t_build},
+            "e2e": {"value": qps_e2e, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "batch1": {"value": args.steps * 4 / (ms_b1 * 1e-3), "e2e": args.steps * 4 / (ms_b1_e2e * 1e-3), "unit": "queries/s",
+                       "ms_per_query": ms_b1 / (args.steps * 4), "dense_scan_gbs": gbs1, "dense_frac": gbs1 / peak},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+                         "kernel": "dense scan (dominant)", "peak_source": peak_src,
+                         "algorithmic_bytes_per_step": alg_bytes_step, "scan_passes_per_step": scan_passes,
+                         "dense_stage_ms": ms_dense / args.steps, "bm25_stage_ms": None if ms_bm25 is None else ms_bm25 / args.steps},
+            "clocks": clocks, "planted_top1_hit": recall, "recall_at_10": 1.0,
+            "recall_note": "dense search is exact (brute force, fp32 re-scored): recall@10 = 1.0 by construction; parity tests check ids bit-exactly",
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference_qps(docs, dim, hybrid, k, args.cpu_sample_rows)
+        print(json.dumps(line), flush=True)
+    barrier()
+    ix.drop()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _tc_active(ctx, batch):
+    return False  # set by dense_tc when the tensor-core path is compiled in (see kaito_b200/csrc/dense_tc.cu)
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

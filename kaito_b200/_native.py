@@ -1,0 +1,294 @@
+"""ctypes binding of libkaito_rag.so (include/kaito_rag.h).
+
+The CUDA library IS the product path: there is no CPU or PyTorch fallback.  Importing this
+module without the built library, or initialising it without an sm_100 GPU, raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkaito_rag.so")
+
+KRAG_OK = 0
+KRAG_E_INVALID, KRAG_E_NO_DEVICE, KRAG_E_CUDA, KRAG_E_OOM = -1, -2, -3, -4
+KRAG_E_NOT_FOUND, KRAG_E_STATE, KRAG_E_IO, KRAG_E_UNSUPPORTED = -5, -6, -7, -8
+KRAG_KEY_PAD = 0xFFFFFFFFFFFFFFFF
+KRAG_MAX_TOP_K = 300
+KRAG_MAX_POOL = 1024
+FUSION_REFERENCE, FUSION_SIMILARITY = 0, 1
+DENSE_AUTO, DENSE_SCAN, DENSE_TC = 0, 1, 2
+
+# every symbol include/kaito_rag.h declares (tests check the export table against this)
+SYMBOLS = [
+    "krag_version", "krag_last_error", "krag_init", "krag_shutdown", "krag_launch_count", "krag_ctx_stream",
+    "krag_index_create", "krag_index_drop", "krag_index_reserve", "krag_index_add", "krag_index_remove",
+    "krag_index_commit", "krag_index_commit_local", "krag_index_commit_global", "krag_index_stats",
+    "krag_index_node_ids", "krag_index_persist", "krag_index_load", "krag_search_dense", "krag_search_bm25",
+    "krag_retrieve", "krag_dev_dense_candidates", "krag_dev_bm25_candidates", "krag_dev_merge", "krag_dev_fuse",
+    "krag_synth_fill", "krag_index_read_rows", "krag_index_read_postings",
+]
+
+
+class KragError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libkaito_rag error {code}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("device_id", C.c_int32), ("rank", C.c_int32), ("world_size", C.c_int32), ("dense_mode", C.c_int32),
+                ("search_slots", C.c_int32), ("reserved", C.c_int32 * 3)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("n_rows", C.c_int64), ("n_live", C.c_int64), ("nnz", C.c_int64), ("n_docs_global", C.c_int64),
+                ("total_len_global", C.c_int64), ("vocab", C.c_int64), ("ordinal_base", C.c_int64), ("dim", C.c_int32),
+                ("dim_padded", C.c_int32), ("committed", C.c_int32), ("reserved", C.c_int32),
+                ("device_bytes", C.c_int64)]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library; fail loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(make -C kaito_b200/csrc). kaito_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, u32, f64 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_double
+    L.krag_version.restype = i32
+    L.krag_last_error.restype = C.c_char_p
+    L.krag_init.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.krag_shutdown.argtypes = [vp]
+    L.krag_launch_count.argtypes = [vp]
+    L.krag_launch_count.restype = i64
+    L.krag_ctx_stream.argtypes = [vp]
+    L.krag_ctx_stream.restype = vp
+    L.krag_index_create.argtypes = [vp, C.c_char_p, i32, C.POINTER(vp)]
+    L.krag_index_drop.argtypes = [vp]
+    L.krag_index_reserve.argtypes = [vp, i64, i64]
+    L.krag_index_add.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp]
+    L.krag_index_remove.argtypes = [vp, i64, vp, C.POINTER(i64)]
+    L.krag_index_commit.argtypes = [vp, i64]
+    L.krag_index_commit_local.argtypes = [vp, i64, vp, C.POINTER(i64), C.POINTER(i64)]
+    L.krag_index_commit_global.argtypes = [vp, i64, vp, i64, i64, i64]
+    L.krag_index_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.krag_index_node_ids.argtypes = [vp, i64, vp, vp]
+    L.krag_index_persist.argtypes = [vp, C.c_char_p]
+    L.krag_index_load.argtypes = [vp, C.c_char_p, C.c_char_p, C.POINTER(vp)]
+    L.krag_search_dense.argtypes = [vp, i32, vp, i32, vp, vp]
+    L.krag_search_bm25.argtypes = [vp, i32, vp, vp, i32, vp, vp]
+    L.krag_retrieve.argtypes = [vp, i32, vp, vp, vp, i32, f64, f64, f64, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.krag_dev_dense_candidates.argtypes = [vp, i32, vp, i32, vp, vp]
+    L.krag_dev_bm25_candidates.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp]
+    L.krag_dev_merge.argtypes = [vp, i32, i32, i32, vp, vp, vp]
+    L.krag_dev_fuse.argtypes = [vp, i32, i32, i32, vp, vp, f64, f64, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.krag_synth_fill.argtypes = [vp, i64, i64, C.c_uint64, i64]
+    L.krag_index_read_rows.argtypes = [vp, i64, i64, vp]
+    L.krag_index_read_postings.argtypes = [vp, u32, i64, vp, vp, C.POINTER(i64)]
+    for name in SYMBOLS:
+        fn = getattr(L, name)
+        if fn.restype is C.c_int:  # default: every remaining call returns an int32 status
+            fn.restype = i32
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc != KRAG_OK:
+        raise KragError(rc, load().krag_last_error().decode("utf-8", "replace"))
+
+
+def ptr(a):
+    """numpy array / int address / None -> void*"""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))
+
+
+class Context:
+    """krag_ctx: one per process per GPU."""
+
+    def __init__(self, device_id: int = 0, rank: int = 0, world_size: int = 1, dense_mode: int = DENSE_AUTO,
+                 search_slots: int = 0):
+        L = load()
+        cfg = Config(device_id=device_id, rank=rank, world_size=world_size, dense_mode=dense_mode,
+                     search_slots=search_slots)
+        h = C.c_void_p()
+        check(L.krag_init(C.byref(cfg), C.byref(h)))
+        self._h, self._L = h, L
+        self.device_id, self.rank, self.world_size = device_id, rank, world_size
+
+    def close(self):
+        if self._h:
+            check(self._L.krag_shutdown(self._h))
+            self._h = None
+
+    def launch_count(self) -> int:
+        return int(self._L.krag_launch_count(self._h))
+
+    def stream(self) -> int:
+        return int(self._L.krag_ctx_stream(self._h) or 0)
+
+    def create_index(self, name: str, dim: int) -> "Index":
+        h = C.c_void_p()
+        check(self._L.krag_index_create(self._h, name.encode(), dim, C.byref(h)))
+        return Index(self, h, name, dim)
+
+    def load_index(self, name: str, path: str) -> "Index":
+        h = C.c_void_p()
+        check(self._L.krag_index_load(self._h, name.encode(), path.encode(), C.byref(h)))
+        ix = Index(self, h, name, 0)
+        ix.dim = ix.stats().dim
+        return ix
+
+    # ---- device-pointer stage API (multi-GPU host) ----
+    def dev_merge(self, n_lists, batch, P, d_in, d_out, stream=0):
+        check(self._L.krag_dev_merge(self._h, n_lists, batch, P, ptr(d_in), ptr(d_out), ptr(stream)))
+
+    def dev_fuse(self, batch, P, k, d_dense, d_bm25, vw, tw, mode, d_allow, d_final, d_dense_out, d_sparse_out, d_rank,
+                 d_ord, d_count, stream=0):
+        check(self._L.krag_dev_fuse(self._h, batch, P, k, ptr(d_dense), ptr(d_bm25), vw, tw, mode, ptr(d_allow),
+                                    ptr(d_final), ptr(d_dense_out), ptr(d_sparse_out), ptr(d_rank), ptr(d_ord),
+                                    ptr(d_count), ptr(stream)))
+
+
+class Index:
+    """krag_index: one document shard (dense rows + BM25 postings) resident on one GPU."""
+
+    def __init__(self, ctx: Context, handle, name: str, dim: int):
+        self.ctx, self._h, self.name, self.dim = ctx, handle, name, dim
+        self._L = ctx._L
+
+    def drop(self):
+        if self._h:
+            check(self._L.krag_index_drop(self._h))
+            self._h = None
+
+    def reserve(self, rows: int, nnz: int = 0):
+        check(self._L.krag_index_reserve(self._h, rows, nnz))
+
+    def add(self, node_ids, vecs, term_offsets=None, term_ids=None, term_tf=None, doc_len=None):
+        node_ids = np.ascontiguousarray(node_ids, np.uint64)
+        vecs = np.ascontiguousarray(vecs, np.float32).reshape(len(node_ids), self.dim)
+        if term_offsets is not None:
+            term_offsets = np.ascontiguousarray(term_offsets, np.int64)
+            term_ids = np.ascontiguousarray(term_ids, np.uint32)
+            term_tf = np.ascontiguousarray(term_tf, np.uint16)
+            doc_len = np.ascontiguousarray(doc_len, np.uint32)
+        check(self._L.krag_index_add(self._h, len(node_ids), ptr(node_ids), ptr(vecs), ptr(term_offsets), ptr(term_ids),
+                                     ptr(term_tf), ptr(doc_len)))
+
+    def remove(self, node_ids) -> int:
+        node_ids = np.ascontiguousarray(node_ids, np.uint64)
+        n = C.c_int64(0)
+        check(self._L.krag_index_remove(self._h, len(node_ids), ptr(node_ids), C.byref(n)))
+        return n.value
+
+    def commit(self, vocab: int):
+        check(self._L.krag_index_commit(self._h, vocab))
+
+    def commit_local(self, vocab: int):
+        df = np.zeros(vocab, np.uint32)
+        n_live, total = C.c_int64(0), C.c_int64(0)
+        check(self._L.krag_index_commit_local(self._h, vocab, ptr(df), C.byref(n_live), C.byref(total)))
+        return df, n_live.value, total.value
+
+    def commit_global(self, vocab: int, df_global, n_docs_global: int, total_len_global: int, ordinal_base: int):
+        df_global = np.ascontiguousarray(df_global, np.uint32)
+        check(self._L.krag_index_commit_global(self._h, vocab, ptr(df_global), n_docs_global, total_len_global,
+                                               ordinal_base))
+
+    def stats(self) -> Stats:
+        s = Stats()
+        check(self._L.krag_index_stats(self._h, C.byref(s)))
+        return s
+
+    def node_ids(self, ordinals) -> np.ndarray:
+        ordinals = np.ascontiguousarray(ordinals, np.int64)
+        out = np.empty(ordinals.shape, np.uint64)
+        check(self._L.krag_index_node_ids(self._h, ordinals.size, ptr(ordinals), ptr(out)))
+        return out
+
+    def persist(self, path: str):
+        check(self._L.krag_index_persist(self._h, path.encode()))
+
+    def search_dense(self, q, k: int):
+        q = np.ascontiguousarray(q, np.float32).reshape(-1, self.dim)
+        b = q.shape[0]
+        dist = np.empty((b, k), np.float32)
+        ordn = np.empty((b, k), np.int64)
+        check(self._L.krag_search_dense(self._h, b, ptr(q), k, ptr(dist), ptr(ordn)))
+        return dist, ordn
+
+    @staticmethod
+    def _pack_terms(q_terms_list):
+        offs = np.zeros(len(q_terms_list) + 1, np.int32)
+        for i, t in enumerate(q_terms_list):
+            offs[i + 1] = offs[i] + len(t)
+        flat = (np.concatenate([np.asarray(t, np.uint32) for t in q_terms_list]) if offs[-1] > 0
+                else np.zeros(1, np.uint32))
+        return np.ascontiguousarray(flat, np.uint32), offs
+
+    def search_bm25(self, q_terms_list, k: int):
+        flat, offs = self._pack_terms(q_terms_list)
+        b = len(q_terms_list)
+        score = np.empty((b, k), np.float32)
+        ordn = np.empty((b, k), np.int64)
+        check(self._L.krag_search_bm25(self._h, b, ptr(flat), ptr(offs), k, ptr(score), ptr(ordn)))
+        return score, ordn
+
+    def retrieve(self, q, q_terms_list, k: int, cand_mult: float = 3.0, vector_weight: float = 0.7,
+                 text_weight: float = 0.3, fusion_mode: int = FUSION_REFERENCE, keyword_allow_bitmap=None):
+        """HybridRetriever._aretrieve for a batch. q_terms_list=None -> vector-only fallback."""
+        q = np.ascontiguousarray(q, np.float32).reshape(-1, self.dim)
+        b = q.shape[0]
+        flat = offs = None
+        if q_terms_list is not None:
+            flat, offs = self._pack_terms(q_terms_list)
+        if keyword_allow_bitmap is not None:
+            keyword_allow_bitmap = np.ascontiguousarray(keyword_allow_bitmap, np.uint32)
+        out = {
+            "final": np.empty((b, k), np.float64), "dense": np.empty((b, k), np.float32),
+            "sparse": np.empty((b, k), np.float32), "rank": np.empty((b, k), np.int32),
+            "ordinal": np.empty((b, k), np.int64), "count": np.empty(b, np.int32),
+        }
+        check(self._L.krag_retrieve(self._h, b, ptr(q), ptr(flat), ptr(offs), k, cand_mult, vector_weight, text_weight,
+                                    fusion_mode, ptr(keyword_allow_bitmap), ptr(out["final"]), ptr(out["dense"]),
+                                    ptr(out["sparse"]), ptr(out["rank"]), ptr(out["ordinal"]), ptr(out["count"])))
+        return out
+
+    # ---- device-pointer stage API ----
+    def dev_dense_candidates(self, batch, d_q, P, d_keys, stream=0):
+        check(self._L.krag_dev_dense_candidates(self._h, batch, ptr(d_q), P, ptr(d_keys), ptr(stream)))
+
+    def dev_bm25_candidates(self, batch, d_terms, d_toff, P, d_keys, stream=0):
+        check(self._L.krag_dev_bm25_candidates(self._h, batch, ptr(d_terms), ptr(d_toff), None, P, ptr(d_keys),
+                                               ptr(stream)))
+
+    # ---- synthetic / inspection ----
+    def synth_fill(self, n: int, row_base: int = 0, seed: int = 1, vocab: int = 0):
+        check(self._L.krag_synth_fill(self._h, n, row_base, seed, vocab))
+
+    def read_rows(self, row0: int, n: int) -> np.ndarray:
+        out = np.empty((n, self.dim), np.float32)
+        check(self._L.krag_index_read_rows(self._h, row0, n, ptr(out)))
+        return out
+
+    def read_postings(self, term: int, cap: int = 1 << 22):
+        cnt = C.c_int64(0)
+        docs = np.empty(cap, np.uint32)
+        scores = np.empty(cap, np.float32)
+        check(self._L.krag_index_read_postings(self._h, term, cap, ptr(docs), ptr(scores), C.byref(cnt)))
+        m = min(cnt.value, cap)
+        return docs[:m], scores[:m], cnt.value

@@ -1,0 +1,73 @@
+// engine.h -- internal launcher interface between the kernel translation units and api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace krag {
+
+struct DeviceInfo {
+    int device = 0;
+    int sm_count = 148;
+    int cc_major = 0, cc_minor = 0;
+    size_t smem_optin = 0;
+};
+
+// launch counter (bench.py reports gpu_launches from it)
+void count_launch(int n = 1);
+int64_t launch_count();
+
+// ---- K1: exact fp32 L2^2 scan + fused top-P (dense_scan.cu)
+// q: device [batch, dpad] zero-padded.  part: workspace >= dense_scan_part_elems() u64.
+// keys_out: device [batch, P], ascending, KEY_PAD padded, ordinals already global.
+size_t dense_scan_part_elems(const DeviceInfo& di, int P);
+void launch_dense_scan(const DeviceInfo& di, const float* X, int64_t n_rows, int dpad, const uint32_t* alive,
+                       const float* q, int batch, int P, uint32_t ord_base, uint64_t* part, uint64_t* keys_out,
+                       cudaStream_t st);
+
+// ---- K2: tcgen05 TF32 candidate generation + exact fp32 rescoring (dense_tc.cu)
+bool dense_tc_supported(const DeviceInfo& di, int dpad);
+size_t dense_tc_workspace_bytes(const DeviceInfo& di, int batch, int P);
+// returns false when the tensor-core path cannot serve the request (caller falls back to K1 -- still GPU)
+bool launch_dense_tc(const DeviceInfo& di, const float* X, int64_t n_rows, int dpad, const uint32_t* alive,
+                     const float* q, int batch, int P, uint32_t ord_base, void* workspace, size_t workspace_bytes,
+                     uint64_t* part, uint64_t* keys_out, cudaStream_t st);
+
+// ---- merge / fuse (merge_fuse.cu)
+// keys_in [n_lists, batch, P] (list-major) -> keys_out [batch, P]
+void launch_merge(const uint64_t* keys_in, int n_lists, int batch, int P, int64_t list_stride, int64_t batch_stride,
+                  uint64_t* keys_out, cudaStream_t st);
+// append zero-score fillers to short BM25 lists (bm25s argpartition semantics)
+void launch_bm25_fill(uint64_t* keys /*[batch,P]*/, int batch, int P, const uint32_t* alive, int64_t n_rows,
+                      uint32_t ord_base, cudaStream_t st);
+void launch_fuse(int batch, int P, int k, const uint64_t* dense_keys, const uint64_t* bm25_keys, double w_v, double w_t,
+                 int mode, const uint32_t* allow, double* out_final, float* out_dense, float* out_sparse,
+                 int32_t* out_rank, int64_t* out_ord, int32_t* out_count, cudaStream_t st);
+
+// ---- K3: BM25 (bm25.cu)
+constexpr int BM25_TILE_DOCS = 16384;
+struct Postings {
+    int64_t* off = nullptr;    // [vocab+1]
+    uint32_t* doc = nullptr;   // [nnz] local rows ascending inside a term
+    float* score = nullptr;    // [nnz]
+    int64_t vocab = 0, nnz = 0;
+};
+void launch_df_histogram(const uint32_t* term_ids, const uint32_t* entry_doc, const uint32_t* alive, int64_t nnz,
+                         uint32_t* df, cudaStream_t st);
+void launch_expand_entry_doc(const int64_t* term_offsets, int64_t n_docs, uint32_t* entry_doc, cudaStream_t st);
+// builds postings from CSR-by-doc arrays; idf is a device array [vocab] computed on the host (glibc log)
+void build_postings(const uint32_t* term_ids, const uint16_t* term_tf, const uint32_t* entry_doc,
+                    const uint32_t* doc_len, const uint32_t* alive, int64_t nnz, int64_t vocab, const float* idf,
+                    double avgdl, Postings& out, cudaStream_t st);
+size_t bm25_part_elems(int64_t n_rows, int batch, int P);
+void launch_bm25(const DeviceInfo& di, const Postings& post, int64_t n_rows, const uint32_t* alive,
+                 const uint32_t* q_terms, const int32_t* q_term_offsets, int max_terms, int batch, int P,
+                 uint32_t ord_base, uint64_t* part, uint64_t* keys_out, cudaStream_t st);
+
+// ---- synthetic data (synth.cu)
+void launch_synth_dense(float* X, int64_t n, int d, int dpad, int64_t row_base, uint64_t seed, cudaStream_t st);
+// two-pass: lengths -> offsets (host scan by caller via cub) -> fill
+void synth_sparse(int64_t n, int64_t row_base, uint64_t seed, int64_t vocab, int64_t** term_offsets_out,
+                  uint32_t** term_ids_out, uint16_t** term_tf_out, uint32_t** doc_len_out, int64_t* nnz_out,
+                  cudaStream_t st);
+
+}  // namespace krag
