@@ -195,6 +195,15 @@ int32_t krag_index_read_rows(krag_index* idx, int64_t row0, int64_t n, float* ou
 int32_t krag_index_read_postings(krag_index* idx, uint32_t term, int64_t cap, uint32_t* docs_out, float* scores_out,
                                  int64_t* n_out);
 
+/* ------------------------------------------------------------------- diagnostics */
+/* queries whose tensor-core result failed the exactness certificate and were re-run on the
+ * exact scan kernel (process-wide counter) */
+int64_t krag_tc_fallback_queries(void);
+/* raw K2 output a[j][r] = |x_r|^2 - 2 x_r.q_j (TF32) for every row, [nq_pad][S] row-major;
+ * call with out == NULL to query S and nq_pad.  Test hook for the tcgen05 kernel. */
+int32_t krag_debug_tc_dump(krag_index* idx, int32_t nq, const float* q, float* out, int64_t out_elems,
+                           int64_t* S_out, int32_t* nq_pad_out);
+
 #ifdef __cplusplus
 }
 #endif

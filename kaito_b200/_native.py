@@ -29,7 +29,8 @@ SYMBOLS = [
     "krag_index_commit", "krag_index_commit_local", "krag_index_commit_global", "krag_index_stats",
     "krag_index_node_ids", "krag_index_persist", "krag_index_load", "krag_search_dense", "krag_search_bm25",
     "krag_retrieve", "krag_dev_dense_candidates", "krag_dev_bm25_candidates", "krag_dev_merge", "krag_dev_fuse",
-    "krag_synth_fill", "krag_index_read_rows", "krag_index_read_postings",
+    "krag_synth_fill", "krag_index_read_rows", "krag_index_read_postings", "krag_tc_fallback_queries",
+    "krag_debug_tc_dump",
 ]
 
 
@@ -94,6 +95,8 @@ def load() -> C.CDLL:
     L.krag_synth_fill.argtypes = [vp, i64, i64, C.c_uint64, i64]
     L.krag_index_read_rows.argtypes = [vp, i64, i64, vp]
     L.krag_index_read_postings.argtypes = [vp, u32, i64, vp, vp, C.POINTER(i64)]
+    L.krag_tc_fallback_queries.restype = i64
+    L.krag_debug_tc_dump.argtypes = [vp, i32, vp, vp, i64, C.POINTER(i64), C.POINTER(i32)]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if fn.restype is C.c_int:  # default: every remaining call returns an int32 status
@@ -283,6 +286,15 @@ class Index:
     def read_rows(self, row0: int, n: int) -> np.ndarray:
         out = np.empty((n, self.dim), np.float32)
         check(self._L.krag_index_read_rows(self._h, row0, n, ptr(out)))
+        return out
+
+    def debug_tc_dump(self, q) -> np.ndarray:
+        """K2 raw output a[j, r] = |x_r|^2 - 2 x_r.q_j for all rows (test hook)."""
+        q = np.ascontiguousarray(q, np.float32).reshape(-1, self.dim)
+        S, nqp = C.c_int64(0), C.c_int32(0)
+        check(self._L.krag_debug_tc_dump(self._h, q.shape[0], ptr(q), None, 0, C.byref(S), C.byref(nqp)))
+        out = np.empty((nqp.value, S.value), np.float32)
+        check(self._L.krag_debug_tc_dump(self._h, q.shape[0], ptr(q), ptr(out), out.size, C.byref(S), C.byref(nqp)))
         return out
 
     def read_postings(self, term: int, cap: int = 1 << 22):

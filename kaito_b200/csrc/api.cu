@@ -118,6 +118,8 @@ struct krag_index {
     std::shared_mutex mu;
     // dense shard
     DevArray<float> X;
+    DevArray<float> xnorm;          // |x|^2 per row (K2 epilogue)
+    DevArray<uint32_t> xn_max;      // [1] bits of max |x|^2 (K2 certificate)
     int64_t n_rows = 0, n_live = 0;
     std::vector<uint32_t> alive_h;
     DevArray<uint32_t> alive_d;
@@ -177,12 +179,12 @@ void dense_candidates_dev(krag_index* ix, Slot* s, const float* d_q, int batch, 
     KRAG_REQUIRE(ix->ord_base + ix->n_rows <= 0xFFFFFFFFll, KRAG_E_UNSUPPORTED, "global ordinal exceeds 32 bits");
     s->part.reserve((int64_t)dense_scan_part_elems(c->di, P), 0, st);
     int mode = c->cfg.dense_mode;
-    bool use_tc = (mode == KRAG_DENSE_TC) || (mode == KRAG_DENSE_AUTO && batch >= 16);
+    bool use_tc = (mode == KRAG_DENSE_TC) || (mode == KRAG_DENSE_AUTO && dense_tc_wants(ix->n_rows, batch));
     if (use_tc && dense_tc_supported(c->di, ix->dpad)) {
-        size_t ws = dense_tc_workspace_bytes(c->di, batch, P);
+        size_t ws = dense_tc_workspace_bytes(c->di, ix->n_rows, P);
         s->tc_ws.reserve((int64_t)ws, 0, st);
-        if (launch_dense_tc(c->di, ix->X.p, ix->n_rows, ix->dpad, alive_ptr(ix), d_q, batch, P, (uint32_t)ix->ord_base,
-                            s->tc_ws.p, ws, s->part.p, d_keys, st))
+        if (launch_dense_tc(c->di, ix->X.p, ix->n_rows, ix->dpad, alive_ptr(ix), ix->xnorm.p, ix->xn_max.p, d_q, batch, P,
+                            (uint32_t)ix->ord_base, s->tc_ws.p, ws, s->part.p, d_keys, st))
             return;
     }
     KRAG_REQUIRE(mode != KRAG_DENSE_TC, KRAG_E_UNSUPPORTED, "tensor-core dense path unavailable for this index/device");
@@ -238,6 +240,11 @@ void mark_alive(krag_index* ix, int64_t row0, int64_t n, cudaStream_t st)
 void ensure_capacity(krag_index* ix, int64_t rows, int64_t nnz, cudaStream_t st)
 {
     ix->X.reserve(rows * ix->dpad, ix->n_rows * ix->dpad, st);
+    ix->xnorm.reserve(rows, ix->n_rows, st);
+    if (ix->xn_max.p == nullptr) {
+        ix->xn_max.reserve(1, 0, st);
+        KRAG_CUDA(cudaMemsetAsync(ix->xn_max.p, 0, sizeof(uint32_t), st));
+    }
     if (nnz >= 0) {
         ix->toff.reserve(rows + 1, ix->n_rows + 1, st);
         ix->dlen.reserve(rows, ix->n_rows, st);
@@ -393,7 +400,7 @@ int32_t krag_index_drop(krag_index* ix)
             std::unique_lock<std::shared_mutex> lk(ix->mu);
             cudaSetDevice(ix->ctx->di.device);
             cudaDeviceSynchronize();
-            ix->X.release(); ix->alive_d.release(); ix->toff.release(); ix->tid.release(); ix->ttf.release();
+            ix->X.release(); ix->xnorm.release(); ix->xn_max.release(); ix->alive_d.release(); ix->toff.release(); ix->tid.release(); ix->ttf.release();
             ix->dlen.release(); ix->entry_doc.release();
             if (ix->post.off) cudaFree(ix->post.off);
             if (ix->post.doc) cudaFree(ix->post.doc);
@@ -441,6 +448,7 @@ int32_t krag_index_add(krag_index* ix, int64_t n, const uint64_t* node_ids, cons
             KRAG_CUDA(cudaMemcpy2DAsync(dst, sizeof(float) * ix->dpad, vecs, sizeof(float) * ix->dim, sizeof(float) * ix->dim,
                                         (size_t)n, cudaMemcpyHostToDevice, st));
         }
+        launch_row_norms(ix->X.p, ix->n_rows, n, ix->dpad, ix->xnorm.p, ix->xn_max.p, st);
         std::vector<int64_t> shifted;
         if (sparse) {
             shifted.resize((size_t)n + 1);
@@ -537,7 +545,7 @@ int32_t krag_index_stats(krag_index* ix, krag_stats_t* out)
         out->n_docs_global = ix->n_docs_global; out->total_len_global = ix->total_len_global; out->vocab = ix->vocab;
         out->ordinal_base = ix->ord_base; out->dim = ix->dim; out->dim_padded = ix->dpad;
         out->committed = ix->committed && ix->committed_rows == ix->n_rows;
-        out->device_bytes = ix->X.bytes() + ix->alive_d.bytes() + ix->toff.bytes() + ix->tid.bytes() + ix->ttf.bytes() +
+        out->device_bytes = ix->X.bytes() + ix->xnorm.bytes() + ix->alive_d.bytes() + ix->toff.bytes() + ix->tid.bytes() + ix->ttf.bytes() +
                             ix->dlen.bytes() + (ix->committed ? (int64_t)(ix->post.nnz * 8 + (ix->post.vocab + 1) * 8) : 0);
     });
 }
@@ -689,7 +697,7 @@ int32_t krag_dev_merge(krag_ctx* c, int32_t n_lists, int32_t batch, int32_t P, c
         KRAG_REQUIRE(c && d_in && d_out && n_lists >= 1 && batch >= 1, KRAG_E_INVALID, "bad argument");
         check_P(P);
         KRAG_CUDA(cudaSetDevice(c->di.device));
-        launch_merge(d_in, n_lists, batch, P, (int64_t)batch * P, P, d_out, (cudaStream_t)stream);
+        launch_merge(d_in, n_lists, P, batch, P, (int64_t)batch * P, P, d_out, (cudaStream_t)stream);
     });
 }
 
@@ -720,8 +728,9 @@ int32_t krag_synth_fill(krag_index* ix, int64_t n, int64_t row_base, uint64_t se
         KRAG_CUDA(cudaSetDevice(ix->ctx->di.device));
         cudaStream_t st = ix->ctx->admin;
         KRAG_REQUIRE(ix->n_rows == 0, KRAG_E_STATE, "synthetic fill needs an empty index");
-        ix->X.reserve(n * ix->dpad, 0, st);
+        ensure_capacity(ix, n, -1, st);
         launch_synth_dense(ix->X.p, n, ix->dim, ix->dpad, row_base, seed, st);
+        launch_row_norms(ix->X.p, 0, n, ix->dpad, ix->xnorm.p, ix->xn_max.p, st);
         if (vocab > 0) {
             int64_t* off = nullptr; uint32_t* ids = nullptr; uint16_t* tf = nullptr; uint32_t* dl = nullptr; int64_t nnz = 0;
             synth_sparse(n, row_base, seed, vocab, &off, &ids, &tf, &dl, &nnz, st);
@@ -768,6 +777,31 @@ int32_t krag_index_read_postings(krag_index* ix, uint32_t term, int64_t cap, uin
         int64_t m = cnt < cap ? cnt : cap;
         if (m > 0 && docs_out) KRAG_CUDA(cudaMemcpy(docs_out, ix->post.doc + be[0], sizeof(uint32_t) * (size_t)m, cudaMemcpyDeviceToHost));
         if (m > 0 && scores_out) KRAG_CUDA(cudaMemcpy(scores_out, ix->post.score + be[0], sizeof(float) * (size_t)m, cudaMemcpyDeviceToHost));
+    });
+}
+
+int64_t krag_tc_fallback_queries(void) { return dense_tc_fallback_queries(); }
+
+int32_t krag_debug_tc_dump(krag_index* ix, int32_t nq, const float* q, float* out, int64_t out_elems, int64_t* S_out, int32_t* nq_pad_out)
+{
+    return guarded([&] {
+        KRAG_REQUIRE(ix && q && S_out && nq_pad_out && nq >= 1 && nq <= 256, KRAG_E_INVALID, "bad argument");
+        std::shared_lock<std::shared_mutex> lk(ix->mu);
+        KRAG_CUDA(cudaSetDevice(ix->ctx->di.device));
+        SlotLease lease(ix->ctx);
+        Slot* s = lease.s;
+        int64_t S = 0; int nqp = 0;
+        KRAG_REQUIRE(dense_tc_debug_dump(ix->ctx->di, ix->X.p, ix->n_rows, ix->dpad, ix->xnorm.p, nullptr, nq, nullptr, &S, &nqp, s->st),
+                     KRAG_E_UNSUPPORTED, "tensor-core path unavailable");
+        *S_out = S; *nq_pad_out = nqp;
+        if (!out) return;
+        KRAG_REQUIRE(out_elems >= S * nqp, KRAG_E_INVALID, "output buffer too small");
+        const float* dq = upload_queries(ix, s, q, nq);
+        s->tc_ws.reserve(S * nqp * 4, 0, s->st);
+        KRAG_REQUIRE(dense_tc_debug_dump(ix->ctx->di, ix->X.p, ix->n_rows, ix->dpad, ix->xnorm.p, dq, nq, (float*)s->tc_ws.p, &S, &nqp, s->st),
+                     KRAG_E_UNSUPPORTED, "tensor-core dump failed");
+        KRAG_CUDA(cudaMemcpyAsync(out, s->tc_ws.p, sizeof(float) * (size_t)(S * nqp), cudaMemcpyDeviceToHost, s->st));
+        KRAG_CUDA(cudaStreamSynchronize(s->st));
     });
 }
 

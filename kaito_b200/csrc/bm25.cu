@@ -288,7 +288,7 @@ void launch_bm25(const DeviceInfo& di, const Postings& post, int64_t n_rows, con
         KRAG_CUDA(cudaGetLastError());
         count_launch();
     }
-    launch_merge(part, (int)n_tiles, batch, P, /*list_stride=*/P, /*batch_stride=*/n_tiles * P, keys_out, st);
+    launch_merge(part, (int)n_tiles, P, batch, P, /*list_stride=*/P, /*batch_stride=*/n_tiles * P, keys_out, st);
     launch_bm25_fill(keys_out, batch, P, alive, n_rows, ord_base, st);
 }
 

@@ -156,7 +156,7 @@ void launch_dense_scan(const DeviceInfo& di, const float* X, int64_t n_rows, int
         else if (nq == 2) ds_launch<2>(di, X, n_rows, dpad, alive, qb, P, ord_base, part, st);
         else ds_launch<1>(di, X, n_rows, dpad, alive, qb, P, ord_base, part, st);
         // part is [nq][grid][P]: lists = CTAs
-        launch_merge(part, grid, nq, P, /*list_stride=*/P, /*batch_stride=*/(int64_t)grid * P,
+        launch_merge(part, grid, P, nq, P, /*list_stride=*/P, /*batch_stride=*/(int64_t)grid * P,
                      keys_out + (size_t)b * P, st);
         b += nq;
     }

@@ -1,14 +1,579 @@
-// dense_tc.cu -- K2: tcgen05 TF32 candidate generation + exact fp32 rescoring.
-// (placeholder translation unit until the tensor-core kernel lands; the dense path then
-// runs on K1, which is still a GPU kernel -- there is no CPU fallback anywhere)
+// dense_tc.cu -- K2: batched dense search on the 5th-gen tensor cores.
+//
+// Replaces faiss IndexFlatL2.search for query batches (its nq >= 20 sgemm path; reference
+// call site presets/ragengine/vector_store/faiss_store.py:44-49 via hybrid_retriever.py:209-213).
+//
+//   1. dense_tc_kernel<NQ, DUMP>  (tcgen05.mma kind::tf32, TMA-staged, accumulators in TMEM)
+//        D[128 corpus rows x NQ queries] = X_tile . Q^T, fp32 corpus fed as TF32 straight
+//        from HBM (no conversion pass; the corpus is streamed exactly once per pass).
+//        epilogue: a = |x|^2 - 2 x.q  per (row, query), compared with a per-query threshold;
+//        rows below it are appended to that query's candidate list (rare: ~C of N rows).
+//        DUMP mode writes `a` for a strided 1/64 sample of the tiles instead.
+//   2. sample_threshold_kernel: per query, the m-th smallest sampled `a` -> threshold that
+//        admits ~C = max(512, 4P) rows of the full corpus.
+//   3. rescore_kernel: EXACT fp32 squared L2 of every candidate in K1's operation order
+//        (bit-identical to dense_scan.cu / the oracle), then the ordinary top-P merge.
+//   4. certify_kernel: a query's result is exact if every non-candidate row is provably
+//        farther than the P-th exact distance:  D_P <= thr + |q|^2 - 2 eps,  eps = worst-case
+//        TF32 dot-product error (2^-9 + 2^-12) |x|_max |q|.  Queries that fail (candidate
+//        overflow, adversarial near-duplicates) are re-run on the exact scan kernel K1.
+//
+// So the tensor cores only PRUNE; every returned score is an exact fp32 distance.
+//
+// Roofline: bytes = n_rows*dpad*4 per pass (HBM), flops = 2*NQ*n_rows*dpad (TF32 pipe).
+// At NQ = 256 the kernel sits on the HBM/TF32 ridge (128 flop/byte).
+#include <cuda.h>
+#include <math_constants.h>
+
+#include <mutex>
+#include <vector>
+
 #include "engine.h"
+#include "select.cuh"
 
 namespace krag {
-bool dense_tc_supported(const DeviceInfo&, int) { return false; }
-size_t dense_tc_workspace_bytes(const DeviceInfo&, int, int) { return 0; }
-bool launch_dense_tc(const DeviceInfo&, const float*, int64_t, int, const uint32_t*, const float*, int, int, uint32_t,
-                     void*, size_t, uint64_t*, uint64_t*, cudaStream_t)
+
+// ------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 {
-    return false;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000ll) { printf("dense_tc: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x); __trap(); }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+constexpr uint64_t TMA_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t TMA_EVICT_LAST = 0x14F0000000000000ull;
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tm)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tm)) : "memory");
+}
+
+// UMMA shared-memory descriptor, K-major operand, SWIZZLE_128B, 8-row groups 1024 B apart
+// (bit layout: cute/arch/mma_sm100_desc.hpp SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);   // start address, 16-byte units   [0,14)
+    d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset = 1024 B     [32,46)
+    d |= (uint64_t)1 << 46;                         // descriptor version 1 (sm_100)   [46,48)
+    d |= (uint64_t)2 << 61;                         // layout type SWIZZLE_128B        [61,64)
+    return d;
+}
+// instruction descriptor for kind::tf32, fp32 accumulate, both operands K-major
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N)
+{
+    return (1u << 4)      /* D format f32 */
+         | (2u << 7)      /* A format tf32 */
+         | (2u << 10)     /* B format tf32 */
+         | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t* v)
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------- the kernel
+constexpr int TC_TILE_M = 128;          // corpus rows per tile (UMMA M)
+constexpr int TC_KBLOCK = 32;           // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int TC_THREADS = 192;         // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int TC_SAMPLE_STRIDE = 64;    // DUMP mode visits every 64th tile
+constexpr int TC_A_BYTES = TC_TILE_M * TC_KBLOCK * 4;  // 16 KB
+
+template <int NQ> struct TcCfg {
+    static constexpr int B_BYTES = NQ * TC_KBLOCK * 4;
+    static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
+    static constexpr int STAGES = (NQ == 256) ? 4 : (NQ == 128 ? 6 : 8);
+    static constexpr int TMEM_COLS = (2 * NQ < 32) ? 32 : 2 * NQ;  // double-buffered accumulators
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + NQ * 4;
+};
+
+template <int NQ, bool DUMP>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+dense_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmQ, int64_t n_rows,
+                int kblocks, int64_t n_ltiles, int tile_stride, const float* __restrict__ xnorm,
+                const uint32_t* __restrict__ alive, const float* __restrict__ thr_g, uint32_t* __restrict__ cand_count,
+                uint32_t* __restrict__ cand_rows, int cap, float* __restrict__ dump, int64_t S)
+{
+    using Cfg = TcCfg<NQ>;
+    extern __shared__ unsigned char tc_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* tail = smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);           // [STAGES]
+    uint64_t* empty_bar = full_bar + Cfg::STAGES;                      // [STAGES]
+    uint64_t* tfull_bar = empty_bar + Cfg::STAGES;                     // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;                              // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* s_thr = reinterpret_cast<float*>(tail + 256);               // [NQ]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmQ);
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (!DUMP) for (int j = threadIdx.x; j < NQ; j += TC_THREADS) s_thr[j] = thr_g[j];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        int stage = 0; uint32_t phase = 0;
+        for (int64_t lt = blockIdx.x; lt < n_ltiles; lt += gridDim.x) {
+            const int row0 = (int)(lt * tile_stride * TC_TILE_M);
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (lane == 0) {
+                    unsigned char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+                    tma_load_2d(sa, &tmX, &full_bar[stage], kb * TC_KBLOCK, row0, TMA_EVICT_FIRST);
+                    tma_load_2d(sa + TC_A_BYTES, &tmQ, &full_bar[stage], kb * TC_KBLOCK, 0, TMA_EVICT_LAST);
+                }
+                __syncwarp();
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        constexpr uint32_t idesc = umma_idesc_tf32(TC_TILE_M, NQ);
+        int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+        for (int64_t lt = blockIdx.x; lt < n_ltiles; lt += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NQ);
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_base = smem_u32(smem + (size_t)stage * Cfg::STAGE_BYTES);
+                    const uint32_t b_base = a_base + TC_A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < TC_KBLOCK / 8; ++k) {   // UMMA K = 8 for tf32 (32 bytes)
+                        umma_tf32(d_tmem, umma_desc_sw128(a_base + k * 32), umma_desc_sw128(b_base + k * 32), idesc,
+                                  (uint32_t)((kb | k) != 0));
+                    }
+                    umma_commit(&empty_bar[stage]);          // smem slot is free once these MMAs retire
+                    if (kb == kblocks - 1) umma_commit(&tfull_bar[acc]);
+                }
+                __syncwarp();
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    } else {
+        // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
+        const int lg = warp & 3;                         // TMEM lane group this warp may access
+        const int row_in_tile = lg * 32 + lane;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int64_t lt = blockIdx.x; lt < n_ltiles; lt += gridDim.x) {
+            const int64_t row = lt * tile_stride * TC_TILE_M + row_in_tile;
+            float xn = CUDART_INF_F;
+            if (row < n_rows && (alive == nullptr || bit_test(alive, (uint32_t)row))) xn = xnorm[row];
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * NQ);
+#pragma unroll 1
+            for (int c0 = 0; c0 < NQ; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_x32(taddr + c0, v);
+                tmem_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float a = fmaf(-2.f, __uint_as_float(v[j]), xn);
+                    if (DUMP) {
+                        dump[(int64_t)(c0 + j) * S + lt * TC_TILE_M + row_in_tile] = a;
+                    } else if (a < s_thr[c0 + j]) {
+                        const uint32_t pos = atomicAdd(&cand_count[c0 + j], 1u);
+                        if (pos < (uint32_t)cap) cand_rows[(size_t)(c0 + j) * cap + pos] = (uint32_t)row;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------- row norms (index time)
+__global__ void __launch_bounds__(256)
+row_norms_kernel(const float* __restrict__ X, int64_t row0, int64_t n, int dpad, float* __restrict__ xnorm,
+                 uint32_t* __restrict__ xn_max_bits)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t r = row0 + (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (r >= row0 + n) return;
+    const float4* p = reinterpret_cast<const float4*>(X + r * dpad);
+    float s = 0.f;
+    for (int i = lane; i < dpad / 4; i += 32) { float4 v = p[i]; s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) { xnorm[r] = s; atomicMax(xn_max_bits, __float_as_uint(s)); }
+}
+void launch_row_norms(const float* X, int64_t row0, int64_t n, int dpad, float* xnorm, uint32_t* xn_max_bits, cudaStream_t st)
+{
+    if (n == 0) return;
+    row_norms_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(X, row0, n, dpad, xnorm, xn_max_bits);
+    KRAG_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+// -------------------------------------------------------- sample -> per-query threshold
+constexpr int ST_THREADS = 512;
+constexpr int ST_CAP = 2048;
+__global__ void __launch_bounds__(ST_THREADS)
+sample_threshold_kernel(const float* __restrict__ dump, int64_t S, int m, int nq_valid, float* __restrict__ thr)
+{
+    __shared__ uint64_t s_buf[ST_CAP];
+    __shared__ int s_count;
+    __shared__ uint64_t s_thr;
+    const int tid = threadIdx.x, j = blockIdx.x;
+    if (j >= nq_valid) { if (tid == 0) thr[j] = -CUDART_INF_F; return; }   // padded query: admits nothing
+    SelectBuf sel{s_buf, &s_count, &s_thr, ST_CAP};
+    select_init(sel, tid);
+    __syncthreads();
+    const float* col = dump + (int64_t)j * S;
+    const int epoch = (ST_CAP - m) / ST_THREADS;
+    uint64_t t = KEY_PAD;
+    int it = 0;
+    for (int64_t i0 = 0; i0 < S; i0 += ST_THREADS, ++it) {
+        int64_t i = i0 + tid;
+        if (i < S) select_push(sel, make_key_asc(col[i], (uint32_t)i), t);
+        if ((it + 1) % epoch == 0) {
+            __syncthreads();
+            if (s_count + epoch * ST_THREADS > ST_CAP) select_prune<ST_THREADS>(sel, m, tid, 0);
+            t = s_thr;
+        }
+    }
+    select_prune<ST_THREADS>(sel, m, tid, 0);
+    if (tid == 0) thr[j] = (s_count >= m) ? key_value_asc(s_buf[m - 1]) : CUDART_INF_F;
+}
+
+// ------------------------------------------------------------------ exact rescoring
+// one 8-lane group per candidate; same arithmetic as dense_scan_kernel / oracle l2sq_row
+__global__ void __launch_bounds__(256)
+rescore_kernel(const float* __restrict__ X, int dpad, const float* __restrict__ Q, const uint32_t* __restrict__ cand_count,
+               const uint32_t* __restrict__ cand_rows, int cap, uint32_t ord_base, uint64_t* __restrict__ exact_keys)
+{
+    extern __shared__ __align__(16) float rs_q[];   // [dpad]
+    const int j = blockIdx.y, tid = threadIdx.x, lane = tid & 31, l8 = lane & 7;
+    const int cnt = (int)min(cand_count[j], (uint32_t)cap);
+    const int c = blockIdx.x * 32 + (tid >> 3);
+    if (blockIdx.x * 32 >= cnt) {   // whole block past the end: pad and leave
+        if (l8 == 0 && c < cap) exact_keys[(size_t)j * cap + c] = KEY_PAD;
+        return;
+    }
+    for (int i = tid; i < dpad; i += 256) rs_q[i] = Q[(size_t)j * dpad + i];
+    __syncthreads();
+    const bool valid = c < cnt;
+    const uint32_t row = valid ? cand_rows[(size_t)j * cap + c] : 0u;
+    const float4* p = reinterpret_cast<const float4*>(X + (size_t)row * dpad) + l8;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int steps = dpad / KRAG_LANES;
+#pragma unroll 4
+    for (int i = 0; i < steps; ++i) {
+        const float4 a = __ldg(p + i * 8);
+        const float4 qv = *reinterpret_cast<const float4*>(rs_q + i * KRAG_LANES + l8 * 4);
+        float t;
+        t = a.x - qv.x; acc.x = fmaf(t, t, acc.x);
+        t = a.y - qv.y; acc.y = fmaf(t, t, acc.y);
+        t = a.z - qv.z; acc.z = fmaf(t, t, acc.z);
+        t = a.w - qv.w; acc.w = fmaf(t, t, acc.w);
+    }
+    float s = (acc.x + acc.y) + (acc.z + acc.w);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (l8 == 0 && c < cap) exact_keys[(size_t)j * cap + c] = valid ? make_key_asc(s, ord_base + row) : KEY_PAD;
+}
+
+// ------------------------------------------------------------------------ certificate
+__global__ void certify_kernel(const float* __restrict__ Q, int dpad, int nq, int P, const float* __restrict__ thr,
+                               const uint32_t* __restrict__ cand_count, int cap, const uint64_t* __restrict__ keys_out,
+                               const uint32_t* __restrict__ xn_max_bits, int32_t* __restrict__ flags)
+{
+    const int j = blockIdx.x * blockDim.x / 32 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (j >= nq) return;
+    float qn = 0.f;
+    for (int i = lane; i < dpad; i += 32) { float v = Q[(size_t)j * dpad + i]; qn = fmaf(v, v, qn); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qn += __shfl_xor_sync(0xffffffffu, qn, o);
+    if (lane == 0) {
+        const uint64_t kP = keys_out[(size_t)j * P + (P - 1)];
+        const float xmax = __uint_as_float(*xn_max_bits);
+        bool ok = cand_count[j] <= (uint32_t)cap && kP != KEY_PAD;
+        if (ok) {
+            const float dP = key_value_asc(kP);
+            // |tf32 dot - exact dot| <= (2^-9 + 2^-12) |x| |q|  (operand truncation 2^-10 each + fp32 accumulation)
+            const float eps = (0.001953125f + 0.000244140625f) * sqrtf(xmax) * sqrtf(qn);
+            const float slack = 4e-6f * (1.f + qn + xmax);   // fp32 rounding of |x|^2, |q|^2 and the epilogue fma
+            ok = dP <= thr[j] + qn - 2.f * eps - slack;
+        }
+        flags[j] = ok ? 1 : 0;
+    }
+}
+
+// ------------------------------------------------------------------------------- host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+static bool make_map(CUtensorMap* tm, const float* base, int64_t rows, int dpad, int box_rows)
+{
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return false;
+    cuuint64_t gdim[2] = {(cuuint64_t)dpad, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)dpad * 4};
+    cuuint32_t box[2] = {(cuuint32_t)TC_KBLOCK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+constexpr int64_t TC_MIN_ROWS = 262144;   // below this the exact scan is cheaper than sample + prune + rescore
+
+bool dense_tc_supported(const DeviceInfo& di, int dpad)
+{
+    return di.cc_major == 10 && dpad % TC_KBLOCK == 0 && di.smem_optin >= TcCfg<256>::SMEM && get_encode() != nullptr;
+}
+
+static int tc_target(int P) { int c = 4 * P; return c < 512 ? 512 : (c > 3072 ? 3072 : c); }
+static int tc_cap(int P) { return 2 * tc_target(P); }
+
+struct TcWorkspace {   // carved out of the caller's byte buffer
+    float* thr; uint32_t* cand_count; int32_t* flags; uint32_t* cand_rows; uint64_t* exact_keys; float* dump;
+};
+static size_t tc_carve(TcWorkspace* w, unsigned char* base, int cap, int64_t S)
+{
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o = (o + bytes + 255) & ~(size_t)255; return base ? base + at : nullptr; };
+    unsigned char* p;
+    p = take(256 * 4); if (w) w->thr = (float*)p;
+    p = take(256 * 4); if (w) w->cand_count = (uint32_t*)p;
+    p = take(256 * 4); if (w) w->flags = (int32_t*)p;
+    p = take((size_t)256 * cap * 4); if (w) w->cand_rows = (uint32_t*)p;
+    p = take((size_t)256 * cap * 8); if (w) w->exact_keys = (uint64_t*)p;
+    p = take((size_t)256 * S * 4); if (w) w->dump = (float*)p;
+    return o;
+}
+static int64_t tc_sample_tiles(int64_t n_rows)
+{
+    int64_t n_tiles = (n_rows + TC_TILE_M - 1) / TC_TILE_M;
+    return (n_tiles + TC_SAMPLE_STRIDE - 1) / TC_SAMPLE_STRIDE;
+}
+size_t dense_tc_workspace_bytes(const DeviceInfo&, int64_t n_rows, int P)
+{
+    return tc_carve(nullptr, nullptr, tc_cap(P), tc_sample_tiles(n_rows) * TC_TILE_M);
+}
+bool dense_tc_wants(int64_t n_rows, int batch) { return n_rows >= TC_MIN_ROWS && batch >= 16; }
+
+template <int NQ>
+static void tc_pass(const DeviceInfo& di, const CUtensorMap& tmX, const CUtensorMap& tmQ, const float* X, int64_t n_rows,
+                    int dpad, const float* xnorm, const uint32_t* xn_max_bits, const uint32_t* alive, const float* q,
+                    int nq, int P, uint32_t ord_base, const TcWorkspace& w, int cap, int64_t S, uint64_t* keys_out,
+                    cudaStream_t st)
+{
+    using Cfg = TcCfg<NQ>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        KRAG_CUDA(cudaFuncSetAttribute(dense_tc_kernel<NQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        KRAG_CUDA(cudaFuncSetAttribute(dense_tc_kernel<NQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        attr_set = true;
+    }
+    const int kblocks = dpad / TC_KBLOCK;
+    const int64_t n_tiles = (n_rows + TC_TILE_M - 1) / TC_TILE_M;
+    const int64_t s_tiles = tc_sample_tiles(n_rows);
+    const int grid_s = (int)(s_tiles < di.sm_count ? s_tiles : di.sm_count);
+    const int grid_m = (int)(n_tiles < di.sm_count ? n_tiles : di.sm_count);
+    // 1. sample pass (1/64 of the tiles), dump a = |x|^2 - 2 x.q
+    dense_tc_kernel<NQ, true><<<grid_s, TC_THREADS, Cfg::SMEM, st>>>(tmX, tmQ, n_rows, kblocks, s_tiles, TC_SAMPLE_STRIDE, xnorm,
+                                                                     alive, nullptr, nullptr, nullptr, 0, w.dump, S);
+    KRAG_CUDA(cudaGetLastError());
+    count_launch();
+    // 2. threshold admitting ~C rows: the m-th smallest of the sample, m = C * sample_fraction
+    int64_t sampled_rows = 0;
+    for (int64_t t = 0; t < s_tiles; ++t) {
+        int64_t r0 = t * TC_SAMPLE_STRIDE * TC_TILE_M;
+        sampled_rows += (r0 + TC_TILE_M <= n_rows) ? TC_TILE_M : (n_rows > r0 ? n_rows - r0 : 0);
+    }
+    int m = (int)((double)tc_target(P) * (double)sampled_rows / (double)n_rows + 0.5);
+    if (m < 4) m = 4;
+    if (m > 1024) m = 1024;
+    sample_threshold_kernel<<<NQ, ST_THREADS, 0, st>>>(w.dump, S, m, nq, w.thr);
+    KRAG_CUDA(cudaGetLastError());
+    count_launch();
+    KRAG_CUDA(cudaMemsetAsync(w.cand_count, 0, 256 * 4, st));
+    // 3. main pass: stream the corpus once, prune on the tensor cores
+    dense_tc_kernel<NQ, false><<<grid_m, TC_THREADS, Cfg::SMEM, st>>>(tmX, tmQ, n_rows, kblocks, n_tiles, 1, xnorm, alive, w.thr,
+                                                                      w.cand_count, w.cand_rows, cap, nullptr, 0);
+    KRAG_CUDA(cudaGetLastError());
+    count_launch();
+    // 4. exact fp32 rescoring of the survivors + top-P
+    dim3 rg((unsigned)((cap + 31) / 32), (unsigned)nq);
+    rescore_kernel<<<rg, 256, (size_t)dpad * 4, st>>>(X, dpad, q, w.cand_count, w.cand_rows, cap, ord_base, w.exact_keys);
+    KRAG_CUDA(cudaGetLastError());
+    count_launch();
+    launch_merge(w.exact_keys, 1, cap, nq, P, cap, cap, keys_out, st);
+    // 5. certificate
+    certify_kernel<<<(nq * 32 + 255) / 256, 256, 0, st>>>(q, dpad, nq, P, w.thr, w.cand_count, cap, keys_out, xn_max_bits, w.flags);
+    KRAG_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+static int64_t g_tc_fallback_queries = 0;
+int64_t dense_tc_fallback_queries() { return g_tc_fallback_queries; }
+
+bool launch_dense_tc(const DeviceInfo& di, const float* X, int64_t n_rows, int dpad, const uint32_t* alive,
+                     const float* xnorm, const uint32_t* xn_max_bits, const float* q, int batch, int P, uint32_t ord_base,
+                     void* workspace, size_t workspace_bytes, uint64_t* part, uint64_t* keys_out, cudaStream_t st)
+{
+    if (n_rows < TC_MIN_ROWS || n_rows >= (1ll << 31) || xnorm == nullptr) return false;
+    const int cap = tc_cap(P);
+    const int64_t S = tc_sample_tiles(n_rows) * TC_TILE_M;
+    TcWorkspace w;
+    if (tc_carve(&w, (unsigned char*)workspace, cap, S) > workspace_bytes) return false;
+    CUtensorMap tmX;
+    if (!make_map(&tmX, X, n_rows, dpad, TC_TILE_M)) return false;
+    std::vector<int32_t> flags(256);
+    for (int b0 = 0; b0 < batch; b0 += 256) {
+        const int nq = batch - b0 < 256 ? batch - b0 : 256;
+        const int NQ = nq <= 64 ? 64 : (nq <= 128 ? 128 : 256);
+        const float* qb = q + (size_t)b0 * dpad;
+        CUtensorMap tmQ;
+        if (!make_map(&tmQ, qb, nq, dpad, NQ)) return false;
+        uint64_t* ko = keys_out + (size_t)b0 * P;
+        if (NQ == 64) tc_pass<64>(di, tmX, tmQ, X, n_rows, dpad, xnorm, xn_max_bits, alive, qb, nq, P, ord_base, w, cap, S, ko, st);
+        else if (NQ == 128) tc_pass<128>(di, tmX, tmQ, X, n_rows, dpad, xnorm, xn_max_bits, alive, qb, nq, P, ord_base, w, cap, S, ko, st);
+        else tc_pass<256>(di, tmX, tmQ, X, n_rows, dpad, xnorm, xn_max_bits, alive, qb, nq, P, ord_base, w, cap, S, ko, st);
+        // uncertified queries (rare) are re-run on the exact scan kernel -- still on the GPU
+        KRAG_CUDA(cudaMemcpyAsync(flags.data(), w.flags, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
+        KRAG_CUDA(cudaStreamSynchronize(st));
+        for (int j = 0; j < nq; ++j) {
+            if (flags[(size_t)j]) continue;
+            ++g_tc_fallback_queries;
+            launch_dense_scan(di, X, n_rows, dpad, alive, qb + (size_t)j * dpad, 1, P, ord_base, part, ko + (size_t)j * P, st);
+        }
+    }
+    return true;
+}
+
+bool dense_tc_debug_dump(const DeviceInfo& di, const float* X, int64_t n_rows, int dpad, const float* xnorm,
+                         const float* q, int nq, float* dump_out, int64_t* S_out, int* nq_pad_out, cudaStream_t st)
+{
+    if (!dense_tc_supported(di, dpad) || nq > 256) return false;
+    const int NQ = nq <= 64 ? 64 : (nq <= 128 ? 128 : 256);
+    const int64_t n_tiles = (n_rows + TC_TILE_M - 1) / TC_TILE_M;
+    const int64_t S = n_tiles * TC_TILE_M;
+    *S_out = S;
+    *nq_pad_out = NQ;
+    if (dump_out == nullptr) return true;   // size query
+    CUtensorMap tmX, tmQ;
+    if (!make_map(&tmX, X, n_rows, dpad, TC_TILE_M) || !make_map(&tmQ, q, nq, dpad, NQ)) return false;
+    const int kblocks = dpad / TC_KBLOCK;
+    const int grid = (int)(n_tiles < di.sm_count ? n_tiles : di.sm_count);
+#define KRAG_TC_DUMP(N)                                                                                                    \
+    do {                                                                                                                   \
+        KRAG_CUDA(cudaFuncSetAttribute(dense_tc_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<N>::SMEM)); \
+        dense_tc_kernel<N, true><<<grid, TC_THREADS, TcCfg<N>::SMEM, st>>>(tmX, tmQ, n_rows, kblocks, n_tiles, 1, xnorm, nullptr,   \
+                                                                           nullptr, nullptr, nullptr, 0, dump_out, S);     \
+    } while (0)
+    if (NQ == 64) KRAG_TC_DUMP(64); else if (NQ == 128) KRAG_TC_DUMP(128); else KRAG_TC_DUMP(256);
+#undef KRAG_TC_DUMP
+    KRAG_CUDA(cudaGetLastError());
+    count_launch();
+    return true;
+}
+
 }  // namespace krag

@@ -26,16 +26,26 @@ void launch_dense_scan(const DeviceInfo& di, const float* X, int64_t n_rows, int
 
 // ---- K2: tcgen05 TF32 candidate generation + exact fp32 rescoring (dense_tc.cu)
 bool dense_tc_supported(const DeviceInfo& di, int dpad);
-size_t dense_tc_workspace_bytes(const DeviceInfo& di, int batch, int P);
+bool dense_tc_wants(int64_t n_rows, int batch);   // size heuristics: is K2 the better kernel for this call?
+size_t dense_tc_workspace_bytes(const DeviceInfo& di, int64_t n_rows, int P);
+// |x|^2 per row (+ running max) maintained at index time for K2's epilogue and certificate
+void launch_row_norms(const float* X, int64_t row0, int64_t n, int dpad, float* xnorm, uint32_t* xn_max_bits,
+                      cudaStream_t st);
 // returns false when the tensor-core path cannot serve the request (caller falls back to K1 -- still GPU)
 bool launch_dense_tc(const DeviceInfo& di, const float* X, int64_t n_rows, int dpad, const uint32_t* alive,
-                     const float* q, int batch, int P, uint32_t ord_base, void* workspace, size_t workspace_bytes,
-                     uint64_t* part, uint64_t* keys_out, cudaStream_t st);
+                     const float* xnorm, const uint32_t* xn_max_bits, const float* q, int batch, int P,
+                     uint32_t ord_base, void* workspace, size_t workspace_bytes, uint64_t* part, uint64_t* keys_out,
+                     cudaStream_t st);
+int64_t dense_tc_fallback_queries();   // queries re-run on K1 because the exactness certificate failed
+// diagnostics: a[j][r] = |x_r|^2 - 2 x_r.q_j for ALL rows through the tensor-core kernel (tests only)
+bool dense_tc_debug_dump(const DeviceInfo& di, const float* X, int64_t n_rows, int dpad, const float* xnorm,
+                         const float* q, int nq, float* dump_out /*[NQ_pad][S]*/, int64_t* S_out, int* nq_pad_out,
+                         cudaStream_t st);
 
 // ---- merge / fuse (merge_fuse.cu)
-// keys_in [n_lists, batch, P] (list-major) -> keys_out [batch, P]
-void launch_merge(const uint64_t* keys_in, int n_lists, int batch, int P, int64_t list_stride, int64_t batch_stride,
-                  uint64_t* keys_out, cudaStream_t st);
+// per query: n_lists lists of list_len keys (element (l,i) at in[b*batch_stride + l*list_stride + i]) -> the P smallest
+void launch_merge(const uint64_t* keys_in, int n_lists, int list_len, int batch, int P, int64_t list_stride,
+                  int64_t batch_stride, uint64_t* keys_out, cudaStream_t st);
 // append zero-score fillers to short BM25 lists (bm25s argpartition semantics)
 void launch_bm25_fill(uint64_t* keys /*[batch,P]*/, int batch, int P, const uint32_t* alive, int64_t n_rows,
                       uint32_t ord_base, cudaStream_t st);

@@ -13,8 +13,8 @@ constexpr int MG_THREADS = 512;
 constexpr int MG_CAP = 2048;  // >= KRAG_MAX_POOL + MG_THREADS
 
 __global__ void __launch_bounds__(MG_THREADS)
-merge_kernel(const uint64_t* __restrict__ in, int n_lists, int P, int64_t list_stride, int64_t batch_stride,
-             uint64_t* __restrict__ out)
+merge_kernel(const uint64_t* __restrict__ in, int n_lists, int list_len, int P, int64_t list_stride,
+             int64_t batch_stride, uint64_t* __restrict__ out)
 {
     __shared__ uint64_t s_buf[MG_CAP];
     __shared__ int s_count;
@@ -24,14 +24,14 @@ merge_kernel(const uint64_t* __restrict__ in, int n_lists, int P, int64_t list_s
     select_init(sel, tid);
     __syncthreads();
     const uint64_t* base = in + (int64_t)blockIdx.x * batch_stride;
-    const int64_t total = (int64_t)n_lists * P;
+    const int64_t total = (int64_t)n_lists * list_len;
     const int epoch = (MG_CAP - P) / MG_THREADS;  // >= 2 for P <= 1024
     uint64_t thr = KEY_PAD;
     int it = 0;
     for (int64_t i0 = 0; i0 < total; i0 += MG_THREADS, ++it) {
         int64_t i = i0 + tid;
         if (i < total) {
-            int l = (int)(i / P), j = (int)(i - (int64_t)l * P);
+            int l = (int)(i / list_len), j = (int)(i - (int64_t)l * list_len);
             uint64_t key = base[(int64_t)l * list_stride + j];
             if (key != KEY_PAD) select_push(sel, key, thr);
         }
@@ -45,10 +45,10 @@ merge_kernel(const uint64_t* __restrict__ in, int n_lists, int P, int64_t list_s
     select_store<MG_THREADS>(sel, P, out + (int64_t)blockIdx.x * P, tid);
 }
 
-void launch_merge(const uint64_t* keys_in, int n_lists, int batch, int P, int64_t list_stride, int64_t batch_stride,
-                  uint64_t* keys_out, cudaStream_t st)
+void launch_merge(const uint64_t* keys_in, int n_lists, int list_len, int batch, int P, int64_t list_stride,
+                  int64_t batch_stride, uint64_t* keys_out, cudaStream_t st)
 {
-    merge_kernel<<<batch, MG_THREADS, 0, st>>>(keys_in, n_lists, P, list_stride, batch_stride, keys_out);
+    merge_kernel<<<batch, MG_THREADS, 0, st>>>(keys_in, n_lists, list_len, P, list_stride, batch_stride, keys_out);
     KRAG_CUDA(cudaGetLastError());
     count_launch();
 }

@@ -1,0 +1,80 @@
+"""GPU tests of K2, the tcgen05 TF32 kernel: raw tensor-core output against numpy, and the
+full prune -> exact-rescore -> certify pipeline bit-exact against the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx_tc():
+    from kaito_b200 import _native
+    c = _native.Context(device_id=0, dense_mode=_native.DENSE_TC)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("n,d,nq", [(128, 32, 3), (1000, 64, 5), (777, 768, 100), (4096, 384, 256), (130, 1024, 64)])
+def test_tc_raw_output_matches_numpy(ctx_tc, oracle, n, d, nq):
+    x = oracle.synth_dense(n, d, seed=n + d)
+    q = oracle.synth_queries(x, nq, seed=n)
+    ix = ctx_tc.create_index(f"tcraw_{n}_{d}", d)
+    try:
+        ix.add(np.arange(n, dtype=np.uint64), x)
+        a = ix.debug_tc_dump(q)                       # [nq_pad, S]
+        ref = (x.astype(np.float64) ** 2).sum(1)[None, :] - 2.0 * (q.astype(np.float64) @ x.astype(np.float64).T)
+        got = a[:nq, :n].astype(np.float64)
+        err = np.abs(got - ref)
+        assert err.max() < 5e-3, err.max()            # worst-case TF32 bound is 2 * 2^-9 for unit vectors
+        assert err.mean() < 3e-4, err.mean()
+        assert np.isinf(a[:nq, n:]).all()             # rows past the end never qualify
+        assert np.allclose(a[nq:, :n], (x.astype(np.float64) ** 2).sum(1)[None, :], atol=1e-5)  # zero-filled queries
+    finally:
+        ix.drop()
+
+
+@pytest.mark.parametrize("batch,P", [(40, 30), (200, 30), (256, 90), (300, 10)])
+def test_tc_pipeline_bit_exact(ctx_tc, oracle, batch, P):
+    from kaito_b200 import _native
+    n, d = 300_000, 128
+    x = oracle.synth_dense(n, d, seed=3)
+    q = oracle.synth_queries(x, batch, seed=batch)
+    ix = ctx_tc.create_index(f"tc_{batch}_{P}", d)
+    try:
+        ix.add(np.arange(n, dtype=np.uint64), x)
+        fb0 = _native.load().krag_tc_fallback_queries()
+        dist, ordn = ix.search_dense(q, P)
+        fb = _native.load().krag_tc_fallback_queries() - fb0
+        rd, ro = oracle.dense_topk(x, q, P)
+        assert np.array_equal(ordn, ro)
+        assert np.array_equal(dist, rd)               # exact fp32 rescoring: bit-identical to K1 / oracle
+        assert fb <= batch // 20, f"{fb} of {batch} queries needed the exact-scan fallback on random data"
+    finally:
+        ix.drop()
+
+
+def test_tc_certificate_fallback_on_adversarial_data(ctx_tc, oracle):
+    """6000 near-duplicates of one row overflow a query's candidate list: the certificate must
+    fail and the exact scan must still return the right answer; tombstones are honoured."""
+    from kaito_b200 import _native
+    n, d = 280_000, 64
+    x = oracle.synth_dense(n, d, seed=9)
+    g = np.random.default_rng(1)
+    dup = g.choice(n, 6000, replace=False)
+    x[dup] = x[dup[0]] + 1e-4 * g.standard_normal((6000, d)).astype(np.float32)
+    q = np.concatenate([x[dup[:1]], oracle.synth_queries(x, 31, seed=4)])
+    ix = ctx_tc.create_index("tc_adv", d)
+    try:
+        ix.add(np.arange(n, dtype=np.uint64), x)
+        ix.remove(np.array([int(dup[1]), int(dup[2])], np.uint64))
+        alive = oracle.alive_bitmap(n, [int(dup[1]), int(dup[2])])
+        fb0 = _native.load().krag_tc_fallback_queries()
+        dist, ordn = ix.search_dense(q, 30)
+        fb = _native.load().krag_tc_fallback_queries() - fb0
+        rd, ro = oracle.dense_topk(x, q, 30, alive)
+        assert np.array_equal(ordn, ro) and np.array_equal(dist, rd)
+        assert fb >= 1
+    finally:
+        ix.drop()
