@@ -199,6 +199,10 @@ int32_t krag_index_read_postings(krag_index* idx, uint32_t term, int64_t cap, ui
 /* queries whose tensor-core result failed the exactness certificate and were re-run on the
  * exact scan kernel (process-wide counter) */
 int64_t krag_tc_fallback_queries(void);
+/* CUDA-event duration of the dominant dense kernel of the last search on this process
+ * (kernel_id 1 = K1 exact scan, 2 = K2 tcgen05 main pass), with the algorithmic bytes and
+ * flops of that launch -- bench.py's roofline line is computed from it. */
+int32_t krag_last_dense_kernel(float* ms, int32_t* kernel_id, int64_t* algorithmic_bytes, int64_t* flops);
 /* raw K2 output a[j][r] = |x_r|^2 - 2 x_r.q_j (TF32) for every row, [nq_pad][S] row-major;
  * call with out == NULL to query S and nq_pad.  Test hook for the tcgen05 kernel. */
 int32_t krag_debug_tc_dump(krag_index* idx, int32_t nq, const float* q, float* out, int64_t out_elems,

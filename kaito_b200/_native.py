@@ -30,7 +30,7 @@ SYMBOLS = [
     "krag_index_node_ids", "krag_index_persist", "krag_index_load", "krag_search_dense", "krag_search_bm25",
     "krag_retrieve", "krag_dev_dense_candidates", "krag_dev_bm25_candidates", "krag_dev_merge", "krag_dev_fuse",
     "krag_synth_fill", "krag_index_read_rows", "krag_index_read_postings", "krag_tc_fallback_queries",
-    "krag_debug_tc_dump",
+    "krag_debug_tc_dump", "krag_last_dense_kernel",
 ]
 
 
@@ -96,6 +96,7 @@ def load() -> C.CDLL:
     L.krag_index_read_rows.argtypes = [vp, i64, i64, vp]
     L.krag_index_read_postings.argtypes = [vp, u32, i64, vp, vp, C.POINTER(i64)]
     L.krag_tc_fallback_queries.restype = i64
+    L.krag_last_dense_kernel.argtypes = [C.POINTER(C.c_float), C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]
     L.krag_debug_tc_dump.argtypes = [vp, i32, vp, vp, i64, C.POINTER(i64), C.POINTER(i32)]
     for name in SYMBOLS:
         fn = getattr(L, name)
@@ -117,6 +118,13 @@ def ptr(a):
     if isinstance(a, np.ndarray):
         return a.ctypes.data_as(C.c_void_p)
     return C.c_void_p(int(a))
+
+
+def last_dense_kernel():
+    """(ms, kernel_id, algorithmic_bytes, flops) of the dominant dense kernel of the last search."""
+    ms, kid, by, fl = C.c_float(0), C.c_int32(0), C.c_int64(0), C.c_int64(0)
+    check(load().krag_last_dense_kernel(C.byref(ms), C.byref(kid), C.byref(by), C.byref(fl)))
+    return ms.value, kid.value, by.value, fl.value
 
 
 class Context:

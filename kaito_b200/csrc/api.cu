@@ -25,6 +25,24 @@ static std::atomic<int64_t> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
+static cudaEvent_t g_t0 = nullptr, g_t1 = nullptr;
+static int g_t_kernel = 0;
+static int64_t g_t_bytes = 0, g_t_flops = 0;
+static bool g_t_valid = false;
+void dense_timer_begin(cudaStream_t st, int kernel_id, int64_t bytes, int64_t flops)
+{
+    if (!g_t0) { cudaEventCreate(&g_t0); cudaEventCreate(&g_t1); }
+    g_t_kernel = kernel_id; g_t_bytes = bytes; g_t_flops = flops; g_t_valid = false;
+    cudaEventRecord(g_t0, st);
+}
+void dense_timer_end(cudaStream_t st) { cudaEventRecord(g_t1, st); g_t_valid = true; }
+bool dense_timer_read(float* ms, int* kernel_id, int64_t* bytes, int64_t* flops)
+{
+    if (!g_t_valid || cudaEventSynchronize(g_t1) != cudaSuccess || cudaEventElapsedTime(ms, g_t0, g_t1) != cudaSuccess) return false;
+    *kernel_id = g_t_kernel; *bytes = g_t_bytes; *flops = g_t_flops;
+    return true;
+}
+
 struct ApiError { int32_t code; std::string msg; };
 #define KRAG_REQUIRE(cond, code, msg)                      \
     do {                                                   \
@@ -302,7 +320,7 @@ void commit_global_impl(krag_index* ix, int64_t vocab, const uint32_t* df_global
         if (ix->n_rows > 0) launch_expand_entry_doc(ix->toff.p, ix->n_rows, ix->entry_doc.p, st);
     }
     build_postings(ix->tid.p, ix->ttf.p, ix->entry_doc.p, ix->dlen.p, alive_ptr(ix), ix->nnz, vocab, d_idf, avgdl,
-                   ix->post, st);
+                   ix->n_rows, ix->post, st);
     KRAG_CUDA(cudaStreamSynchronize(st));
     KRAG_CUDA(cudaFree(d_idf));
     ix->entry_doc.release();
@@ -405,6 +423,8 @@ int32_t krag_index_drop(krag_index* ix)
             if (ix->post.off) cudaFree(ix->post.off);
             if (ix->post.doc) cudaFree(ix->post.doc);
             if (ix->post.score) cudaFree(ix->post.score);
+            if (ix->post.tile_slot) cudaFree(ix->post.tile_slot);
+            if (ix->post.tile_off) cudaFree(ix->post.tile_off);
         }
         delete ix;
     });
@@ -781,6 +801,16 @@ int32_t krag_index_read_postings(krag_index* ix, uint32_t term, int64_t cap, uin
 }
 
 int64_t krag_tc_fallback_queries(void) { return dense_tc_fallback_queries(); }
+
+int32_t krag_last_dense_kernel(float* ms, int32_t* kernel_id, int64_t* algorithmic_bytes, int64_t* flops)
+{
+    return guarded([&] {
+        KRAG_REQUIRE(ms && kernel_id && algorithmic_bytes && flops, KRAG_E_INVALID, "null argument");
+        int kid = 0;
+        KRAG_REQUIRE(dense_timer_read(ms, &kid, algorithmic_bytes, flops), KRAG_E_STATE, "no dense kernel timed yet");
+        *kernel_id = kid;
+    });
+}
 
 int32_t krag_debug_tc_dump(krag_index* ix, int32_t nq, const float* q, float* out, int64_t out_elems, int64_t* S_out, int32_t* nq_pad_out)
 {

@@ -95,9 +95,73 @@ __global__ void df_to_i64_kernel(const uint32_t* __restrict__ df_local, int64_t 
         out[i] = i < vocab ? (int64_t)df_local[i] : 0;
 }
 
+// ---- tile index (frequent terms only)
+__global__ void tile_flag_kernel(const int64_t* __restrict__ off, int64_t vocab, int32_t* __restrict__ flag)
+{
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t <= vocab; t += (int64_t)gridDim.x * blockDim.x)
+        flag[t] = (t < vocab && off[t + 1] - off[t] > BM25_RARE_MAX) ? 1 : 0;
+}
+__global__ void tile_slot_kernel(const int32_t* __restrict__ flag, const int32_t* __restrict__ scan, int64_t vocab,
+                                 int32_t* __restrict__ slot)
+{
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < vocab; t += (int64_t)gridDim.x * blockDim.x)
+        slot[t] = flag[t] ? scan[t] : -1;
+}
+__global__ void tile_index_kernel(const uint32_t* __restrict__ sorted_terms, const uint32_t* __restrict__ post_doc,
+                                  const int64_t* __restrict__ off, const int32_t* __restrict__ slot, int64_t nnz_live,
+                                  int64_t n_tiles, uint32_t* __restrict__ tile_off)
+{
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz_live; p += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t t = sorted_terms[p];
+        const int32_t sl = slot[t];
+        if (sl < 0) continue;
+        const int64_t b = off[t], e = off[t + 1];
+        const int64_t i = p - b;
+        const int64_t tile_d = post_doc[p] / BM25_TILE_DOCS;
+        const int64_t prev = (i == 0) ? -1 : (int64_t)(post_doc[p - 1] / BM25_TILE_DOCS);
+        uint32_t* row = tile_off + (int64_t)sl * (n_tiles + 1);
+        for (int64_t tl = prev + 1; tl <= tile_d; ++tl) row[tl] = (uint32_t)i;
+        if (p == e - 1) for (int64_t tl = tile_d + 1; tl <= n_tiles; ++tl) row[tl] = (uint32_t)(e - b);
+    }
+}
+static void build_tile_index(const uint32_t* sorted_terms, const uint32_t* post_doc, const int64_t* off, int64_t nnz_live,
+                             int64_t vocab, int64_t n_rows, Postings& out, cudaStream_t st)
+{
+    int32_t *flag = nullptr, *scan = nullptr, *slot = nullptr;
+    KRAG_CUDA(cudaMalloc(&flag, sizeof(int32_t) * (size_t)(vocab + 1)));
+    KRAG_CUDA(cudaMalloc(&scan, sizeof(int32_t) * (size_t)(vocab + 1)));
+    KRAG_CUDA(cudaMalloc(&slot, sizeof(int32_t) * (size_t)vocab));
+    tile_flag_kernel<<<256, 256, 0, st>>>(off, vocab, flag);
+    count_launch();
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, flag, scan, (int)(vocab + 1), st);
+    void* tmp = nullptr;
+    KRAG_CUDA(cudaMalloc(&tmp, bytes ? bytes : 16));
+    cub::DeviceScan::ExclusiveSum(tmp, bytes, flag, scan, (int)(vocab + 1), st);
+    count_launch();
+    tile_slot_kernel<<<256, 256, 0, st>>>(flag, scan, vocab, slot);
+    count_launch();
+    int32_t n_slots = 0;
+    KRAG_CUDA(cudaMemcpyAsync(&n_slots, scan + vocab, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    KRAG_CUDA(cudaStreamSynchronize(st));
+    KRAG_CUDA(cudaFree(tmp)); KRAG_CUDA(cudaFree(flag)); KRAG_CUDA(cudaFree(scan));
+    int64_t n_tiles = (n_rows + BM25_TILE_DOCS - 1) / BM25_TILE_DOCS;
+    if (n_tiles < 1) n_tiles = 1;
+    uint32_t* tile_off = nullptr;
+    KRAG_CUDA(cudaMalloc(&tile_off, sizeof(uint32_t) * (size_t)((int64_t)(n_slots > 0 ? n_slots : 1) * (n_tiles + 1))));
+    if (n_slots > 0) {
+        tile_index_kernel<<<148 * 8, 256, 0, st>>>(sorted_terms, post_doc, off, slot, nnz_live, n_tiles, tile_off);
+        KRAG_CUDA(cudaGetLastError());
+        count_launch();
+    }
+    if (out.tile_slot) cudaFree(out.tile_slot);
+    if (out.tile_off) cudaFree(out.tile_off);
+    out.tile_slot = slot; out.tile_off = tile_off; out.n_slots = n_slots; out.n_tiles = n_tiles;
+}
+
 void build_postings(const uint32_t* term_ids, const uint16_t* term_tf, const uint32_t* entry_doc,
                     const uint32_t* doc_len, const uint32_t* alive, int64_t nnz, int64_t vocab, const float* idf,
-                    double avgdl, Postings& out, cudaStream_t st)
+                    double avgdl, int64_t n_docs_rows, Postings& out, cudaStream_t st)
 {
     // local df (live docs only) -> exclusive scan -> offsets
     uint32_t* df_local = nullptr;
@@ -151,11 +215,23 @@ void build_postings(const uint32_t* term_ids, const uint16_t* term_tf, const uin
             score_postings_kernel<<<148 * 8, 256, 0, st>>>(k_out, v_out, doc_len, idf, avgdl, nnz_live, post_doc,
                                                           post_score);
             count_launch();
+            build_tile_index(k_out, post_doc, off, nnz_live, vocab, n_docs_rows, out, st);
         }
         KRAG_CUDA(cudaStreamSynchronize(st));
         KRAG_CUDA(cudaFree(sort_tmp));
         KRAG_CUDA(cudaFree(k_in)); KRAG_CUDA(cudaFree(k_out));
         KRAG_CUDA(cudaFree(v_in)); KRAG_CUDA(cudaFree(v_out));
+    }
+    if (nnz_live == 0 || nnz == 0) {   // no postings: every term is "rare" with an empty list
+        int32_t* slot = nullptr;
+        KRAG_CUDA(cudaMalloc(&slot, sizeof(int32_t) * (size_t)vocab));
+        KRAG_CUDA(cudaMemset(slot, 0xFF, sizeof(int32_t) * (size_t)vocab));
+        uint32_t* toff = nullptr;
+        KRAG_CUDA(cudaMalloc(&toff, 16));
+        if (out.tile_slot) cudaFree(out.tile_slot);
+        if (out.tile_off) cudaFree(out.tile_off);
+        out.tile_slot = slot; out.tile_off = toff; out.n_slots = 0;
+        out.n_tiles = (n_docs_rows + BM25_TILE_DOCS - 1) / BM25_TILE_DOCS < 1 ? 1 : (n_docs_rows + BM25_TILE_DOCS - 1) / BM25_TILE_DOCS;
     }
     if (out.off) cudaFree(out.off);
     if (out.doc) cudaFree(out.doc);
@@ -165,94 +241,171 @@ void build_postings(const uint32_t* term_ids, const uint16_t* term_tf, const uin
 
 // -------------------------------------------------------------------------- query time
 constexpr int BQ_THREADS = 512;
-constexpr int BQ_WARPS = BQ_THREADS / 32;
-constexpr int BQ_MAX_TERMS = 64;  // terms applied per pass; longer queries loop
+constexpr int BQ_MAX_TERMS = 32;    // query terms resolved per pass; longer queries loop
+constexpr int BQ_MAX_SLABS = 96;    // 512-posting slabs per pass
+constexpr int BQ_PREFETCH = 8;      // slabs held in registers at a time
 
-// warp-cooperative lower_bound over a sorted u32 range: first index in [lo,hi) with a[i] >= target
-__device__ __forceinline__ int64_t warp_lower_bound(const uint32_t* __restrict__ a, int64_t lo, int64_t hi, uint32_t target,
-                                                    int lane)
-{
-    while (hi - lo > 32) {
-        int64_t step = (hi - lo + 31) / 32;
-        int64_t idx = lo + (int64_t)lane * step;
-        bool less = idx < hi && a[idx] < target;
-        unsigned m = __ballot_sync(0xffffffffu, less);
-        int c = __popc(m);  // probes below target form a prefix
-        if (c == 0) return lo;
-        int64_t nlo = lo + (int64_t)(c - 1) * step + 1;
-        int64_t nhi = lo + (int64_t)c * step;
-        lo = nlo;
-        hi = nhi < hi ? nhi : hi;
-    }
-    bool less = lo + lane < hi && a[lo + lane] < target;
-    return lo + __popc(__ballot_sync(0xffffffffu, less));
-}
-
+// A "slab" is up to 512 consecutive postings of one query term that fall into this CTA's doc
+// range (frequent terms: looked up in the tile index; rare terms: the whole <= 256-entry list,
+// filtered by doc).  Slabs are applied in query-term order with a barrier in between, which
+// fixes the per-document fp32 summation order to the oracle's.
 __global__ void __launch_bounds__(BQ_THREADS)
 bm25_tile_kernel(const int64_t* __restrict__ post_off, const uint32_t* __restrict__ post_doc,
-                 const float* __restrict__ post_score, int64_t vocab, const uint32_t* __restrict__ q_terms,
-                 const int32_t* __restrict__ q_term_offsets, int64_t n_rows, const uint32_t* __restrict__ alive, int P,
-                 int cap, uint32_t ord_base, uint64_t* __restrict__ part /*[batch][n_tiles][P]*/)
+                 const float* __restrict__ post_score, const int32_t* __restrict__ tile_slot,
+                 const uint32_t* __restrict__ tile_off, int64_t n_tiles_idx, int64_t vocab,
+                 const uint32_t* __restrict__ q_terms, const int32_t* __restrict__ q_term_offsets, int64_t n_rows,
+                 const uint32_t* __restrict__ alive, int P, int cap, uint32_t ord_base, int batch, int n_tiles,
+                 uint64_t* __restrict__ part /*[batch][n_tiles][P]*/, unsigned long long* __restrict__ g_thr /*[batch]*/)
 {
     extern __shared__ __align__(16) unsigned char bsm[];
     float* acc = reinterpret_cast<float*>(bsm);                                          // [BM25_TILE_DOCS]
     uint64_t* sbuf = reinterpret_cast<uint64_t*>(bsm + (size_t)BM25_TILE_DOCS * 4);      // [cap]
     __shared__ int s_count;
     __shared__ uint64_t s_thr;
-    __shared__ int64_t s_lo[BQ_MAX_TERMS], s_hi[BQ_MAX_TERMS];
+    __shared__ int64_t s_lo[BQ_MAX_TERMS];
+    __shared__ int s_len[BQ_MAX_TERMS];
+    __shared__ int64_t s_slab_lo[BQ_MAX_SLABS];
+    __shared__ int s_slab_n[BQ_MAX_SLABS];
+    __shared__ int s_nslab, s_next_term, s_next_off;
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.x, qi = blockIdx.y;
+    const int tid = threadIdx.x;
+    // the accumulators are zeroed once: every touched entry is reset by the claim step
+    for (int i = tid; i < BM25_TILE_DOCS / 4; i += BQ_THREADS) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    SelectBuf sel{sbuf, &s_count, &s_thr, cap};
+
+    // persistent loop over (tile, query) work items, query fastest: by the time a query's next doc tile is
+    // processed, g_thr[q] (min over finished tiles of their P-th best key -- an upper bound of the global
+    // P-th best) prunes almost every candidate before it reaches the select buffer
+    const int64_t n_items = (int64_t)n_tiles * batch;
+    for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const int tile = (int)(item / batch), qi = (int)(item - (int64_t)tile * batch);
     const int64_t t0 = (int64_t)tile * BM25_TILE_DOCS;
     const int tile_n = (int)min((int64_t)BM25_TILE_DOCS, n_rows - t0);
     const int tb = q_term_offsets[qi], te = q_term_offsets[qi + 1];
-
-    for (int i = tid; i < BM25_TILE_DOCS / 4; i += BQ_THREADS) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    SelectBuf sel{sbuf, &s_count, &s_thr, cap};
-    select_init(sel, tid);
-
-    for (int c0 = tb; c0 < te; c0 += BQ_MAX_TERMS) {
-        const int nt = min(BQ_MAX_TERMS, te - c0);
-        __syncthreads();
-        // posting sub-ranges of this tile, one warp per term
-        for (int j = warp; j < nt; j += BQ_WARPS) {
-            uint32_t t = q_terms[c0 + j];
-            int64_t lo = 0, hi = 0;
-            if ((int64_t)t < vocab) {
-                int64_t b = post_off[t], e = post_off[t + 1];
-                lo = warp_lower_bound(post_doc, b, e, (uint32_t)t0, lane);
-                hi = warp_lower_bound(post_doc, lo, e, (uint32_t)(t0 + tile_n), lane);
-            }
-            if (lane == 0) { s_lo[j] = lo; s_hi[j] = hi; }
-        }
-        __syncthreads();
-        // apply the terms in query order; a barrier between terms fixes the fp32 order
-        for (int j = 0; j < nt; ++j) {
-            const int64_t lo = s_lo[j], hi = s_hi[j];
-            for (int64_t p = lo + tid; p < hi; p += BQ_THREADS) acc[post_doc[p] - (uint32_t)t0] += post_score[p];
-            __syncthreads();
-        }
+    __syncthreads();   // previous item fully stored
+    if (tid == 0) {
+        const unsigned long long h = __ldcg(&g_thr[qi]);
+        s_count = 0;
+        s_thr = (h == KEY_PAD) ? KEY_PAD : h + 1;   // admit keys <= hint
     }
     __syncthreads();
-    // select over the tile: only matched (score > 0), live documents are candidates
-    const int epoch = (cap - P) / BQ_THREADS > 0 ? (cap - P) / BQ_THREADS : 1;
-    uint64_t thr = KEY_PAD;
-    int it = 0;
-    for (int i0 = 0; i0 < tile_n; i0 += BQ_THREADS, ++it) {
-        int i = i0 + tid;
-        if (i < tile_n) {
-            float s = acc[i];
-            if (s > 0.f && (alive == nullptr || bit_test(alive, (uint32_t)(t0 + i))))
-                select_push(sel, make_key_desc(s, ord_base + (uint32_t)(t0 + i)), thr);
+    uint64_t thr = s_thr;
+
+    // posting range of each term of the chunk [c0, c0+nt) inside this tile
+    auto resolve = [&](int c0, int nt) {
+        __syncthreads();
+        if (tid < nt) {
+            const uint32_t t = q_terms[c0 + tid];
+            int64_t lo = 0; int len = 0;
+            if ((int64_t)t < vocab) {
+                const int64_t b = post_off[t];
+                const int32_t sl = tile_slot[t];
+                if (sl >= 0) {
+                    const uint32_t* row = tile_off + (int64_t)sl * (n_tiles_idx + 1);
+                    const uint32_t o0 = row[tile], o1 = row[tile + 1];
+                    lo = b + o0; len = (int)(o1 - o0);
+                } else {
+                    lo = b; len = (int)(post_off[t + 1] - b);   // rare: whole list, filtered by doc range below
+                }
+            }
+            s_lo[tid] = lo; s_len[tid] = len;
         }
-        if ((it + 1) % epoch == 0) {
-            __syncthreads();
-            if (s_count + epoch * BQ_THREADS > cap) select_prune<BQ_THREADS>(sel, P, tid, 0);
-            thr = s_thr;
+        if (tid == 0) { s_next_term = 0; s_next_off = 0; }
+        __syncthreads();
+    };
+    // next pass of at most BQ_MAX_SLABS slabs of the resolved chunk; returns the slab count
+    auto next_pass = [&](int nt) -> int {
+        if (tid == 0) {
+            int ns = 0, j = s_next_term, o = s_next_off;
+            while (j < nt && ns < BQ_MAX_SLABS) {
+                const int rem = s_len[j] - o;
+                if (rem <= 0) { ++j; o = 0; continue; }
+                s_slab_lo[ns] = s_lo[j] + o; s_slab_n[ns] = rem < BQ_THREADS ? rem : BQ_THREADS; ++ns;
+                o += BQ_THREADS;
+            }
+            s_nslab = ns; s_next_term = j; s_next_off = o;
+        }
+        __syncthreads();
+        return s_nslab;
+    };
+    // acc[doc] += score, slab after slab (query-term order), BQ_PREFETCH slabs in registers at a time
+    auto accumulate = [&](int ns) {
+        for (int s0 = 0; s0 < ns; s0 += BQ_PREFETCH) {
+            uint32_t d[BQ_PREFETCH]; float sc[BQ_PREFETCH];
+#pragma unroll
+            for (int u = 0; u < BQ_PREFETCH; ++u) {
+                d[u] = 0xFFFFFFFFu; sc[u] = 0.f;
+                if (s0 + u < ns && tid < s_slab_n[s0 + u]) {
+                    const int64_t p = s_slab_lo[s0 + u] + tid;
+                    d[u] = post_doc[p]; sc[u] = post_score[p];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < BQ_PREFETCH; ++u) {
+                if (s0 + u < ns) {
+                    const uint32_t rel = d[u] - (uint32_t)t0;     // wraps to a huge value for docs below t0
+                    if (d[u] != 0xFFFFFFFFu && rel < (uint32_t)tile_n) acc[rel] += sc[u];
+                    __syncthreads();
+                }
+            }
+        }
+    };
+    // every touched document is pushed exactly once with its final score (first claimer takes it)
+    auto claim = [&](int ns) {
+        for (int s0 = 0; s0 < ns; s0 += BQ_PREFETCH) {
+            uint32_t d[BQ_PREFETCH];
+#pragma unroll
+            for (int u = 0; u < BQ_PREFETCH; ++u) {
+                d[u] = 0xFFFFFFFFu;
+                if (s0 + u < ns && tid < s_slab_n[s0 + u]) d[u] = post_doc[s_slab_lo[s0 + u] + tid];
+            }
+#pragma unroll
+            for (int u = 0; u < BQ_PREFETCH; ++u) {
+                if (s0 + u < ns) {
+                    const uint32_t rel = d[u] - (uint32_t)t0;
+                    if (d[u] != 0xFFFFFFFFu && rel < (uint32_t)tile_n) {
+                        const float sum = atomicExch(&acc[rel], 0.f);
+                        if (sum > 0.f && (alive == nullptr || bit_test(alive, d[u])))
+                            select_push(sel, make_key_desc(sum, ord_base + d[u]), thr);
+                    }
+                    __syncthreads();
+                    if (s_count + BQ_THREADS > cap) select_prune<BQ_THREADS>(sel, P, tid, 0);
+                    thr = s_thr;
+                }
+            }
+        }
+    };
+
+    bool done = false;
+    if (te - tb <= BQ_MAX_TERMS) {
+        // common case: the whole query resolves in one chunk; if it also fits one pass, accumulate and claim
+        // without resolving twice
+        resolve(tb, te - tb);
+        const int ns = next_pass(te - tb);
+        const bool more = (s_next_term < te - tb);   // uniform: written before the barrier inside next_pass
+        if (!more) {
+            accumulate(ns);
+            claim(ns);
+            done = true;
+        }
+    }
+    if (!done) {
+        // general case: ALL terms are accumulated before any document is claimed
+        for (int sweep = 0; sweep < 2; ++sweep) {
+            for (int c0 = tb; c0 < te; c0 += BQ_MAX_TERMS) {
+                const int nt = min(BQ_MAX_TERMS, te - c0);
+                resolve(c0, nt);
+                for (int ns = next_pass(nt); ns > 0; ns = next_pass(nt)) {
+                    if (sweep == 0) accumulate(ns); else claim(ns);
+                    __syncthreads();
+                }
+            }
         }
     }
     select_prune<BQ_THREADS>(sel, P, tid, 0);
-    select_store<BQ_THREADS>(sel, P, part + ((size_t)qi * gridDim.x + tile) * P, tid);
+    select_store<BQ_THREADS>(sel, P, part + ((size_t)qi * n_tiles + tile) * P, tid);
+    if (tid == 0 && s_count == P) atomicMin(&g_thr[qi], (unsigned long long)sbuf[P - 1]);
+    }   // work items
 }
 
 static int bq_cap(int P) { return P <= 512 ? 1024 : 2048; }
@@ -261,14 +414,14 @@ size_t bm25_part_elems(int64_t n_rows, int batch, int P)
 {
     int64_t n_tiles = (n_rows + BM25_TILE_DOCS - 1) / BM25_TILE_DOCS;
     if (n_tiles < 1) n_tiles = 1;
-    return (size_t)n_tiles * batch * P;
+    return (size_t)n_tiles * batch * P + (size_t)batch;   // + per-query threshold hints
 }
 
 void launch_bm25(const DeviceInfo& di, const Postings& post, int64_t n_rows, const uint32_t* alive,
                  const uint32_t* q_terms, const int32_t* q_term_offsets, int max_terms, int batch, int P,
                  uint32_t ord_base, uint64_t* part, uint64_t* keys_out, cudaStream_t st)
 {
-    (void)di; (void)max_terms;
+    (void)max_terms;
     int64_t n_tiles = (n_rows + BM25_TILE_DOCS - 1) / BM25_TILE_DOCS;
     if (n_tiles < 1) n_tiles = 1;
     const int cap = bq_cap(P);
@@ -278,17 +431,19 @@ void launch_bm25(const DeviceInfo& di, const Postings& post, int64_t n_rows, con
         KRAG_CUDA(cudaFuncSetAttribute(bm25_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_set = true;
     }
-    // grid.y is limited to 65535: split very large batches
-    for (int b0 = 0; b0 < batch; b0 += 32768) {
-        int nb = batch - b0 < 32768 ? batch - b0 : 32768;
-        dim3 grid((unsigned)n_tiles, (unsigned)nb);
-        bm25_tile_kernel<<<grid, BQ_THREADS, smem, st>>>(post.off, post.doc, post.score, post.vocab, q_terms,
-                                                         q_term_offsets + b0, n_rows, alive, P, cap, ord_base,
-                                                         part + (size_t)b0 * n_tiles * P);
-        KRAG_CUDA(cudaGetLastError());
-        count_launch();
-    }
-    launch_merge(part, (int)n_tiles, P, batch, P, /*list_stride=*/P, /*batch_stride=*/n_tiles * P, keys_out, st);
+    unsigned long long* g_thr = reinterpret_cast<unsigned long long*>(part + (size_t)n_tiles * batch * P);
+    KRAG_CUDA(cudaMemsetAsync(g_thr, 0xFF, sizeof(unsigned long long) * (size_t)batch, st));
+    const int64_t n_items = n_tiles * batch;
+    const int per_sm = (smem <= 74 * 1024) ? 3 : 2;
+    const int64_t max_grid = (int64_t)per_sm * di.sm_count;
+    const int grid = (int)(n_items < max_grid ? n_items : max_grid);
+    bm25_tile_kernel<<<grid, BQ_THREADS, smem, st>>>(post.off, post.doc, post.score, post.tile_slot, post.tile_off,
+                                                     post.n_tiles, post.vocab, q_terms, q_term_offsets, n_rows, alive, P,
+                                                     cap, ord_base, batch, (int)n_tiles, part, g_thr);
+    KRAG_CUDA(cudaGetLastError());
+    count_launch();
+    launch_merge(part, (int)n_tiles, P, batch, P, /*list_stride=*/P, /*batch_stride=*/n_tiles * P, keys_out, st,
+                 reinterpret_cast<const uint64_t*>(g_thr));
     launch_bm25_fill(keys_out, batch, P, alive, n_rows, ord_base, st);
 }
 

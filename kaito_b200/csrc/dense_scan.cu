@@ -26,7 +26,7 @@ template <int NQ>
 __global__ void __launch_bounds__(DS_THREADS, 2)
 dense_scan_kernel(const float* __restrict__ X, int64_t n_rows, int dpad, const uint32_t* __restrict__ alive,
                   const float* __restrict__ Q, int P, int cap, int epoch_iters, uint32_t ord_base,
-                  uint64_t* __restrict__ part /*[NQ][gridDim.x][P]*/)
+                  uint64_t* __restrict__ part /*[NQ][gridDim.x][P]*/, unsigned long long* __restrict__ g_thr /*[NQ]*/)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* sq = reinterpret_cast<float*>(smem_raw);                                   // [NQ][dpad]
@@ -101,8 +101,14 @@ dense_scan_kernel(const float* __restrict__ X, int64_t n_rows, int dpad, const u
             __syncthreads();
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
-                if (*sel[q].count + epoch_iters * DS_TILE_ROWS > cap) select_prune<DS_THREADS>(sel[q], P, tid, 0);
+                if (*sel[q].count + epoch_iters * DS_TILE_ROWS > cap) {
+                    select_prune<DS_THREADS>(sel[q], P, tid, 0);
+                    // publish this CTA's P-th best: an upper bound of the global P-th best for everyone
+                    if (tid == 0 && *sel[q].count == P) atomicMin(&g_thr[q], (unsigned long long)sel[q].buf[P - 1]);
+                }
+                const unsigned long long h = __ldcg(&g_thr[q]);
                 thr[q] = *sel[q].thr;
+                if (h != KEY_PAD && h + 1 < thr[q]) thr[q] = h + 1;   // admit keys <= hint only
             }
         }
     }
@@ -110,6 +116,7 @@ dense_scan_kernel(const float* __restrict__ X, int64_t n_rows, int dpad, const u
     for (int q = 0; q < NQ; ++q) {
         select_prune<DS_THREADS>(sel[q], P, tid, 0);
         select_store<DS_THREADS>(sel[q], P, part + ((size_t)q * gridDim.x + blockIdx.x) * P, tid);
+        if (tid == 0 && *sel[q].count == P) atomicMin(&g_thr[q], (unsigned long long)sel[q].buf[P - 1]);
     }
 }
 
@@ -121,11 +128,11 @@ static int ds_grid(const DeviceInfo& di, int64_t n_rows)
     return (int)(n_tiles < g ? (n_tiles > 0 ? n_tiles : 1) : g);
 }
 
-size_t dense_scan_part_elems(const DeviceInfo& di, int P) { return (size_t)4 * 2 * di.sm_count * P; }
+size_t dense_scan_part_elems(const DeviceInfo& di, int P) { return (size_t)4 * 2 * di.sm_count * P + 4; }
 
 template <int NQ>
 static void ds_launch(const DeviceInfo& di, const float* X, int64_t n_rows, int dpad, const uint32_t* alive,
-                      const float* q, int P, uint32_t ord_base, uint64_t* part, cudaStream_t st)
+                      const float* q, int P, uint32_t ord_base, uint64_t* part, unsigned long long* g_thr, cudaStream_t st)
 {
     const int cap = ds_cap(P);
     const int epoch = (cap - P) / DS_TILE_ROWS > 0 ? (cap - P) / DS_TILE_ROWS : 1;
@@ -136,7 +143,10 @@ static void ds_launch(const DeviceInfo& di, const float* X, int64_t n_rows, int 
         attr_set = true;
     }
     const int grid = ds_grid(di, n_rows);
-    dense_scan_kernel<NQ><<<grid, DS_THREADS, smem, st>>>(X, n_rows, dpad, alive, q, P, cap, epoch, ord_base, part);
+    KRAG_CUDA(cudaMemsetAsync(g_thr, 0xFF, sizeof(unsigned long long) * NQ, st));
+    dense_timer_begin(st, 1, n_rows * (int64_t)dpad * 4, 3 * (int64_t)NQ * n_rows * dpad);
+    dense_scan_kernel<NQ><<<grid, DS_THREADS, smem, st>>>(X, n_rows, dpad, alive, q, P, cap, epoch, ord_base, part, g_thr);
+    dense_timer_end(st);
     KRAG_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -146,18 +156,19 @@ void launch_dense_scan(const DeviceInfo& di, const float* X, int64_t n_rows, int
                        cudaStream_t st)
 {
     const int grid = ds_grid(di, n_rows);
+    unsigned long long* g_thr = reinterpret_cast<unsigned long long*>(part + (size_t)4 * 2 * di.sm_count * P);
     int b = 0;
     while (b < batch) {
         int nq = batch - b >= 4 ? 4 : (batch - b >= 2 ? 2 : 1);
         // smem budget: NQ * (dpad*4 + cap*8) must stay under 100 KB (2 CTAs per SM)
         while (nq > 1 && (size_t)nq * ((size_t)dpad * 4 + (size_t)ds_cap(P) * 8) > 96 * 1024) nq >>= 1;
         const float* qb = q + (size_t)b * dpad;
-        if (nq == 4) ds_launch<4>(di, X, n_rows, dpad, alive, qb, P, ord_base, part, st);
-        else if (nq == 2) ds_launch<2>(di, X, n_rows, dpad, alive, qb, P, ord_base, part, st);
-        else ds_launch<1>(di, X, n_rows, dpad, alive, qb, P, ord_base, part, st);
+        if (nq == 4) ds_launch<4>(di, X, n_rows, dpad, alive, qb, P, ord_base, part, g_thr, st);
+        else if (nq == 2) ds_launch<2>(di, X, n_rows, dpad, alive, qb, P, ord_base, part, g_thr, st);
+        else ds_launch<1>(di, X, n_rows, dpad, alive, qb, P, ord_base, part, g_thr, st);
         // part is [nq][grid][P]: lists = CTAs
         launch_merge(part, grid, P, nq, P, /*list_stride=*/P, /*batch_stride=*/(int64_t)grid * P,
-                     keys_out + (size_t)b * P, st);
+                     keys_out + (size_t)b * P, st, reinterpret_cast<const uint64_t*>(g_thr));
         b += nq;
     }
 }

@@ -136,16 +136,20 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 // ------------------------------------------------------------------------- the kernel
 constexpr int TC_TILE_M = 128;          // corpus rows per tile (UMMA M)
 constexpr int TC_KBLOCK = 32;           // fp32 elements per k-block = one 128-byte swizzle row
-constexpr int TC_THREADS = 192;         // warp 0: TMA producer, warp 1: MMA issuer, warps 2-5: epilogue
+constexpr int TC_THREADS = 352;         // warp 0: corpus TMA, warp 1: MMA issuer, warp 2: query TMA, warps 3-10: epilogue
 constexpr int TC_SAMPLE_STRIDE = 64;    // DUMP mode visits every 64th tile
 constexpr int TC_A_BYTES = TC_TILE_M * TC_KBLOCK * 4;  // 16 KB
 
+// Two independent shared-memory rings.  The corpus ring is deep because its slabs come from
+// HBM (latency ~2 us under load: ~100 KB must be in flight per SM to sustain 6.5 TB/s); the
+// query ring is shallow because its slabs are L2 hits re-read for every tile.
 template <int NQ> struct TcCfg {
-    static constexpr int B_BYTES = NQ * TC_KBLOCK * 4;
-    static constexpr int STAGE_BYTES = TC_A_BYTES + B_BYTES;
-    static constexpr int STAGES = (NQ == 256) ? 4 : (NQ == 128 ? 6 : 8);
+    static constexpr int Q_BYTES = NQ * TC_KBLOCK * 4;
+    static constexpr int Q_STAGES = (NQ == 256) ? 3 : 4;
+    static constexpr int A_STAGES = (NQ == 256) ? 7 : (NQ == 128 ? 9 : 11);
     static constexpr int TMEM_COLS = (2 * NQ < 32) ? 32 : 2 * NQ;  // double-buffered accumulators
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + NQ * 4;
+    static constexpr int BAR_BYTES = 512;
+    static constexpr size_t SMEM = (size_t)A_STAGES * TC_A_BYTES + (size_t)Q_STAGES * Q_BYTES + 1024 /*align*/ + BAR_BYTES + NQ * 4;
 };
 
 template <int NQ, bool DUMP>
@@ -157,82 +161,106 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 {
     using Cfg = TcCfg<NQ>;
     extern __shared__ unsigned char tc_smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* tail = smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);           // [STAGES]
-    uint64_t* empty_bar = full_bar + Cfg::STAGES;                      // [STAGES]
-    uint64_t* tfull_bar = empty_bar + Cfg::STAGES;                     // [2]
-    uint64_t* tempty_bar = tfull_bar + 2;                              // [2]
+    unsigned char* smem_a = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* smem_q = smem_a + (size_t)Cfg::A_STAGES * TC_A_BYTES;
+    unsigned char* tail = smem_q + (size_t)Cfg::Q_STAGES * Cfg::Q_BYTES;
+    uint64_t* afull = reinterpret_cast<uint64_t*>(tail);               // [A_STAGES]
+    uint64_t* aempty = afull + Cfg::A_STAGES;                           // [A_STAGES]
+    uint64_t* qfull = aempty + Cfg::A_STAGES;                           // [Q_STAGES]
+    uint64_t* qempty = qfull + Cfg::Q_STAGES;                           // [Q_STAGES]
+    uint64_t* tfull_bar = qempty + Cfg::Q_STAGES;                       // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;                               // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-    float* s_thr = reinterpret_cast<float*>(tail + 256);               // [NQ]
+    float* s_thr = reinterpret_cast<float*>(tail + Cfg::BAR_BYTES);     // [NQ]
+    static_assert((2 * (Cfg::A_STAGES + Cfg::Q_STAGES) + 4) * 8 + 8 <= Cfg::BAR_BYTES, "barrier area too small");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmX);
         tma_prefetch_desc(&tmQ);
-        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+        for (int s = 0; s < Cfg::A_STAGES; ++s) { mbar_init(&afull[s], 1); mbar_init(&aempty[s], 1); }
+        for (int s = 0; s < Cfg::Q_STAGES; ++s) { mbar_init(&qfull[s], 1); mbar_init(&qempty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 8); }
         fence_barrier_init();
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (!DUMP) for (int j = threadIdx.x; j < NQ; j += TC_THREADS) s_thr[j] = thr_g[j];
+    // s_thr[j] = thr_j / 2:  a = |x|^2 - 2 x.q < thr_j   <=>   x.q + thr_j/2 > |x|^2/2
+    if (!DUMP) for (int j = threadIdx.x; j < NQ; j += TC_THREADS) s_thr[j] = 0.5f * thr_g[j];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== corpus producer (HBM stream, read once) =====================
         int stage = 0; uint32_t phase = 0;
         for (int64_t lt = blockIdx.x; lt < n_ltiles; lt += gridDim.x) {
             const int row0 = (int)(lt * tile_stride * TC_TILE_M);
             for (int kb = 0; kb < kblocks; ++kb) {
-                mbar_wait(&empty_bar[stage], phase ^ 1);
+                mbar_wait(&aempty[stage], phase ^ 1);
                 if (lane == 0) {
-                    unsigned char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
-                    mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-                    tma_load_2d(sa, &tmX, &full_bar[stage], kb * TC_KBLOCK, row0, TMA_EVICT_FIRST);
-                    tma_load_2d(sa + TC_A_BYTES, &tmQ, &full_bar[stage], kb * TC_KBLOCK, 0, TMA_EVICT_LAST);
+                    mbar_expect_tx(&afull[stage], TC_A_BYTES);
+                    tma_load_2d(smem_a + (size_t)stage * TC_A_BYTES, &tmX, &afull[stage], kb * TC_KBLOCK, row0, TMA_EVICT_FIRST);
                 }
                 __syncwarp();
-                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                if (++stage == Cfg::A_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== query producer (L2-resident, re-read per tile) =====================
+        int stage = 0; uint32_t phase = 0;
+        for (int64_t lt = blockIdx.x; lt < n_ltiles; lt += gridDim.x) {
+            for (int kb = 0; kb < kblocks; ++kb) {
+                mbar_wait(&qempty[stage], phase ^ 1);
+                if (lane == 0) {
+                    mbar_expect_tx(&qfull[stage], Cfg::Q_BYTES);
+                    tma_load_2d(smem_q + (size_t)stage * Cfg::Q_BYTES, &tmQ, &qfull[stage], kb * TC_KBLOCK, 0, TMA_EVICT_LAST);
+                }
+                __syncwarp();
+                if (++stage == Cfg::Q_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         constexpr uint32_t idesc = umma_idesc_tf32(TC_TILE_M, NQ);
-        int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+        int sa = 0, sq = 0; uint32_t pa = 0, pq = 0; int acc = 0; uint32_t acc_phase = 0;
         for (int64_t lt = blockIdx.x; lt < n_ltiles; lt += gridDim.x) {
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NQ);
             for (int kb = 0; kb < kblocks; ++kb) {
-                mbar_wait(&full_bar[stage], phase);
+                mbar_wait(&qfull[sq], pq);
+                mbar_wait(&afull[sa], pa);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t a_base = smem_u32(smem + (size_t)stage * Cfg::STAGE_BYTES);
-                    const uint32_t b_base = a_base + TC_A_BYTES;
+                    const uint32_t a_base = smem_u32(smem_a + (size_t)sa * TC_A_BYTES);
+                    const uint32_t b_base = smem_u32(smem_q + (size_t)sq * Cfg::Q_BYTES);
 #pragma unroll
                     for (int k = 0; k < TC_KBLOCK / 8; ++k) {   // UMMA K = 8 for tf32 (32 bytes)
                         umma_tf32(d_tmem, umma_desc_sw128(a_base + k * 32), umma_desc_sw128(b_base + k * 32), idesc,
                                   (uint32_t)((kb | k) != 0));
                     }
-                    umma_commit(&empty_bar[stage]);          // smem slot is free once these MMAs retire
+                    umma_commit(&aempty[sa]);                // slots are free once these MMAs retire
+                    umma_commit(&qempty[sq]);
                     if (kb == kblocks - 1) umma_commit(&tfull_bar[acc]);
                 }
                 __syncwarp();
-                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                if (++sa == Cfg::A_STAGES) { sa = 0; pa ^= 1; }
+                if (++sq == Cfg::Q_STAGES) { sq = 0; pq ^= 1; }
             }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1;
         }
     } else {
-        // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
+        // ===================== epilogue: 8 warps, two per TMEM lane group, half of the columns each =====
+        // (the epilogue paces the kernel when it is slower than the 96 MMAs of a tile, so it is kept to
+        //  ~2 instructions per (row, query) pair: one add and one 3-input max; hits are ~1 in 20000)
         const int lg = warp & 3;                         // TMEM lane group this warp may access
+        const int col_half = (warp - 3) >> 2;            // 0: columns [0, NQ/2), 1: [NQ/2, NQ)
         const int row_in_tile = lg * 32 + lane;
         int acc = 0; uint32_t acc_phase = 0;
         for (int64_t lt = blockIdx.x; lt < n_ltiles; lt += gridDim.x) {
@@ -242,19 +270,36 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * NQ);
+            const float half_xn = 0.5f * xn;
 #pragma unroll 1
-            for (int c0 = 0; c0 < NQ; c0 += 32) {
+            for (int c0 = col_half * (NQ / 2); c0 < (col_half + 1) * (NQ / 2); c0 += 32) {
                 uint32_t v[32];
                 tmem_ld_x32(taddr + c0, v);
                 tmem_wait_ld();
+                if (DUMP) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float a = fmaf(-2.f, __uint_as_float(v[j]), xn);
-                    if (DUMP) {
-                        dump[(int64_t)(c0 + j) * S + lt * TC_TILE_M + row_in_tile] = a;
-                    } else if (a < s_thr[c0 + j]) {
-                        const uint32_t pos = atomicAdd(&cand_count[c0 + j], 1u);
-                        if (pos < (uint32_t)cap) cand_rows[(size_t)(c0 + j) * cap + pos] = (uint32_t)row;
+                    for (int j = 0; j < 32; ++j)
+                        dump[(int64_t)(c0 + j) * S + lt * TC_TILE_M + row_in_tile] = fmaf(-2.f, __uint_as_float(v[j]), xn);
+                } else {
+                    float t[32];
+                    float mx = -CUDART_INF_F;
+#pragma unroll
+                    for (int j4 = 0; j4 < 32; j4 += 4) {
+                        const float4 h = *reinterpret_cast<const float4*>(s_thr + c0 + j4);   // warp-uniform: broadcast
+                        t[j4 + 0] = __uint_as_float(v[j4 + 0]) + h.x;
+                        t[j4 + 1] = __uint_as_float(v[j4 + 1]) + h.y;
+                        t[j4 + 2] = __uint_as_float(v[j4 + 2]) + h.z;
+                        t[j4 + 3] = __uint_as_float(v[j4 + 3]) + h.w;
+                        mx = fmaxf(mx, fmaxf(fmaxf(t[j4 + 0], t[j4 + 1]), fmaxf(t[j4 + 2], t[j4 + 3])));
+                    }
+                    if (mx > half_xn) {   // rare: some pair in this chunk passes  x.q + thr/2 > |x|^2/2
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (t[j] > half_xn) {
+                                const uint32_t pos = atomicAdd(&cand_count[c0 + j], 1u);
+                                if (pos < (uint32_t)cap) cand_rows[(size_t)(c0 + j) * cap + pos] = (uint32_t)row;
+                            }
+                        }
                     }
                 }
             }
@@ -430,7 +475,8 @@ bool dense_tc_supported(const DeviceInfo& di, int dpad)
 }
 
 static int tc_target(int P) { int c = 4 * P; return c < 512 ? 512 : (c > 3072 ? 3072 : c); }
-static int tc_cap(int P) { return 2 * tc_target(P); }
+// Gamma(m)-distributed sample estimate (m = C/64 >= 8): 4x the target is a < 1e-8 overflow tail
+static int tc_cap(int P) { return 4 * tc_target(P); }
 
 struct TcWorkspace {   // carved out of the caller's byte buffer
     float* thr; uint32_t* cand_count; int32_t* flags; uint32_t* cand_rows; uint64_t* exact_keys; float* dump;
@@ -496,8 +542,10 @@ static void tc_pass(const DeviceInfo& di, const CUtensorMap& tmX, const CUtensor
     count_launch();
     KRAG_CUDA(cudaMemsetAsync(w.cand_count, 0, 256 * 4, st));
     // 3. main pass: stream the corpus once, prune on the tensor cores
+    dense_timer_begin(st, 2, n_rows * (int64_t)dpad * 4, 2 * (int64_t)NQ * n_rows * dpad);
     dense_tc_kernel<NQ, false><<<grid_m, TC_THREADS, Cfg::SMEM, st>>>(tmX, tmQ, n_rows, kblocks, n_tiles, 1, xnorm, alive, w.thr,
                                                                       w.cand_count, w.cand_rows, cap, nullptr, 0);
+    dense_timer_end(st);
     KRAG_CUDA(cudaGetLastError());
     count_launch();
     // 4. exact fp32 rescoring of the survivors + top-P

@@ -12,6 +12,12 @@ struct DeviceInfo {
     size_t smem_optin = 0;
 };
 
+// CUDA-event bracket around the dominant dense kernel of the last search (roofline evidence):
+// recorded on the launching stream; read back after the stream is synchronised.
+void dense_timer_begin(cudaStream_t st, int kernel_id, int64_t algorithmic_bytes, int64_t flops);
+void dense_timer_end(cudaStream_t st);
+bool dense_timer_read(float* ms, int* kernel_id, int64_t* bytes, int64_t* flops);
+
 // launch counter (bench.py reports gpu_launches from it)
 void count_launch(int n = 1);
 int64_t launch_count();
@@ -45,7 +51,7 @@ bool dense_tc_debug_dump(const DeviceInfo& di, const float* X, int64_t n_rows, i
 // ---- merge / fuse (merge_fuse.cu)
 // per query: n_lists lists of list_len keys (element (l,i) at in[b*batch_stride + l*list_stride + i]) -> the P smallest
 void launch_merge(const uint64_t* keys_in, int n_lists, int list_len, int batch, int P, int64_t list_stride,
-                  int64_t batch_stride, uint64_t* keys_out, cudaStream_t st);
+                  int64_t batch_stride, uint64_t* keys_out, cudaStream_t st, const uint64_t* thr_hint = nullptr);
 // append zero-score fillers to short BM25 lists (bm25s argpartition semantics)
 void launch_bm25_fill(uint64_t* keys /*[batch,P]*/, int batch, int P, const uint32_t* alive, int64_t n_rows,
                       uint32_t ord_base, cudaStream_t st);
@@ -60,14 +66,20 @@ struct Postings {
     uint32_t* doc = nullptr;   // [nnz] local rows ascending inside a term
     float* score = nullptr;    // [nnz]
     int64_t vocab = 0, nnz = 0;
+    // tile index: for terms with more than BM25_RARE_MAX postings, the offset (relative to off[t]) of the
+    // first posting whose doc lies in each BM25_TILE_DOCS-sized doc range; removes per-query searches
+    int32_t* tile_slot = nullptr;   // [vocab]  slot of a frequent term, -1 for rare terms
+    uint32_t* tile_off = nullptr;   // [n_slots][n_tiles + 1]
+    int64_t n_slots = 0, n_tiles = 0;
 };
+constexpr int BM25_RARE_MAX = 256;
 void launch_df_histogram(const uint32_t* term_ids, const uint32_t* entry_doc, const uint32_t* alive, int64_t nnz,
                          uint32_t* df, cudaStream_t st);
 void launch_expand_entry_doc(const int64_t* term_offsets, int64_t n_docs, uint32_t* entry_doc, cudaStream_t st);
 // builds postings from CSR-by-doc arrays; idf is a device array [vocab] computed on the host (glibc log)
 void build_postings(const uint32_t* term_ids, const uint16_t* term_tf, const uint32_t* entry_doc,
                     const uint32_t* doc_len, const uint32_t* alive, int64_t nnz, int64_t vocab, const float* idf,
-                    double avgdl, Postings& out, cudaStream_t st);
+                    double avgdl, int64_t n_docs_rows, Postings& out, cudaStream_t st);
 size_t bm25_part_elems(int64_t n_rows, int batch, int P);
 void launch_bm25(const DeviceInfo& di, const Postings& post, int64_t n_rows, const uint32_t* alive,
                  const uint32_t* q_terms, const int32_t* q_term_offsets, int max_terms, int batch, int P,

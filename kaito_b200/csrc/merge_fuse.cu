@@ -14,7 +14,7 @@ constexpr int MG_CAP = 2048;  // >= KRAG_MAX_POOL + MG_THREADS
 
 __global__ void __launch_bounds__(MG_THREADS)
 merge_kernel(const uint64_t* __restrict__ in, int n_lists, int list_len, int P, int64_t list_stride,
-             int64_t batch_stride, uint64_t* __restrict__ out)
+             int64_t batch_stride, uint64_t* __restrict__ out, const uint64_t* __restrict__ thr_hint)
 {
     __shared__ uint64_t s_buf[MG_CAP];
     __shared__ int s_count;
@@ -22,11 +22,13 @@ merge_kernel(const uint64_t* __restrict__ in, int n_lists, int list_len, int P, 
     const int tid = threadIdx.x;
     SelectBuf sel{s_buf, &s_count, &s_thr, MG_CAP};
     select_init(sel, tid);
+    // thr_hint[q] (optional) is an upper bound of the P-th smallest key: only keys <= hint can be in the result
+    if (tid == 0 && thr_hint != nullptr && thr_hint[blockIdx.x] != KEY_PAD) s_thr = thr_hint[blockIdx.x] + 1;
     __syncthreads();
     const uint64_t* base = in + (int64_t)blockIdx.x * batch_stride;
     const int64_t total = (int64_t)n_lists * list_len;
     const int epoch = (MG_CAP - P) / MG_THREADS;  // >= 2 for P <= 1024
-    uint64_t thr = KEY_PAD;
+    uint64_t thr = s_thr;
     int it = 0;
     for (int64_t i0 = 0; i0 < total; i0 += MG_THREADS, ++it) {
         int64_t i = i0 + tid;
@@ -46,9 +48,9 @@ merge_kernel(const uint64_t* __restrict__ in, int n_lists, int list_len, int P, 
 }
 
 void launch_merge(const uint64_t* keys_in, int n_lists, int list_len, int batch, int P, int64_t list_stride,
-                  int64_t batch_stride, uint64_t* keys_out, cudaStream_t st)
+                  int64_t batch_stride, uint64_t* keys_out, cudaStream_t st, const uint64_t* thr_hint)
 {
-    merge_kernel<<<batch, MG_THREADS, 0, st>>>(keys_in, n_lists, list_len, P, list_stride, batch_stride, keys_out);
+    merge_kernel<<<batch, MG_THREADS, 0, st>>>(keys_in, n_lists, list_len, P, list_stride, batch_stride, keys_out, thr_hint);
     KRAG_CUDA(cudaGetLastError());
     count_launch();
 }

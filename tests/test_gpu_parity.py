@@ -82,6 +82,25 @@ def test_bm25_postings_and_query_bit_exact(ctx_scan, oracle, n, vocab):
         ix.drop()
 
 
+def test_bm25_long_queries_dense_postings(ctx_scan, oracle):
+    """tiny vocabulary -> every term is frequent (thousands of postings per doc tile) and queries of
+    40-70 terms span several term chunks and slab passes of the kernel's general path"""
+    n, vocab = 40000, 48
+    ix, x, (off, ids, tf, dl) = _sparse_index(ctx_scan, oracle, n, vocab)
+    try:
+        post = oracle.bm25_build(off, ids, tf, dl, vocab)
+        g = np.random.default_rng(3)
+        qs = [g.integers(0, vocab, m).astype(np.uint32) for m in (40, 70, 33, 1, 5)]
+        for P in (30, 600):
+            score, ordn = ix.search_bm25(qs, P)
+            for b, qt in enumerate(qs):
+                rs, ro = oracle.bm25_query(post, qt, P)
+                assert np.array_equal(ordn[b], ro), (b, P)
+                assert np.array_equal(score[b], rs)
+    finally:
+        ix.drop()
+
+
 def test_bm25_zero_fill_and_tombstones(ctx_scan, oracle):
     ix, x, (off, ids, tf, dl) = _sparse_index(ctx_scan, oracle, 500, 800)
     try:
