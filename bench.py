@@ -124,46 +124,60 @@ def synth_query_terms(batch, seed, vocab=VOCAB, s=1.07, rank_offset=100):
 
 
 # ------------------------------------------------------------------ CPU baseline (oracle)
-def cpu_reference_qps(n_docs, dim, hybrid, k, sample_rows, n_queries=8, seed=0):
-    """Restated reference path (oracle) on all host cores over `sample_rows` documents, linearly
-    extrapolated to n_docs. Prebuilt postings (the reference rebuilds them per query, which is
-    slower still -- reported separately as rebuild_s)."""
-    from oracle import oracle as o
-    o.build()
-    n = int(min(sample_rows, n_docs))
-    x = o.synth_dense(n, dim, seed + 1)
-    q = o.synth_queries(x, n_queries, seed + 2)
-    P = o.pool_size(k)
-    post = None
-    rebuild_s = None
-    qs = None
-    if hybrid:
-        vocab = 1 << 16
-        ns = min(n, 100_000)
-        off, ids, tf, dl = o.synth_sparse(ns, vocab, seed + 3)
+class CpuReference:
+    """Restated reference path (oracle: FAISS-flat scan + bm25s-lucene + _fuse) on all host cores over a
+    bounded sample of the workload; the per-query time is extrapolated linearly in N (both stages are O(N)).
+    Postings are prebuilt (the reference rebuilds them on every query, which is slower still and reported
+    separately as bm25_rebuild_per_query_s_extrapolated)."""
+
+    def __init__(self, n_docs, dim, hybrid, k, sample_rows, n_queries=8, seed=0):
+        from oracle import oracle as o
+        o.build()
+        self.o, self.n_docs, self.dim, self.hybrid, self.k, self.nq = o, n_docs, dim, hybrid, k, n_queries
+        self.n = int(min(sample_rows, n_docs))
+        self.x = o.synth_dense(self.n, dim, seed + 1)
+        self.q = o.synth_queries(self.x, n_queries, seed + 2)
+        self.P = o.pool_size(k)
+        self.rebuild_s = None
+        if hybrid:
+            vocab = 1 << 16
+            self.ns = min(self.n, 100_000)
+            off, ids, tf, dl = o.synth_sparse(self.ns, vocab, seed + 3)
+            t0 = time.perf_counter()
+            self.post = o.bm25_build(off, ids, tf, dl, vocab)
+            self.rebuild_s = (time.perf_counter() - t0) * (n_docs / self.ns)
+            self.qs = o.synth_query_terms(vocab, n_queries, seed + 4)
+        o.dense_topk(self.x, self.q[:1], self.P)  # warm: page-touch the sample, start the OpenMP team
+
+    def step(self):
+        """one pass of n_queries queries over the sample; returns extrapolated seconds per query at n_docs"""
+        o = self.o
         t0 = time.perf_counter()
-        post = o.bm25_build(off, ids, tf, dl, vocab)
-        rebuild_s = (time.perf_counter() - t0) * (n_docs / ns)
-        qs = o.synth_query_terms(vocab, n_queries, seed + 4)
-        sparse_scale = n_docs / ns
-    o.dense_topk(x, q[:1], P)  # warm: page-touch the sample, start the OpenMP team
-    t0 = time.perf_counter()
-    dd, do = o.dense_topk(x, q, P)
-    t_dense = (time.perf_counter() - t0) / n_queries
-    t_sparse = 0.0
-    if hybrid:
-        t0 = time.perf_counter()
-        for b in range(n_queries):
-            bs, bo = o.bm25_query(post, qs[b], P)
-            o.fuse(dd[b], do[b], bs, bo, k)
-        t_sparse = (time.perf_counter() - t0) / n_queries * sparse_scale
-    per_query = t_dense * (n_docs / n) + t_sparse
-    return {"value": 1.0 / per_query, "unit": "queries/s", "cores": o.threads(), "kind": "port",
-            "sample": f"oracle (restated FAISS-flat + bm25s + _fuse; real wheels not installable offline) on {n} of "
-                      f"{n_docs} rows x {dim} fp32, {n_queries} queries, all host threads, prebuilt postings, "
-                      f"extrapolated linearly in N",
-            "per_query_s_extrapolated": per_query,
-            "bm25_rebuild_per_query_s_extrapolated": rebuild_s}
+        dd, do = o.dense_topk(self.x, self.q, self.P)
+        t_dense = (time.perf_counter() - t0) / self.nq
+        t_sparse = 0.0
+        if self.hybrid:
+            t0 = time.perf_counter()
+            for b in range(self.nq):
+                bs, bo = o.bm25_query(self.post, self.qs[b], self.P)
+                o.fuse(dd[b], do[b], bs, bo, self.k)
+            t_sparse = (time.perf_counter() - t0) / self.nq * (self.n_docs / self.ns)
+        return t_dense * (self.n_docs / self.n) + t_sparse
+
+    def describe(self, per_query):
+        return {"value": 1.0 / per_query, "unit": "queries/s", "cores": self.o.threads(), "kind": "port",
+                "sample": f"oracle (restated FAISS-flat + bm25s + _fuse; the real wheels are not installable offline) on "
+                          f"{self.n} of {self.n_docs} rows x {self.dim} fp32, {self.nq} queries per step, all host threads, "
+                          f"prebuilt postings, extrapolated linearly in N",
+                "per_query_s_extrapolated": per_query,
+                "bm25_rebuild_per_query_s_extrapolated": self.rebuild_s}
+
+
+def cpu_reference_qps(n_docs, dim, hybrid, k, sample_rows):
+    ref = CpuReference(n_docs, dim, hybrid, k, sample_rows)
+    ref.step()
+    t = float(np.median([ref.step() for _ in range(3)]))
+    return ref.describe(t)
 
 
 def run_reference(args):
@@ -172,20 +186,17 @@ def run_reference(args):
     if rank != 0:
         return
     docs, dim, hybrid = WORKLOADS[args.workload]
-    vals = []
-    for i in range(args.warmup + args.steps):
-        r = cpu_reference_qps(docs, dim, hybrid, args.k, max(20_000, args.cpu_sample_rows // 4), n_queries=4, seed=i)
-        if i >= args.warmup:
-            vals.append(r)
-    v = float(np.mean([r["value"] for r in vals]))
-    base = vals[-1]
-    base["value"] = v
+    ref = CpuReference(docs, dim, hybrid, args.k, args.cpu_sample_rows)
+    for _ in range(args.warmup):
+        ref.step()
+    per_query = float(np.mean([ref.step() for _ in range(args.steps)]))
+    v = 1.0 / per_query
     line = {"impl": "reference", "metric": "rag_retrieve_queries_per_sec", "value": v, "unit": "queries/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / v,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * per_query * ref.nq,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {docs} docs x {dim} fp32" + (" + BM25 postings, hybrid fuse" if hybrid else ""),
-                       "top_k": args.k, "batch": 1},
-            "cpu_baseline": base,
+            "config": {"workload": f"{args.workload}: {docs} docs x {dim} fp32" + (" + BM25 postings, hybrid weighted fusion" if hybrid else ", dense only"),
+                       "top_k": args.k, "global_batch": ref.nq, "parallelism": "host threads"},
+            "cpu_baseline": ref.describe(per_query),
             "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 

@@ -1,0 +1,248 @@
+"""RAGService HTTP surface over the CUDA engine -- the drop-in for presets/ragengine/main.py that the
+unmodified KAITO ragengine controller deploys (pod contract: SURVEY.md section 8 b1).
+
+Routes, status codes and detail strings follow the reference (presets/ragengine/main.py): GET /metrics :165,
+GET /health :180, POST /index :217, POST /v1/chat/completions :275, GET /indexes :356,
+GET /indexes/{name}/documents :393, POST /indexes/{name}/documents :495,
+POST /indexes/{name}/documents/delete :546, POST /persist/{name} :596, POST /load/{name} :652,
+POST /retrieve :704, DELETE /indexes/{name} :774.  Unknown JSON fields are ignored (test/rage2e sends
+`context_token_ratio`, rag_test.go:1254).  Prometheus metric names: metrics/prometheus_metrics.py:27-201.
+
+The host language north_star asks for is Go; no Go toolchain exists in this image, so the host is Python
+like the reference service itself, and binds the same C ABI a cgo host would.
+"""
+from __future__ import annotations
+
+import json
+import os
+import time
+from urllib.parse import unquote
+
+from fastapi import FastAPI, HTTPException, Query, Request, Response
+from prometheus_client import CONTENT_TYPE_LATEST, CollectorRegistry, Counter, Gauge, Histogram, generate_latest
+from pydantic import BaseModel, Field
+
+from . import vector_store as vs
+
+RAG_MAX_TOP_K = vs.RAG_MAX_TOP_K
+
+
+# --------------------------------------------------------------------------- wire models (models.py:24-93)
+class Document(BaseModel):
+    doc_id: str = Field(default="")
+    text: str
+    metadata: dict | None = Field(default_factory=dict)
+    hash_value: str | None = None
+    is_truncated: bool = False
+
+
+class IndexRequest(BaseModel):
+    index_name: str
+    documents: list[Document]
+
+
+class UpdateDocumentRequest(BaseModel):
+    documents: list[Document]
+
+
+class DeleteDocumentRequest(BaseModel):
+    doc_ids: list[str]
+
+
+class RetrieveRequest(BaseModel):
+    index_name: str
+    query: str
+    max_node_count: int = Field(default=5, ge=1, le=RAG_MAX_TOP_K)
+    metadata_filter: dict | None = None
+
+
+class HealthStatus(BaseModel):
+    status: str
+    detail: str | None = None
+
+
+def env_config() -> dict:
+    """config.py names, plus the spellings the controller actually injects (SURVEY.md section 0 Q8:
+    manifests.go:171-194 sets MODEL_ID / EMBEDDING_TYPE, the reference service reads
+    LOCAL_EMBEDDING_MODEL_ID / EMBEDDING_SOURCE_TYPE -- both are honoured here)."""
+    g = os.getenv
+    return {
+        "embedding_source": g("EMBEDDING_SOURCE_TYPE") or g("EMBEDDING_TYPE") or "local",
+        "embedding_model": g("LOCAL_EMBEDDING_MODEL_ID") or g("MODEL_ID") or "BAAI/bge-small-en-v1.5",
+        "vector_db_type": g("VECTOR_DB_TYPE", "faiss"),
+        "persist_dir": g("DEFAULT_VECTOR_DB_PERSIST_DIR", "storage"),
+        "llm_inference_url": g("LLM_INFERENCE_URL"),
+        "device_id": int(g("KRAG_DEVICE_ID", "0")),
+    }
+
+
+def create_app(store: vs.VectorStore, cfg: dict | None = None) -> FastAPI:
+    cfg = cfg or env_config()
+    app = FastAPI(title="KAITO RAGEngine service (B200-native)")
+    reg = CollectorRegistry()
+    lat = lambda n, d, labels=("status",): Histogram(n, d, labelnames=list(labels), registry=reg)  # noqa: E731
+    cnt = lambda n, d, labels=("status",): Counter(n, d, labelnames=list(labels), registry=reg)    # noqa: E731
+    M = {
+        "index": (lat("rag_index_latency_seconds", "Time to call '/index' API in seconds"), cnt("rag_index_requests", "index requests")),
+        "indexes": (lat("rag_indexes_latency_seconds", "list indexes latency"), cnt("rag_indexes_requests", "list indexes requests")),
+        "documents": (lat("rag_indexes_document_latency_seconds", "list documents latency"), cnt("rag_indexes_document_requests", "list documents requests")),
+        "update": (lat("rag_indexes_update_document_latency_seconds", "update latency"), cnt("rag_indexes_update_document_requests", "update requests")),
+        "retrieve": (lat("rag_indexes_retrieve_latency_seconds", "retrieve latency"), cnt("rag_indexes_retrieve_requests", "retrieve requests")),
+        "delete_doc": (lat("rag_indexes_delete_document_latency_seconds", "delete doc latency"), cnt("rag_indexes_delete_document_requests", "delete doc requests")),
+        "persist": (lat("rag_persist_latency_seconds", "persist latency"), cnt("rag_persist_requests", "persist requests")),
+        "load": (lat("rag_load_latency_seconds", "load latency"), cnt("rag_load_requests", "load requests")),
+        "delete": (lat("rag_delete_index_latency_seconds", "delete index latency"), cnt("rag_delete_index_requests", "delete index requests")),
+        "chat": (lat("rag_chat_latency_seconds", "chat latency"), cnt("rag_chat_requests", "chat requests")),
+    }
+    e2e_total = Counter("e2e_request", "Total requests", labelnames=["status", "method", "path"], registry=reg)
+    e2e_lat = Histogram("e2e_request_latency_seconds", "End to end latency", labelnames=["status", "method", "path"], registry=reg)
+    running = Gauge("num_requests_running", "Number of requests currently being processed", registry=reg)
+    vs_lat = Histogram("rag_vector_store_operation_latency_seconds", "vector store op latency", labelnames=["operation", "status"], registry=reg)
+    res_count = Histogram("rag_retrieve_result_count", "results per retrieve", registry=reg, buckets=[0, 1, 2, 5, 10, 20, 50, 100, 300])
+    low_score = Histogram("rag_lowest_source_score", "lowest score", registry=reg)
+    avg_score = Histogram("rag_avg_source_score", "average score", registry=reg)
+    emb_lat = Histogram("rag_embedding_latency_seconds", "Time to embed in seconds", labelnames=["status", "mode"], registry=reg)
+    app.state.store, app.state.registry = store, reg
+
+    @app.middleware("http")
+    async def track_requests(request: Request, call_next):   # main.py:97-128
+        running.inc()
+        t0 = time.perf_counter()
+        status = "500"
+        try:
+            resp = await call_next(request)
+            status = str(resp.status_code)
+            return resp
+        finally:
+            running.dec()
+            e2e_total.labels(status, request.method, request.url.path).inc()
+            e2e_lat.labels(status, request.method, request.url.path).observe(time.perf_counter() - t0)
+
+    def run(kind, fn):
+        """observe latency/status like the reference's per-route try/finally blocks"""
+        h, c = M[kind]
+        t0 = time.perf_counter()
+        try:
+            out = fn()
+            c.labels("success").inc(); h.labels("success").observe(time.perf_counter() - t0)
+            return out
+        except vs.HTTPException as e:
+            c.labels("failure").inc(); h.labels("failure").observe(time.perf_counter() - t0)
+            raise HTTPException(status_code=e.status_code, detail=e.detail)
+        except HTTPException:
+            c.labels("failure").inc(); h.labels("failure").observe(time.perf_counter() - t0)
+            raise
+        except Exception as e:
+            c.labels("failure").inc(); h.labels("failure").observe(time.perf_counter() - t0)
+            raise HTTPException(status_code=500, detail=str(e))
+
+    @app.get("/metrics")
+    async def metrics():
+        return Response(generate_latest(reg), media_type=CONTENT_TYPE_LATEST)
+
+    @app.get("/health", response_model=HealthStatus)
+    def health_check():
+        if app.state.store is None:
+            raise HTTPException(status_code=500, detail="RAG operations not initialized")
+        return HealthStatus(status="Healthy")
+
+    @app.post("/index", response_model=list[Document])
+    def index_documents(request: IndexRequest):   # main.py:250-272
+        def go():
+            docs = [{"text": d.text, "metadata": d.metadata or {}} for d in request.documents]
+            t0 = time.perf_counter()
+            ids = store.index_documents(request.index_name, docs)
+            emb_lat.labels("success", "local").observe(time.perf_counter() - t0)
+            return [Document(doc_id=i, text=d.text, metadata=d.metadata) for i, d in zip(ids, request.documents)]
+        return run("index", go)
+
+    @app.post("/retrieve")
+    def retrieve_from_index(request: RetrieveRequest):   # main.py:742-771
+        def go():
+            out = store.retrieve(request.index_name, request.query, request.max_node_count, request.metadata_filter)
+            res_count.observe(out["count"])
+            vs_lat.labels("query", "success").observe(getattr(store, "last_retrieve_seconds", 0.0))
+            scores = [r["score"] for r in out["results"]]
+            if scores:
+                low_score.observe(min(scores)); avg_score.observe(sum(scores) / len(scores))
+            return out
+        return run("retrieve", go)
+
+    @app.post("/v1/chat/completions")
+    async def chat_completions(request: dict):   # main.py:326-353
+        if not cfg.get("llm_inference_url"):
+            M["chat"][1].labels("failure").inc()
+            raise HTTPException(status_code=503, detail="LLM inference URL is not configured; chat completions are unavailable. "
+                                                        "Use /retrieve for retrieval-only deployments.")
+        raise HTTPException(status_code=501, detail="chat completion proxying is not part of this build (SURVEY.md section 8 f3)")
+
+    @app.get("/indexes", response_model=list[str])
+    def list_indexes():
+        return run("indexes", store.list_indexes)
+
+    @app.get("/indexes/{index_name}/documents")
+    def list_documents(index_name: str, limit: int = Query(10, ge=1, le=100), offset: int = Query(0, ge=0),
+                       max_text_length: int | None = Query(1000, ge=1), metadata_filter: str | None = Query(None)):
+        def go():
+            mf = None
+            if metadata_filter:
+                try:
+                    mf = json.loads(metadata_filter)
+                except json.JSONDecodeError:
+                    raise HTTPException(status_code=400, detail="Invalid metadata filter format. Must be a valid JSON string.")
+            return store.list_documents_in_index(unquote(index_name), limit, offset, max_text_length, mf)
+        return run("documents", go)
+
+    @app.post("/indexes/{index_name}/documents")
+    def update_documents(index_name: str, request: UpdateDocumentRequest):
+        return run("update", lambda: store.update_documents(unquote(index_name), [d.model_dump() for d in request.documents]))
+
+    @app.post("/indexes/{index_name}/documents/delete")
+    def delete_documents(index_name: str, request: DeleteDocumentRequest):
+        return run("delete_doc", lambda: store.delete_documents(unquote(index_name), request.doc_ids))
+
+    @app.post("/persist/{index_name}")
+    def persist_index(index_name: str, path: str | None = Query(None)):   # main.py:619-649
+        def go():
+            p = path or os.path.join(cfg["persist_dir"], index_name)
+            store.persist(unquote(index_name), p)
+            return {"message": f"Successfully persisted index {index_name} to {p}."}
+        return run("persist", go)
+
+    @app.post("/load/{index_name}")
+    def load_index(index_name: str, path: str | None = Query(None), overwrite: bool = Query(False)):   # main.py:675-701
+        def go():
+            p = path or os.path.join(cfg["persist_dir"], index_name)
+            store.load(unquote(index_name), p, overwrite)
+            return {"message": f"Successfully loaded index {index_name} from {p}."}
+        return run("load", go)
+
+    @app.delete("/indexes/{index_name}")
+    def delete_index(index_name: str):
+        def go():
+            store.delete_index(unquote(index_name))
+            return {"message": f"Successfully deleted index {index_name}."}
+        return run("delete", go)
+
+    return app
+
+
+def main():
+    """entry point of the image's `python3 main.py` shim (preset_rag.go:186): port 5000, /health probes."""
+    import uvicorn
+    from . import _native
+    from .embedding import HashingEmbedding
+    cfg = env_config()
+    if cfg["vector_db_type"] not in ("faiss", "krag"):
+        raise SystemExit(f"VECTOR_DB_TYPE={cfg['vector_db_type']} is not served by this image (faiss-compatible engine only)")
+    engine = _native.Context(device_id=cfg["device_id"])
+    # the GPU BERT forward (K5) is not built yet: the service refuses to pretend it has a language model
+    if os.getenv("KRAG_ALLOW_HASHING_EMBEDDING") != "1":
+        raise SystemExit("no embedding model available: K5 (bge forward) is not built; set KRAG_ALLOW_HASHING_EMBEDDING=1 "
+                         "to start with the deterministic hashing embedder (functional tests only)")
+    app = create_app(vs.VectorStore(HashingEmbedding(384), engine), cfg)
+    uvicorn.run(app, host="0.0.0.0", port=5000)
+
+
+if __name__ == "__main__":
+    main()

@@ -108,8 +108,9 @@ class ShardedRetriever:
         if hybrid:
             self.stages.bm25_candidates(terms, toff, B, P, local[1])
         if self.world > 1:
-            gathered = self._tensor("gathered", (self.world, nl, B, P), torch.int64)
-            dist.all_gather_into_tensor(gathered, local, group=self.group)
+            flat = self._tensor("gathered", (self.world * nl, B, P), torch.int64)
+            dist.all_gather_into_tensor(flat, local, group=self.group)   # concatenation along dim 0
+            gathered = flat.view(self.world, nl, B, P)
             merged = self._tensor("merged", (nl, B, P), torch.int64)
             # [G, nl, B, P] -> per list a [G, B, P] view (list stride = nl*B*P is handled by a copy-free slice
             # only when nl == 1; otherwise gather the two lists into contiguous blocks)

@@ -1,0 +1,215 @@
+"""Host-side text pipeline for the sparse side of /retrieve.
+
+The reference tokenises inside `BM25Retriever.from_defaults` (hybrid_retriever.py:122-125) with
+bm25s + PyStemmer, neither vendored nor installable offline [3P-unverified]; this module
+restates that pipeline from the published algorithms:
+
+  bm25s.tokenize(texts, stopwords="english", stemmer=Stemmer.Stemmer("english")):
+    lower-case, regex r"(?u)\\b\\w\\w+\\b", drop the 33-word English stop list, then stem
+    each remaining token with the Snowball English ("Porter2") stemmer.
+
+Term ids are assigned by `Vocabulary` in first-seen order; they are what the C ABI takes
+(`term_ids`, `q_terms` in include/kaito_rag.h).  Text stays on the host.
+"""
+from __future__ import annotations
+
+import re
+from collections import Counter
+
+import numpy as np
+
+TOKEN_PATTERN = re.compile(r"(?u)\b\w\w+\b")
+
+# bm25s.stopwords.STOPWORDS_EN
+STOPWORDS_EN = frozenset((
+    "a", "an", "and", "are", "as", "at", "be", "but", "by", "for", "if", "in", "into", "is", "it", "no", "not", "of",
+    "on", "or", "such", "that", "the", "their", "then", "there", "these", "they", "this", "to", "was", "will", "with",
+))
+
+# ---------------------------------------------------------------- Snowball English stemmer
+_VOWELS = "aeiouy"
+_DOUBLES = ("bb", "dd", "ff", "gg", "mm", "nn", "pp", "rr", "tt")
+_LI_ENDING = "cdeghkmnrt"
+_EXCEPTIONS = {"skis": "ski", "skies": "sky", "dying": "die", "lying": "lie", "tying": "tie", "idly": "idl",
+               "gently": "gentl", "ugly": "ugli", "early": "earli", "only": "onli", "singly": "singl", "sky": "sky",
+               "news": "news", "howe": "howe", "atlas": "atlas", "cosmos": "cosmos", "bias": "bias", "andes": "andes"}
+_EXCEPTIONS_1A = frozenset(("inning", "outing", "canning", "herring", "earring", "proceed", "exceed", "succeed"))
+_STEP2 = (("ization", "ize"), ("ational", "ate"), ("fulness", "ful"), ("ousness", "ous"), ("iveness", "ive"),
+          ("tional", "tion"), ("biliti", "ble"), ("lessli", "less"), ("entli", "ent"), ("ation", "ate"),
+          ("alism", "al"), ("aliti", "al"), ("ousli", "ous"), ("iviti", "ive"), ("fulli", "ful"), ("enci", "ence"),
+          ("anci", "ance"), ("abli", "able"), ("izer", "ize"), ("ator", "ate"), ("alli", "al"), ("bli", "ble"),
+          ("ogi", "og"), ("li", ""))
+_STEP3 = (("ational", "ate"), ("tional", "tion"), ("alize", "al"), ("icate", "ic"), ("iciti", "ic"), ("ative", ""),
+          ("ical", "ic"), ("ness", ""), ("ful", ""))
+_STEP4 = ("ement", "ance", "ence", "able", "ible", "ment", "ant", "ent", "ism", "ate", "iti", "ous", "ive", "ize",
+          "ion", "al", "er", "ic")
+
+
+def _is_vowel(w: str, i: int) -> bool:
+    return w[i] in _VOWELS
+
+
+def _region_after_vc(w: str, start: int) -> int:
+    """index after the first non-vowel that follows a vowel, searching from `start`"""
+    for i in range(start + 1, len(w)):
+        if not _is_vowel(w, i) and _is_vowel(w, i - 1):
+            return i + 1
+    return len(w)
+
+
+def _r1_r2(w: str):
+    if w.startswith(("gener", "arsen")):
+        r1 = 5
+    elif w.startswith("commun"):
+        r1 = 6
+    else:
+        r1 = _region_after_vc(w, 0)
+    return r1, _region_after_vc(w, r1)
+
+
+def _ends_short_syllable(w: str) -> bool:
+    n = len(w)
+    if n == 2:
+        return _is_vowel(w, 0) and not _is_vowel(w, 1)
+    if n >= 3:
+        return (not _is_vowel(w, n - 3)) and _is_vowel(w, n - 2) and (not _is_vowel(w, n - 1)) and w[-1] not in "wxY"
+    return False
+
+
+def _contains_vowel(w: str) -> bool:
+    return any(c in _VOWELS for c in w)
+
+
+def stem(word: str) -> str:
+    """Snowball English (Porter2) stem of a lower-case token."""
+    if len(word) <= 2:
+        return word
+    if word in _EXCEPTIONS:
+        return _EXCEPTIONS[word]
+    w = word[1:] if word.startswith("'") else word
+    # mark consonant y
+    chars = list(w)
+    for i, c in enumerate(chars):
+        if c == "y" and (i == 0 or chars[i - 1] in _VOWELS):
+            chars[i] = "Y"
+    w = "".join(chars)
+    r1, r2 = _r1_r2(w)
+
+    # step 0
+    for suf in ("'s'", "'s", "'"):
+        if w.endswith(suf):
+            w = w[: -len(suf)]
+            break
+    # step 1a
+    if w.endswith("sses"):
+        w = w[:-2]
+    elif w.endswith(("ied", "ies")):
+        w = w[:-2] if len(w) > 4 else w[:-1]
+    elif w.endswith(("us", "ss")):
+        pass
+    elif w.endswith("s"):
+        if _contains_vowel(w[:-2]):
+            w = w[:-1]
+    if w in _EXCEPTIONS_1A:
+        return w.replace("Y", "y")
+    # step 1b
+    if w.endswith("eedly"):
+        if len(w) - 5 >= r1:
+            w = w[:-3]
+    elif w.endswith("eed"):
+        if len(w) - 3 >= r1:
+            w = w[:-1]
+    else:
+        for suf in ("ingly", "edly", "ing", "ed"):
+            if w.endswith(suf):
+                stem_part = w[: -len(suf)]
+                if _contains_vowel(stem_part):
+                    w = stem_part
+                    if w.endswith(("at", "bl", "iz")):
+                        w += "e"
+                    elif w.endswith(_DOUBLES):
+                        w = w[:-1]
+                    elif _ends_short_syllable(w) and r1 >= len(w):
+                        w += "e"
+                break
+    # step 1c
+    if len(w) > 2 and w[-1] in "yY" and w[-2] not in _VOWELS:
+        w = w[:-1] + "i"
+    # step 2
+    for suf, rep in _STEP2:
+        if w.endswith(suf):
+            if len(w) - len(suf) >= r1:
+                if suf == "ogi":
+                    if w[: -len(suf)].endswith("l"):
+                        w = w[: -len(suf)] + rep
+                elif suf == "li":
+                    if len(w) > 2 and w[-3] in _LI_ENDING:
+                        w = w[:-2]
+                else:
+                    w = w[: -len(suf)] + rep
+            break
+    # step 3
+    for suf, rep in _STEP3:
+        if w.endswith(suf):
+            if len(w) - len(suf) >= r1:
+                if suf == "ative":
+                    if len(w) - len(suf) >= r2:
+                        w = w[: -len(suf)]
+                else:
+                    w = w[: -len(suf)] + rep
+            break
+    # step 4
+    for suf in _STEP4:
+        if w.endswith(suf):
+            if len(w) - len(suf) >= r2:
+                if suf == "ion":
+                    if len(w) > 3 and w[-4] in "st":
+                        w = w[:-3]
+                else:
+                    w = w[: -len(suf)]
+            break
+    # step 5
+    if w.endswith("e"):
+        if len(w) - 1 >= r2 or (len(w) - 1 >= r1 and not _ends_short_syllable(w[:-1])):
+            w = w[:-1]
+    elif w.endswith("l"):
+        if len(w) - 1 >= r2 and w[:-1].endswith("l"):
+            w = w[:-1]
+    return w.replace("Y", "y")
+
+
+# ------------------------------------------------------------------------------ tokenise
+def tokenize(text: str) -> list[str]:
+    """bm25s-style tokens of one text: lower-case, \\w\\w+ words, stop words removed, stemmed."""
+    return [stem(t) for t in TOKEN_PATTERN.findall(text.lower()) if t not in STOPWORDS_EN]
+
+
+class Vocabulary:
+    """term string <-> dense u32 id in first-seen order (the host owns the vocabulary)."""
+
+    def __init__(self):
+        self.ids: dict[str, int] = {}
+        self.terms: list[str] = []
+
+    def __len__(self):
+        return len(self.terms)
+
+    def add(self, term: str) -> int:
+        i = self.ids.get(term)
+        if i is None:
+            i = len(self.terms)
+            self.ids[term] = i
+            self.terms.append(term)
+        return i
+
+    def doc_terms(self, text: str):
+        """(unique term ids u32, tf u16, doc_len) of one node; grows the vocabulary."""
+        toks = tokenize(text)
+        cnt = Counter(self.add(t) for t in toks)
+        ids = np.fromiter(cnt.keys(), np.uint32, len(cnt))
+        tf = np.fromiter((min(v, 65535) for v in cnt.values()), np.uint16, len(cnt))
+        return ids, tf, len(toks)
+
+    def query_terms(self, text: str) -> np.ndarray:
+        """term ids of a query in token order, duplicates kept, unknown terms dropped (bm25s semantics)."""
+        return np.asarray([self.ids[t] for t in tokenize(text) if t in self.ids], np.uint32)

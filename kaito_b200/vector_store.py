@@ -1,0 +1,316 @@
+"""Host-side mirror of the reference RAGService store classes for the /index and /retrieve
+paths, backed by libkaito_rag (CUDA) instead of LlamaIndex + FAISS + bm25s.
+
+Mirrors (paths relative to /root/reference/presets/ragengine/):
+  BaseVectorStore            vector_store/base.py:60-978   (index_documents, retrieve, CRUD, persist/load)
+  FaissVectorStoreHandler    vector_store/faiss_store.py:25-50
+  HybridRetriever            vector_store/retriever/hybrid_retriever.py:60-237
+Same method names, argument meaning and error behaviour (HTTP status + detail strings), so
+the reference's own store tests read the same against this class.  The arithmetic of the
+path (dense scan, BM25, fusion) runs in the CUDA library through `engine` (a
+kaito_b200._native.Context); there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import os
+import threading
+import time
+
+import numpy as np
+
+from . import text as _text
+
+RAG_MAX_TOP_K = int(os.getenv("RAG_MAX_TOP_K", 300))  # config.py:127
+
+
+class HTTPException(Exception):
+    """fastapi.HTTPException stand-in so the store has no web dependency (same fields)."""
+
+    def __init__(self, status_code: int, detail: str):
+        super().__init__(f"{status_code}: {detail}")
+        self.status_code, self.detail = status_code, detail
+
+
+def generate_doc_id(text: str) -> str:
+    """BaseVectorStore.generate_doc_id, vector_store/base.py:82-85."""
+    return hashlib.sha256(text.encode("utf-8")).hexdigest()
+
+
+def embed_text(text: str, metadata: dict | None) -> str:
+    """node.get_content(MetadataMode.EMBED): LlamaIndex's default templates put "key: value" lines,
+    a blank line, then the content [3P-unverified]; used for both the embedding and BM25 sides."""
+    if not metadata:
+        return text
+    meta = "\n".join(f"{k}: {v}" for k, v in metadata.items())
+    return f"{meta}\n\n{text}"
+
+
+class SentenceSplitter:
+    """Stand-in for LlamaIndex SentenceSplitter() (custom_transformer.py:32): chunk_size 1024, overlap 200,
+    counted in word tokens here (the reference counts tiktoken tokens; the BPE table is not available
+    offline).  Texts below the chunk size -- everything the reference's tests index -- stay one node."""
+
+    def __init__(self, chunk_size: int = 1024, chunk_overlap: int = 200):
+        self.chunk_size, self.chunk_overlap = chunk_size, chunk_overlap
+
+    def split(self, text: str) -> list[str]:
+        words = text.split()
+        if len(words) <= self.chunk_size:
+            return [text]
+        out, start = [], 0
+        while start < len(words):
+            end = min(len(words), start + self.chunk_size)
+            out.append(" ".join(words[start:end]))
+            if end == len(words):
+                break
+            start = end - self.chunk_overlap
+        return out
+
+
+class _Node:
+    __slots__ = ("node_id", "ref_doc_id", "text", "metadata", "ordinal", "alive")
+
+    def __init__(self, node_id, ref_doc_id, text, metadata, ordinal):
+        self.node_id, self.ref_doc_id, self.text, self.metadata, self.ordinal, self.alive = \
+            node_id, ref_doc_id, text, metadata, ordinal, True
+
+
+class _IndexState:
+    def __init__(self, index):
+        self.index = index                       # kaito_b200._native.Index (or a test double)
+        self.vocab = _text.Vocabulary()
+        self.nodes: list[_Node] = []             # by ordinal (== insertion order == engine row)
+        self.ref_docs: dict[str, dict] = {}      # doc_id -> {"text", "metadata", "nodes": [ordinal]}
+        self.committed = False
+
+
+class HybridRetriever:
+    """hybrid_retriever.py:60-237: pool size, weights, keyword post-filter, fuse -- on the GPU."""
+
+    def __init__(self, state: _IndexState, embed_model, max_results: int = 10, candidate_multiplier: float = 3.0,
+                 vector_weight: float = 0.7, text_weight: float = 0.3, metadata_filter: dict | None = None):
+        total = vector_weight + text_weight
+        self._vector_weight = vector_weight / total
+        self._text_weight = text_weight / total
+        self._state, self._embed = state, embed_model
+        self._max_results = max_results
+        self._candidate_multiplier = max(1.0, candidate_multiplier)
+        self._candidate_pool_size = int(max_results * self._candidate_multiplier)
+        self._metadata_filter = metadata_filter
+
+    def _allow_bitmap(self):
+        if not self._metadata_filter:
+            return None
+        nodes = self._state.nodes
+        bm = np.zeros((len(nodes) + 31) // 32, np.uint32)
+        for n in nodes:
+            if all((n.metadata or {}).get(k) == v for k, v in self._metadata_filter.items()):
+                bm[n.ordinal >> 5] |= np.uint32(1 << (n.ordinal & 31))
+        return bm
+
+    def retrieve(self, query: str) -> list[tuple[_Node, float]]:
+        st = self._state
+        q = np.asarray(self._embed.get_query_embedding(query), np.float32).reshape(1, -1)
+        # BM25 unavailable (empty docstore / nothing committed) -> vector-only fallback (:113-121, :216-218)
+        terms = [st.vocab.query_terms(query)] if st.committed else None
+        out = st.index.retrieve(q, terms, self._max_results, cand_mult=self._candidate_multiplier,
+                                vector_weight=self._vector_weight, text_weight=self._text_weight,
+                                keyword_allow_bitmap=self._allow_bitmap() if terms is not None else None)
+        c = int(out["count"][0])
+        return [(st.nodes[int(o)], float(s)) for o, s in zip(out["ordinal"][0, :c], out["final"][0, :c])]
+
+
+class VectorStore:
+    """BaseVectorStore + FaissVectorStoreHandler over the CUDA engine."""
+
+    def __init__(self, embed_model, engine):
+        self.embed_model = embed_model
+        self.engine = engine
+        self.dimension = embed_model.get_embedding_dimension()   # faiss_store.py:28
+        self.index_map: dict[str, _IndexState] = {}
+        self.splitter = SentenceSplitter()
+        # many readers / one writer (aiorwlock in the reference, base.py:77-79); the engine enforces the same
+        # discipline per index internally, this lock protects the host-side docstore
+        self._lock = threading.RLock()
+
+    # ------------------------------------------------------------------ /index
+    def index_documents(self, index_name: str, documents: list[dict]) -> list[str]:
+        """base.py:90-97: create on first use, else append with per-document dedupe (:99-131)."""
+        with self._lock:
+            st = self.index_map.get(index_name)
+            if st is None:
+                st = _IndexState(self.engine.create_index(index_name, self.dimension))
+                self.index_map[index_name] = st
+            ids, fresh = [], []
+            for doc in documents:
+                doc_id = generate_doc_id(doc["text"])
+                ids.append(doc_id)
+                if doc_id in st.ref_docs or any(d[0] == doc_id for d in fresh):
+                    continue                                   # "already exists ... Skipping." (:123-126)
+                fresh.append((doc_id, doc["text"], doc.get("metadata") or {}))
+            if fresh:
+                self._insert(st, fresh)
+            return ids
+
+    def _insert(self, st: _IndexState, docs):
+        node_ids, texts, offs, tids, tfs, dls, new_nodes = [], [], [0], [], [], [], []
+        base = len(st.nodes)
+        for doc_id, text, metadata in docs:
+            if metadata.get("split_type") == "code":
+                raise HTTPException(501, "code splitting (tree-sitter) is not available in this build")
+            ords = []
+            for i, chunk in enumerate(self.splitter.split(text)):
+                ordinal = base + len(new_nodes)
+                new_nodes.append(_Node(f"{doc_id}-{i}", doc_id, chunk, metadata, ordinal))
+                et = embed_text(chunk, metadata)
+                texts.append(et)
+                t_ids, t_tf, dl = st.vocab.doc_terms(et)
+                tids.append(t_ids); tfs.append(t_tf); dls.append(dl)
+                offs.append(offs[-1] + len(t_ids))
+                node_ids.append(ordinal)
+                ords.append(ordinal)
+            st.ref_docs[doc_id] = {"text": text, "metadata": metadata, "nodes": ords}
+        vecs = np.asarray(self.embed_model.get_text_embedding_batch(texts), np.float32)
+        st.index.add(np.asarray(node_ids, np.uint64), vecs, np.asarray(offs, np.int64),
+                     np.concatenate(tids) if tids else np.zeros(0, np.uint32),
+                     np.concatenate(tfs) if tfs else np.zeros(0, np.uint16), np.asarray(dls, np.uint32))
+        st.nodes.extend(new_nodes)
+        self._commit(st)
+
+    def _commit(self, st: _IndexState):
+        # the reference rebuilds BM25 on every query (hybrid_retriever.py:104-130); here once per mutation
+        st.index.commit(max(1, len(st.vocab)))
+        st.committed = True
+
+    # --------------------------------------------------------------- /retrieve
+    def retrieve(self, index_name: str, query: str, max_node_count: int = 5, metadata_filter: dict | None = None):
+        """base.py:870-978."""
+        if index_name not in self.index_map:
+            raise HTTPException(404, f"No such index: '{index_name}' exists.")
+        try:
+            if not query or query.strip() == "":
+                raise HTTPException(400, "Query string cannot be empty.")
+            top_k = min(max_node_count, RAG_MAX_TOP_K)
+            st = self.index_map[index_name]
+            retriever = HybridRetriever(st, self.embed_model, max_results=top_k, metadata_filter=metadata_filter)
+            t0 = time.time()
+            nodes = retriever.retrieve(query)
+            self.last_retrieve_seconds = time.time() - t0
+            results = [{"doc_id": n.ref_doc_id or n.node_id, "node_id": n.node_id, "text": n.text, "score": s,
+                        "metadata": n.metadata if n.metadata else None} for n, s in nodes]
+            return {"query": query, "results": results, "count": len(results)}
+        except HTTPException:
+            raise
+        except Exception as e:  # same envelope as base.py:972-978
+            raise HTTPException(500, f"Retrieve failed: {e}")
+
+    # ------------------------------------------------------------------- CRUD
+    def list_indexes(self) -> list[str]:
+        return list(self.index_map.keys())
+
+    def document_exists(self, index_name: str, doc_id: str) -> bool:
+        st = self.index_map.get(index_name)
+        return bool(st and doc_id in st.ref_docs)
+
+    def list_documents_in_index(self, index_name: str, limit: int = 10, offset: int = 0, max_text_length: int | None = 1000,
+                                metadata_filter: dict | None = None):
+        if index_name not in self.index_map:
+            raise HTTPException(404, f"No such index: '{index_name}' exists.")
+        st = self.index_map[index_name]
+        docs = []
+        for doc_id, d in st.ref_docs.items():
+            if metadata_filter and not all(d["metadata"].get(k) == v for k, v in metadata_filter.items()):
+                continue
+            docs.append((doc_id, d))
+        total = len(docs)
+        out = []
+        for doc_id, d in docs[offset:offset + limit]:
+            t = d["text"]
+            trunc = max_text_length is not None and len(t) > max_text_length
+            out.append({"doc_id": doc_id, "text": t[:max_text_length] if trunc else t, "metadata": d["metadata"],
+                        "hash_value": generate_doc_id(t), "is_truncated": trunc})
+        return {"documents": out, "count": len(out), "total_items": total}
+
+    def delete_documents(self, index_name: str, doc_ids: list[str]):
+        if index_name not in self.index_map:
+            raise HTTPException(404, f"No such index: '{index_name}' exists.")
+        with self._lock:
+            st = self.index_map[index_name]
+            deleted, missing, rows = [], [], []
+            for d in doc_ids:
+                rec = st.ref_docs.pop(d, None)
+                if rec is None:
+                    missing.append(d)
+                    continue
+                deleted.append(d)
+                for o in rec["nodes"]:
+                    st.nodes[o].alive = False
+                    rows.append(o)
+            if rows:
+                st.index.remove(np.asarray(rows, np.uint64))
+                self._commit(st)
+            return {"deleted_doc_ids": deleted, "not_found_doc_ids": missing}
+
+    def update_documents(self, index_name: str, documents: list[dict]):
+        """base.py:529-561 semantics: by doc_id; unchanged text -> unchanged, else delete + re-insert."""
+        if index_name not in self.index_map:
+            raise HTTPException(404, f"No such index: '{index_name}' exists.")
+        with self._lock:
+            st = self.index_map[index_name]
+            updated, unchanged, missing = [], [], []
+            for doc in documents:
+                rec = st.ref_docs.get(doc.get("doc_id", ""))
+                if rec is None:
+                    missing.append(doc)
+                elif rec["text"] == doc["text"] and (doc.get("metadata") or {}) == rec["metadata"]:
+                    unchanged.append(doc)
+                else:
+                    self.delete_documents(index_name, [doc["doc_id"]])
+                    self._insert(st, [(doc["doc_id"], doc["text"], doc.get("metadata") or {})])
+                    updated.append(doc)
+            return {"updated_documents": updated, "unchanged_documents": unchanged, "not_found_documents": missing}
+
+    def delete_index(self, index_name: str):
+        if index_name not in self.index_map:
+            raise HTTPException(404, f"No such index: '{index_name}' exists.")
+        with self._lock:
+            self.index_map.pop(index_name).index.drop()
+
+    # -------------------------------------------------------- persist / load
+    def persist(self, index_name: str, path: str):
+        """base.py:779-809. Own format: the engine snapshot + docstore.json."""
+        if index_name not in self.index_map:
+            raise HTTPException(404, f"No such index: '{index_name}' exists.")
+        st = self.index_map[index_name]
+        os.makedirs(path, exist_ok=True)
+        st.index.persist(path)
+        with open(os.path.join(path, "docstore.json"), "w") as f:
+            json.dump({"version": 1, "vocab": st.vocab.terms, "ref_docs": st.ref_docs,
+                       "nodes": [[n.node_id, n.ref_doc_id, n.text, n.metadata, n.alive] for n in st.nodes]}, f)
+
+    def load(self, index_name: str, path: str, overwrite: bool = False):
+        """base.py:811-868."""
+        if index_name in self.index_map and not overwrite:
+            raise HTTPException(409, f"Index '{index_name}' already exists. Use a different name or delete the existing index first.")
+        try:
+            with open(os.path.join(path, "docstore.json")) as f:
+                ds = json.load(f)
+            with self._lock:
+                if index_name in self.index_map:
+                    self.index_map.pop(index_name).index.drop()
+                st = _IndexState(self.engine.load_index(index_name, path))
+                for t in ds["vocab"]:
+                    st.vocab.add(t)
+                st.ref_docs = ds["ref_docs"]
+                for i, (nid, rid, text, meta, alive) in enumerate(ds["nodes"]):
+                    n = _Node(nid, rid, text, meta, i)
+                    n.alive = alive
+                    st.nodes.append(n)
+                st.committed = True
+                self.index_map[index_name] = st
+        except HTTPException:
+            raise
+        except Exception as e:
+            raise HTTPException(500, f"Loading failed: {e}")

@@ -1,0 +1,75 @@
+"""HTTP surface (kaito_b200.service) against the reference's API tests
+(presets/ragengine/tests/api/test_main.py:28-62) and the e2e contract (test/rage2e/rag_test.go:1248-1384).
+CPU: engine double backed by the oracle.  GPU (-m gpu): the CUDA engine."""
+import re
+
+import pytest
+from starlette.testclient import TestClient
+
+from kaito_b200.embedding import HashingEmbedding
+from kaito_b200.service import create_app
+from kaito_b200.vector_store import VectorStore
+
+CFG = {"persist_dir": "storage", "llm_inference_url": None}
+
+
+def _exercise(client, tmp_path):
+    assert client.get("/health").json() == {"status": "Healthy", "detail": None}
+    req = {"index_name": "test_index", "documents": [{"text": "This is a test document"}, {"text": "Another test document"}]}
+    r = client.post("/index", json=req)
+    assert r.status_code == 200
+    doc1, doc2 = r.json()
+    assert doc1["text"] == "This is a test document" and len(doc1["doc_id"]) == 64 and not doc1["metadata"]
+    assert doc2["text"] == "Another test document" and len(doc2["doc_id"]) == 64
+    m = client.get("/metrics")
+    assert m.status_code == 200
+    assert len(re.findall(r'rag_index_requests_total{status="success"} ([1-9]\d*).0', m.text)) == 1   # test_main.py:52-62
+    # /retrieve: e2e sends an unknown field (rag_test.go:1254); top-1 doc id/text checks (:1343, :1363)
+    r = client.post("/retrieve", json={"index_name": "test_index", "query": "another test document", "max_node_count": 2,
+                                       "context_token_ratio": 0.5})
+    assert r.status_code == 200
+    body = r.json()
+    assert body["query"] == "another test document" and body["count"] == len(body["results"]) <= 2
+    assert {x["doc_id"] for x in body["results"]} <= {doc1["doc_id"], doc2["doc_id"]}
+    for x in body["results"]:
+        assert set(x) >= {"doc_id", "node_id", "text", "score", "metadata"}
+    assert client.post("/retrieve", json={"index_name": "nope", "query": "q"}).status_code == 404
+    assert client.post("/retrieve", json={"index_name": "nope", "query": "q"}).json() == {"detail": "No such index: 'nope' exists."}
+    assert client.post("/retrieve", json={"index_name": "test_index", "query": "  "}).json() == {"detail": "Query string cannot be empty."}
+    assert client.post("/retrieve", json={"index_name": "test_index", "query": "q", "max_node_count": 0}).status_code == 422
+    assert client.post("/retrieve", json={"index_name": "test_index", "query": "q", "max_node_count": 301}).status_code == 422
+    assert client.get("/indexes").json() == ["test_index"]
+    d = client.get("/indexes/test_index/documents", params={"limit": 1}).json()
+    assert d["count"] == 1 and d["total_items"] == 2
+    assert client.get("/indexes/test_index/documents", params={"metadata_filter": "{bad"}).status_code == 400
+    r = client.post("/indexes/test_index/documents/delete", json={"doc_ids": [doc1["doc_id"], "x"]})
+    assert r.json() == {"deleted_doc_ids": [doc1["doc_id"]], "not_found_doc_ids": ["x"]}
+    assert client.post("/v1/chat/completions", json={"messages": []}).status_code == 503   # main.py:331-335
+    m = client.get("/metrics").text
+    for name in ("rag_indexes_retrieve_requests_total", "rag_indexes_retrieve_latency_seconds", "rag_retrieve_result_count",
+                 "rag_vector_store_operation_latency_seconds", "rag_lowest_source_score", "rag_avg_source_score",
+                 "e2e_request_latency_seconds", "num_requests_running", "rag_embedding_latency_seconds"):
+        assert name in m, name
+    return body
+
+
+def test_service_cpu(oracle, tmp_path):
+    from tests.oracle_engine import OracleEngine
+    app = create_app(VectorStore(HashingEmbedding(64), OracleEngine(oracle)), dict(CFG))
+    _exercise(TestClient(app), tmp_path)
+
+
+@pytest.mark.gpu
+def test_service_gpu(ctx, oracle, tmp_path):
+    from tests.oracle_engine import OracleEngine
+    store = VectorStore(HashingEmbedding(64), ctx)
+    client = TestClient(create_app(store, dict(CFG)))
+    a = _exercise(client, tmp_path)
+    b = _exercise(TestClient(create_app(VectorStore(HashingEmbedding(64), OracleEngine(oracle)), dict(CFG))), tmp_path)
+    assert a == b   # same ids, order and fp64 scores on the wire
+    # persist / load round trip through the HTTP API (lifecycle hooks use these: lifecycle/manager.py:126-326)
+    p = str(tmp_path / "snap")
+    assert client.post("/persist/test_index", params={"path": p}).status_code == 200
+    assert client.post("/load/test_index", params={"path": p}).status_code == 409
+    assert client.post("/load/test_index", params={"path": p, "overwrite": "true"}).status_code == 200
+    assert client.delete("/indexes/test_index").status_code == 200
