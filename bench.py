@@ -324,7 +324,8 @@ def run_ours(args):
         tflops = kern_flops / (kern_ms * 1e-3) / 1e12
         tf32_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0   # TF32 dense = half the measured bf16 rate
         kname = {1: "K1 dense_scan_kernel (exact fp32 L2^2 scan + fused top-P)",
-                 2: "K2 dense_tc_kernel (tcgen05 TF32 prune pass; exact fp32 rescoring follows)"}
+                 2: "K2 dense_tc_kernel (tcgen05 cta_group::1 TF32 prune pass; exact fp32 rescoring follows)",
+                 3: "K2 dense_tc2_kernel (tcgen05 cta_group::2 TF32 prune pass, CTA pairs; exact fp32 rescoring follows)"}
         qps = B * args.steps / (ms_dev * 1e-3)
         qps_e2e = B * args.steps / (ms_e2e * 1e-3)
         h2d, d2h = ShardedRetriever.io_bytes(B, dim, n_terms, k)

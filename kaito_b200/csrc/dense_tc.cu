@@ -25,6 +25,8 @@
 #include <cuda.h>
 #include <math_constants.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 #include <vector>
 
@@ -318,6 +320,237 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     }
 }
 
+// ---------------------------------------------------------- 2-CTA main pass (cta_group::2)
+// A CTA pair (one cluster of 2, one CTA per SM of a TPC) computes D[256 rows x NQ] per pair-tile with
+// tcgen05.mma.cta_group::2 (M = 256): each CTA stages ITS 128 corpus rows and HALF of the query slab,
+// the pair's tensor cores share the operands.  Per 128-cycle MMA each SM now reads 8 KB of operands
+// (A 4 KB + B half 4 KB) and TMA writes 32 KB per 512 cycles: 64 + 64 B/clk against the 128 B/clk
+// shared-memory port, versus 96 + 96 for the 1-CTA kernel (which caps its tensor pipe at 67%).
+// The halved query slab also doubles the query ring depth (6 stages) and halves L2->SM traffic.
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta)
+{
+    asm volatile(
+        "{\n\t.reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+        ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+constexpr uint32_t TC_PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit: the pair leader's copy of a barrier
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* tm, uint64_t* leader_bar, int c0, int c1,
+                                                uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(leader_bar) & TC_PEER_MASK), "r"(c0),
+          "r"(c1), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar)   // arrives on `bar` in BOTH CTAs of the pair
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+
+// One ring; a stage holds TC2_KB_PER_STAGE k-blocks of this CTA's corpus rows and of its half of the
+// query rows, so the single MMA-issuing thread pays one barrier wait and one commit per 8 MMAs (it was
+// the bottleneck at 2 waits + 2 commits per 4 MMAs: ~770 cycles per k-block against 512 cycles of MMA work).
+constexpr int TC2_KB_PER_STAGE = 2;
+template <int NQ> struct Tc2Cfg {
+    static constexpr int QH_BYTES = (NQ / 2) * TC_KBLOCK * 4;          // this CTA's half of one query k-block
+    static constexpr int STAGE_BYTES = TC2_KB_PER_STAGE * (TC_A_BYTES + QH_BYTES);
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;          // 3 at NQ = 256, 4 at NQ = 128, 5 at NQ = 64
+    static constexpr int TMEM_COLS = (2 * NQ < 32) ? 32 : 2 * NQ;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + BAR_BYTES + NQ * 4;
+};
+
+__device__ __forceinline__ uint64_t desc_with_lo(uint64_t base_desc, uint32_t lo)
+{
+    return (base_desc & 0xFFFFFFFF00000000ull) | (uint64_t)lo;
+}
+
+template <int NQ>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+dense_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmQh, int64_t n_rows,
+                 int kblocks, int64_t n_ptiles, const float* __restrict__ xnorm, const uint32_t* __restrict__ alive,
+                 const float* __restrict__ thr_g, uint32_t* __restrict__ cand_count, uint32_t* __restrict__ cand_rows, int cap)
+{
+    using Cfg = Tc2Cfg<NQ>;
+    extern __shared__ unsigned char tc_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* tail = smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);             // used in the leader only (2 arrivals + tx of both CTAs)
+    uint64_t* empty_bar = full_bar + Cfg::STAGES;                        // per CTA
+    uint64_t* tfull_bar = empty_bar + Cfg::STAGES;                       // per CTA   [2]
+    uint64_t* tempty_bar = tfull_bar + 2;                                // leader only [2], 16 arrivals (8 warps x 2 CTAs)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* s_thr = reinterpret_cast<float*>(tail + Cfg::BAR_BYTES);
+    static_assert((2 * Cfg::STAGES + 4) * 8 + 8 <= Cfg::BAR_BYTES, "barrier area too small");
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();          // 0 = pair leader
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int n_stages_per_tile = (kblocks + TC2_KB_PER_STAGE - 1) / TC2_KB_PER_STAGE;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmQh);
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 16); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    for (int j = threadIdx.x; j < NQ; j += TC_THREADS) s_thr[j] = 0.5f * thr_g[j];
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                // both CTAs' barriers are initialised before any remote signal
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== producer: this CTA's 128 corpus rows + its half of the query rows =====================
+        int stage = 0; uint32_t phase = 0;
+        for (int64_t pt = pair; pt < n_ptiles; pt += n_pairs) {
+            const int row0 = (int)(pt * (2 * TC_TILE_M) + rank * TC_TILE_M);
+            for (int sk = 0; sk < n_stages_per_tile; ++sk) {
+                const int nkb = min(TC2_KB_PER_STAGE, kblocks - sk * TC2_KB_PER_STAGE);
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (lane == 0) {
+                    unsigned char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
+                    unsigned char* sq = sa + TC2_KB_PER_STAGE * TC_A_BYTES;
+                    if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * nkb * (TC_A_BYTES + Cfg::QH_BYTES));   // both CTAs' bytes
+                    else mbar_arrive_remote(&full_bar[stage], 0);
+                    for (int u = 0; u < nkb; ++u) {
+                        const int kb = sk * TC2_KB_PER_STAGE + u;
+                        tma_load_2d_2sm(sa + (size_t)u * TC_A_BYTES, &tmX, &full_bar[stage], kb * TC_KBLOCK, row0, TMA_EVICT_FIRST);
+                        tma_load_2d_2sm(sq + (size_t)u * Cfg::QH_BYTES, &tmQh, &full_bar[stage], kb * TC_KBLOCK, (int)rank * (NQ / 2),
+                                        TMA_EVICT_LAST);
+                    }
+                }
+                __syncwarp();
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            // ===================== MMA issuer (pair leader only) =====================
+            constexpr uint32_t idesc = umma_idesc_tf32(2 * TC_TILE_M, NQ);
+            const uint64_t desc0 = umma_desc_sw128(smem_u32(smem));      // descriptor of ring byte 0; only the low word moves
+            const uint32_t lo0 = (uint32_t)desc0;
+            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            for (int64_t pt = pair; pt < n_ptiles; pt += n_pairs) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NQ);
+                for (int sk = 0; sk < n_stages_per_tile; ++sk) {
+                    const int nkb = min(TC2_KB_PER_STAGE, kblocks - sk * TC2_KB_PER_STAGE);
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t a_lo = lo0 + (uint32_t)((stage * Cfg::STAGE_BYTES) >> 4);
+                        const uint32_t q_lo = a_lo + (uint32_t)((TC2_KB_PER_STAGE * TC_A_BYTES) >> 4);
+#pragma unroll
+                        for (int u = 0; u < TC2_KB_PER_STAGE; ++u) {
+                            if (u < nkb) {
+#pragma unroll
+                                for (int k = 0; k < TC_KBLOCK / 8; ++k)   // UMMA K = 8 (32 bytes = 2 descriptor units)
+                                    umma_tf32_2sm(d_tmem, desc_with_lo(desc0, a_lo + (uint32_t)((u * TC_A_BYTES) >> 4) + 2 * k),
+                                                  desc_with_lo(desc0, q_lo + (uint32_t)((u * Cfg::QH_BYTES) >> 4) + 2 * k), idesc,
+                                                  (uint32_t)((sk | u | k) != 0));
+                            }
+                        }
+                        umma_commit_2sm(&empty_bar[stage]);            // frees the stage in both CTAs
+                        if (sk == n_stages_per_tile - 1) umma_commit_2sm(&tfull_bar[acc]);
+                    }
+                    __syncwarp();
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= 3) {
+        // ===================== epilogue: 8 warps per CTA over this CTA's 128 TMEM lanes =====================
+        const int lg = warp & 3;
+        const int col_half = (warp - 3) >> 2;
+        const int row_in_tile = lg * 32 + lane;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int64_t pt = pair; pt < n_ptiles; pt += n_pairs) {
+            const int64_t row = pt * (2 * TC_TILE_M) + rank * TC_TILE_M + row_in_tile;
+            float xn = CUDART_INF_F;
+            if (row < n_rows && (alive == nullptr || bit_test(alive, (uint32_t)row))) xn = xnorm[row];
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * NQ);
+            const float half_xn = 0.5f * xn;
+#pragma unroll 1
+            for (int c0 = col_half * (NQ / 2); c0 < (col_half + 1) * (NQ / 2); c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_x32(taddr + c0, v);
+                tmem_wait_ld();
+                float t[32];
+                float mx = -CUDART_INF_F;
+#pragma unroll
+                for (int j4 = 0; j4 < 32; j4 += 4) {
+                    const float4 h = *reinterpret_cast<const float4*>(s_thr + c0 + j4);
+                    t[j4 + 0] = __uint_as_float(v[j4 + 0]) + h.x;
+                    t[j4 + 1] = __uint_as_float(v[j4 + 1]) + h.y;
+                    t[j4 + 2] = __uint_as_float(v[j4 + 2]) + h.z;
+                    t[j4 + 3] = __uint_as_float(v[j4 + 3]) + h.w;
+                    mx = fmaxf(mx, fmaxf(fmaxf(t[j4 + 0], t[j4 + 1]), fmaxf(t[j4 + 2], t[j4 + 3])));
+                }
+                if (mx > half_xn) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (t[j] > half_xn) {
+                            const uint32_t pos = atomicAdd(&cand_count[c0 + j], 1u);
+                            if (pos < (uint32_t)cap) cand_rows[(size_t)(c0 + j) * cap + pos] = (uint32_t)row;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (rank == 0) mbar_arrive(&tempty_bar[acc]);
+                else mbar_arrive_remote(&tempty_bar[acc], 0);
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                                // the peer may still be reading operands from this CTA's smem
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    }
+}
+
 // ------------------------------------------------------------- row norms (index time)
 __global__ void __launch_bounds__(256)
 row_norms_kernel(const float* __restrict__ X, int64_t row0, int64_t n, int dpad, float* __restrict__ xnorm,
@@ -505,6 +738,13 @@ size_t dense_tc_workspace_bytes(const DeviceInfo&, int64_t n_rows, int P)
 }
 bool dense_tc_wants(int64_t n_rows, int batch) { return n_rows >= TC_MIN_ROWS && batch >= 16; }
 
+static bool tc_use_2cta()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("KRAG_TC_2CTA"); v = (e == nullptr || e[0] != '0') ? 1 : 0; }
+    return v == 1;
+}
+
 template <int NQ>
 static void tc_pass(const DeviceInfo& di, const CUtensorMap& tmX, const CUtensorMap& tmQ, const float* X, int64_t n_rows,
                     int dpad, const float* xnorm, const uint32_t* xn_max_bits, const uint32_t* alive, const float* q,
@@ -542,9 +782,34 @@ static void tc_pass(const DeviceInfo& di, const CUtensorMap& tmX, const CUtensor
     count_launch();
     KRAG_CUDA(cudaMemsetAsync(w.cand_count, 0, 256 * 4, st));
     // 3. main pass: stream the corpus once, prune on the tensor cores
-    dense_timer_begin(st, 2, n_rows * (int64_t)dpad * 4, 2 * (int64_t)NQ * n_rows * dpad);
-    dense_tc_kernel<NQ, false><<<grid_m, TC_THREADS, Cfg::SMEM, st>>>(tmX, tmQ, n_rows, kblocks, n_tiles, 1, xnorm, alive, w.thr,
-                                                                      w.cand_count, w.cand_rows, cap, nullptr, 0);
+    dense_timer_begin(st, tc_use_2cta() ? 3 : 2, n_rows * (int64_t)dpad * 4, 2 * (int64_t)NQ * n_rows * dpad);
+    if (tc_use_2cta()) {
+        using Cfg2 = Tc2Cfg<NQ>;
+        static bool attr2_set = false;
+        if (!attr2_set) {
+            KRAG_CUDA(cudaFuncSetAttribute(dense_tc2_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg2::SMEM));
+            attr2_set = true;
+        }
+        CUtensorMap tmQh;
+        if (!make_map(&tmQh, q, nq, dpad, NQ / 2)) throw CudaError{cudaErrorUnknown, "cuTensorMapEncodeTiled(Q half)", __FILE__, __LINE__};
+        const int64_t n_ptiles = (n_rows + 2 * TC_TILE_M - 1) / (2 * TC_TILE_M);
+        const int64_t max_pairs = di.sm_count / 2;
+        const int n_pairs = (int)(n_ptiles < max_pairs ? n_ptiles : max_pairs);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * n_pairs));
+        cfg.blockDim = dim3(TC_THREADS);
+        cfg.dynamicSmemBytes = Cfg2::SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        KRAG_CUDA(cudaLaunchKernelEx(&cfg, dense_tc2_kernel<NQ>, tmX, tmQh, n_rows, kblocks, n_ptiles, xnorm, alive,
+                                     (const float*)w.thr, w.cand_count, w.cand_rows, cap));
+    } else {
+        dense_tc_kernel<NQ, false><<<grid_m, TC_THREADS, Cfg::SMEM, st>>>(tmX, tmQ, n_rows, kblocks, n_tiles, 1, xnorm, alive, w.thr,
+                                                                          w.cand_count, w.cand_rows, cap, nullptr, 0);
+    }
     dense_timer_end(st);
     KRAG_CUDA(cudaGetLastError());
     count_launch();
