@@ -195,7 +195,28 @@ int32_t krag_index_read_rows(krag_index* idx, int64_t row0, int64_t n, float* ou
 int32_t krag_index_read_postings(krag_index* idx, uint32_t term, int64_t cap, uint32_t* docs_out, float* scores_out,
                                  int64_t* n_out);
 
+/* ------------------------------------------------------------- embedding forward (K5) */
+/* replaces: LocalHuggingFaceEmbedding (embedding/huggingface_local_embedding.py:34-53) -> sentence-
+ * transformers BertModel forward, CLS pooling, L2 normalisation.  Tokenisation (WordPiece) stays in
+ * the host.  Weights are loaded by their Hugging Face BertModel names ("embeddings.word_embeddings.weight",
+ * "encoder.layer.0.attention.self.query.weight", ...), fp32, row-major as torch stores them. */
+typedef struct krag_embedder krag_embedder;
+typedef struct krag_bert_config {
+    int32_t layers, hidden, heads, intermediate, vocab, max_position, type_vocab;
+    float ln_eps;
+} krag_bert_config;
+int32_t krag_embedder_create(krag_ctx* ctx, const krag_bert_config* cfg, krag_embedder** out);
+int32_t krag_embedder_load_tensor(krag_embedder* e, const char* name, const float* data, int64_t n_elems);
+int32_t krag_embedder_finalize(krag_embedder* e);
+/* tok_ids: packed token ids of all sequences ([CLS] ... [SEP] each); tok_offsets [batch+1]; out [batch, hidden] */
+int32_t krag_embed(krag_embedder* e, int32_t batch, const int32_t* tok_ids, const int32_t* tok_offsets, float* out);
+int32_t krag_embedder_destroy(krag_embedder* e);
+
 /* ------------------------------------------------------------------- diagnostics */
+/* C[M,N] = A[M,K] . B[N,K]^T + bias (+erf-GELU) (+residual) through K5's tcgen05 TF32 GEMM; host buffers.
+ * N % 128 == 0, K % 32 == 0.  Test hook. */
+int32_t krag_debug_gemm_tf32(krag_ctx* ctx, int32_t M, int32_t N, int32_t K, const float* A, const float* B,
+                             const float* bias, const float* residual, int32_t gelu, float* C_out);
 /* queries whose tensor-core result failed the exactness certificate and were re-run on the
  * exact scan kernel (process-wide counter) */
 int64_t krag_tc_fallback_queries(void);

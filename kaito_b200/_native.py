@@ -30,7 +30,8 @@ SYMBOLS = [
     "krag_index_node_ids", "krag_index_persist", "krag_index_load", "krag_search_dense", "krag_search_bm25",
     "krag_retrieve", "krag_dev_dense_candidates", "krag_dev_bm25_candidates", "krag_dev_merge", "krag_dev_fuse",
     "krag_synth_fill", "krag_index_read_rows", "krag_index_read_postings", "krag_tc_fallback_queries",
-    "krag_debug_tc_dump", "krag_last_dense_kernel",
+    "krag_debug_tc_dump", "krag_last_dense_kernel", "krag_embedder_create", "krag_embedder_load_tensor",
+    "krag_embedder_finalize", "krag_embed", "krag_embedder_destroy", "krag_debug_gemm_tf32",
 ]
 
 
@@ -50,6 +51,11 @@ class Stats(C.Structure):
                 ("total_len_global", C.c_int64), ("vocab", C.c_int64), ("ordinal_base", C.c_int64), ("dim", C.c_int32),
                 ("dim_padded", C.c_int32), ("committed", C.c_int32), ("reserved", C.c_int32),
                 ("device_bytes", C.c_int64)]
+
+
+class BertConfig(C.Structure):
+    _fields_ = [("layers", C.c_int32), ("hidden", C.c_int32), ("heads", C.c_int32), ("intermediate", C.c_int32),
+                ("vocab", C.c_int32), ("max_position", C.c_int32), ("type_vocab", C.c_int32), ("ln_eps", C.c_float)]
 
 
 _lib = None
@@ -95,6 +101,12 @@ def load() -> C.CDLL:
     L.krag_synth_fill.argtypes = [vp, i64, i64, C.c_uint64, i64]
     L.krag_index_read_rows.argtypes = [vp, i64, i64, vp]
     L.krag_index_read_postings.argtypes = [vp, u32, i64, vp, vp, C.POINTER(i64)]
+    L.krag_embedder_create.argtypes = [vp, C.POINTER(BertConfig), C.POINTER(vp)]
+    L.krag_embedder_load_tensor.argtypes = [vp, C.c_char_p, vp, i64]
+    L.krag_embedder_finalize.argtypes = [vp]
+    L.krag_embed.argtypes = [vp, i32, vp, vp, vp]
+    L.krag_embedder_destroy.argtypes = [vp]
+    L.krag_debug_gemm_tf32.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, i32, vp]
     L.krag_tc_fallback_queries.restype = i64
     L.krag_last_dense_kernel.argtypes = [C.POINTER(C.c_float), C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]
     L.krag_debug_tc_dump.argtypes = [vp, i32, vp, vp, i64, C.POINTER(i64), C.POINTER(i32)]
@@ -172,6 +184,52 @@ class Context:
         check(self._L.krag_dev_fuse(self._h, batch, P, k, ptr(d_dense), ptr(d_bm25), vw, tw, mode, ptr(d_allow),
                                     ptr(d_final), ptr(d_dense_out), ptr(d_sparse_out), ptr(d_rank), ptr(d_ord),
                                     ptr(d_count), ptr(stream)))
+
+
+class Embedder:
+    """krag_embedder: BERT-family encoder forward on the GPU (K5)."""
+
+    def __init__(self, ctx: "Context", layers, hidden, heads, intermediate, vocab, max_position=512, type_vocab=2,
+                 ln_eps=1e-12):
+        self.ctx, self._L, self.hidden = ctx, ctx._L, hidden
+        cfg = BertConfig(layers, hidden, heads, intermediate, vocab, max_position, type_vocab, ln_eps)
+        h = C.c_void_p()
+        check(self._L.krag_embedder_create(ctx._h, C.byref(cfg), C.byref(h)))
+        self._h = h
+
+    def load_state_dict(self, state: dict):
+        """state: Hugging Face BertModel names -> numpy fp32 arrays (pooler / position_ids entries are ignored)"""
+        for name, arr in state.items():
+            if name.startswith("pooler.") or name.endswith("position_ids"):
+                continue
+            a = np.ascontiguousarray(arr, np.float32)
+            check(self._L.krag_embedder_load_tensor(self._h, name.encode(), ptr(a), a.size))
+        check(self._L.krag_embedder_finalize(self._h))
+
+    def embed(self, token_lists) -> np.ndarray:
+        offs = np.zeros(len(token_lists) + 1, np.int32)
+        for i, t in enumerate(token_lists):
+            offs[i + 1] = offs[i] + len(t)
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(t, np.int32) for t in token_lists]), np.int32)
+        out = np.empty((len(token_lists), self.hidden), np.float32)
+        check(self._L.krag_embed(self._h, len(token_lists), ptr(flat), ptr(offs), ptr(out)))
+        return out
+
+    def destroy(self):
+        if self._h:
+            check(self._L.krag_embedder_destroy(self._h))
+            self._h = None
+
+
+def debug_gemm_tf32(ctx: "Context", A, B, bias, residual=None, gelu=False) -> np.ndarray:
+    A = np.ascontiguousarray(A, np.float32); B = np.ascontiguousarray(B, np.float32)
+    bias = np.ascontiguousarray(bias, np.float32)
+    if residual is not None:
+        residual = np.ascontiguousarray(residual, np.float32)
+    out = np.empty((A.shape[0], B.shape[0]), np.float32)
+    check(load().krag_debug_gemm_tf32(ctx._h, A.shape[0], B.shape[0], A.shape[1], ptr(A), ptr(B), ptr(bias), ptr(residual),
+                                      1 if gelu else 0, ptr(out)))
+    return out
 
 
 class Index:

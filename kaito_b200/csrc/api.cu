@@ -15,6 +15,7 @@
 
 #include "../../include/kaito_rag.h"
 #include "common.cuh"
+#include "embed_config.h"
 #include "engine.h"
 
 namespace krag {
@@ -832,6 +833,72 @@ int32_t krag_debug_tc_dump(krag_index* ix, int32_t nq, const float* q, float* ou
                      KRAG_E_UNSUPPORTED, "tensor-core dump failed");
         KRAG_CUDA(cudaMemcpyAsync(out, s->tc_ws.p, sizeof(float) * (size_t)(S * nqp), cudaMemcpyDeviceToHost, s->st));
         KRAG_CUDA(cudaStreamSynchronize(s->st));
+    });
+}
+
+// ---------------------------------------------------------------------- K5 embedder
+struct krag_embedder { krag_ctx* ctx; Embedder* e; };
+
+int32_t krag_embedder_create(krag_ctx* c, const krag_bert_config* cfg, krag_embedder** out)
+{
+    return guarded([&] {
+        KRAG_REQUIRE(c && cfg && out, KRAG_E_INVALID, "null argument");
+        KRAG_CUDA(cudaSetDevice(c->di.device));
+        BertConfig bc{cfg->layers, cfg->hidden, cfg->heads, cfg->intermediate, cfg->vocab, cfg->max_position, cfg->type_vocab, cfg->ln_eps};
+        krag_embedder* h = new krag_embedder{c, embedder_create(c->di, bc)};
+        *out = h;
+    });
+}
+int32_t krag_embedder_load_tensor(krag_embedder* h, const char* name, const float* data, int64_t n)
+{
+    return guarded([&] {
+        KRAG_REQUIRE(h && name && data && n > 0, KRAG_E_INVALID, "bad argument");
+        KRAG_CUDA(cudaSetDevice(h->ctx->di.device));
+        embedder_load(h->e, name, data, n);
+    });
+}
+int32_t krag_embedder_finalize(krag_embedder* h)
+{
+    return guarded([&] {
+        KRAG_REQUIRE(h, KRAG_E_INVALID, "null embedder");
+        KRAG_CUDA(cudaSetDevice(h->ctx->di.device));
+        embedder_finalize(h->e);
+    });
+}
+int32_t krag_embed(krag_embedder* h, int32_t batch, const int32_t* tok_ids, const int32_t* tok_offsets, float* out)
+{
+    return guarded([&] {
+        KRAG_REQUIRE(h && tok_ids && tok_offsets && out && batch >= 1, KRAG_E_INVALID, "bad argument");
+        KRAG_REQUIRE(tok_offsets[0] == 0, KRAG_E_INVALID, "tok_offsets must start at 0");
+        KRAG_CUDA(cudaSetDevice(h->ctx->di.device));
+        embedder_forward(h->e, batch, tok_ids, tok_offsets, out);
+    });
+}
+int32_t krag_embedder_destroy(krag_embedder* h)
+{
+    return guarded([&] {
+        KRAG_REQUIRE(h, KRAG_E_INVALID, "null embedder");
+        cudaSetDevice(h->ctx->di.device);
+        embedder_destroy(h->e);
+        delete h;
+    });
+}
+int32_t krag_debug_gemm_tf32(krag_ctx* c, int32_t M, int32_t N, int32_t K, const float* A, const float* B, const float* bias,
+                             const float* residual, int32_t gelu, float* C_out)
+{
+    return guarded([&] {
+        KRAG_REQUIRE(c && A && B && bias && C_out && M >= 1 && N % 128 == 0 && K % 32 == 0, KRAG_E_INVALID, "bad argument (N % 128, K % 32)");
+        KRAG_CUDA(cudaSetDevice(c->di.device));
+        float *dA, *dB, *db, *dr = nullptr, *dC;
+        KRAG_CUDA(cudaMalloc(&dA, 4 * (size_t)M * K)); KRAG_CUDA(cudaMalloc(&dB, 4 * (size_t)N * K)); KRAG_CUDA(cudaMalloc(&db, 4 * (size_t)N));
+        KRAG_CUDA(cudaMalloc(&dC, 4 * (size_t)M * N));
+        KRAG_CUDA(cudaMemcpy(dA, A, 4 * (size_t)M * K, cudaMemcpyHostToDevice)); KRAG_CUDA(cudaMemcpy(dB, B, 4 * (size_t)N * K, cudaMemcpyHostToDevice));
+        KRAG_CUDA(cudaMemcpy(db, bias, 4 * (size_t)N, cudaMemcpyHostToDevice));
+        if (residual) { KRAG_CUDA(cudaMalloc(&dr, 4 * (size_t)M * N)); KRAG_CUDA(cudaMemcpy(dr, residual, 4 * (size_t)M * N, cudaMemcpyHostToDevice)); }
+        launch_gemm_tf32(c->di, dA, dB, M, N, K, db, dr, gelu != 0, dC, c->admin);
+        KRAG_CUDA(cudaStreamSynchronize(c->admin));
+        KRAG_CUDA(cudaMemcpy(C_out, dC, 4 * (size_t)M * N, cudaMemcpyDeviceToHost));
+        cudaFree(dA); cudaFree(dB); cudaFree(db); cudaFree(dC); if (dr) cudaFree(dr);
     });
 }
 

@@ -1,0 +1,533 @@
+// embed.cu -- K5: BERT-family (bge-small / bge-base / bge-large) encoder forward on the GPU.
+//
+// Replaces the torch / sentence-transformers forward behind
+// presets/ragengine/embedding/huggingface_local_embedding.py:34-53 (LlamaIndex HuggingFaceEmbedding ->
+// BertModel, CLS pooling, L2 normalisation; reached from embedding/base.py:25-26 on /retrieve and from
+// VectorStoreIndex.from_documents on /index, vector_store/base.py:155-166).
+//
+//   tokens (packed, variable length: no padding rows)  ->  word+position+type embeddings -> LayerNorm
+//   L x [ QKV GEMM -> attention -> O GEMM (+bias +residual) -> LayerNorm -> FFN1 GEMM (+bias, erf-GELU)
+//         -> FFN2 GEMM (+bias +residual) -> LayerNorm ]  ->  CLS row  ->  L2 normalise
+//
+// The four GEMMs per layer (24 S d^2 of the 24 S d^2 + 4 S^2 d flops) run on tcgen05.mma kind::tf32 with
+// fp32 accumulation in TMEM, operands staged by TMA (fp32 weights/activations are consumed as TF32, no
+// conversion pass); bias / GELU / residual are fused into the TMEM epilogue.  LayerNorm, softmax and the
+// attention products are fp32 CUDA-core code (attention is 4 S^2 d: 2% of the flops at S = 32 queries).
+#include <math_constants.h>
+
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+#include "embed_config.h"
+#include "tc_ptx.cuh"
+#include "common.cuh"
+
+namespace krag {
+
+// ------------------------------------------------------------------ GEMM: C = A . B^T (+bias)(gelu)(+res)
+// A [M, K] row-major (activations), B [N, K] row-major (nn.Linear weight), C [M, N] row-major, all fp32.
+// Persistent CTAs over 128 x 128 output tiles (n fastest so neighbouring CTAs share the A tile in L2);
+// one TMA warp, one MMA-issuing thread, four epilogue warps; stage = 2 k-blocks of 32 floats for A and B.
+constexpr int GM_TILE = 128;
+constexpr int GM_KB = 32;                 // floats per k-block (128-byte swizzle row)
+constexpr int GM_KB_PER_STAGE = 2;
+constexpr int GM_SLAB = GM_TILE * GM_KB * 4;                     // 16 KB
+constexpr int GM_STAGE_BYTES = GM_KB_PER_STAGE * 2 * GM_SLAB;    // 64 KB
+constexpr int GM_STAGES = 3;
+constexpr int GM_THREADS = 192;
+constexpr size_t GM_SMEM = (size_t)GM_STAGES * GM_STAGE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+
+__global__ void __launch_bounds__(GM_THREADS, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
+                 const float* __restrict__ bias, const float* __restrict__ residual, int act_gelu, float* __restrict__ C)
+{
+    extern __shared__ unsigned char gm_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gm_smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* tail = smem + (size_t)GM_STAGES * GM_STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* empty_bar = full_bar + GM_STAGES;
+    uint64_t* tfull_bar = empty_bar + GM_STAGES;      // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;             // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tiles = (M + GM_TILE - 1) / GM_TILE, n_tiles = N / GM_TILE;
+    const int total = m_tiles * n_tiles;
+    const int kblocks = K / GM_KB;
+    const int stages_per_tile = (kblocks + GM_KB_PER_STAGE - 1) / GM_KB_PER_STAGE;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < GM_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        int stage = 0; uint32_t phase = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            const int m0 = (t / n_tiles) * GM_TILE, n0 = (t % n_tiles) * GM_TILE;
+            for (int sk = 0; sk < stages_per_tile; ++sk) {
+                const int nkb = min(GM_KB_PER_STAGE, kblocks - sk * GM_KB_PER_STAGE);
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (lane == 0) {
+                    unsigned char* sa = smem + (size_t)stage * GM_STAGE_BYTES;
+                    unsigned char* sb = sa + GM_KB_PER_STAGE * GM_SLAB;
+                    mbar_expect_tx(&full_bar[stage], nkb * 2 * GM_SLAB);
+                    for (int u = 0; u < nkb; ++u) {
+                        const int k0 = (sk * GM_KB_PER_STAGE + u) * GM_KB;
+                        tma_load_2d(sa + (size_t)u * GM_SLAB, &tmA, &full_bar[stage], k0, m0, TMA_EVICT_FIRST);
+                        tma_load_2d(sb + (size_t)u * GM_SLAB, &tmB, &full_bar[stage], k0, n0, TMA_EVICT_LAST);
+                    }
+                }
+                __syncwarp();
+                if (++stage == GM_STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = umma_idesc_tf32(GM_TILE, GM_TILE);
+        const uint64_t desc0 = umma_desc_sw128(smem_u32(smem));
+        const uint32_t lo0 = (uint32_t)desc0;
+        int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * GM_TILE);
+            for (int sk = 0; sk < stages_per_tile; ++sk) {
+                const int nkb = min(GM_KB_PER_STAGE, kblocks - sk * GM_KB_PER_STAGE);
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_lo = lo0 + (uint32_t)((stage * GM_STAGE_BYTES) >> 4);
+                    const uint32_t b_lo = a_lo + (uint32_t)((GM_KB_PER_STAGE * GM_SLAB) >> 4);
+#pragma unroll
+                    for (int u = 0; u < GM_KB_PER_STAGE; ++u) {
+                        if (u < nkb) {
+#pragma unroll
+                            for (int k = 0; k < GM_KB / 8; ++k) {
+                                const uint64_t ad = (desc0 & 0xFFFFFFFF00000000ull) | (uint64_t)(a_lo + (uint32_t)((u * GM_SLAB) >> 4) + 2 * k);
+                                const uint64_t bd = (desc0 & 0xFFFFFFFF00000000ull) | (uint64_t)(b_lo + (uint32_t)((u * GM_SLAB) >> 4) + 2 * k);
+                                umma_tf32(d_tmem, ad, bd, idesc, (uint32_t)((sk | u | k) != 0));
+                            }
+                        }
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (sk == stages_per_tile - 1) umma_commit(&tfull_bar[acc]);
+                }
+                __syncwarp();
+                if (++stage == GM_STAGES) { stage = 0; phase ^= 1; }
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    } else {
+        const int lg = warp & 3;
+        const int r_in = lg * 32 + lane;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = blockIdx.x; t < total; t += gridDim.x) {
+            const int m0 = (t / n_tiles) * GM_TILE, n0 = (t % n_tiles) * GM_TILE;
+            const int row = m0 + r_in;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * GM_TILE);
+#pragma unroll 1
+            for (int c0 = 0; c0 < GM_TILE; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_x32(taddr + c0, v);
+                tmem_wait_ld();
+                if (row < M) {
+                    float* crow = C + (size_t)row * N + n0 + c0;
+                    const float* rrow = residual ? residual + (size_t)row * N + n0 + c0 : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
+                        float4 o;
+                        o.x = __uint_as_float(v[j + 0]) + b4.x; o.y = __uint_as_float(v[j + 1]) + b4.y;
+                        o.z = __uint_as_float(v[j + 2]) + b4.z; o.w = __uint_as_float(v[j + 3]) + b4.w;
+                        if (act_gelu) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
+                        if (rrow) {
+                            const float4 r4 = *reinterpret_cast<const float4*>(rrow + j);
+                            o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+                        }
+                        *reinterpret_cast<float4*>(crow + j) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    }
+}
+
+// --------------------------------------------------------------------------- fp32 row kernels
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// one warp per row: y = LayerNorm(x) * g + b   (two-pass variance like torch)
+__device__ __forceinline__ void warp_layernorm_row(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ g,
+                                                   const float* __restrict__ b, int d, float eps, int lane)
+{
+    float s = 0.f;
+    for (int i = lane; i < d; i += 32) s += x[i];
+    const float mean = warp_sum(s) / (float)d;
+    float v = 0.f;
+    for (int i = lane; i < d; i += 32) { float t = x[i] - mean; v += t * t; }
+    const float rstd = rsqrtf(warp_sum(v) / (float)d + eps);
+    for (int i = lane; i < d; i += 32) y[i] = (x[i] - mean) * rstd * g[i] + b[i];
+}
+
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ g, const float* __restrict__ b,
+                 int rows, int d, float eps)
+{
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    warp_layernorm_row(x + (size_t)r * d, y + (size_t)r * d, g, b, d, eps, lane);
+}
+
+// embeddings: x[t] = LN(word[id] + pos[p] + type[0]); one warp per token; scratch row in shared memory
+__global__ void __launch_bounds__(256)
+embed_ln_kernel(const int32_t* __restrict__ tok, const int32_t* __restrict__ pos, const float* __restrict__ word,
+                const float* __restrict__ pemb, const float* __restrict__ temb, const float* __restrict__ g,
+                const float* __restrict__ b, float* __restrict__ x, int n_tok, int d, int vocab, float eps)
+{
+    extern __shared__ float e_sm[];   // [8][d]
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t = blockIdx.x * 8 + w;
+    if (t >= n_tok) return;
+    float* row = e_sm + (size_t)w * d;
+    int id = tok[t];
+    id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+    const float* wr = word + (size_t)id * d;
+    const float* pr = pemb + (size_t)pos[t] * d;
+    for (int i = lane; i < d; i += 32) row[i] = (wr[i] + temb[i]) + pr[i];   // torch: inputs_embeds + token_type + position
+    __syncwarp();
+    warp_layernorm_row(row, x + (size_t)t * d, g, b, d, eps, lane);
+}
+
+// ------------------------------------------------------------------------------- attention
+// packed variable-length sequences: qkv [n_tok, 3d] (Q | K | V, heads contiguous inside each), out [n_tok, d].
+// grid (ceil(max_len / 16), heads, batch); 8 warps, 2 query rows per warp; keys processed in chunks of 64.
+constexpr int AT_ROWS = 16;
+constexpr int AT_CHUNK = 64;
+__global__ void __launch_bounds__(256)
+attention_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ seq_off, float* __restrict__ out, int d, int heads,
+                 int max_len)
+{
+    extern __shared__ float a_sm[];
+    const int dh = d / heads;
+    const int b = blockIdx.z, h = blockIdx.y;
+    const int t0 = seq_off[b], len = seq_off[b + 1] - t0;
+    const int r0 = blockIdx.x * AT_ROWS;
+    if (r0 >= len) return;
+    float* s_q = a_sm;                                  // [AT_ROWS][dh]
+    float* s_kT = s_q + AT_ROWS * dh;                   // [dh][AT_CHUNK + 1]
+    float* s_v = s_kT + dh * (AT_CHUNK + 1);            // [AT_CHUNK][dh]
+    float* s_p = s_v + AT_CHUNK * dh;                   // [AT_ROWS][max_len] scores / probabilities
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float scale = rsqrtf((float)dh);
+    const int nrows = min(AT_ROWS, len - r0);
+    for (int i = tid; i < nrows * dh; i += 256) {
+        const int r = i / dh, c = i % dh;
+        s_q[i] = qkv[(size_t)(t0 + r0 + r) * 3 * d + h * dh + c];
+    }
+    // pass 1: scores
+    for (int k0 = 0; k0 < len; k0 += AT_CHUNK) {
+        const int nk = min(AT_CHUNK, len - k0);
+        __syncthreads();
+        for (int i = tid; i < nk * dh; i += 256) {
+            const int kk = i / dh, c = i % dh;
+            s_kT[c * (AT_CHUNK + 1) + kk] = qkv[(size_t)(t0 + k0 + kk) * 3 * d + d + h * dh + c];
+        }
+        __syncthreads();
+        for (int rr = 0; rr < 2; ++rr) {
+            const int r = warp * 2 + rr;
+            if (r >= nrows) break;
+            for (int kk = lane; kk < nk; kk += 32) {
+                float acc = 0.f;
+                for (int c = 0; c < dh; ++c) acc = fmaf(s_q[r * dh + c], s_kT[c * (AT_CHUNK + 1) + kk], acc);
+                s_p[r * max_len + k0 + kk] = acc * scale;
+            }
+        }
+    }
+    __syncthreads();
+    // softmax per row (fp32, max-subtracted like torch)
+    for (int rr = 0; rr < 2; ++rr) {
+        const int r = warp * 2 + rr;
+        if (r >= nrows) break;
+        float* p = s_p + r * max_len;
+        float m = -CUDART_INF_F;
+        for (int k = lane; k < len; k += 32) m = fmaxf(m, p[k]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float s = 0.f;
+        for (int k = lane; k < len; k += 32) { float e = expf(p[k] - m); p[k] = e; s += e; }
+        s = warp_sum(s);
+        const float inv = 1.f / s;
+        for (int k = lane; k < len; k += 32) p[k] *= inv;
+    }
+    // pass 2: out = P . V
+    float o_acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};      // [row of the warp][dh / 32 columns per lane, dh <= 64]
+    for (int k0 = 0; k0 < len; k0 += AT_CHUNK) {
+        const int nk = min(AT_CHUNK, len - k0);
+        __syncthreads();
+        for (int i = tid; i < nk * dh; i += 256) {
+            const int kk = i / dh, c = i % dh;
+            s_v[kk * dh + c] = qkv[(size_t)(t0 + k0 + kk) * 3 * d + 2 * d + h * dh + c];
+        }
+        __syncthreads();
+        for (int rr = 0; rr < 2; ++rr) {
+            const int r = warp * 2 + rr;
+            if (r >= nrows) break;
+            for (int kk = 0; kk < nk; ++kk) {
+                const float p = s_p[r * max_len + k0 + kk];
+                if (lane < dh) o_acc[rr][0] = fmaf(p, s_v[kk * dh + lane], o_acc[rr][0]);
+                if (lane + 32 < dh) o_acc[rr][1] = fmaf(p, s_v[kk * dh + lane + 32], o_acc[rr][1]);
+            }
+        }
+    }
+    for (int rr = 0; rr < 2; ++rr) {
+        const int r = warp * 2 + rr;
+        if (r >= nrows) break;
+        float* orow = out + (size_t)(t0 + r0 + r) * d + h * dh;
+        if (lane < dh) orow[lane] = o_acc[rr][0];
+        if (lane + 32 < dh) orow[lane + 32] = o_acc[rr][1];
+    }
+}
+
+// CLS pooling + L2 normalisation (F.normalize, eps 1e-12): one warp per sequence
+__global__ void __launch_bounds__(256)
+cls_normalize_kernel(const float* __restrict__ x, const int32_t* __restrict__ seq_off, float* __restrict__ out, int batch, int d)
+{
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (b >= batch) return;
+    const float* row = x + (size_t)seq_off[b] * d;
+    float s = 0.f;
+    for (int i = lane; i < d; i += 32) s = fmaf(row[i], row[i], s);
+    const float n = fmaxf(sqrtf(warp_sum(s)), 1e-12f);
+    for (int i = lane; i < d; i += 32) out[(size_t)b * d + i] = row[i] / n;
+}
+
+// ------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn emb_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+static void emb_map(CUtensorMap* tm, const float* base, int rows, int cols)
+{
+    EncodeTiledFn enc = emb_encode();
+    if (!enc) throw CudaError{cudaErrorUnknown, "cuTensorMapEncodeTiled unavailable", __FILE__, __LINE__};
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)cols * 4};
+    cuuint32_t box[2] = {(cuuint32_t)GM_KB, (cuuint32_t)GM_TILE};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        throw CudaError{cudaErrorUnknown, "cuTensorMapEncodeTiled failed", __FILE__, __LINE__};
+}
+
+void launch_gemm_tf32(const DeviceInfo& di, const float* A, const float* B, int M, int N, int K, const float* bias,
+                      const float* residual, bool gelu, float* C, cudaStream_t st)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        KRAG_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GM_SMEM));
+        attr_set = true;
+    }
+    CUtensorMap tmA, tmB;
+    emb_map(&tmA, A, M, K);
+    emb_map(&tmB, B, N, K);
+    const int total = ((M + GM_TILE - 1) / GM_TILE) * (N / GM_TILE);
+    const int grid = total < di.sm_count ? total : di.sm_count;
+    gemm_tf32_kernel<<<grid, GM_THREADS, GM_SMEM, st>>>(tmA, tmB, M, N, K, bias, residual, gelu ? 1 : 0, C);
+    KRAG_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+
+struct Embedder {
+    DeviceInfo di;
+    BertConfig cfg;
+    std::map<std::string, float*> t;      // HF tensor name -> device copy
+    std::vector<float*> wqkv, bqkv;       // fused per layer at finalize
+    bool finalized = false;
+    cudaStream_t st = nullptr;
+    // workspaces, grown on demand
+    int cap_tok = 0, cap_batch = 0;
+    int32_t *d_tok = nullptr, *d_pos = nullptr, *d_off = nullptr;
+    float *x = nullptr, *x2 = nullptr, *qkv = nullptr, *ctx = nullptr, *ffn = nullptr, *out = nullptr;
+};
+
+static float* emb_get(Embedder* e, const std::string& name, int64_t n)
+{
+    auto it = e->t.find(name);
+    if (it == e->t.end()) throw std::runtime_error("embedder: tensor not loaded: " + name);
+    (void)n;
+    return it->second;
+}
+static std::string lname(int l, const char* s) { return "encoder.layer." + std::to_string(l) + "." + s; }
+
+Embedder* embedder_create(const DeviceInfo& di, const BertConfig& cfg)
+{
+    if (cfg.hidden % 128 || cfg.inter % 128 || cfg.hidden % cfg.heads || cfg.hidden / cfg.heads > 64 || (cfg.hidden / cfg.heads) % 32)
+        throw std::runtime_error("embedder: hidden/intermediate must be multiples of 128 and head_dim 32 or 64");
+    Embedder* e = new Embedder();
+    e->di = di; e->cfg = cfg;
+    KRAG_CUDA(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));
+    return e;
+}
+
+void embedder_load(Embedder* e, const char* name, const float* data, int64_t n)
+{
+    float* p = nullptr;
+    KRAG_CUDA(cudaMalloc(&p, sizeof(float) * (size_t)n));
+    KRAG_CUDA(cudaMemcpy(p, data, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice));
+    auto it = e->t.find(name);
+    if (it != e->t.end()) cudaFree(it->second);
+    e->t[name] = p;
+    e->finalized = false;
+}
+
+void embedder_finalize(Embedder* e)
+{
+    const int d = e->cfg.hidden;
+    for (float* p : e->wqkv) cudaFree(p);
+    for (float* p : e->bqkv) cudaFree(p);
+    e->wqkv.clear(); e->bqkv.clear();
+    emb_get(e, "embeddings.word_embeddings.weight", 0); emb_get(e, "embeddings.position_embeddings.weight", 0);
+    emb_get(e, "embeddings.token_type_embeddings.weight", 0); emb_get(e, "embeddings.LayerNorm.weight", 0);
+    emb_get(e, "embeddings.LayerNorm.bias", 0);
+    for (int l = 0; l < e->cfg.layers; ++l) {
+        float *w = nullptr, *b = nullptr;
+        KRAG_CUDA(cudaMalloc(&w, sizeof(float) * (size_t)3 * d * d));
+        KRAG_CUDA(cudaMalloc(&b, sizeof(float) * (size_t)3 * d));
+        const char* names[3] = {"attention.self.query", "attention.self.key", "attention.self.value"};
+        for (int j = 0; j < 3; ++j) {
+            KRAG_CUDA(cudaMemcpy(w + (size_t)j * d * d, emb_get(e, lname(l, names[j]) + ".weight", 0), sizeof(float) * (size_t)d * d, cudaMemcpyDeviceToDevice));
+            KRAG_CUDA(cudaMemcpy(b + (size_t)j * d, emb_get(e, lname(l, names[j]) + ".bias", 0), sizeof(float) * (size_t)d, cudaMemcpyDeviceToDevice));
+        }
+        e->wqkv.push_back(w); e->bqkv.push_back(b);
+        for (const char* s : {"attention.output.dense.weight", "attention.output.dense.bias", "attention.output.LayerNorm.weight",
+                              "attention.output.LayerNorm.bias", "intermediate.dense.weight", "intermediate.dense.bias",
+                              "output.dense.weight", "output.dense.bias", "output.LayerNorm.weight", "output.LayerNorm.bias"})
+            emb_get(e, lname(l, s), 0);
+    }
+    e->finalized = true;
+}
+
+void embedder_destroy(Embedder* e)
+{
+    for (auto& kv : e->t) cudaFree(kv.second);
+    for (float* p : e->wqkv) cudaFree(p);
+    for (float* p : e->bqkv) cudaFree(p);
+    for (void* p : {(void*)e->d_tok, (void*)e->d_pos, (void*)e->d_off, (void*)e->x, (void*)e->x2, (void*)e->qkv, (void*)e->ctx, (void*)e->ffn, (void*)e->out})
+        if (p) cudaFree(p);
+    if (e->st) cudaStreamDestroy(e->st);
+    delete e;
+}
+
+int embedder_hidden(const Embedder* e) { return e->cfg.hidden; }
+
+// tok_ids: packed tokens of all sequences; tok_offsets [batch+1]; out_host [batch, hidden]
+void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int32_t* tok_offsets, float* out_host)
+{
+    if (!e->finalized) throw std::runtime_error("embedder: call finalize after loading the weights");
+    const BertConfig& c = e->cfg;
+    const int d = c.hidden, n_tok = tok_offsets[batch];
+    cudaStream_t st = e->st;
+    int max_len = 0;
+    std::vector<int32_t> pos((size_t)n_tok);
+    for (int b = 0; b < batch; ++b) {
+        const int len = tok_offsets[b + 1] - tok_offsets[b];
+        if (len < 1 || len > c.max_pos) throw std::runtime_error("embedder: sequence length must be in [1, max_position]");
+        max_len = len > max_len ? len : max_len;
+        for (int i = 0; i < len; ++i) pos[(size_t)tok_offsets[b] + i] = i;
+    }
+    if (n_tok > e->cap_tok || batch > e->cap_batch) {
+        for (void* p : {(void*)e->d_tok, (void*)e->d_pos, (void*)e->d_off, (void*)e->x, (void*)e->x2, (void*)e->qkv, (void*)e->ctx, (void*)e->ffn, (void*)e->out})
+            if (p) cudaFree(p);
+        const size_t T = (size_t)(n_tok > e->cap_tok ? n_tok : e->cap_tok), Bc = (size_t)(batch > e->cap_batch ? batch : e->cap_batch);
+        KRAG_CUDA(cudaMalloc(&e->d_tok, 4 * T)); KRAG_CUDA(cudaMalloc(&e->d_pos, 4 * T)); KRAG_CUDA(cudaMalloc(&e->d_off, 4 * (Bc + 1)));
+        KRAG_CUDA(cudaMalloc(&e->x, 4 * T * d)); KRAG_CUDA(cudaMalloc(&e->x2, 4 * T * d)); KRAG_CUDA(cudaMalloc(&e->qkv, 4 * T * 3 * d));
+        KRAG_CUDA(cudaMalloc(&e->ctx, 4 * T * d)); KRAG_CUDA(cudaMalloc(&e->ffn, 4 * T * c.inter)); KRAG_CUDA(cudaMalloc(&e->out, 4 * Bc * d));
+        e->cap_tok = (int)T; e->cap_batch = (int)Bc;
+    }
+    KRAG_CUDA(cudaMemcpyAsync(e->d_tok, tok_ids, 4 * (size_t)n_tok, cudaMemcpyHostToDevice, st));
+    KRAG_CUDA(cudaMemcpyAsync(e->d_pos, pos.data(), 4 * (size_t)n_tok, cudaMemcpyHostToDevice, st));
+    KRAG_CUDA(cudaMemcpyAsync(e->d_off, tok_offsets, 4 * (size_t)(batch + 1), cudaMemcpyHostToDevice, st));
+
+    embed_ln_kernel<<<(n_tok + 7) / 8, 256, (size_t)8 * d * 4, st>>>(
+        e->d_tok, e->d_pos, e->t["embeddings.word_embeddings.weight"], e->t["embeddings.position_embeddings.weight"],
+        e->t["embeddings.token_type_embeddings.weight"], e->t["embeddings.LayerNorm.weight"], e->t["embeddings.LayerNorm.bias"], e->x,
+        n_tok, d, c.vocab, c.eps);
+    KRAG_CUDA(cudaGetLastError());
+    count_launch();
+    const int dh = d / c.heads;
+    const size_t at_smem = sizeof(float) * ((size_t)AT_ROWS * dh + (size_t)dh * (AT_CHUNK + 1) + (size_t)AT_CHUNK * dh + (size_t)AT_ROWS * max_len);
+    static bool at_attr = false;
+    if (!at_attr) { KRAG_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); at_attr = true; }
+    const int ln_grid = (n_tok * 32 + 255) / 256;
+    for (int l = 0; l < c.layers; ++l) {
+        launch_gemm_tf32(e->di, e->x, e->wqkv[(size_t)l], n_tok, 3 * d, d, e->bqkv[(size_t)l], nullptr, false, e->qkv, st);
+        attention_kernel<<<dim3((unsigned)((max_len + AT_ROWS - 1) / AT_ROWS), (unsigned)c.heads, (unsigned)batch), 256, at_smem, st>>>(
+            e->qkv, e->d_off, e->ctx, d, c.heads, max_len);
+        KRAG_CUDA(cudaGetLastError());
+        count_launch();
+        launch_gemm_tf32(e->di, e->ctx, e->t[lname(l, "attention.output.dense.weight")], n_tok, d, d,
+                         e->t[lname(l, "attention.output.dense.bias")], e->x, false, e->x2, st);
+        layernorm_kernel<<<ln_grid, 256, 0, st>>>(e->x2, e->x, e->t[lname(l, "attention.output.LayerNorm.weight")],
+                                                  e->t[lname(l, "attention.output.LayerNorm.bias")], n_tok, d, c.eps);
+        count_launch();
+        launch_gemm_tf32(e->di, e->x, e->t[lname(l, "intermediate.dense.weight")], n_tok, c.inter, d,
+                         e->t[lname(l, "intermediate.dense.bias")], nullptr, true, e->ffn, st);
+        launch_gemm_tf32(e->di, e->ffn, e->t[lname(l, "output.dense.weight")], n_tok, d, c.inter, e->t[lname(l, "output.dense.bias")],
+                         e->x, false, e->x2, st);
+        layernorm_kernel<<<ln_grid, 256, 0, st>>>(e->x2, e->x, e->t[lname(l, "output.LayerNorm.weight")],
+                                                  e->t[lname(l, "output.LayerNorm.bias")], n_tok, d, c.eps);
+        count_launch();
+    }
+    cls_normalize_kernel<<<(batch * 32 + 255) / 256, 256, 0, st>>>(e->x, e->d_off, e->out, batch, d);
+    KRAG_CUDA(cudaGetLastError());
+    count_launch();
+    KRAG_CUDA(cudaMemcpyAsync(out_host, e->out, 4 * (size_t)batch * d, cudaMemcpyDeviceToHost, st));
+    KRAG_CUDA(cudaStreamSynchronize(st));
+}
+
+}  // namespace krag

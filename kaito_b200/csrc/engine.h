@@ -85,6 +85,19 @@ void launch_bm25(const DeviceInfo& di, const Postings& post, int64_t n_rows, con
                  const uint32_t* q_terms, const int32_t* q_term_offsets, int max_terms, int batch, int P,
                  uint32_t ord_base, uint64_t* part, uint64_t* keys_out, cudaStream_t st);
 
+// ---- K5: BERT encoder forward (embed.cu)
+struct BertConfig;
+struct Embedder;
+Embedder* embedder_create(const DeviceInfo& di, const BertConfig& cfg);
+void embedder_load(Embedder* e, const char* name, const float* data, int64_t n);
+void embedder_finalize(Embedder* e);
+void embedder_destroy(Embedder* e);
+int embedder_hidden(const Embedder* e);
+void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int32_t* tok_offsets, float* out_host);
+// C[M,N] = A[M,K] . B[N,K]^T + bias (+gelu) (+residual), fp32 in/out, TF32 tensor cores; device pointers
+void launch_gemm_tf32(const DeviceInfo& di, const float* A, const float* B, int M, int N, int K, const float* bias,
+                      const float* residual, bool gelu, float* C, cudaStream_t st);
+
 // ---- synthetic data (synth.cu)
 void launch_synth_dense(float* X, int64_t n, int d, int dpad, int64_t row_base, uint64_t seed, cudaStream_t st);
 // two-pass: lengths -> offsets (host scan by caller via cub) -> fill

@@ -48,3 +48,63 @@ class HashingEmbedding(BaseEmbeddingModel):
 
     def get_embedding_dimension(self) -> int:
         return self.dim
+
+
+BGE_QUERY_INSTRUCTION = "Represent this question for searching relevant passages: "
+
+
+class GpuBertEmbedding(BaseEmbeddingModel):
+    """bge-small / bge-base / bge-large on the GPU (K5, kaito_b200/csrc/embed.cu): WordPiece on the host,
+    BERT encoder forward + CLS pooling + L2 normalisation in libkaito_rag.  Mirrors
+    LocalHuggingFaceEmbedding (embedding/huggingface_local_embedding.py:31-61); queries get the bge
+    instruction prefix LlamaIndex adds for BAAI/bge-* models [3P-unverified]."""
+
+    def __init__(self, engine, tokenizer, config: dict, state_dict: dict, query_instruction: str | None = BGE_QUERY_INSTRUCTION,
+                 max_batch_tokens: int = 65536):
+        from . import _native
+        self.tokenizer, self.query_instruction, self.max_batch_tokens = tokenizer, query_instruction, max_batch_tokens
+        self.dim = config["hidden_size"]
+        self._emb = _native.Embedder(engine, config["num_hidden_layers"], config["hidden_size"], config["num_attention_heads"],
+                                     config["intermediate_size"], config["vocab_size"], config.get("max_position_embeddings", 512),
+                                     config.get("type_vocab_size", 2), config.get("layer_norm_eps", 1e-12))
+        self._emb.load_state_dict(state_dict)
+
+    @classmethod
+    def from_pretrained(cls, engine, model_dir: str, **kw):
+        """model_dir: a Hugging Face snapshot (config.json, vocab.txt, model.safetensors or pytorch_model.bin)."""
+        import json
+        import os
+        from .text import WordPieceTokenizer
+        cfg = json.load(open(os.path.join(model_dir, "config.json")))
+        st_path = os.path.join(model_dir, "model.safetensors")
+        if os.path.exists(st_path):
+            from safetensors.numpy import load_file
+            state = load_file(st_path)
+        else:
+            import torch
+            state = {k: v.float().numpy() for k, v in torch.load(os.path.join(model_dir, "pytorch_model.bin"), map_location="cpu").items()}
+        state = {k[5:] if k.startswith("bert.") else k: v for k, v in state.items()}
+        return cls(engine, WordPieceTokenizer.from_file(os.path.join(model_dir, "vocab.txt")), cfg, state, **kw)
+
+    def get_embedding_dimension(self) -> int:
+        return self.dim
+
+    def _embed_tokens(self, token_lists):
+        import numpy as np
+        out, batch, ntok = [], [], 0
+        for t in token_lists:
+            if batch and ntok + len(t) > self.max_batch_tokens:
+                out.append(self._emb.embed(batch)); batch, ntok = [], 0
+            batch.append(t); ntok += len(t)
+        if batch:
+            out.append(self._emb.embed(batch))
+        return np.concatenate(out)
+
+    def get_text_embedding_batch(self, texts):
+        return self._embed_tokens([self.tokenizer.encode(t) for t in texts])
+
+    def get_text_embedding(self, text: str):
+        return self.get_text_embedding_batch([text])[0]
+
+    def get_query_embedding(self, query: str):
+        return self.get_text_embedding((self.query_instruction or "") + query)

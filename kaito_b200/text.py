@@ -213,3 +213,88 @@ class Vocabulary:
     def query_terms(self, text: str) -> np.ndarray:
         """term ids of a query in token order, duplicates kept, unknown terms dropped (bm25s semantics)."""
         return np.asarray([self.ids[t] for t in tokenize(text) if t in self.ids], np.uint32)
+
+
+# ------------------------------------------------------------------ WordPiece (BERT / bge tokeniser)
+import unicodedata  # noqa: E402
+
+
+def _is_punct(ch: str) -> bool:
+    cp = ord(ch)
+    if (33 <= cp <= 47) or (58 <= cp <= 64) or (91 <= cp <= 96) or (123 <= cp <= 126):
+        return True
+    return unicodedata.category(ch).startswith("P")
+
+
+def _is_cjk(cp: int) -> bool:
+    return ((0x4E00 <= cp <= 0x9FFF) or (0x3400 <= cp <= 0x4DBF) or (0x20000 <= cp <= 0x2A6DF) or (0x2A700 <= cp <= 0x2B73F)
+            or (0x2B740 <= cp <= 0x2B81F) or (0x2B820 <= cp <= 0x2CEAF) or (0xF900 <= cp <= 0xFAFF) or (0x2F800 <= cp <= 0x2FA1F))
+
+
+class WordPieceTokenizer:
+    """BertTokenizer (uncased) restated: BasicTokenizer (clean, CJK spacing, lower-case, accent strip,
+    punctuation split) + greedy longest-match WordPiece with "##" continuations.  Produces the ids the
+    embedder takes: [CLS] tokens [SEP], truncated to max_length.  The reference reaches the same
+    tokenizer through sentence-transformers (embedding/huggingface_local_embedding.py:34-53)."""
+
+    def __init__(self, vocab: dict[str, int] | list[str], do_lower_case: bool = True, max_length: int = 512):
+        if not isinstance(vocab, dict):
+            vocab = {t: i for i, t in enumerate(vocab)}
+        self.vocab, self.lower, self.max_length = vocab, do_lower_case, max_length
+        self.unk, self.cls, self.sep = vocab["[UNK]"], vocab["[CLS]"], vocab["[SEP]"]
+
+    @classmethod
+    def from_file(cls, path: str, **kw):
+        with open(path, encoding="utf-8") as f:
+            return cls([line.rstrip("\n") for line in f], **kw)
+
+    def _basic(self, text: str) -> list[str]:
+        out = []
+        for ch in text:
+            cp = ord(ch)
+            if cp == 0 or cp == 0xFFFD or (unicodedata.category(ch) in ("Cc", "Cf") and ch not in "\t\n\r"):
+                continue
+            if _is_cjk(cp):
+                out.append(f" {ch} ")
+            elif ch in " \t\n\r" or unicodedata.category(ch) == "Zs":
+                out.append(" ")
+            else:
+                out.append(ch)
+        toks = []
+        for tok in "".join(out).split():
+            if self.lower:
+                tok = tok.lower()
+                tok = "".join(c for c in unicodedata.normalize("NFD", tok) if unicodedata.category(c) != "Mn")
+            cur = []
+            for ch in tok:
+                if _is_punct(ch):
+                    if cur:
+                        toks.append("".join(cur)); cur = []
+                    toks.append(ch)
+                else:
+                    cur.append(ch)
+            if cur:
+                toks.append("".join(cur))
+        return toks
+
+    def _wordpiece(self, word: str) -> list[int]:
+        if len(word) > 100:
+            return [self.unk]
+        ids, start = [], 0
+        while start < len(word):
+            end, cur = len(word), None
+            while start < end:
+                sub = word[start:end] if start == 0 else "##" + word[start:end]
+                if sub in self.vocab:
+                    cur = self.vocab[sub]
+                    break
+                end -= 1
+            if cur is None:
+                return [self.unk]
+            ids.append(cur)
+            start = end
+        return ids
+
+    def encode(self, text: str) -> list[int]:
+        ids = [i for w in self._basic(text) for i in self._wordpiece(w)]
+        return [self.cls] + ids[: self.max_length - 2] + [self.sep]

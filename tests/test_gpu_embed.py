@@ -1,0 +1,91 @@
+"""K5 (BERT encoder forward on tcgen05 TF32 GEMMs) against transformers.BertModel in fp32 on the CPU with
+the same seeded random weights (the real bge weights are not available offline), CLS pooling + L2 norm as
+sentence-transformers does for bge (embedding/huggingface_local_embedding.py:34-53).  Tolerances are written
+out: TF32 operands carry 10 mantissa bits, so the embeddings agree to ~1e-3, not bit-exactly."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("M,N,K,gelu,res", [(10, 128, 32, False, False), (300, 384, 384, False, True),
+                                           (1000, 1152, 384, False, False), (257, 1536, 384, True, False),
+                                           (129, 384, 1536, False, True), (4096, 768, 768, True, True)])
+def test_gemm_tf32_matches_numpy(ctx, M, N, K, gelu, res):
+    from kaito_b200 import _native
+    g = np.random.default_rng(M + N + K)
+    A = g.standard_normal((M, K)).astype(np.float32)
+    B = (g.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    bias = g.standard_normal(N).astype(np.float32)
+    R = g.standard_normal((M, N)).astype(np.float32) if res else None
+    got = _native.debug_gemm_tf32(ctx, A, B, bias, R, gelu)
+    ref = A.astype(np.float64) @ B.astype(np.float64).T + bias
+    if gelu:
+        from math import erf
+        ref = 0.5 * ref * (1 + np.vectorize(erf)(ref / np.sqrt(2)))
+    if res:
+        ref = ref + R
+    err = np.abs(got - ref)
+    assert err.max() < 2e-2 and err.mean() < 1e-3, (err.max(), err.mean())   # |a.b| ~ 1, TF32 unit roundoff 2^-11
+
+
+def _torch_reference(cfg, state, token_lists):
+    import torch
+    from transformers import BertConfig, BertModel
+    m = BertModel(BertConfig(**cfg), add_pooling_layer=False).eval()
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in state.items()}, strict=False)
+    out = []
+    with torch.no_grad():
+        for t in token_lists:
+            h = m(input_ids=torch.tensor([t])).last_hidden_state[0, 0]
+            out.append(torch.nn.functional.normalize(h, dim=0).numpy())
+    return np.stack(out)
+
+
+def _random_state(cfg, seed):
+    import torch
+    from transformers import BertConfig, BertModel
+    torch.manual_seed(seed)
+    m = BertModel(BertConfig(**cfg), add_pooling_layer=False)
+    # default init is N(0, 0.02): give LayerNorm/bias non-trivial values so every term of the forward is exercised
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if n.endswith("bias"):
+                p.normal_(0, 0.05)
+            elif "LayerNorm.weight" in n:
+                p.normal_(1.0, 0.1)
+            elif p.dim() == 2 and "embeddings" not in n:
+                p.normal_(0, 0.06)
+    return {k: v.detach().numpy().astype(np.float32) for k, v in m.state_dict().items()}
+
+
+@pytest.mark.parametrize("name,cfg,lens", [
+    ("small-2L", dict(num_hidden_layers=2, hidden_size=384, num_attention_heads=12, intermediate_size=1536, vocab_size=1000,
+                      max_position_embeddings=512), [1, 3, 17, 64, 130, 512]),
+    ("bge-small", dict(num_hidden_layers=12, hidden_size=384, num_attention_heads=12, intermediate_size=1536, vocab_size=2000,
+                       max_position_embeddings=512), [9, 32, 200]),
+    ("base-3L", dict(num_hidden_layers=3, hidden_size=768, num_attention_heads=12, intermediate_size=3072, vocab_size=1500,
+                     max_position_embeddings=512), [5, 33, 256]),
+    ("large-2L", dict(num_hidden_layers=2, hidden_size=1024, num_attention_heads=16, intermediate_size=4096, vocab_size=1200,
+                      max_position_embeddings=512), [7, 128]),
+])
+def test_bert_forward_matches_transformers(ctx, name, cfg, lens):
+    from kaito_b200 import _native
+    state = _random_state(cfg, seed=len(name))
+    g = np.random.default_rng(3)
+    toks = [g.integers(0, cfg["vocab_size"], n).tolist() for n in lens]
+    emb = _native.Embedder(ctx, cfg["num_hidden_layers"], cfg["hidden_size"], cfg["num_attention_heads"],
+                           cfg["intermediate_size"], cfg["vocab_size"], cfg["max_position_embeddings"])
+    try:
+        emb.load_state_dict(state)
+        got = emb.embed(toks)
+        ref = _torch_reference(cfg, state, toks)
+        assert np.allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-5)
+        cos = (got * ref).sum(1)
+        assert cos.min() > 0.9999, cos
+        assert np.abs(got - ref).max() < 5e-3, np.abs(got - ref).max()
+        # batching must not change a sequence's embedding (packed, no padding): same bits alone and in a batch
+        alone = emb.embed([toks[-1]])
+        assert np.array_equal(alone[0], got[-1])
+    finally:
+        emb.destroy()
