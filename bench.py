@@ -34,6 +34,46 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 VOCAB = 1 << 20
+BGE = {  # BertConfig of BAAI/bge-*-en-v1.5 (random-init weights here: no checkpoints offline)
+    "bge-small": dict(num_hidden_layers=12, hidden_size=384, num_attention_heads=12, intermediate_size=1536, vocab_size=30522),
+    "bge-base": dict(num_hidden_layers=12, hidden_size=768, num_attention_heads=12, intermediate_size=3072, vocab_size=30522),
+    "bge-large": dict(num_hidden_layers=24, hidden_size=1024, num_attention_heads=16, intermediate_size=4096, vocab_size=30522),
+}
+
+
+def pick_embedding(name, dim):
+    if name == "none":
+        return None
+    if name == "auto":
+        name = {384: "bge-small", 768: "bge-base", 1024: "bge-large"}.get(dim)
+    if name is None or BGE[name]["hidden_size"] != dim:
+        return None
+    return name
+
+
+def random_bert_state(cfg, seed=0):
+    """Hugging Face BertModel tensor names with N(0, 0.02) weights (the init of an untrained BERT)."""
+    g = np.random.default_rng(seed)
+    d, i, v = cfg["hidden_size"], cfg["intermediate_size"], cfg["vocab_size"]
+    n = lambda *s: (0.02 * g.standard_normal(s, dtype=np.float32))  # noqa: E731
+    st = {"embeddings.word_embeddings.weight": n(v, d), "embeddings.position_embeddings.weight": n(512, d),
+          "embeddings.token_type_embeddings.weight": n(2, d), "embeddings.LayerNorm.weight": np.ones(d, np.float32),
+          "embeddings.LayerNorm.bias": np.zeros(d, np.float32)}
+    for l in range(cfg["num_hidden_layers"]):
+        p = f"encoder.layer.{l}."
+        for nm in ("attention.self.query", "attention.self.key", "attention.self.value", "attention.output.dense"):
+            st[p + nm + ".weight"] = n(d, d); st[p + nm + ".bias"] = np.zeros(d, np.float32)
+        st[p + "intermediate.dense.weight"] = n(i, d); st[p + "intermediate.dense.bias"] = np.zeros(i, np.float32)
+        st[p + "output.dense.weight"] = n(d, i); st[p + "output.dense.bias"] = np.zeros(d, np.float32)
+        for nm in ("attention.output.LayerNorm", "output.LayerNorm"):
+            st[p + nm + ".weight"] = np.ones(d, np.float32); st[p + nm + ".bias"] = np.zeros(d, np.float32)
+    return st
+
+
+def bert_flops(cfg, seq):
+    """L * (24 S d^2 + 4 S^2 d) per sequence of S tokens"""
+    L, d = cfg["num_hidden_layers"], cfg["hidden_size"]
+    return L * (24 * seq * d * d + 4 * seq * seq * d)
 WORKLOADS = {
     # name: (docs, dim, hybrid)
     "c3": (10_000_000, 768, True),
@@ -53,6 +93,9 @@ def parse():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--dense-mode", type=int, default=0, help="0 auto, 1 scan (K1), 2 tensor-core (K2)")
+    ap.add_argument("--embedding", default="auto", choices=["auto", "none", "bge-small", "bge-base", "bge-large"],
+                    help="query embedding forward (K5) inside the step; auto = the bge model whose width is the corpus dim")
+    ap.add_argument("--query-tokens", type=int, default=32, help="WordPiece tokens per query incl. [CLS]/[SEP]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-rows", type=int, default=400_000)
     return ap.parse_args()
@@ -130,9 +173,25 @@ class CpuReference:
     Postings are prebuilt (the reference rebuilds them on every query, which is slower still and reported
     separately as bm25_rebuild_per_query_s_extrapolated)."""
 
-    def __init__(self, n_docs, dim, hybrid, k, sample_rows, n_queries=8, seed=0):
+    def __init__(self, n_docs, dim, hybrid, k, sample_rows, n_queries=8, seed=0, embedding=None, query_tokens=32):
         from oracle import oracle as o
         o.build()
+        self.embed_s = 0.0
+        self.embedding = embedding
+        if embedding:
+            # the reference embeds every query with torch BertModel on the CPU (huggingface_local_embedding.py:34-53)
+            import torch
+            from transformers import BertConfig, BertModel
+            torch.manual_seed(0)
+            m = BertModel(BertConfig(**BGE[embedding]), add_pooling_layer=False).eval()
+            ids = torch.randint(0, 30522, (n_queries, query_tokens))
+            with torch.no_grad():
+                m(input_ids=ids[:1])
+                t0 = time.perf_counter()
+                for b in range(n_queries):      # one query per request, as the service receives them
+                    torch.nn.functional.normalize(m(input_ids=ids[b:b + 1]).last_hidden_state[:, 0], dim=1)
+                self.embed_s = (time.perf_counter() - t0) / n_queries
+            del m
         self.o, self.n_docs, self.dim, self.hybrid, self.k, self.nq = o, n_docs, dim, hybrid, k, n_queries
         self.n = int(min(sample_rows, n_docs))
         self.x = o.synth_dense(self.n, dim, seed + 1)
@@ -162,7 +221,7 @@ class CpuReference:
                 bs, bo = o.bm25_query(self.post, self.qs[b], self.P)
                 o.fuse(dd[b], do[b], bs, bo, self.k)
             t_sparse = (time.perf_counter() - t0) / self.nq * (self.n_docs / self.ns)
-        return t_dense * (self.n_docs / self.n) + t_sparse
+        return t_dense * (self.n_docs / self.n) + t_sparse + self.embed_s
 
     def describe(self, per_query):
         return {"value": 1.0 / per_query, "unit": "queries/s", "cores": self.o.threads(), "kind": "port",
@@ -170,11 +229,13 @@ class CpuReference:
                           f"{self.n} of {self.n_docs} rows x {self.dim} fp32, {self.nq} queries per step, all host threads, "
                           f"prebuilt postings, extrapolated linearly in N",
                 "per_query_s_extrapolated": per_query,
+                "query_embedding_s": self.embed_s if self.embedding else None,
+                "query_embedding": f"torch CPU BertModel {self.embedding} shapes, measured per query, not extrapolated" if self.embedding else "excluded",
                 "bm25_rebuild_per_query_s_extrapolated": self.rebuild_s}
 
 
-def cpu_reference_qps(n_docs, dim, hybrid, k, sample_rows):
-    ref = CpuReference(n_docs, dim, hybrid, k, sample_rows)
+def cpu_reference_qps(n_docs, dim, hybrid, k, sample_rows, embedding=None, query_tokens=32):
+    ref = CpuReference(n_docs, dim, hybrid, k, sample_rows, embedding=embedding, query_tokens=query_tokens)
     ref.step()
     t = float(np.median([ref.step() for _ in range(3)]))
     return ref.describe(t)
@@ -186,7 +247,8 @@ def run_reference(args):
     if rank != 0:
         return
     docs, dim, hybrid = WORKLOADS[args.workload]
-    ref = CpuReference(docs, dim, hybrid, args.k, args.cpu_sample_rows)
+    ref = CpuReference(docs, dim, hybrid, args.k, args.cpu_sample_rows, embedding=pick_embedding(args.embedding, dim),
+                       query_tokens=args.query_tokens)
     for _ in range(args.warmup):
         ref.step()
     per_query = float(np.mean([ref.step() for _ in range(args.steps)]))
@@ -195,7 +257,8 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * per_query * ref.nq,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {docs} docs x {dim} fp32" + (" + BM25 postings, hybrid weighted fusion" if hybrid else ", dense only"),
-                       "top_k": args.k, "global_batch": ref.nq, "parallelism": "host threads"},
+                       "top_k": args.k, "global_batch": ref.nq, "parallelism": "host threads",
+                       "query_embedding": ref.describe(per_query)["query_embedding"]},
             "cpu_baseline": ref.describe(per_query),
             "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -262,10 +325,31 @@ def run_ours(args):
         d_terms = d_toff = None
         n_terms = 0
 
+    emb_name = pick_embedding(args.embedding, dim)
+    embedder = flat_tok = tok_off = None
+    if emb_name:
+        ecfg = BGE[emb_name]
+        embedder = _native.Embedder(ctx, ecfg["num_hidden_layers"], ecfg["hidden_size"], ecfg["num_attention_heads"],
+                                    ecfg["intermediate_size"], ecfg["vocab_size"])
+        embedder.load_state_dict(random_bert_state(ecfg))
+        tok_lists = [np.random.default_rng(100 + b).integers(1000, 30000, args.query_tokens) for b in range(B)]
+        flat_tok, tok_off = _native.Embedder.pack(tok_lists)
+        flat_tok1, tok_off1 = _native.Embedder.pack(tok_lists[:1])
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def step_dev():   # token ids (host, 32 KB) -> K5 embeddings on the device -> candidates -> merge -> fuse
+        if embedder:
+            embedder.embed_dev(flat_tok, tok_off, qpad.data_ptr(), st.dim_padded, stages.stream())
+        return sr.retrieve_dev(qpad, d_terms, d_toff, k)
+
+    def step_e2e():   # host buffers in (token ids or vectors, term ids), host results out
+        if embedder:
+            return sr.retrieve(None, terms_list, k, embedder=embedder, tokens=(flat_tok, tok_off))
+        return sr.retrieve(qh, terms_list, k)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -286,16 +370,31 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     l0 = ctx.launch_count()
-    ms_dev = timed(lambda: sr.retrieve_dev(qpad, d_terms, d_toff, k), args.steps, args.warmup)
+    ms_dev = timed(step_dev, args.steps, args.warmup)
     launches = (ctx.launch_count() - l0) // (args.steps + args.warmup) * args.steps
-    ms_e2e = timed(lambda: sr.retrieve(qh, terms_list, k), args.steps, args.warmup)
+    ms_e2e = timed(step_e2e, args.steps, args.warmup)
     # batch-1 (latency mode)
     q1, t1 = qpad[:1], None
     if hybrid:
         d_t1 = torch.from_numpy(terms_list[0].view(np.int32)).to(dev)
         d_o1 = torch.tensor([0, len(terms_list[0])], dtype=torch.int32, device=dev)
-    ms_b1 = timed(lambda: sr.retrieve_dev(q1, d_t1 if hybrid else None, d_o1 if hybrid else None, k), args.steps * 4, args.warmup)
-    ms_b1_e2e = timed(lambda: sr.retrieve(qh[:1], terms_list[:1] if hybrid else None, k), args.steps * 4, args.warmup)
+    def step_b1():
+        if embedder:
+            embedder.embed_dev(flat_tok1, tok_off1, q1.data_ptr(), st.dim_padded, stages.stream())
+        return sr.retrieve_dev(q1, d_t1 if hybrid else None, d_o1 if hybrid else None, k)
+
+    def step_b1_e2e():
+        if embedder:
+            return sr.retrieve(None, terms_list[:1] if hybrid else None, k, embedder=embedder, tokens=(flat_tok1, tok_off1))
+        return sr.retrieve(qh[:1], terms_list[:1] if hybrid else None, k)
+
+    ms_b1 = timed(step_b1, args.steps * 4, args.warmup)
+    ms_b1_e2e = timed(step_b1_e2e, args.steps * 4, args.warmup)
+    ms_embed = ms_embed1 = None
+    if embedder:
+        ms_embed = timed(lambda: embedder.embed_dev(flat_tok, tok_off, qpad.data_ptr(), st.dim_padded, stages.stream()), args.steps, args.warmup)
+        ms_embed1 = timed(lambda: embedder.embed_dev(flat_tok1, tok_off1, q1.data_ptr(), st.dim_padded, stages.stream()), args.steps * 4, args.warmup)
+        qpad[:, :dim] = qt      # restore the planted/random query vectors for the stage timings below
     # dominant kernel: the dense candidate stage alone; the library brackets the kernel itself with
     # CUDA events on the launching stream (krag_last_dense_kernel), read after each timed region
     keys = torch.empty((B, P), dtype=torch.int64, device=dev)
@@ -329,6 +428,15 @@ def run_ours(args):
         qps = B * args.steps / (ms_dev * 1e-3)
         qps_e2e = B * args.steps / (ms_e2e * 1e-3)
         h2d, d2h = ShardedRetriever.io_bytes(B, dim, n_terms, k)
+        embed_info = None
+        if embedder:
+            h2d = int(flat_tok.nbytes + tok_off.nbytes + n_terms * 4 + (B + 1) * 4)   # token ids replace the query vectors
+            fl = bert_flops(BGE[emb_name], args.query_tokens) * B
+            etf = fl / (ms_embed / args.steps * 1e-3) / 1e12
+            embed_info = {"model_shape": emb_name, "weights": "random init N(0, 0.02) (no checkpoints offline)", "tokens_per_query": args.query_tokens,
+                          "batch_ms": ms_embed / args.steps, "batch1_ms": ms_embed1 / (args.steps * 4), "flops_per_batch": fl,
+                          "tflops": etf, "tensor_frac_of_tf32_peak": etf / tf32_peak,
+                          "queries_per_s": B / (ms_embed / args.steps * 1e-3)}
         line = {
             "metric": "rag_retrieve_queries_per_sec", "value": qps, "unit": "queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
@@ -337,7 +445,9 @@ def run_ours(args):
                                    (f" + BM25 postings nnz={st.nnz} (local), vocab 2^20, hybrid weighted fusion" if hybrid else ", dense only"),
                        "global_batch": B, "top_k": k, "candidate_pool": P, "parallelism": f"doc-shard x{world}",
                        "rows_per_gpu": n_local, "cache": "inputs larger than L2 (corpus >> 126 MB); no explicit flush",
-                       "query_vectors": "precomputed (embedding forward not in the timed region)",
+                       "query_embedding": (f"K5 BERT forward ({emb_name} shapes, {args.query_tokens} tokens/query, random-init weights) "
+                                           "INSIDE the timed region of value, e2e and batch1") if embedder else
+                                          "precomputed query vectors (embedding forward not in the timed region)",
                        "dense_kernel": kname[kern_id], "dense_kernel_batch1": kname[kern1_id],
                        "tc_certificate_fallback_queries": fallbacks,
                        "index_build_s": t_build},
@@ -352,13 +462,16 @@ def run_ours(args):
                          "tensor_tflops": tflops, "tensor_peak_tf32": tf32_peak, "tensor_frac": tflops / tf32_peak,
                          "tensor_peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (TF32 dense rate)",
                          "dense_stage_ms": ms_dense / args.steps, "bm25_stage_ms": None if ms_bm25 is None else ms_bm25 / args.steps},
+            "embed": embed_info,
             "clocks": clocks, "planted_top1_hit": recall, "recall_at_10": 1.0,
             "recall_note": "dense search is exact (brute force, fp32 re-scored): recall@10 = 1.0 by construction; parity tests check ids bit-exactly",
         }
         if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_reference_qps(docs, dim, hybrid, k, args.cpu_sample_rows)
+            line["cpu_baseline"] = cpu_reference_qps(docs, dim, hybrid, k, args.cpu_sample_rows, emb_name, args.query_tokens)
         print(json.dumps(line), flush=True)
     barrier()
+    if embedder:
+        embedder.destroy()
     ix.drop()
     ctx.close()
     if world > 1:

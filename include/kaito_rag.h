@@ -210,6 +210,10 @@ int32_t krag_embedder_load_tensor(krag_embedder* e, const char* name, const floa
 int32_t krag_embedder_finalize(krag_embedder* e);
 /* tok_ids: packed token ids of all sequences ([CLS] ... [SEP] each); tok_offsets [batch+1]; out [batch, hidden] */
 int32_t krag_embed(krag_embedder* e, int32_t batch, const int32_t* tok_ids, const int32_t* tok_offsets, float* out);
+/* same, result left on the device: rows of d_out with stride ld_out floats (>= hidden; the padded query layout
+ * krag_dev_dense_candidates takes); `stream` (cudaStream_t) is made to wait for the embeddings. tok_* are HOST. */
+int32_t krag_embed_dev(krag_embedder* e, int32_t batch, const int32_t* tok_ids, const int32_t* tok_offsets, float* d_out,
+                       int32_t ld_out, void* stream);
 int32_t krag_embedder_destroy(krag_embedder* e);
 
 /* ------------------------------------------------------------------- diagnostics */

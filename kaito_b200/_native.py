@@ -31,7 +31,7 @@ SYMBOLS = [
     "krag_retrieve", "krag_dev_dense_candidates", "krag_dev_bm25_candidates", "krag_dev_merge", "krag_dev_fuse",
     "krag_synth_fill", "krag_index_read_rows", "krag_index_read_postings", "krag_tc_fallback_queries",
     "krag_debug_tc_dump", "krag_last_dense_kernel", "krag_embedder_create", "krag_embedder_load_tensor",
-    "krag_embedder_finalize", "krag_embed", "krag_embedder_destroy", "krag_debug_gemm_tf32",
+    "krag_embedder_finalize", "krag_embed", "krag_embed_dev", "krag_embedder_destroy", "krag_debug_gemm_tf32",
 ]
 
 
@@ -105,6 +105,7 @@ def load() -> C.CDLL:
     L.krag_embedder_load_tensor.argtypes = [vp, C.c_char_p, vp, i64]
     L.krag_embedder_finalize.argtypes = [vp]
     L.krag_embed.argtypes = [vp, i32, vp, vp, vp]
+    L.krag_embed_dev.argtypes = [vp, i32, vp, vp, vp, i32, vp]
     L.krag_embedder_destroy.argtypes = [vp]
     L.krag_debug_gemm_tf32.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, i32, vp]
     L.krag_tc_fallback_queries.restype = i64
@@ -214,6 +215,17 @@ class Embedder:
         out = np.empty((len(token_lists), self.hidden), np.float32)
         check(self._L.krag_embed(self._h, len(token_lists), ptr(flat), ptr(offs), ptr(out)))
         return out
+
+    @staticmethod
+    def pack(token_lists):
+        offs = np.zeros(len(token_lists) + 1, np.int32)
+        for i, t in enumerate(token_lists):
+            offs[i + 1] = offs[i] + len(t)
+        return np.ascontiguousarray(np.concatenate([np.asarray(t, np.int32) for t in token_lists]), np.int32), offs
+
+    def embed_dev(self, flat_tokens: np.ndarray, offsets: np.ndarray, d_out: int, ld_out: int, stream: int = 0):
+        """embeddings written to device memory (row stride ld_out floats); `stream` waits for them"""
+        check(self._L.krag_embed_dev(self._h, len(offsets) - 1, ptr(flat_tokens), ptr(offsets), ptr(d_out), ld_out, ptr(stream)))
 
     def destroy(self):
         if self._h:

@@ -874,6 +874,16 @@ int32_t krag_embed(krag_embedder* h, int32_t batch, const int32_t* tok_ids, cons
         embedder_forward(h->e, batch, tok_ids, tok_offsets, out);
     });
 }
+int32_t krag_embed_dev(krag_embedder* h, int32_t batch, const int32_t* tok_ids, const int32_t* tok_offsets, float* d_out,
+                       int32_t ld_out, void* stream)
+{
+    return guarded([&] {
+        KRAG_REQUIRE(h && tok_ids && tok_offsets && d_out && batch >= 1 && ld_out >= embedder_hidden(h->e), KRAG_E_INVALID, "bad argument");
+        KRAG_REQUIRE(tok_offsets[0] == 0, KRAG_E_INVALID, "tok_offsets must start at 0");
+        KRAG_CUDA(cudaSetDevice(h->ctx->di.device));
+        embedder_forward(h->e, batch, tok_ids, tok_offsets, nullptr, d_out, ld_out, (cudaStream_t)stream);
+    });
+}
 int32_t krag_embedder_destroy(krag_embedder* h)
 {
     return guarded([&] {

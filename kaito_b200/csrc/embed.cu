@@ -324,7 +324,8 @@ attention_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ seq_
 
 // CLS pooling + L2 normalisation (F.normalize, eps 1e-12): one warp per sequence
 __global__ void __launch_bounds__(256)
-cls_normalize_kernel(const float* __restrict__ x, const int32_t* __restrict__ seq_off, float* __restrict__ out, int batch, int d)
+cls_normalize_kernel(const float* __restrict__ x, const int32_t* __restrict__ seq_off, float* __restrict__ out, int batch, int d,
+                     int ld_out)
 {
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (b >= batch) return;
@@ -332,7 +333,7 @@ cls_normalize_kernel(const float* __restrict__ x, const int32_t* __restrict__ se
     float s = 0.f;
     for (int i = lane; i < d; i += 32) s = fmaf(row[i], row[i], s);
     const float n = fmaxf(sqrtf(warp_sum(s)), 1e-12f);
-    for (int i = lane; i < d; i += 32) out[(size_t)b * d + i] = row[i] / n;
+    for (int i = lane; i < d; i += 32) out[(size_t)b * ld_out + i] = row[i] / n;
 }
 
 // ------------------------------------------------------------------------------------ host
@@ -389,6 +390,7 @@ struct Embedder {
     std::vector<float*> wqkv, bqkv;       // fused per layer at finalize
     bool finalized = false;
     cudaStream_t st = nullptr;
+    cudaEvent_t done = nullptr;
     // workspaces, grown on demand
     int cap_tok = 0, cap_batch = 0;
     int32_t *d_tok = nullptr, *d_pos = nullptr, *d_off = nullptr;
@@ -466,7 +468,11 @@ void embedder_destroy(Embedder* e)
 int embedder_hidden(const Embedder* e) { return e->cfg.hidden; }
 
 // tok_ids: packed tokens of all sequences; tok_offsets [batch+1]; out_host [batch, hidden]
-void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int32_t* tok_offsets, float* out_host)
+// out_host != nullptr: embeddings are copied to the host and the call returns synchronised.
+// out_dev  != nullptr: embeddings are written to device rows of stride ld_out floats and `consumer` (a stream of
+//                      the caller) is made to wait for them -- no host round trip.
+void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int32_t* tok_offsets, float* out_host,
+                      float* out_dev, int ld_out, cudaStream_t consumer)
 {
     if (!e->finalized) throw std::runtime_error("embedder: call finalize after loading the weights");
     const BertConfig& c = e->cfg;
@@ -523,11 +529,21 @@ void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int3
                                                   e->t[lname(l, "output.LayerNorm.bias")], n_tok, d, c.eps);
         count_launch();
     }
-    cls_normalize_kernel<<<(batch * 32 + 255) / 256, 256, 0, st>>>(e->x, e->d_off, e->out, batch, d);
-    KRAG_CUDA(cudaGetLastError());
-    count_launch();
-    KRAG_CUDA(cudaMemcpyAsync(out_host, e->out, 4 * (size_t)batch * d, cudaMemcpyDeviceToHost, st));
-    KRAG_CUDA(cudaStreamSynchronize(st));
+    if (out_dev) {
+        cls_normalize_kernel<<<(batch * 32 + 255) / 256, 256, 0, st>>>(e->x, e->d_off, out_dev, batch, d, ld_out);
+        KRAG_CUDA(cudaGetLastError());
+        count_launch();
+        if (!e->done) KRAG_CUDA(cudaEventCreateWithFlags(&e->done, cudaEventDisableTiming));
+        KRAG_CUDA(cudaEventRecord(e->done, st));
+        KRAG_CUDA(cudaStreamWaitEvent(consumer, e->done, 0));
+    }
+    if (out_host) {
+        cls_normalize_kernel<<<(batch * 32 + 255) / 256, 256, 0, st>>>(e->x, e->d_off, e->out, batch, d, d);
+        KRAG_CUDA(cudaGetLastError());
+        count_launch();
+        KRAG_CUDA(cudaMemcpyAsync(out_host, e->out, 4 * (size_t)batch * d, cudaMemcpyDeviceToHost, st));
+        KRAG_CUDA(cudaStreamSynchronize(st));
+    }
 }
 
 }  // namespace krag

@@ -93,7 +93,8 @@ void embedder_load(Embedder* e, const char* name, const float* data, int64_t n);
 void embedder_finalize(Embedder* e);
 void embedder_destroy(Embedder* e);
 int embedder_hidden(const Embedder* e);
-void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int32_t* tok_offsets, float* out_host);
+void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int32_t* tok_offsets, float* out_host,
+                      float* out_dev = nullptr, int ld_out = 0, cudaStream_t consumer = nullptr);
 // C[M,N] = A[M,K] . B[N,K]^T + bias (+gelu) (+residual), fp32 in/out, TF32 tensor cores; device pointers
 void launch_gemm_tf32(const DeviceInfo& di, const float* A, const float* B, int M, int N, int K, const float* bias,
                       const float* residual, bool gelu, float* C, cudaStream_t st);

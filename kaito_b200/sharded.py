@@ -130,14 +130,24 @@ class ShardedRetriever:
         self.stages.fuse(B, P, k, merged[0], merged[1] if hybrid else None, vector_weight, text_weight, mode, out)
         return out
 
-    def retrieve(self, q_host: np.ndarray, q_terms_list, k: int, **kw):
-        """End to end with HOST buffers: pinned H2D of the queries, the pipeline, D2H of the result."""
-        B, d = q_host.shape
-        pin_q = self._pinned("pin_q", (B, self.dpad), torch.float32)
-        pin_q.zero_()
-        pin_q[:, :d] = torch.from_numpy(q_host)
-        q = self._tensor("q", (B, self.dpad), torch.float32)
-        q.copy_(pin_q, non_blocking=True)
+    def retrieve(self, q_host: np.ndarray | None, q_terms_list, k: int, embedder=None, tokens=None, **kw):
+        """End to end with HOST buffers: pinned H2D of the queries, the pipeline, D2H of the result.
+        With `embedder` (kaito_b200._native.Embedder) and `tokens` = (flat int32 token ids, int32 offsets [B+1])
+        the query vectors are produced on the GPU by the BERT forward (K5) instead of being uploaded."""
+        if embedder is not None:
+            flat_tok, tok_off = tokens
+            B = len(tok_off) - 1
+            q = self._tensor("q", (B, self.dpad), torch.float32)
+            if self.dpad != embedder.hidden:
+                q.zero_()                        # padding columns of the row layout must be zero
+            embedder.embed_dev(flat_tok, tok_off, q.data_ptr(), self.dpad, self.stages.stream())
+        else:
+            B, d = q_host.shape
+            pin_q = self._pinned("pin_q", (B, self.dpad), torch.float32)
+            pin_q.zero_()
+            pin_q[:, :d] = torch.from_numpy(q_host)
+            q = self._tensor("q", (B, self.dpad), torch.float32)
+            q.copy_(pin_q, non_blocking=True)
         terms = toff = None
         if q_terms_list is not None:
             offs = np.zeros(B + 1, np.int32)
