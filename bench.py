@@ -343,8 +343,8 @@ def run_ours(args):
 
     def step_dev():   # token ids (host, 32 KB) -> K5 embeddings on the device -> candidates -> merge -> fuse
         if embedder:
-            embedder.embed_dev(flat_tok, tok_off, qpad.data_ptr(), st.dim_padded, stages.stream())
-        return sr.retrieve_dev(qpad, d_terms, d_toff, k)
+            sr.embed_into(embedder, flat_tok, tok_off, qpad)      # queries split across ranks + one all-gather
+        return sr.retrieve_dev(qpad, d_terms, d_toff, k, toff_host=offs if hybrid else None)
 
     def step_e2e():   # host buffers in (token ids or vectors, term ids), host results out
         if embedder:
@@ -377,11 +377,12 @@ def run_ours(args):
     q1, t1 = qpad[:1], None
     if hybrid:
         d_t1 = torch.from_numpy(terms_list[0].view(np.int32)).to(dev)
-        d_o1 = torch.tensor([0, len(terms_list[0])], dtype=torch.int32, device=dev)
+        offs1 = np.array([0, len(terms_list[0])], np.int32)
+        d_o1 = torch.from_numpy(offs1).to(dev)
     def step_b1():
         if embedder:
             embedder.embed_dev(flat_tok1, tok_off1, q1.data_ptr(), st.dim_padded, stages.stream())
-        return sr.retrieve_dev(q1, d_t1 if hybrid else None, d_o1 if hybrid else None, k)
+        return sr.retrieve_dev(q1, d_t1 if hybrid else None, d_o1 if hybrid else None, k, toff_host=offs1 if hybrid else None)
 
     def step_b1_e2e():
         if embedder:
@@ -392,7 +393,7 @@ def run_ours(args):
     ms_b1_e2e = timed(step_b1_e2e, args.steps * 4, args.warmup)
     ms_embed = ms_embed1 = None
     if embedder:
-        ms_embed = timed(lambda: embedder.embed_dev(flat_tok, tok_off, qpad.data_ptr(), st.dim_padded, stages.stream()), args.steps, args.warmup)
+        ms_embed = timed(lambda: sr.embed_into(embedder, flat_tok, tok_off, qpad), args.steps, args.warmup)
         ms_embed1 = timed(lambda: embedder.embed_dev(flat_tok1, tok_off1, q1.data_ptr(), st.dim_padded, stages.stream()), args.steps * 4, args.warmup)
         qpad[:, :dim] = qt      # restore the planted/random query vectors for the stage timings below
     # dominant kernel: the dense candidate stage alone; the library brackets the kernel itself with
@@ -404,7 +405,7 @@ def run_ours(args):
     kern1_ms, kern1_id, kern1_bytes, _ = _native.last_dense_kernel()
     ms_bm25 = None
     if hybrid:
-        ms_bm25 = timed(lambda: stages.bm25_candidates(d_terms, d_toff, B, P, keys), args.steps, args.warmup)
+        ms_bm25 = timed(lambda: stages.bm25_candidates(d_terms, d_toff, B, P, keys, offs), args.steps, args.warmup)
     fallbacks = int(_native.load().krag_tc_fallback_queries())
     clocks = sampler.stop() if rank == 0 else None
 

@@ -353,8 +353,9 @@ class Index:
     def dev_dense_candidates(self, batch, d_q, P, d_keys, stream=0):
         check(self._L.krag_dev_dense_candidates(self._h, batch, ptr(d_q), P, ptr(d_keys), ptr(stream)))
 
-    def dev_bm25_candidates(self, batch, d_terms, d_toff, P, d_keys, stream=0):
-        check(self._L.krag_dev_bm25_candidates(self._h, batch, ptr(d_terms), ptr(d_toff), None, P, ptr(d_keys),
+    def dev_bm25_candidates(self, batch, d_terms, d_toff, P, d_keys, stream=0, h_toff=None):
+        """h_toff: optional host copy (int32 [batch+1]) of the offsets; saves a 4-byte device read-back"""
+        check(self._L.krag_dev_bm25_candidates(self._h, batch, ptr(d_terms), ptr(d_toff), ptr(h_toff), P, ptr(d_keys),
                                                ptr(stream)))
 
     # ---- synthetic / inspection ----

@@ -108,7 +108,7 @@ struct Slot {
     DevArray<uint32_t> terms;
     DevArray<int32_t> toff;
     DevArray<uint64_t> dense_keys, bm25_keys, part;
-    DevArray<unsigned char> tc_ws;
+    DevArray<unsigned char> tc_ws, bm25_res;
     DevArray<uint32_t> allow;
     DevArray<double> out_final;
     DevArray<float> out_dense, out_sparse;
@@ -211,12 +211,19 @@ void dense_candidates_dev(krag_index* ix, Slot* s, const float* d_q, int batch, 
                       s->part.p, d_keys, st);
 }
 
-void bm25_candidates_dev(krag_index* ix, Slot* s, const uint32_t* d_terms, const int32_t* d_toff, int batch, int P,
-                         uint64_t* d_keys, cudaStream_t st)
+void bm25_candidates_dev(krag_index* ix, Slot* s, const uint32_t* d_terms, const int32_t* d_toff, int n_terms_total, int batch,
+                         int P, uint64_t* d_keys, cudaStream_t st)
 {
     KRAG_REQUIRE(ix->committed, KRAG_E_STATE, "index has no committed postings (call krag_index_commit)");
+    if (n_terms_total < 0) {   // caller did not provide the host copy of the offsets: read the total back (4 bytes)
+        int32_t tot = 0;
+        KRAG_CUDA(cudaMemcpyAsync(&tot, d_toff + batch, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        KRAG_CUDA(cudaStreamSynchronize(st));
+        n_terms_total = tot;
+    }
     s->part.reserve((int64_t)bm25_part_elems(ix->committed_rows, batch, P), 0, st);
-    launch_bm25(ix->ctx->di, ix->post, ix->committed_rows, alive_ptr(ix), d_terms, d_toff, 0, batch, P,
+    s->bm25_res.reserve((int64_t)(n_terms_total > 0 ? n_terms_total : 1) * 16, 0, st);
+    launch_bm25(ix->ctx->di, ix->post, ix->committed_rows, alive_ptr(ix), d_terms, d_toff, n_terms_total, s->bm25_res.p, batch, P,
                 (uint32_t)ix->ord_base, s->part.p, d_keys, st);
 }
 
@@ -383,7 +390,7 @@ int32_t krag_shutdown(krag_ctx* c)
         cudaDeviceSynchronize();
         for (Slot* s : c->all_slots) {
             s->q.release(); s->terms.release(); s->toff.release(); s->dense_keys.release(); s->bm25_keys.release();
-            s->part.release(); s->tc_ws.release(); s->allow.release(); s->out_final.release(); s->out_dense.release();
+            s->part.release(); s->tc_ws.release(); s->bm25_res.release(); s->allow.release(); s->out_final.release(); s->out_dense.release();
             s->out_sparse.release(); s->out_rank.release(); s->out_count.release(); s->out_ord.release();
             cudaStreamDestroy(s->st);
             delete s;
@@ -619,7 +626,7 @@ int32_t krag_search_bm25(krag_index* ix, int32_t batch, const uint32_t* q_terms,
         Slot* s = lease.s;
         upload_terms(s, q_terms, q_toff, batch);
         s->bm25_keys.reserve((int64_t)batch * k, 0, s->st);
-        bm25_candidates_dev(ix, s, s->terms.p, s->toff.p, batch, k, s->bm25_keys.p, s->st);
+        bm25_candidates_dev(ix, s, s->terms.p, s->toff.p, q_toff[batch], batch, k, s->bm25_keys.p, s->st);
         std::vector<uint64_t> keys((size_t)batch * k);
         KRAG_CUDA(cudaMemcpyAsync(keys.data(), s->bm25_keys.p, sizeof(uint64_t) * keys.size(), cudaMemcpyDeviceToHost, s->st));
         KRAG_CUDA(cudaStreamSynchronize(s->st));
@@ -659,7 +666,7 @@ int32_t krag_retrieve(krag_index* ix, int32_t batch, const float* q, const uint3
         if (hybrid) {
             upload_terms(s, q_terms, q_toff, batch);
             s->bm25_keys.reserve((int64_t)batch * P, 0, st);
-            bm25_candidates_dev(ix, s, s->terms.p, s->toff.p, batch, P, s->bm25_keys.p, st);
+            bm25_candidates_dev(ix, s, s->terms.p, s->toff.p, q_toff[batch], batch, P, s->bm25_keys.p, st);
             if (keyword_allow_bitmap) {
                 // bitmap is over local rows; fuse tests global ordinals -> shift by ord_base words is only
                 // valid when ord_base % 32 == 0; the host path is single-shard (ord_base == 0)
@@ -701,14 +708,13 @@ int32_t krag_dev_dense_candidates(krag_index* ix, int32_t batch, const float* d_
 int32_t krag_dev_bm25_candidates(krag_index* ix, int32_t batch, const uint32_t* d_terms, const int32_t* d_toff,
                                  const int32_t* h_toff, int32_t P, uint64_t* d_keys, void* stream)
 {
-    (void)h_toff;
     return guarded([&] {
         KRAG_REQUIRE(ix && d_toff && d_keys && batch >= 1, KRAG_E_INVALID, "bad argument");
         check_P(P);
         std::shared_lock<std::shared_mutex> lk(ix->mu);
         KRAG_CUDA(cudaSetDevice(ix->ctx->di.device));
         SlotLease lease(ix->ctx);
-        bm25_candidates_dev(ix, lease.s, d_terms, d_toff, batch, P, d_keys, (cudaStream_t)stream);
+        bm25_candidates_dev(ix, lease.s, d_terms, d_toff, h_toff ? h_toff[batch] : -1, batch, P, d_keys, (cudaStream_t)stream);
     });
 }
 

@@ -253,8 +253,9 @@ __global__ void __launch_bounds__(BQ_THREADS)
 bm25_tile_kernel(const int64_t* __restrict__ post_off, const uint32_t* __restrict__ post_doc,
                  const float* __restrict__ post_score, const int32_t* __restrict__ tile_slot,
                  const uint32_t* __restrict__ tile_off, int64_t n_tiles_idx, int64_t vocab,
-                 const uint32_t* __restrict__ q_terms, const int32_t* __restrict__ q_term_offsets, int64_t n_rows,
-                 const uint32_t* __restrict__ alive, int P, int cap, uint32_t ord_base, int batch, int n_tiles,
+                 const uint32_t* __restrict__ q_terms, const int32_t* __restrict__ q_term_offsets,
+                 const int32_t* __restrict__ q_slot, const int64_t* __restrict__ q_base, const int32_t* __restrict__ q_rare_len,
+                 int64_t n_rows, const uint32_t* __restrict__ alive, int P, int cap, uint32_t ord_base, int batch, int n_tiles,
                  uint64_t* __restrict__ part /*[batch][n_tiles][P]*/, unsigned long long* __restrict__ g_thr /*[batch]*/)
 {
     extern __shared__ __align__(16) unsigned char bsm[];
@@ -295,18 +296,15 @@ bm25_tile_kernel(const int64_t* __restrict__ post_off, const uint32_t* __restric
     auto resolve = [&](int c0, int nt) {
         __syncthreads();
         if (tid < nt) {
-            const uint32_t t = q_terms[c0 + tid];
+            // (slot, base, rare length) of every query term were resolved once per batch by bm25_resolve_kernel
+            const int32_t sl = q_slot[c0 + tid];
             int64_t lo = 0; int len = 0;
-            if ((int64_t)t < vocab) {
-                const int64_t b = post_off[t];
-                const int32_t sl = tile_slot[t];
-                if (sl >= 0) {
-                    const uint32_t* row = tile_off + (int64_t)sl * (n_tiles_idx + 1);
-                    const uint32_t o0 = row[tile], o1 = row[tile + 1];
-                    lo = b + o0; len = (int)(o1 - o0);
-                } else {
-                    lo = b; len = (int)(post_off[t + 1] - b);   // rare: whole list, filtered by doc range below
-                }
+            if (sl >= 0) {
+                const uint32_t* row = tile_off + (int64_t)sl * (n_tiles_idx + 1);
+                const uint32_t o0 = row[tile], o1 = row[tile + 1];
+                lo = q_base[c0 + tid] + o0; len = (int)(o1 - o0);
+            } else if (sl == -1) {
+                lo = q_base[c0 + tid]; len = q_rare_len[c0 + tid];   // rare: whole list, filtered by doc range below
             }
             s_lo[tid] = lo; s_len[tid] = len;
         }
@@ -383,7 +381,41 @@ bm25_tile_kernel(const int64_t* __restrict__ post_off, const uint32_t* __restric
         resolve(tb, te - tb);
         const int ns = next_pass(te - tb);
         const bool more = (s_next_term < te - tb);   // uniform: written before the barrier inside next_pass
-        if (!more) {
+        if (!more && ns <= BQ_PREFETCH) {
+            // all slabs of the item fit the register window: accumulate and claim from the same registers
+            uint32_t d[BQ_PREFETCH]; float sc[BQ_PREFETCH];
+#pragma unroll
+            for (int u = 0; u < BQ_PREFETCH; ++u) {
+                d[u] = 0xFFFFFFFFu; sc[u] = 0.f;
+                if (u < ns && tid < s_slab_n[u]) {
+                    const int64_t p = s_slab_lo[u] + tid;
+                    d[u] = post_doc[p]; sc[u] = post_score[p];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < BQ_PREFETCH; ++u) {
+                if (u < ns) {
+                    const uint32_t rel = d[u] - (uint32_t)t0;
+                    if (d[u] != 0xFFFFFFFFu && rel < (uint32_t)tile_n) acc[rel] += sc[u];
+                    __syncthreads();
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < BQ_PREFETCH; ++u) {
+                if (u < ns) {
+                    const uint32_t rel = d[u] - (uint32_t)t0;
+                    if (d[u] != 0xFFFFFFFFu && rel < (uint32_t)tile_n) {
+                        const float sum = atomicExch(&acc[rel], 0.f);
+                        if (sum > 0.f && (alive == nullptr || bit_test(alive, d[u])))
+                            select_push(sel, make_key_desc(sum, ord_base + d[u]), thr);
+                    }
+                    __syncthreads();
+                    if (s_count + BQ_THREADS > cap) select_prune<BQ_THREADS>(sel, P, tid, 0);
+                    thr = s_thr;
+                }
+            }
+            done = true;
+        } else if (!more) {
             accumulate(ns);
             claim(ns);
             done = true;
@@ -408,6 +440,23 @@ bm25_tile_kernel(const int64_t* __restrict__ post_off, const uint32_t* __restric
     }   // work items
 }
 
+// once per batch: (tile-index slot, posting base, rare length) of every query term position
+__global__ void bm25_resolve_kernel(const uint32_t* __restrict__ q_terms, int n_terms, const int64_t* __restrict__ post_off,
+                                    const int32_t* __restrict__ tile_slot, int64_t vocab, int32_t* __restrict__ q_slot,
+                                    int64_t* __restrict__ q_base, int32_t* __restrict__ q_rare_len)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_terms) return;
+    const uint32_t t = q_terms[i];
+    int32_t sl = -2; int64_t b = 0; int32_t rl = 0;
+    if ((int64_t)t < vocab) {
+        b = post_off[t];
+        sl = tile_slot[t];
+        if (sl < 0) { sl = -1; rl = (int32_t)(post_off[t + 1] - b); }
+    }
+    q_slot[i] = sl; q_base[i] = b; q_rare_len[i] = rl;
+}
+
 static int bq_cap(int P) { return P <= 512 ? 1024 : 2048; }
 
 size_t bm25_part_elems(int64_t n_rows, int batch, int P)
@@ -418,10 +467,19 @@ size_t bm25_part_elems(int64_t n_rows, int batch, int P)
 }
 
 void launch_bm25(const DeviceInfo& di, const Postings& post, int64_t n_rows, const uint32_t* alive,
-                 const uint32_t* q_terms, const int32_t* q_term_offsets, int max_terms, int batch, int P,
+                 const uint32_t* q_terms, const int32_t* q_term_offsets, int n_terms_total, void* resolve_ws, int batch, int P,
                  uint32_t ord_base, uint64_t* part, uint64_t* keys_out, cudaStream_t st)
 {
-    (void)max_terms;
+    // resolve_ws: >= n_terms_total * 16 bytes
+    int64_t* q_base = reinterpret_cast<int64_t*>(resolve_ws);
+    int32_t* q_slot = reinterpret_cast<int32_t*>(q_base + (n_terms_total > 0 ? n_terms_total : 1));
+    int32_t* q_rare = q_slot + (n_terms_total > 0 ? n_terms_total : 1);
+    if (n_terms_total > 0) {
+        bm25_resolve_kernel<<<(n_terms_total + 255) / 256, 256, 0, st>>>(q_terms, n_terms_total, post.off, post.tile_slot, post.vocab,
+                                                                         q_slot, q_base, q_rare);
+        KRAG_CUDA(cudaGetLastError());
+        count_launch();
+    }
     int64_t n_tiles = (n_rows + BM25_TILE_DOCS - 1) / BM25_TILE_DOCS;
     if (n_tiles < 1) n_tiles = 1;
     const int cap = bq_cap(P);
@@ -438,8 +496,8 @@ void launch_bm25(const DeviceInfo& di, const Postings& post, int64_t n_rows, con
     const int64_t max_grid = (int64_t)per_sm * di.sm_count;
     const int grid = (int)(n_items < max_grid ? n_items : max_grid);
     bm25_tile_kernel<<<grid, BQ_THREADS, smem, st>>>(post.off, post.doc, post.score, post.tile_slot, post.tile_off,
-                                                     post.n_tiles, post.vocab, q_terms, q_term_offsets, n_rows, alive, P,
-                                                     cap, ord_base, batch, (int)n_tiles, part, g_thr);
+                                                     post.n_tiles, post.vocab, q_terms, q_term_offsets, q_slot, q_base, q_rare, n_rows,
+                                                     alive, P, cap, ord_base, batch, (int)n_tiles, part, g_thr);
     KRAG_CUDA(cudaGetLastError());
     count_launch();
     launch_merge(part, (int)n_tiles, P, batch, P, /*list_stride=*/P, /*batch_stride=*/n_tiles * P, keys_out, st,

@@ -228,50 +228,6 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 // (A 4 KB + B half 4 KB) and TMA writes 32 KB per 512 cycles: 64 + 64 B/clk against the 128 B/clk
 // shared-memory port, versus 96 + 96 for the 1-CTA kernel (which caps its tensor pipe at 67%).
 // The halved query slab also doubles the query ring depth (6 stages) and halves L2->SM traffic.
-__device__ __forceinline__ uint32_t cluster_ctarank()
-{
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta)
-{
-    asm volatile(
-        "{\n\t.reg .b32 ra;\n\t"
-        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
-        ::"r"(smem_u32(bar)), "r"(cta) : "memory");
-}
-constexpr uint32_t TC_PEER_MASK = 0xFEFFFFFFu;   // clears the CTA-rank bit: the pair leader's copy of a barrier
-__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* tm, uint64_t* leader_bar, int c0, int c1,
-                                                uint64_t policy)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-        " [%0], [%1, {%3, %4}], [%2], %5;"
-        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(leader_bar) & TC_PEER_MASK), "r"(c0),
-          "r"(c1), "l"(policy)
-        : "memory");
-}
-__device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar)   // arrives on `bar` in BOTH CTAs of the pair
-{
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
-}
-
 // One ring; a stage holds TC2_KB_PER_STAGE k-blocks of this CTA's corpus rows and of its half of the
 // query rows, so the single MMA-issuing thread pays one barrier wait and one commit per 8 MMAs (it was
 // the bottleneck at 2 waits + 2 commits per 4 MMAs: ~770 cycles per k-block against 512 cycles of MMA work).

@@ -14,6 +14,7 @@
 // conversion pass); bias / GELU / residual are fused into the TMEM epilogue.  LayerNorm, softmax and the
 // attention products are fp32 CUDA-core code (attention is 4 S^2 d: 2% of the flops at S = 32 queries).
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include <map>
 #include <stdexcept>
@@ -182,6 +183,174 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
 }
 
+// ---------------------------------------------------------------- 2-CTA GEMM (cta_group::2, M = 256 per pair)
+// Same structure as dense_tc2_kernel (dense_tc.cu): a CTA pair owns a 256 x BN output tile; each CTA stages its
+// 128 activation rows and HALF of the BN weight rows, the pair's tensor cores share the operands
+// (per SM and 128-cycle MMA: 8 KB operand reads + 64 B/clk of TMA writes instead of 12 KB + 96 B/clk, which capped
+// the 1-CTA kernel at ~40% tensor-pipe activity on these shapes); one ring, 2 k-blocks per stage, one issuer thread.
+template <int BN> struct Gm2Cfg {
+    static constexpr int BH_BYTES = (BN / 2) * GM_KB * 4;              // this CTA's half of one weight k-block
+    static constexpr int STAGE_BYTES = GM_KB_PER_STAGE * (GM_SLAB + BH_BYTES);
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;          // 3 at BN = 256, 4 at BN = 128
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+};
+constexpr int GM2_THREADS = 320;   // warp 0: TMA, warp 1: MMA issuer (leader), warps 2-9: epilogue (2 per TMEM lane group)
+
+template <int BN>
+__global__ void __launch_bounds__(GM2_THREADS, 1)
+gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh, int M, int N, int K,
+                  const float* __restrict__ bias, const float* __restrict__ residual, int act_gelu, float* __restrict__ C)
+{
+    using Cfg = Gm2Cfg<BN>;
+    extern __shared__ unsigned char gm_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gm_smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* tail = smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);             // leader only: 2 arrivals + tx bytes of both CTAs
+    uint64_t* empty_bar = full_bar + Cfg::STAGES;                        // per CTA
+    uint64_t* tfull_bar = empty_bar + Cfg::STAGES;                       // per CTA [2]
+    uint64_t* tempty_bar = tfull_bar + 2;                                // leader only [2]: 16 arrivals
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int m_ptiles = (M + 2 * GM_TILE - 1) / (2 * GM_TILE), n_tiles = N / BN;
+    const int total = m_ptiles * n_tiles;
+    const int kblocks = K / GM_KB;
+    const int stages_per_tile = (kblocks + GM_KB_PER_STAGE - 1) / GM_KB_PER_STAGE;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmBh);
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 16); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        int stage = 0; uint32_t phase = 0;
+        for (int t = pair; t < total; t += n_pairs) {
+            const int m0 = (t / n_tiles) * (2 * GM_TILE) + (int)rank * GM_TILE, n0 = (t % n_tiles) * BN + (int)rank * (BN / 2);
+            for (int sk = 0; sk < stages_per_tile; ++sk) {
+                const int nkb = min(GM_KB_PER_STAGE, kblocks - sk * GM_KB_PER_STAGE);
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (lane == 0) {
+                    unsigned char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
+                    unsigned char* sb = sa + GM_KB_PER_STAGE * GM_SLAB;
+                    if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * nkb * (GM_SLAB + Cfg::BH_BYTES));
+                    else mbar_arrive_remote(&full_bar[stage], 0);
+                    for (int u = 0; u < nkb; ++u) {
+                        const int k0 = (sk * GM_KB_PER_STAGE + u) * GM_KB;
+                        tma_load_2d_2sm(sa + (size_t)u * GM_SLAB, &tmA, &full_bar[stage], k0, m0, TMA_EVICT_FIRST);
+                        tma_load_2d_2sm(sb + (size_t)u * Cfg::BH_BYTES, &tmBh, &full_bar[stage], k0, n0, TMA_EVICT_LAST);
+                    }
+                }
+                __syncwarp();
+                if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32(2 * GM_TILE, BN);
+            const uint64_t desc0 = umma_desc_sw128(smem_u32(smem));
+            const uint32_t lo0 = (uint32_t)desc0;
+            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            for (int t = pair; t < total; t += n_pairs) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int sk = 0; sk < stages_per_tile; ++sk) {
+                    const int nkb = min(GM_KB_PER_STAGE, kblocks - sk * GM_KB_PER_STAGE);
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t a_lo = lo0 + (uint32_t)((stage * Cfg::STAGE_BYTES) >> 4);
+                        const uint32_t b_lo = a_lo + (uint32_t)((GM_KB_PER_STAGE * GM_SLAB) >> 4);
+#pragma unroll
+                        for (int u = 0; u < GM_KB_PER_STAGE; ++u) {
+                            if (u < nkb) {
+#pragma unroll
+                                for (int k = 0; k < GM_KB / 8; ++k) {
+                                    const uint64_t ad = (desc0 & 0xFFFFFFFF00000000ull) | (uint64_t)(a_lo + (uint32_t)((u * GM_SLAB) >> 4) + 2 * k);
+                                    const uint64_t bd = (desc0 & 0xFFFFFFFF00000000ull) | (uint64_t)(b_lo + (uint32_t)((u * Cfg::BH_BYTES) >> 4) + 2 * k);
+                                    umma_tf32_2sm(d_tmem, ad, bd, idesc, (uint32_t)((sk | u | k) != 0));
+                                }
+                            }
+                        }
+                        umma_commit_2sm(&empty_bar[stage]);
+                        if (sk == stages_per_tile - 1) umma_commit_2sm(&tfull_bar[acc]);
+                    }
+                    __syncwarp();
+                    if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else {
+        // 8 epilogue warps: lane group = warp & 3, column half = (warp - 2) >> 2
+        const int lg = warp & 3;
+        const int col_half = (warp - 2) >> 2;
+        const int r_in = lg * 32 + lane;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int t = pair; t < total; t += n_pairs) {
+            const int m0 = (t / n_tiles) * (2 * GM_TILE) + (int)rank * GM_TILE, n0 = (t % n_tiles) * BN;
+            const int row = m0 + r_in;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+            for (int c0 = col_half * (BN / 2); c0 < (col_half + 1) * (BN / 2); c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_x32(taddr + c0, v);
+                tmem_wait_ld();
+                if (row < M) {
+                    float* crow = C + (size_t)row * N + n0 + c0;
+                    const float* rrow = residual ? residual + (size_t)row * N + n0 + c0 : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
+                        float4 o;
+                        o.x = __uint_as_float(v[j + 0]) + b4.x; o.y = __uint_as_float(v[j + 1]) + b4.y;
+                        o.z = __uint_as_float(v[j + 2]) + b4.z; o.w = __uint_as_float(v[j + 3]) + b4.w;
+                        if (act_gelu) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
+                        if (rrow) {
+                            const float4 r4 = *reinterpret_cast<const float4*>(rrow + j);
+                            o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+                        }
+                        *reinterpret_cast<float4*>(crow + j) = o;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (rank == 0) mbar_arrive(&tempty_bar[acc]);
+                else mbar_arrive_remote(&tempty_bar[acc], 0);
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    }
+}
+
 // --------------------------------------------------------------------------- fp32 row kernels
 __device__ __forceinline__ float warp_sum(float v)
 {
@@ -322,6 +491,110 @@ attention_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ seq_
     }
 }
 
+// short sequences (queries; len <= S2 in {32, 64}): one CTA of 128 threads per (sequence, head).  Both products
+// are register-tiled out of shared memory: thread (ty, tx) owns S2/8 rows x S2/16 score columns, then S2/8 rows x 4
+// output columns; operands are stored transposed where needed so every shared-memory read is a conflict-free
+// vector load.  fp32 throughout (scores, max-subtracted softmax, P.V) like torch's math path.
+constexpr int ATS_MAX = 64;
+template <int S2>
+__global__ void __launch_bounds__(128)
+attention_tiled_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ seq_off, float* __restrict__ out, int d, int heads)
+{
+    constexpr int RPT = S2 / 8;        // rows per thread
+    constexpr int CPT = S2 / 16;       // score columns per thread
+    constexpr int LD = S2 + 4;         // padded leading dimension (keeps 16-byte alignment, staggers banks)
+    extern __shared__ __align__(16) float as_sm[];
+    const int dh = d / heads;          // 32 or 64
+    float* s_qT = as_sm;               // [dh][LD]   q transposed: s_qT[c][r]
+    float* s_kT = s_qT + 64 * LD;      // [dh][LD]   k transposed: s_kT[c][key]
+    float* s_v = s_kT + 64 * LD;       // [S2][64]   v: s_v[key][c]
+    float* s_pT = s_v + S2 * 64;       // [S2][LD]   probabilities transposed: s_pT[key][r]
+    const int b = blockIdx.x, h = blockIdx.y;
+    const int t0 = seq_off[b], len = seq_off[b + 1] - t0;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    {   // a warp moves 4 rows x 8 columns per step: 32-byte global segments, and with LD = S2 + 4 the
+        // transposed stores (bank = 4 c + r) touch 32 distinct banks
+        const int warp = tid >> 5, lane = tid & 31, cl = lane & 7, rl = lane >> 3;
+        const int cblocks = dh / 8;
+        for (int blk = warp; blk < cblocks * (S2 / 4); blk += 4) {
+            const int c = (blk % cblocks) * 8 + cl, r = (blk / cblocks) * 4 + rl;
+            float q = 0.f, k = 0.f, v = 0.f;
+            if (r < len) {
+                const float* base = qkv + (size_t)(t0 + r) * 3 * d + h * dh + c;
+                q = base[0]; k = base[d]; v = base[2 * d];
+            }
+            s_qT[c * LD + r] = q; s_kT[c * LD + r] = k; s_v[r * 64 + c] = v;
+        }
+    }
+    __syncthreads();
+    // ---- scores
+    float acc[RPT][CPT];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i)
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) acc[i][j] = 0.f;
+    for (int c = 0; c < dh; ++c) {
+        float qv[RPT], kv[CPT];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) qv[i] = s_qT[c * LD + ty * RPT + i];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) kv[j] = s_kT[c * LD + tx * CPT + j];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i)
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) acc[i][j] = fmaf(qv[i], kv[j], acc[i][j]);
+    }
+    const float scale = rsqrtf((float)dh);
+    // ---- softmax over each row: its S2 columns live in the 16 threads tx = 0..15 of one half-warp
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        float m = -CUDART_INF_F;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            acc[i][j] = (tx * CPT + j < len) ? acc[i][j] * scale : -CUDART_INF_F;
+            m = fmaxf(m, acc[i][j]);
+        }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) { acc[i][j] = (tx * CPT + j < len) ? expf(acc[i][j] - m) : 0.f; sum += acc[i][j]; }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) s_pT[(tx * CPT + j) * LD + ty * RPT + i] = acc[i][j] * inv;
+    }
+    __syncthreads();
+    // ---- out = P . V : thread (ty, tx) owns rows ty*RPT.. and columns tx*4.. (dh = 64) / tx*2.. (dh = 32)
+    const int cw = dh / 16;            // 4 or 2 output columns per thread
+    float o_acc[RPT][4];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o_acc[i][j] = 0.f;
+    for (int k = 0; k < len; ++k) {
+        float pv[RPT], vv[4];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) pv[i] = s_pT[k * LD + ty * RPT + i];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) vv[j] = j < cw ? s_v[k * 64 + tx * cw + j] : 0.f;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o_acc[i][j] = fmaf(pv[i], vv[j], o_acc[i][j]);
+    }
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const int r = ty * RPT + i;
+        if (r < len) {
+            float* orow = out + (size_t)(t0 + r) * d + h * dh + tx * cw;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (j < cw) orow[j] = o_acc[i][j];
+        }
+    }
+}
+
 // CLS pooling + L2 normalisation (F.normalize, eps 1e-12): one warp per sequence
 __global__ void __launch_bounds__(256)
 cls_normalize_kernel(const float* __restrict__ x, const int32_t* __restrict__ seq_off, float* __restrict__ out, int batch, int d,
@@ -351,13 +624,13 @@ static EncodeTiledFn emb_encode()
     }
     return fn;
 }
-static void emb_map(CUtensorMap* tm, const float* base, int rows, int cols)
+static void emb_map(CUtensorMap* tm, const float* base, int rows, int cols, int box_rows = GM_TILE)
 {
     EncodeTiledFn enc = emb_encode();
     if (!enc) throw CudaError{cudaErrorUnknown, "cuTensorMapEncodeTiled unavailable", __FILE__, __LINE__};
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)cols * 4};
-    cuuint32_t box[2] = {(cuuint32_t)GM_KB, (cuuint32_t)GM_TILE};
+    cuuint32_t box[2] = {(cuuint32_t)GM_KB, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     if (enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
@@ -374,6 +647,37 @@ void launch_gemm_tf32(const DeviceInfo& di, const float* A, const float* B, int 
     }
     CUtensorMap tmA, tmB;
     emb_map(&tmA, A, M, K);
+    static int use2 = -1;
+    if (use2 < 0) { const char* ev = getenv("KRAG_GEMM_2CTA"); use2 = (ev == nullptr || ev[0] != '0') ? 1 : 0; }
+    if (use2 && M > GM_TILE) {   // CTA pairs need at least two 128-row tiles to be worth it
+        const int BN = (N % 256 == 0) ? 256 : 128;
+        emb_map(&tmB, B, N, K, BN / 2);
+        const int total2 = ((M + 2 * GM_TILE - 1) / (2 * GM_TILE)) * (N / BN);
+        const int max_pairs = di.sm_count / 2;
+        const int n_pairs = total2 < max_pairs ? total2 : max_pairs;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * n_pairs));
+        cfg.blockDim = dim3(GM2_THREADS);
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        const int gelu_i = gelu ? 1 : 0;
+        if (BN == 256) {
+            static bool a256 = false;
+            if (!a256) { KRAG_CUDA(cudaFuncSetAttribute(gemm2_tf32_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm2Cfg<256>::SMEM)); a256 = true; }
+            cfg.dynamicSmemBytes = Gm2Cfg<256>::SMEM;
+            KRAG_CUDA(cudaLaunchKernelEx(&cfg, gemm2_tf32_kernel<256>, tmA, tmB, M, N, K, bias, residual, gelu_i, C));
+        } else {
+            static bool a128 = false;
+            if (!a128) { KRAG_CUDA(cudaFuncSetAttribute(gemm2_tf32_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm2Cfg<128>::SMEM)); a128 = true; }
+            cfg.dynamicSmemBytes = Gm2Cfg<128>::SMEM;
+            KRAG_CUDA(cudaLaunchKernelEx(&cfg, gemm2_tf32_kernel<128>, tmA, tmB, M, N, K, bias, residual, gelu_i, C));
+        }
+        count_launch();
+        return;
+    }
     emb_map(&tmB, B, N, K);
     const int total = ((M + GM_TILE - 1) / GM_TILE) * (N / GM_TILE);
     const int grid = total < di.sm_count ? total : di.sm_count;
@@ -507,13 +811,25 @@ void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int3
     count_launch();
     const int dh = d / c.heads;
     const size_t at_smem = sizeof(float) * ((size_t)AT_ROWS * dh + (size_t)dh * (AT_CHUNK + 1) + (size_t)AT_CHUNK * dh + (size_t)AT_ROWS * max_len);
+    const size_t ats_smem32 = sizeof(float) * ((size_t)2 * 64 * (32 + 4) + (size_t)32 * 64 + (size_t)32 * (32 + 4));
+    const size_t ats_smem64 = sizeof(float) * ((size_t)2 * 64 * (64 + 4) + (size_t)64 * 64 + (size_t)64 * (64 + 4));
     static bool at_attr = false;
-    if (!at_attr) { KRAG_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); at_attr = true; }
+    if (!at_attr) {
+        KRAG_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        KRAG_CUDA(cudaFuncSetAttribute(attention_tiled_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+        KRAG_CUDA(cudaFuncSetAttribute(attention_tiled_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+        at_attr = true;
+    }
     const int ln_grid = (n_tok * 32 + 255) / 256;
     for (int l = 0; l < c.layers; ++l) {
         launch_gemm_tf32(e->di, e->x, e->wqkv[(size_t)l], n_tok, 3 * d, d, e->bqkv[(size_t)l], nullptr, false, e->qkv, st);
-        attention_kernel<<<dim3((unsigned)((max_len + AT_ROWS - 1) / AT_ROWS), (unsigned)c.heads, (unsigned)batch), 256, at_smem, st>>>(
-            e->qkv, e->d_off, e->ctx, d, c.heads, max_len);
+        if (max_len <= 32)
+            attention_tiled_kernel<32><<<dim3((unsigned)batch, (unsigned)c.heads), 128, ats_smem32, st>>>(e->qkv, e->d_off, e->ctx, d, c.heads);
+        else if (max_len <= ATS_MAX)
+            attention_tiled_kernel<64><<<dim3((unsigned)batch, (unsigned)c.heads), 128, ats_smem64, st>>>(e->qkv, e->d_off, e->ctx, d, c.heads);
+        else
+            attention_kernel<<<dim3((unsigned)((max_len + AT_ROWS - 1) / AT_ROWS), (unsigned)c.heads, (unsigned)batch), 256, at_smem, st>>>(
+                e->qkv, e->d_off, e->ctx, d, c.heads, max_len);
         KRAG_CUDA(cudaGetLastError());
         count_launch();
         launch_gemm_tf32(e->di, e->ctx, e->t[lname(l, "attention.output.dense.weight")], n_tok, d, d,

@@ -82,7 +82,7 @@ void build_postings(const uint32_t* term_ids, const uint16_t* term_tf, const uin
                     double avgdl, int64_t n_docs_rows, Postings& out, cudaStream_t st);
 size_t bm25_part_elems(int64_t n_rows, int batch, int P);
 void launch_bm25(const DeviceInfo& di, const Postings& post, int64_t n_rows, const uint32_t* alive,
-                 const uint32_t* q_terms, const int32_t* q_term_offsets, int max_terms, int batch, int P,
+                 const uint32_t* q_terms, const int32_t* q_term_offsets, int n_terms_total, void* resolve_ws, int batch, int P,
                  uint32_t ord_base, uint64_t* part, uint64_t* keys_out, cudaStream_t st);
 
 // ---- K5: BERT encoder forward (embed.cu)

@@ -46,8 +46,8 @@ class NativeStages:
     def dense_candidates(self, q: torch.Tensor, P: int, out: torch.Tensor):
         self.index.dev_dense_candidates(q.shape[0], q.data_ptr(), P, out.data_ptr(), self.stream())
 
-    def bm25_candidates(self, terms: torch.Tensor, toff: torch.Tensor, batch: int, P: int, out: torch.Tensor):
-        self.index.dev_bm25_candidates(batch, terms.data_ptr(), toff.data_ptr(), P, out.data_ptr(), self.stream())
+    def bm25_candidates(self, terms: torch.Tensor, toff: torch.Tensor, batch: int, P: int, out: torch.Tensor, toff_host=None):
+        self.index.dev_bm25_candidates(batch, terms.data_ptr(), toff.data_ptr(), P, out.data_ptr(), self.stream(), toff_host)
 
     def merge(self, gathered: torch.Tensor, n_lists: int, batch: int, P: int, out: torch.Tensor):
         self.ctx.dev_merge(n_lists, batch, P, gathered.data_ptr(), out.data_ptr(), self.stream())
@@ -96,7 +96,8 @@ class ShardedRetriever:
         return t
 
     def retrieve_dev(self, q: torch.Tensor, terms: torch.Tensor | None, toff: torch.Tensor | None, k: int,
-                     cand_mult: float = 3.0, vector_weight: float = 0.7, text_weight: float = 0.3, mode: int = 0):
+                     cand_mult: float = 3.0, vector_weight: float = 0.7, text_weight: float = 0.3, mode: int = 0,
+                     toff_host: np.ndarray | None = None):
         """Inputs already on this rank's device (q: [B, dim_padded] fp32 zero padded).
         Returns a dict of device tensors [B, k] (+ count [B])."""
         B = q.shape[0]
@@ -106,7 +107,7 @@ class ShardedRetriever:
         local = self._tensor("local", (nl, B, P), torch.int64)
         self.stages.dense_candidates(q, P, local[0])
         if hybrid:
-            self.stages.bm25_candidates(terms, toff, B, P, local[1])
+            self.stages.bm25_candidates(terms, toff, B, P, local[1], toff_host)
         if self.world > 1:
             flat = self._tensor("gathered", (self.world * nl, B, P), torch.int64)
             dist.all_gather_into_tensor(flat, local, group=self.group)   # concatenation along dim 0
@@ -130,6 +131,26 @@ class ShardedRetriever:
         self.stages.fuse(B, P, k, merged[0], merged[1] if hybrid else None, vector_weight, text_weight, mode, out)
         return out
 
+    def embed_into(self, embedder, flat_tok: np.ndarray, tok_off: np.ndarray, q: torch.Tensor):
+        """Query embeddings (K5) into q [B, dim_padded] on every rank.  The embedder weights are replicated; the
+        QUERIES are split across the ranks (each embeds B/G of them) and the rows are all-gathered, so the
+        embedding stage scales with the number of GPUs like the corpus scan does."""
+        B = len(tok_off) - 1
+        if self.dpad != embedder.hidden:
+            q.zero_()                            # padding columns of the row layout must be zero
+        if self.world == 1 or B % self.world:
+            embedder.embed_dev(flat_tok, tok_off, q.data_ptr(), self.dpad, self.stages.stream())
+            return
+        per = B // self.world
+        lo = self.rank * per
+        f = np.ascontiguousarray(flat_tok[tok_off[lo]:tok_off[lo + per]])
+        o = np.ascontiguousarray(tok_off[lo:lo + per + 1] - tok_off[lo])
+        loc = self._tensor("q_local", (per, self.dpad), torch.float32)
+        if self.dpad != embedder.hidden:
+            loc.zero_()
+        embedder.embed_dev(f, o, loc.data_ptr(), self.dpad, self.stages.stream())
+        dist.all_gather_into_tensor(q, loc, group=self.group)
+
     def retrieve(self, q_host: np.ndarray | None, q_terms_list, k: int, embedder=None, tokens=None, **kw):
         """End to end with HOST buffers: pinned H2D of the queries, the pipeline, D2H of the result.
         With `embedder` (kaito_b200._native.Embedder) and `tokens` = (flat int32 token ids, int32 offsets [B+1])
@@ -138,9 +159,7 @@ class ShardedRetriever:
             flat_tok, tok_off = tokens
             B = len(tok_off) - 1
             q = self._tensor("q", (B, self.dpad), torch.float32)
-            if self.dpad != embedder.hidden:
-                q.zero_()                        # padding columns of the row layout must be zero
-            embedder.embed_dev(flat_tok, tok_off, q.data_ptr(), self.dpad, self.stages.stream())
+            self.embed_into(embedder, flat_tok, tok_off, q)
         else:
             B, d = q_host.shape
             pin_q = self._pinned("pin_q", (B, self.dpad), torch.float32)
@@ -162,7 +181,7 @@ class ShardedRetriever:
             toff = self._tensor("toff", (B + 1,), torch.int32)
             terms.copy_(pin_t, non_blocking=True)
             toff.copy_(pin_o, non_blocking=True)
-        out = self.retrieve_dev(q, terms, toff, k, **kw)
+        out = self.retrieve_dev(q, terms, toff, k, toff_host=offs if q_terms_list is not None else None, **kw)
         host = {name: self._pinned("pin_out_" + name, tuple(t.shape), t.dtype) for name, t in out.items()}
         for name, t in out.items():
             host[name].copy_(t, non_blocking=True)

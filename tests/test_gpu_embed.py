@@ -62,6 +62,12 @@ def _random_state(cfg, seed):
 @pytest.mark.parametrize("name,cfg,lens", [
     ("small-2L", dict(num_hidden_layers=2, hidden_size=384, num_attention_heads=12, intermediate_size=1536, vocab_size=1000,
                       max_position_embeddings=512), [1, 3, 17, 64, 130, 512]),
+    ("short-32", dict(num_hidden_layers=2, hidden_size=768, num_attention_heads=12, intermediate_size=3072, vocab_size=900,
+                      max_position_embeddings=512), [1, 5, 32, 31]),
+    ("short-64", dict(num_hidden_layers=2, hidden_size=384, num_attention_heads=12, intermediate_size=1536, vocab_size=900,
+                      max_position_embeddings=512), [33, 64, 7, 2]),
+    ("short-64-large", dict(num_hidden_layers=1, hidden_size=1024, num_attention_heads=16, intermediate_size=4096, vocab_size=900,
+                            max_position_embeddings=512), [40, 64]),
     ("bge-small", dict(num_hidden_layers=12, hidden_size=384, num_attention_heads=12, intermediate_size=1536, vocab_size=2000,
                        max_position_embeddings=512), [9, 32, 200]),
     ("base-3L", dict(num_hidden_layers=3, hidden_size=768, num_attention_heads=12, intermediate_size=3072, vocab_size=1500,

@@ -55,7 +55,7 @@ class OracleStages:
         d, o = self.o.dense_topk(self.x, q.numpy()[:, : self.x.shape[1]], P)
         out.copy_(torch.from_numpy(keys_asc(d, np.where(o >= 0, o + self.base, -1)).view(np.int64)))
 
-    def bm25_candidates(self, terms, toff, batch, P, out):
+    def bm25_candidates(self, terms, toff, batch, P, out, toff_host=None):
         t, off = terms.numpy().view(np.uint32), toff.numpy()
         for b in range(batch):
             s, o = self.o.bm25_query(self.post, t[off[b]:off[b + 1]], P)
