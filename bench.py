@@ -78,7 +78,7 @@ WORKLOADS = {
     # name: (docs, dim, hybrid)
     "c3": (10_000_000, 768, True),
     "c2": (1_000_000, 768, False),
-    "headline": (100_000_000, 768, False),   # needs >= 2 GPUs in fp32 (8 recommended)
+    "headline": (100_000_000, 768, True),    # BASELINE.json metric corpus: needs >= 4 GPUs in fp32 (8 recommended)
     "tiny": (200_000, 768, True),            # functional check of the harness
 }
 
@@ -423,6 +423,12 @@ def run_ours(args):
         gbs1 = kern1_bytes / (kern1_ms * 1e-3) / 1e9
         tflops = kern_flops / (kern_ms * 1e-3) / 1e12
         tf32_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0   # TF32 dense = half the measured bf16 rate
+        # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel on the same workload from the committed
+        # ncu --set full capture (profiles/traffic.json names the report); null when no capture matches this run
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath) and world == 1:
+            traffic = json.load(open(tpath)).get(args.workload, {}).get(str(kern_id))
         kname = {1: "K1 dense_scan_kernel (exact fp32 L2^2 scan + fused top-P)",
                  2: "K2 dense_tc_kernel (tcgen05 cta_group::1 TF32 prune pass; exact fp32 rescoring follows)",
                  3: "K2 dense_tc2_kernel (tcgen05 cta_group::2 TF32 prune pass, CTA pairs; exact fp32 rescoring follows)"}
@@ -457,7 +463,7 @@ def run_ours(args):
             "batch1": {"value": args.steps * 4 / (ms_b1 * 1e-3), "e2e": args.steps * 4 / (ms_b1_e2e * 1e-3), "unit": "queries/s",
                        "ms_per_query": ms_b1 / (args.steps * 4), "dense_kernel_ms": kern1_ms, "dense_kernel_gbs": gbs1, "dense_frac": gbs1 / peak},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": traffic,
                          "kernel": kname[kern_id], "peak_source": peak_src, "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_launch": kern_bytes, "flops_per_launch": kern_flops,
                          "tensor_tflops": tflops, "tensor_peak_tf32": tf32_peak, "tensor_frac": tflops / tf32_peak,
