@@ -240,7 +240,7 @@ void build_postings(const uint32_t* term_ids, const uint16_t* term_tf, const uin
 }
 
 // -------------------------------------------------------------------------- query time
-constexpr int BQ_THREADS = 512;
+constexpr int BQ_THREADS = 256;   // a term contributes ~200 postings to a 16384-doc tile: 256-wide slabs keep the lanes busy
 constexpr int BQ_MAX_TERMS = 32;    // query terms resolved per pass; longer queries loop
 constexpr int BQ_MAX_SLABS = 96;    // 512-posting slabs per pass
 constexpr int BQ_PREFETCH = 8;      // slabs held in registers at a time
