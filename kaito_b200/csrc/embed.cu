@@ -595,6 +595,122 @@ attention_tiled_kernel(const float* __restrict__ qkv, const int32_t* __restrict_
     }
 }
 
+// long sequences (chunks on the /index path; len up to max_position): flash-style fp32 attention.
+// One CTA of 128 threads per (sequence, head, block of 64 query rows); keys are visited in chunks of 64 with an
+// online (running max / running sum) softmax, so no S x S score matrix is materialised.  Both products are
+// register-tiled exactly like attention_tiled_kernel<64>: thread (ty, tx) owns 8 rows x 4 score columns and
+// 8 rows x (dh/16) output columns.
+__global__ void __launch_bounds__(128)
+attention_flash_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ seq_off, float* __restrict__ out, int d, int heads)
+{
+    constexpr int S2 = 64, RPT = 8, CPT = 4, LD = S2 + 4;
+    extern __shared__ __align__(16) float af_sm[];
+    const int dh = d / heads;
+    float* s_qT = af_sm;               // [dh][LD]
+    float* s_kT = s_qT + 64 * LD;      // [dh][LD]
+    float* s_v = s_kT + 64 * LD;       // [64][64]
+    float* s_pT = s_v + S2 * 64;       // [64 keys][LD rows]
+    const int b = blockIdx.z, h = blockIdx.y;
+    const int t0 = seq_off[b], len = seq_off[b + 1] - t0;
+    const int r0 = blockIdx.x * S2;
+    if (r0 >= len) return;
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int warp = tid >> 5, lane = tid & 31, cl = lane & 7, rl = lane >> 3;
+    const int cblocks = dh / 8;
+    for (int blk = warp; blk < cblocks * (S2 / 4); blk += 4) {       // Q rows of this block, transposed
+        const int c = (blk % cblocks) * 8 + cl, r = (blk / cblocks) * 4 + rl;
+        s_qT[c * LD + r] = (r0 + r < len) ? qkv[(size_t)(t0 + r0 + r) * 3 * d + h * dh + c] : 0.f;
+    }
+    const float scale = rsqrtf((float)dh);
+    const int cw = dh / 16;
+    float m_run[RPT], l_run[RPT], o_acc[RPT][4];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        m_run[i] = -CUDART_INF_F; l_run[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o_acc[i][j] = 0.f;
+    }
+    for (int k0 = 0; k0 < len; k0 += S2) {
+        __syncthreads();                                             // previous chunk fully consumed (s_kT, s_v, s_pT)
+        for (int blk = warp; blk < cblocks * (S2 / 4); blk += 4) {
+            const int c = (blk % cblocks) * 8 + cl, r = (blk / cblocks) * 4 + rl;
+            float k = 0.f, v = 0.f;
+            if (k0 + r < len) {
+                const float* base = qkv + (size_t)(t0 + k0 + r) * 3 * d + d + h * dh + c;
+                k = base[0]; v = base[d];
+            }
+            s_kT[c * LD + r] = k; s_v[r * 64 + c] = v;
+        }
+        __syncthreads();
+        float acc[RPT][CPT];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i)
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) acc[i][j] = 0.f;
+        for (int c = 0; c < dh; ++c) {
+            float qv[RPT], kv[CPT];
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) qv[i] = s_qT[c * LD + ty * RPT + i];
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) kv[j] = s_kT[c * LD + tx * CPT + j];
+#pragma unroll
+            for (int i = 0; i < RPT; ++i)
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) acc[i][j] = fmaf(qv[i], kv[j], acc[i][j]);
+        }
+        // online softmax: a row's 64 chunk columns live in the 16 threads tx = 0..15 of one half-warp
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            float m = -CUDART_INF_F;
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                acc[i][j] = (k0 + tx * CPT + j < len) ? acc[i][j] * scale : -CUDART_INF_F;
+                m = fmaxf(m, acc[i][j]);
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            const float m_new = fmaxf(m_run[i], m);                  // finite: every chunk holds at least one valid key
+            const float corr = expf(m_run[i] - m_new);               // exp(-inf) = 0 on the first chunk
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) {
+                const float p = (k0 + tx * CPT + j < len) ? expf(acc[i][j] - m_new) : 0.f;
+                sum += p;
+                s_pT[(tx * CPT + j) * LD + ty * RPT + i] = p;
+            }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            l_run[i] = l_run[i] * corr + sum;
+            m_run[i] = m_new;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o_acc[i][j] *= corr;
+        }
+        __syncthreads();
+        const int nk = min(S2, len - k0);
+        for (int k = 0; k < nk; ++k) {
+            float pv[RPT], vv[4];
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) pv[i] = s_pT[k * LD + ty * RPT + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) vv[j] = j < cw ? s_v[k * 64 + tx * cw + j] : 0.f;
+#pragma unroll
+            for (int i = 0; i < RPT; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o_acc[i][j] = fmaf(pv[i], vv[j], o_acc[i][j]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        const int r = r0 + ty * RPT + i;
+        if (r < len) {
+            const float inv = 1.f / l_run[i];
+            float* orow = out + (size_t)(t0 + r) * d + h * dh + tx * cw;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (j < cw) orow[j] = o_acc[i][j] * inv;
+        }
+    }
+}
+
 // CLS pooling + L2 normalisation (F.normalize, eps 1e-12): one warp per sequence
 __global__ void __launch_bounds__(256)
 cls_normalize_kernel(const float* __restrict__ x, const int32_t* __restrict__ seq_off, float* __restrict__ out, int batch, int d,
@@ -649,7 +765,11 @@ void launch_gemm_tf32(const DeviceInfo& di, const float* A, const float* B, int 
     emb_map(&tmA, A, M, K);
     static int use2 = -1;
     if (use2 < 0) { const char* ev = getenv("KRAG_GEMM_2CTA"); use2 = (ev == nullptr || ev[0] != '0') ? 1 : 0; }
-    if (use2 && M > GM_TILE) {   // CTA pairs need at least two 128-row tiles to be worth it
+    // CTA pairs (256 x BN tiles) win when there are enough tiles to fill the 74 pairs; small problems (few query
+    // tokens per rank) are latency-bound by the K loop of a single tile, where 128 x 128 tiles on single CTAs
+    // halve the per-tile MMA time and quadruple the number of CTAs
+    const int pair_tiles = ((M + 2 * GM_TILE - 1) / (2 * GM_TILE)) * (N / ((N % 256 == 0) ? 256 : 128));
+    if (use2 && M > GM_TILE && pair_tiles >= di.sm_count / 4) {
         const int BN = (N % 256 == 0) ? 256 : 128;
         emb_map(&tmB, B, N, K, BN / 2);
         const int total2 = ((M + 2 * GM_TILE - 1) / (2 * GM_TILE)) * (N / BN);
@@ -818,8 +938,11 @@ void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int3
         KRAG_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         KRAG_CUDA(cudaFuncSetAttribute(attention_tiled_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
         KRAG_CUDA(cudaFuncSetAttribute(attention_tiled_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+        KRAG_CUDA(cudaFuncSetAttribute(attention_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
         at_attr = true;
     }
+    static int use_flash = -1;
+    if (use_flash < 0) { const char* ev = getenv("KRAG_ATTN_FLASH"); use_flash = (ev == nullptr || ev[0] != '0') ? 1 : 0; }
     const int ln_grid = (n_tok * 32 + 255) / 256;
     for (int l = 0; l < c.layers; ++l) {
         launch_gemm_tf32(e->di, e->x, e->wqkv[(size_t)l], n_tok, 3 * d, d, e->bqkv[(size_t)l], nullptr, false, e->qkv, st);
@@ -827,6 +950,9 @@ void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int3
             attention_tiled_kernel<32><<<dim3((unsigned)batch, (unsigned)c.heads), 128, ats_smem32, st>>>(e->qkv, e->d_off, e->ctx, d, c.heads);
         else if (max_len <= ATS_MAX)
             attention_tiled_kernel<64><<<dim3((unsigned)batch, (unsigned)c.heads), 128, ats_smem64, st>>>(e->qkv, e->d_off, e->ctx, d, c.heads);
+        else if (use_flash)
+            attention_flash_kernel<<<dim3((unsigned)((max_len + 63) / 64), (unsigned)c.heads, (unsigned)batch), 128, ats_smem64, st>>>(
+                e->qkv, e->d_off, e->ctx, d, c.heads);
         else
             attention_kernel<<<dim3((unsigned)((max_len + AT_ROWS - 1) / AT_ROWS), (unsigned)c.heads, (unsigned)batch), 256, at_smem, st>>>(
                 e->qkv, e->d_off, e->ctx, d, c.heads, max_len);
