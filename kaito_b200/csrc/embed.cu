@@ -18,6 +18,7 @@
 
 #include <map>
 #include <stdexcept>
+#include <tuple>
 #include <string>
 #include <vector>
 
@@ -815,6 +816,8 @@ struct Embedder {
     bool finalized = false;
     cudaStream_t st = nullptr;
     cudaEvent_t done = nullptr;
+    std::map<std::tuple<int, int, int>, cudaGraphExec_t> graphs;   // captured forward per (n_tok, batch, max_len)
+    std::map<std::tuple<int, int, int>, int> seen;
     // workspaces, grown on demand
     int cap_tok = 0, cap_batch = 0;
     int32_t *d_tok = nullptr, *d_pos = nullptr, *d_off = nullptr;
@@ -880,6 +883,7 @@ void embedder_finalize(Embedder* e)
 
 void embedder_destroy(Embedder* e)
 {
+    for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
     for (auto& kv : e->t) cudaFree(kv.second);
     for (float* p : e->wqkv) cudaFree(p);
     for (float* p : e->bqkv) cudaFree(p);
@@ -911,6 +915,9 @@ void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int3
         for (int i = 0; i < len; ++i) pos[(size_t)tok_offsets[b] + i] = i;
     }
     if (n_tok > e->cap_tok || batch > e->cap_batch) {
+        for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);   // captured pointers are about to change
+        e->graphs.clear(); e->seen.clear();
+        KRAG_CUDA(cudaStreamSynchronize(st));
         for (void* p : {(void*)e->d_tok, (void*)e->d_pos, (void*)e->d_off, (void*)e->x, (void*)e->x2, (void*)e->qkv, (void*)e->ctx, (void*)e->ffn, (void*)e->out})
             if (p) cudaFree(p);
         const size_t T = (size_t)(n_tok > e->cap_tok ? n_tok : e->cap_tok), Bc = (size_t)(batch > e->cap_batch ? batch : e->cap_batch);
@@ -923,6 +930,9 @@ void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int3
     KRAG_CUDA(cudaMemcpyAsync(e->d_pos, pos.data(), 4 * (size_t)n_tok, cudaMemcpyHostToDevice, st));
     KRAG_CUDA(cudaMemcpyAsync(e->d_off, tok_offsets, 4 * (size_t)(batch + 1), cudaMemcpyHostToDevice, st));
 
+    // The forward is ~7 kernels per layer; for a handful of query tokens it is bound by launch gaps and kernel
+    // prologues, so each (n_tok, batch, max_len) shape is captured into a CUDA graph the second time it is seen.
+    auto run_layers = [&]() {
     embed_ln_kernel<<<(n_tok + 7) / 8, 256, (size_t)8 * d * 4, st>>>(
         e->d_tok, e->d_pos, e->t["embeddings.word_embeddings.weight"], e->t["embeddings.position_embeddings.weight"],
         e->t["embeddings.token_type_embeddings.weight"], e->t["embeddings.LayerNorm.weight"], e->t["embeddings.LayerNorm.bias"], e->x,
@@ -970,6 +980,28 @@ void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int3
         layernorm_kernel<<<ln_grid, 256, 0, st>>>(e->x2, e->x, e->t[lname(l, "output.LayerNorm.weight")],
                                                   e->t[lname(l, "output.LayerNorm.bias")], n_tok, d, c.eps);
         count_launch();
+    }
+    };   // run_layers
+    static int use_graph = -1;
+    if (use_graph < 0) { const char* ev = getenv("KRAG_EMBED_GRAPH"); use_graph = (ev == nullptr || ev[0] != '0') ? 1 : 0; }
+    const std::tuple<int, int, int> key(n_tok, batch, max_len);
+    auto git = e->graphs.find(key);
+    if (use_graph && git != e->graphs.end()) {
+        KRAG_CUDA(cudaGraphLaunch(git->second, st));
+        count_launch(1 + 7 * c.layers);
+    } else if (use_graph && e->seen[key]++ >= 1) {
+        if (e->graphs.size() >= 64) { for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second); e->graphs.clear(); }
+        cudaGraph_t g = nullptr;
+        cudaGraphExec_t ex = nullptr;
+        KRAG_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        try { run_layers(); } catch (...) { cudaStreamEndCapture(st, &g); if (g) cudaGraphDestroy(g); throw; }
+        KRAG_CUDA(cudaStreamEndCapture(st, &g));
+        KRAG_CUDA(cudaGraphInstantiate(&ex, g, 0));
+        KRAG_CUDA(cudaGraphDestroy(g));
+        e->graphs[key] = ex;
+        KRAG_CUDA(cudaGraphLaunch(ex, st));
+    } else {
+        run_layers();
     }
     if (out_dev) {
         cls_normalize_kernel<<<(batch * 32 + 255) / 256, 256, 0, st>>>(e->x, e->d_off, out_dev, batch, d, ld_out);

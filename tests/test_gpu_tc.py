@@ -35,7 +35,7 @@ def test_tc_raw_output_matches_numpy(ctx_tc, oracle, n, d, nq):
         ix.drop()
 
 
-@pytest.mark.parametrize("batch,P", [(40, 30), (200, 30), (256, 90), (300, 10)])
+@pytest.mark.parametrize("batch,P", [(40, 30), (200, 30), (256, 90), (300, 10), (24, 900)])
 def test_tc_pipeline_bit_exact(ctx_tc, oracle, batch, P):
     from kaito_b200 import _native
     n, d = 300_000, 128
