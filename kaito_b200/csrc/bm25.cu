@@ -244,6 +244,7 @@ constexpr int BQ_THREADS = 256;   // a term contributes ~200 postings to a 16384
 constexpr int BQ_MAX_TERMS = 32;    // query terms resolved per pass; longer queries loop
 constexpr int BQ_MAX_SLABS = 96;    // 512-posting slabs per pass
 constexpr int BQ_PREFETCH = 8;      // slabs held in registers at a time
+constexpr int BQ_GROUP = 8;         // consecutive doc tiles handled by one work item (same query): one resolve, one select, one store
 
 // A "slab" is up to 512 consecutive postings of one query term that fall into this CTA's doc
 // range (frequent terms: looked up in the tile index; rare terms: the whole <= 256-entry list,
@@ -256,7 +257,7 @@ bm25_tile_kernel(const int64_t* __restrict__ post_off, const uint32_t* __restric
                  const uint32_t* __restrict__ q_terms, const int32_t* __restrict__ q_term_offsets,
                  const int32_t* __restrict__ q_slot, const int64_t* __restrict__ q_base, const int32_t* __restrict__ q_rare_len,
                  int64_t n_rows, const uint32_t* __restrict__ alive, int P, int cap, uint32_t ord_base, int batch, int n_tiles,
-                 uint64_t* __restrict__ part /*[batch][n_tiles][P]*/, unsigned long long* __restrict__ g_thr /*[batch]*/)
+                 uint64_t* __restrict__ part /*[batch][n_groups][P]*/, unsigned long long* __restrict__ g_thr /*[batch]*/)
 {
     extern __shared__ __align__(16) unsigned char bsm[];
     float* acc = reinterpret_cast<float*>(bsm);                                          // [BM25_TILE_DOCS]
@@ -268,29 +269,49 @@ bm25_tile_kernel(const int64_t* __restrict__ post_off, const uint32_t* __restric
     __shared__ int64_t s_slab_lo[BQ_MAX_SLABS];
     __shared__ int s_slab_n[BQ_MAX_SLABS];
     __shared__ int s_nslab, s_next_term, s_next_off;
+    __shared__ int32_t s_slot[BQ_MAX_TERMS], s_rare[BQ_MAX_TERMS];
+    __shared__ int64_t s_base[BQ_MAX_TERMS];
+    __shared__ uint32_t s_toff[BQ_MAX_TERMS][BQ_GROUP + 1];
 
     const int tid = threadIdx.x;
     // the accumulators are zeroed once: every touched entry is reset by the claim step
     for (int i = tid; i < BM25_TILE_DOCS / 4; i += BQ_THREADS) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     SelectBuf sel{sbuf, &s_count, &s_thr, cap};
 
-    // persistent loop over (tile, query) work items, query fastest: by the time a query's next doc tile is
-    // processed, g_thr[q] (min over finished tiles of their P-th best key -- an upper bound of the global
-    // P-th best) prunes almost every candidate before it reaches the select buffer
-    const int64_t n_items = (int64_t)n_tiles * batch;
+    // persistent loop over (tile group, query) work items, query fastest.  A work item covers BQ_GROUP consecutive
+    // doc tiles of one query: the term -> posting-range lookups are fetched once for the whole group, the select
+    // buffer (and its threshold) carries over from tile to tile, and one top-P list is stored per item.
+    // g_thr[q] (min over finished items of their P-th best key -- an upper bound of the global P-th best) prunes
+    // almost every candidate of later items before it reaches the select buffer.
+    const int n_groups = (n_tiles + BQ_GROUP - 1) / BQ_GROUP;
+    const int64_t n_items = (int64_t)n_groups * batch;
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const int tile = (int)(item / batch), qi = (int)(item - (int64_t)tile * batch);
-    const int64_t t0 = (int64_t)tile * BM25_TILE_DOCS;
-    const int tile_n = (int)min((int64_t)BM25_TILE_DOCS, n_rows - t0);
+    const int tg = (int)(item / batch), qi = (int)(item - (int64_t)tg * batch);
+    const int tile0 = tg * BQ_GROUP, gcount = min(BQ_GROUP, n_tiles - tile0);
     const int tb = q_term_offsets[qi], te = q_term_offsets[qi + 1];
+    const bool single_chunk = (te - tb <= BQ_MAX_TERMS);
     __syncthreads();   // previous item fully stored
     if (tid == 0) {
         const unsigned long long h = __ldcg(&g_thr[qi]);
         s_count = 0;
         s_thr = (h == KEY_PAD) ? KEY_PAD : h + 1;   // admit keys <= hint
     }
+    if (single_chunk && tid < te - tb) {
+        // one fetch per item: slot/base of the term and its posting offsets at the group's tile boundaries
+        const int32_t sl = q_slot[tb + tid];
+        s_slot[tid] = sl; s_base[tid] = q_base[tb + tid]; s_rare[tid] = q_rare_len[tb + tid];
+        if (sl >= 0) {
+            const uint32_t* row = tile_off + (int64_t)sl * (n_tiles_idx + 1) + tile0;
+            for (int g = 0; g <= gcount; ++g) s_toff[tid][g] = row[g];
+        }
+    }
     __syncthreads();
     uint64_t thr = s_thr;
+
+    for (int gi = 0; gi < gcount; ++gi) {
+    const int tile = tile0 + gi;
+    const int64_t t0 = (int64_t)tile * BM25_TILE_DOCS;
+    const int tile_n = (int)min((int64_t)BM25_TILE_DOCS, n_rows - t0);
 
     // posting range of each term of the chunk [c0, c0+nt) inside this tile
     auto resolve = [&](int c0, int nt) {
@@ -375,10 +396,19 @@ bm25_tile_kernel(const int64_t* __restrict__ post_off, const uint32_t* __restric
     };
 
     bool done = false;
-    if (te - tb <= BQ_MAX_TERMS) {
-        // common case: the whole query resolves in one chunk; if it also fits one pass, accumulate and claim
-        // without resolving twice
-        resolve(tb, te - tb);
+    if (single_chunk) {
+        // common case: the whole query resolves in one chunk (ranges come from the per-item shared-memory copy);
+        // if it also fits one pass, accumulate and claim without resolving twice
+        __syncthreads();
+        if (tid < te - tb) {
+            const int32_t sl = s_slot[tid];
+            int64_t lo = 0; int len = 0;
+            if (sl >= 0) { lo = s_base[tid] + s_toff[tid][gi]; len = (int)(s_toff[tid][gi + 1] - s_toff[tid][gi]); }
+            else if (sl == -1) { lo = s_base[tid]; len = s_rare[tid]; }
+            s_lo[tid] = lo; s_len[tid] = len;
+        }
+        if (tid == 0) { s_next_term = 0; s_next_off = 0; }
+        __syncthreads();
         const int ns = next_pass(te - tb);
         const bool more = (s_next_term < te - tb);   // uniform: written before the barrier inside next_pass
         if (!more && ns <= BQ_PREFETCH) {
@@ -434,8 +464,9 @@ bm25_tile_kernel(const int64_t* __restrict__ post_off, const uint32_t* __restric
             }
         }
     }
+    }   // tiles of the group
     select_prune<BQ_THREADS>(sel, P, tid, 0);
-    select_store<BQ_THREADS>(sel, P, part + ((size_t)qi * n_tiles + tile) * P, tid);
+    select_store<BQ_THREADS>(sel, P, part + ((size_t)qi * n_groups + tg) * P, tid);
     if (tid == 0 && s_count == P) atomicMin(&g_thr[qi], (unsigned long long)sbuf[P - 1]);
     }   // work items
 }
@@ -457,13 +488,14 @@ __global__ void bm25_resolve_kernel(const uint32_t* __restrict__ q_terms, int n_
     q_slot[i] = sl; q_base[i] = b; q_rare_len[i] = rl;
 }
 
-static int bq_cap(int P) { return P <= 512 ? 1024 : 2048; }
+static int bq_cap(int P) { return P <= 256 ? 512 : (P <= 512 ? 1024 : 2048); }   // cap - P >= BQ_THREADS; small caps keep 3 CTAs per SM
 
 size_t bm25_part_elems(int64_t n_rows, int batch, int P)
 {
     int64_t n_tiles = (n_rows + BM25_TILE_DOCS - 1) / BM25_TILE_DOCS;
     if (n_tiles < 1) n_tiles = 1;
-    return (size_t)n_tiles * batch * P + (size_t)batch;   // + per-query threshold hints
+    const int64_t n_groups = (n_tiles + BQ_GROUP - 1) / BQ_GROUP;
+    return (size_t)n_groups * batch * P + (size_t)batch;   // + per-query threshold hints
 }
 
 void launch_bm25(const DeviceInfo& di, const Postings& post, int64_t n_rows, const uint32_t* alive,
@@ -489,9 +521,10 @@ void launch_bm25(const DeviceInfo& di, const Postings& post, int64_t n_rows, con
         KRAG_CUDA(cudaFuncSetAttribute(bm25_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_set = true;
     }
-    unsigned long long* g_thr = reinterpret_cast<unsigned long long*>(part + (size_t)n_tiles * batch * P);
+    const int64_t n_groups = (n_tiles + BQ_GROUP - 1) / BQ_GROUP;
+    unsigned long long* g_thr = reinterpret_cast<unsigned long long*>(part + (size_t)n_groups * batch * P);
     KRAG_CUDA(cudaMemsetAsync(g_thr, 0xFF, sizeof(unsigned long long) * (size_t)batch, st));
-    const int64_t n_items = n_tiles * batch;
+    const int64_t n_items = n_groups * batch;
     const int per_sm = (smem <= 74 * 1024) ? 3 : 2;
     const int64_t max_grid = (int64_t)per_sm * di.sm_count;
     const int grid = (int)(n_items < max_grid ? n_items : max_grid);
@@ -500,7 +533,7 @@ void launch_bm25(const DeviceInfo& di, const Postings& post, int64_t n_rows, con
                                                      alive, P, cap, ord_base, batch, (int)n_tiles, part, g_thr);
     KRAG_CUDA(cudaGetLastError());
     count_launch();
-    launch_merge(part, (int)n_tiles, P, batch, P, /*list_stride=*/P, /*batch_stride=*/n_tiles * P, keys_out, st,
+    launch_merge(part, (int)n_groups, P, batch, P, /*list_stride=*/P, /*batch_stride=*/n_groups * P, keys_out, st,
                  reinterpret_cast<const uint64_t*>(g_thr));
     launch_bm25_fill(keys_out, batch, P, alive, n_rows, ord_base, st);
 }
