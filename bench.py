@@ -92,7 +92,7 @@ def parse():
     ap.add_argument("--workload", default=os.environ.get("KRAG_BENCH_WORKLOAD", "c3"), choices=list(WORKLOADS))
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--k", type=int, default=10)
-    ap.add_argument("--dense-mode", type=int, default=0, help="0 auto, 1 scan (K1), 2 tensor-core (K2)")
+    ap.add_argument("--dense-mode", type=int, default=0, help="0 auto, 1 scan (K1), 2 tensor-core TF32 (K2), 3 K2 pruning on a bf16 shadow (opt-in, +50%% memory)")
     ap.add_argument("--embedding", default="auto", choices=["auto", "none", "bge-small", "bge-base", "bge-large"],
                     help="query embedding forward (K5) inside the step; auto = the bge model whose width is the corpus dim")
     ap.add_argument("--query-tokens", type=int, default=32, help="WordPiece tokens per query incl. [CLS]/[SEP]")
@@ -431,7 +431,8 @@ def run_ours(args):
             traffic = json.load(open(tpath)).get(args.workload, {}).get(str(kern_id))
         kname = {1: "K1 dense_scan_kernel (exact fp32 L2^2 scan + fused top-P)",
                  2: "K2 dense_tc_kernel (tcgen05 cta_group::1 TF32 prune pass; exact fp32 rescoring follows)",
-                 3: "K2 dense_tc2_kernel (tcgen05 cta_group::2 TF32 prune pass, CTA pairs; exact fp32 rescoring follows)"}
+                 3: "K2 dense_tc2_kernel (tcgen05 cta_group::2 TF32 prune pass, CTA pairs; exact fp32 rescoring follows)",
+                 4: "K2 dense_tc2_kernel<bf16> (OPT-IN: prune pass over a bf16 shadow of the corpus, kind::f16; exact fp32 rescoring of the fp32 corpus follows)"}
         qps = B * args.steps / (ms_dev * 1e-3)
         qps_e2e = B * args.steps / (ms_e2e * 1e-3)
         h2d, d2h = ShardedRetriever.io_bytes(B, dim, n_terms, k)
@@ -448,7 +449,7 @@ def run_ours(args):
             "metric": "rag_retrieve_queries_per_sec", "value": qps, "unit": "queries/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {docs} docs x {dim} fp32 resident" +
+            "config": {"workload": f"{args.workload}: {docs} docs x {dim} fp32 resident" + (" (+ bf16 shadow for the prune pass: OPT-IN mode, not the default)" if args.dense_mode == 3 else "") +
                                    (f" + BM25 postings nnz={st.nnz} (local), vocab 2^20, hybrid weighted fusion" if hybrid else ", dense only"),
                        "global_batch": B, "top_k": k, "candidate_pool": P, "parallelism": f"doc-shard x{world}",
                        "rows_per_gpu": n_local, "cache": "inputs larger than L2 (corpus >> 126 MB); no explicit flush",

@@ -49,6 +49,8 @@ extern "C" {
 #define KRAG_DENSE_AUTO 0   /* exact fp32 scan for small batches, tensor-core path for large */
 #define KRAG_DENSE_SCAN 1   /* K1: exact fp32 CUDA-core scan */
 #define KRAG_DENSE_TC 2     /* K2: tcgen05 TF32 candidates + exact fp32 rescoring */
+#define KRAG_DENSE_TC_BF16 3 /* K2 pruning on a bf16 SHADOW copy of the corpus (+50% memory); the returned distances are
+                               still exact fp32 re-scores of the fp32 corpus and carry the same exactness certificate */
 
 typedef struct krag_ctx krag_ctx;
 typedef struct krag_index krag_index;

@@ -20,7 +20,7 @@ KRAG_KEY_PAD = 0xFFFFFFFFFFFFFFFF
 KRAG_MAX_TOP_K = 300
 KRAG_MAX_POOL = 1024
 FUSION_REFERENCE, FUSION_SIMILARITY = 0, 1
-DENSE_AUTO, DENSE_SCAN, DENSE_TC = 0, 1, 2
+DENSE_AUTO, DENSE_SCAN, DENSE_TC, DENSE_TC_BF16 = 0, 1, 2, 3
 
 # every symbol include/kaito_rag.h declares (tests check the export table against this)
 SYMBOLS = [

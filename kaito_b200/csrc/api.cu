@@ -138,6 +138,7 @@ struct krag_index {
     // dense shard
     DevArray<float> X;
     DevArray<float> xnorm;          // |x|^2 per row (K2 epilogue)
+    DevArray<uint16_t> Xh;          // optional bf16 shadow of X (KRAG_DENSE_TC_BF16): prune pass only
     DevArray<uint32_t> xn_max;      // [1] bits of max |x|^2 (K2 certificate)
     int64_t n_rows = 0, n_live = 0;
     std::vector<uint32_t> alive_h;
@@ -198,15 +199,17 @@ void dense_candidates_dev(krag_index* ix, Slot* s, const float* d_q, int batch, 
     KRAG_REQUIRE(ix->ord_base + ix->n_rows <= 0xFFFFFFFFll, KRAG_E_UNSUPPORTED, "global ordinal exceeds 32 bits");
     s->part.reserve((int64_t)dense_scan_part_elems(c->di, P), 0, st);
     int mode = c->cfg.dense_mode;
-    bool use_tc = (mode == KRAG_DENSE_TC) || (mode == KRAG_DENSE_AUTO && dense_tc_wants(ix->n_rows, batch));
+    bool use_tc = (mode == KRAG_DENSE_TC) || (mode == KRAG_DENSE_TC_BF16 && dense_tc_wants(ix->n_rows, batch)) ||
+                  (mode == KRAG_DENSE_AUTO && dense_tc_wants(ix->n_rows, batch));
     if (use_tc && dense_tc_supported(c->di, ix->dpad)) {
         size_t ws = dense_tc_workspace_bytes(c->di, ix->n_rows, P);
         s->tc_ws.reserve((int64_t)ws, 0, st);
         if (launch_dense_tc(c->di, ix->X.p, ix->n_rows, ix->dpad, alive_ptr(ix), ix->xnorm.p, ix->xn_max.p, d_q, batch, P,
-                            (uint32_t)ix->ord_base, s->tc_ws.p, ws, s->part.p, d_keys, st))
+                            (uint32_t)ix->ord_base, s->tc_ws.p, ws, s->part.p, d_keys, st,
+                            mode == KRAG_DENSE_TC_BF16 ? ix->Xh.p : nullptr))
             return;
     }
-    KRAG_REQUIRE(mode != KRAG_DENSE_TC, KRAG_E_UNSUPPORTED, "tensor-core dense path unavailable for this index/device");
+    KRAG_REQUIRE(mode != KRAG_DENSE_TC || !dense_tc_wants(ix->n_rows, 16), KRAG_E_UNSUPPORTED, "tensor-core dense path unavailable for this index/device");
     launch_dense_scan(c->di, ix->X.p, ix->n_rows, ix->dpad, alive_ptr(ix), d_q, batch, P, (uint32_t)ix->ord_base,
                       s->part.p, d_keys, st);
 }
@@ -267,6 +270,7 @@ void ensure_capacity(krag_index* ix, int64_t rows, int64_t nnz, cudaStream_t st)
 {
     ix->X.reserve(rows * ix->dpad, ix->n_rows * ix->dpad, st);
     ix->xnorm.reserve(rows, ix->n_rows, st);
+    if (ix->ctx->cfg.dense_mode == KRAG_DENSE_TC_BF16) ix->Xh.reserve(rows * ix->dpad, ix->n_rows * ix->dpad, st);
     if (ix->xn_max.p == nullptr) {
         ix->xn_max.reserve(1, 0, st);
         KRAG_CUDA(cudaMemsetAsync(ix->xn_max.p, 0, sizeof(uint32_t), st));
@@ -426,7 +430,7 @@ int32_t krag_index_drop(krag_index* ix)
             std::unique_lock<std::shared_mutex> lk(ix->mu);
             cudaSetDevice(ix->ctx->di.device);
             cudaDeviceSynchronize();
-            ix->X.release(); ix->xnorm.release(); ix->xn_max.release(); ix->alive_d.release(); ix->toff.release(); ix->tid.release(); ix->ttf.release();
+            ix->X.release(); ix->Xh.release(); ix->xnorm.release(); ix->xn_max.release(); ix->alive_d.release(); ix->toff.release(); ix->tid.release(); ix->ttf.release();
             ix->dlen.release(); ix->entry_doc.release();
             if (ix->post.off) cudaFree(ix->post.off);
             if (ix->post.doc) cudaFree(ix->post.doc);
@@ -477,6 +481,7 @@ int32_t krag_index_add(krag_index* ix, int64_t n, const uint64_t* node_ids, cons
                                         (size_t)n, cudaMemcpyHostToDevice, st));
         }
         launch_row_norms(ix->X.p, ix->n_rows, n, ix->dpad, ix->xnorm.p, ix->xn_max.p, st);
+        if (ix->Xh.p) launch_f32_to_bf16(dst, ix->Xh.p + ix->n_rows * ix->dpad, n * ix->dpad, st);
         std::vector<int64_t> shifted;
         if (sparse) {
             shifted.resize((size_t)n + 1);
@@ -573,7 +578,7 @@ int32_t krag_index_stats(krag_index* ix, krag_stats_t* out)
         out->n_docs_global = ix->n_docs_global; out->total_len_global = ix->total_len_global; out->vocab = ix->vocab;
         out->ordinal_base = ix->ord_base; out->dim = ix->dim; out->dim_padded = ix->dpad;
         out->committed = ix->committed && ix->committed_rows == ix->n_rows;
-        out->device_bytes = ix->X.bytes() + ix->xnorm.bytes() + ix->alive_d.bytes() + ix->toff.bytes() + ix->tid.bytes() + ix->ttf.bytes() +
+        out->device_bytes = ix->X.bytes() + ix->Xh.bytes() + ix->xnorm.bytes() + ix->alive_d.bytes() + ix->toff.bytes() + ix->tid.bytes() + ix->ttf.bytes() +
                             ix->dlen.bytes() + (ix->committed ? (int64_t)(ix->post.nnz * 8 + (ix->post.vocab + 1) * 8) : 0);
     });
 }
@@ -758,6 +763,7 @@ int32_t krag_synth_fill(krag_index* ix, int64_t n, int64_t row_base, uint64_t se
         ensure_capacity(ix, n, -1, st);
         launch_synth_dense(ix->X.p, n, ix->dim, ix->dpad, row_base, seed, st);
         launch_row_norms(ix->X.p, 0, n, ix->dpad, ix->xnorm.p, ix->xn_max.p, st);
+        if (ix->Xh.p) launch_f32_to_bf16(ix->X.p, ix->Xh.p, n * ix->dpad, st);
         if (vocab > 0) {
             int64_t* off = nullptr; uint32_t* ids = nullptr; uint16_t* tf = nullptr; uint32_t* dl = nullptr; int64_t nnz = 0;
             synth_sparse(n, row_base, seed, vocab, &off, &ids, &tf, &dl, &nnz, st);

@@ -23,6 +23,7 @@
 // Roofline: bytes = n_rows*dpad*4 per pass (HBM), flops = 2*NQ*n_rows*dpad (TF32 pipe).
 // At NQ = 256 the kernel sits on the HBM/TF32 ridge (128 flop/byte).
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <math_constants.h>
 
 #include <stdlib.h>
@@ -228,6 +229,45 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 // (A 4 KB + B half 4 KB) and TMA writes 32 KB per 512 cycles: 64 + 64 B/clk against the 128 B/clk
 // shared-memory port, versus 96 + 96 for the 1-CTA kernel (which caps its tensor pipe at 67%).
 // The halved query slab also doubles the query ring depth (6 stages) and halves L2->SM traffic.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N)
+{
+    return (1u << 4) /* D f32 */ | (1u << 7) /* A bf16 */ | (1u << 10) /* B bf16 */ | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+template <bool BF16>
+__device__ __forceinline__ void umma_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    if (BF16) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+    } else {
+        umma_tf32_2sm(d_tmem, adesc, bdesc, idesc, accumulate);
+    }
+}
+// fp32 -> bf16 (round to nearest even) shadow rows; n4 = number of float4 groups
+__global__ void f32_to_bf16_kernel(const float4* __restrict__ in, uint2* __restrict__ out, int64_t n4)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = in[i];
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&a); o.y = *reinterpret_cast<const uint32_t*>(&b);
+        out[i] = o;
+    }
+}
+void launch_f32_to_bf16(const float* in, uint16_t* out, int64_t n_elems, cudaStream_t st)
+{
+    if (n_elems == 0) return;
+    const int64_t n4 = n_elems / 4;
+    int64_t blocks = (n4 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    f32_to_bf16_kernel<<<(unsigned)blocks, 256, 0, st>>>(reinterpret_cast<const float4*>(in), reinterpret_cast<uint2*>(out), n4);
+    KRAG_CUDA(cudaGetLastError());
+    count_launch();
+}
+
 // One ring; a stage holds TC2_KB_PER_STAGE k-blocks of this CTA's corpus rows and of its half of the
 // query rows, so the single MMA-issuing thread pays one barrier wait and one commit per 8 MMAs (it was
 // the bottleneck at 2 waits + 2 commits per 4 MMAs: ~770 cycles per k-block against 512 cycles of MMA work).
@@ -246,7 +286,10 @@ __device__ __forceinline__ uint64_t desc_with_lo(uint64_t base_desc, uint32_t lo
     return (base_desc & 0xFFFFFFFF00000000ull) | (uint64_t)lo;
 }
 
-template <int NQ>
+// BF16 = true: the operands are a bf16 SHADOW of the corpus (and of the queries): k-blocks are still 128 bytes per row
+// (64 elements), the MMA is kind::f16 with K = 16 -- half the HBM bytes and half the tensor time of the TF32 pass.
+// Only the pruning changes; the rescoring that produces the returned distances always reads the fp32 corpus.
+template <int NQ, bool BF16>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 dense_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmQh, int64_t n_rows,
                  int kblocks, int64_t n_ptiles, const float* __restrict__ xnorm, const uint32_t* __restrict__ alive,
@@ -302,8 +345,9 @@ dense_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                     else mbar_arrive_remote(&full_bar[stage], 0);
                     for (int u = 0; u < nkb; ++u) {
                         const int kb = sk * TC2_KB_PER_STAGE + u;
-                        tma_load_2d_2sm(sa + (size_t)u * TC_A_BYTES, &tmX, &full_bar[stage], kb * TC_KBLOCK, row0, TMA_EVICT_FIRST);
-                        tma_load_2d_2sm(sq + (size_t)u * Cfg::QH_BYTES, &tmQh, &full_bar[stage], kb * TC_KBLOCK, (int)rank * (NQ / 2),
+                        constexpr int KBE = BF16 ? 2 * TC_KBLOCK : TC_KBLOCK;   // elements per 128-byte k-block
+                        tma_load_2d_2sm(sa + (size_t)u * TC_A_BYTES, &tmX, &full_bar[stage], kb * KBE, row0, TMA_EVICT_FIRST);
+                        tma_load_2d_2sm(sq + (size_t)u * Cfg::QH_BYTES, &tmQh, &full_bar[stage], kb * KBE, (int)rank * (NQ / 2),
                                         TMA_EVICT_LAST);
                     }
                 }
@@ -314,7 +358,7 @@ dense_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     } else if (warp == 1) {
         if (rank == 0) {
             // ===================== MMA issuer (pair leader only) =====================
-            constexpr uint32_t idesc = umma_idesc_tf32(2 * TC_TILE_M, NQ);
+            constexpr uint32_t idesc = BF16 ? umma_idesc_bf16(2 * TC_TILE_M, NQ) : umma_idesc_tf32(2 * TC_TILE_M, NQ);
             const uint64_t desc0 = umma_desc_sw128(smem_u32(smem));      // descriptor of ring byte 0; only the low word moves
             const uint32_t lo0 = (uint32_t)desc0;
             int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
@@ -334,7 +378,7 @@ dense_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
                             if (u < nkb) {
 #pragma unroll
                                 for (int k = 0; k < TC_KBLOCK / 8; ++k)   // UMMA K = 8 (32 bytes = 2 descriptor units)
-                                    umma_tf32_2sm(d_tmem, desc_with_lo(desc0, a_lo + (uint32_t)((u * TC_A_BYTES) >> 4) + 2 * k),
+                                    umma_2sm<BF16>(d_tmem, desc_with_lo(desc0, a_lo + (uint32_t)((u * TC_A_BYTES) >> 4) + 2 * k),
                                                   desc_with_lo(desc0, q_lo + (uint32_t)((u * Cfg::QH_BYTES) >> 4) + 2 * k), idesc,
                                                   (uint32_t)((sk | u | k) != 0));
                             }
@@ -503,7 +547,7 @@ rescore_kernel(const float* __restrict__ X, int dpad, const float* __restrict__ 
 // ------------------------------------------------------------------------ certificate
 __global__ void certify_kernel(const float* __restrict__ Q, int dpad, int nq, int P, const float* __restrict__ thr,
                                const uint32_t* __restrict__ cand_count, int cap, const uint64_t* __restrict__ keys_out,
-                               const uint32_t* __restrict__ xn_max_bits, int32_t* __restrict__ flags)
+                               const uint32_t* __restrict__ xn_max_bits, float eps_rel, int32_t* __restrict__ flags)
 {
     const int j = blockIdx.x * blockDim.x / 32 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (j >= nq) return;
@@ -518,7 +562,7 @@ __global__ void certify_kernel(const float* __restrict__ Q, int dpad, int nq, in
         if (ok) {
             const float dP = key_value_asc(kP);
             // |tf32 dot - exact dot| <= (2^-9 + 2^-12) |x| |q|  (operand truncation 2^-10 each + fp32 accumulation)
-            const float eps = (0.001953125f + 0.000244140625f) * sqrtf(xmax) * sqrtf(qn);
+            const float eps = eps_rel * sqrtf(xmax) * sqrtf(qn);   // eps_rel: 2^-9+2^-12 (TF32 truncation), 2^-8+2^-12 (bf16 RN)
             const float slack = 4e-6f * (1.f + qn + xmax);   // fp32 rounding of |x|^2, |q|^2 and the epilogue fma
             ok = dP <= thr[j] + qn - 2.f * eps - slack;
         }
@@ -543,15 +587,15 @@ static EncodeTiledFn get_encode()
     });
     return fn;
 }
-static bool make_map(CUtensorMap* tm, const float* base, int64_t rows, int dpad, int box_rows)
+static bool make_map(CUtensorMap* tm, const void* base, int64_t rows, int dpad, int box_rows, bool bf16 = false)
 {
     EncodeTiledFn enc = get_encode();
     if (!enc) return false;
     cuuint64_t gdim[2] = {(cuuint64_t)dpad, (cuuint64_t)rows};
-    cuuint64_t gstride[1] = {(cuuint64_t)dpad * 4};
-    cuuint32_t box[2] = {(cuuint32_t)TC_KBLOCK, (cuuint32_t)box_rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)dpad * (bf16 ? 2 : 4)};
+    cuuint32_t box[2] = {(cuuint32_t)(bf16 ? 2 * TC_KBLOCK : TC_KBLOCK), (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+    CUresult r = enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
@@ -564,12 +608,16 @@ bool dense_tc_supported(const DeviceInfo& di, int dpad)
     return di.cc_major == 10 && dpad % TC_KBLOCK == 0 && di.smem_optin >= TcCfg<256>::SMEM && get_encode() != nullptr;
 }
 
-static int tc_target(int P) { int c = 4 * P; return c < 512 ? 512 : (c > 3072 ? 3072 : c); }
+static int tc_target(int P, bool bf16 = false)
+{
+    int c = (bf16 ? 6 : 4) * P, lo = bf16 ? 1024 : 512;   // bf16 pruning needs a wider margin for its certificate
+    return c < lo ? lo : (c > 3072 ? 3072 : c);
+}
 // Gamma(m)-distributed sample estimate (m = C/64 >= 8): 4x the target is a < 1e-8 overflow tail
-static int tc_cap(int P) { return 4 * tc_target(P); }
+static int tc_cap(int P) { return 4 * tc_target(P, true); }   // sized for either mode
 
 struct TcWorkspace {   // carved out of the caller's byte buffer
-    float* thr; uint32_t* cand_count; int32_t* flags; uint32_t* cand_rows; uint64_t* exact_keys; float* dump;
+    float* thr; uint32_t* cand_count; int32_t* flags; uint32_t* cand_rows; uint64_t* exact_keys; float* dump; uint16_t* q_bf16;
 };
 static size_t tc_carve(TcWorkspace* w, unsigned char* base, int cap, int64_t S)
 {
@@ -582,6 +630,7 @@ static size_t tc_carve(TcWorkspace* w, unsigned char* base, int cap, int64_t S)
     p = take((size_t)256 * cap * 4); if (w) w->cand_rows = (uint32_t*)p;
     p = take((size_t)256 * cap * 8); if (w) w->exact_keys = (uint64_t*)p;
     p = take((size_t)256 * S * 4); if (w) w->dump = (float*)p;
+    p = take((size_t)256 * 16384 * 2); if (w) w->q_bf16 = (uint16_t*)p;   // queries as bf16 (dim <= 16384)
     return o;
 }
 static int64_t tc_sample_tiles(int64_t n_rows)
@@ -606,9 +655,10 @@ template <int NQ>
 static void tc_pass(const DeviceInfo& di, const CUtensorMap& tmX, const CUtensorMap& tmQ, const float* X, int64_t n_rows,
                     int dpad, const float* xnorm, const uint32_t* xn_max_bits, const uint32_t* alive, const float* q,
                     int nq, int P, uint32_t ord_base, const TcWorkspace& w, int cap, int64_t S, uint64_t* keys_out,
-                    cudaStream_t st)
+                    const uint16_t* Xh, cudaStream_t st)
 {
     using Cfg = TcCfg<NQ>;
+    const bool bf16 = Xh != nullptr;
     static bool attr_set = false;
     if (!attr_set) {
         KRAG_CUDA(cudaFuncSetAttribute(dense_tc_kernel<NQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
@@ -631,7 +681,7 @@ static void tc_pass(const DeviceInfo& di, const CUtensorMap& tmX, const CUtensor
         int64_t r0 = t * TC_SAMPLE_STRIDE * TC_TILE_M;
         sampled_rows += (r0 + TC_TILE_M <= n_rows) ? TC_TILE_M : (n_rows > r0 ? n_rows - r0 : 0);
     }
-    int m = (int)((double)tc_target(P) * (double)sampled_rows / (double)n_rows + 0.5);
+    int m = (int)((double)tc_target(P, bf16) * (double)sampled_rows / (double)n_rows + 0.5);
     if (m < 4) m = 4;
     if (m > 1024) m = 1024;
     sample_threshold_kernel<<<NQ, ST_THREADS, 0, st>>>(w.dump, S, m, nq, w.thr);
@@ -639,16 +689,22 @@ static void tc_pass(const DeviceInfo& di, const CUtensorMap& tmX, const CUtensor
     count_launch();
     KRAG_CUDA(cudaMemsetAsync(w.cand_count, 0, 256 * 4, st));
     // 3. main pass: stream the corpus once, prune on the tensor cores
-    dense_timer_begin(st, tc_use_2cta() ? 3 : 2, n_rows * (int64_t)dpad * 4, 2 * (int64_t)NQ * n_rows * dpad);
-    if (tc_use_2cta()) {
+    if (bf16) launch_f32_to_bf16(q, w.q_bf16, (int64_t)nq * dpad, st);
+    dense_timer_begin(st, bf16 ? 4 : (tc_use_2cta() ? 3 : 2), n_rows * (int64_t)dpad * (bf16 ? 2 : 4), 2 * (int64_t)NQ * n_rows * dpad);
+    if (tc_use_2cta() || bf16) {
         using Cfg2 = Tc2Cfg<NQ>;
         static bool attr2_set = false;
         if (!attr2_set) {
-            KRAG_CUDA(cudaFuncSetAttribute(dense_tc2_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg2::SMEM));
+            KRAG_CUDA(cudaFuncSetAttribute(dense_tc2_kernel<NQ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg2::SMEM));
+            KRAG_CUDA(cudaFuncSetAttribute(dense_tc2_kernel<NQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg2::SMEM));
             attr2_set = true;
         }
-        CUtensorMap tmQh;
-        if (!make_map(&tmQh, q, nq, dpad, NQ / 2)) throw CudaError{cudaErrorUnknown, "cuTensorMapEncodeTiled(Q half)", __FILE__, __LINE__};
+        CUtensorMap tmQh, tmXh;
+        if (!make_map(&tmQh, bf16 ? (const void*)w.q_bf16 : (const void*)q, nq, dpad, NQ / 2, bf16))
+            throw CudaError{cudaErrorUnknown, "cuTensorMapEncodeTiled(Q half)", __FILE__, __LINE__};
+        if (bf16 && !make_map(&tmXh, Xh, n_rows, dpad, TC_TILE_M, true))
+            throw CudaError{cudaErrorUnknown, "cuTensorMapEncodeTiled(bf16 shadow)", __FILE__, __LINE__};
+        const int kb2 = bf16 ? dpad / (2 * TC_KBLOCK) : kblocks;
         const int64_t n_ptiles = (n_rows + 2 * TC_TILE_M - 1) / (2 * TC_TILE_M);
         const int64_t max_pairs = di.sm_count / 2;
         const int n_pairs = (int)(n_ptiles < max_pairs ? n_ptiles : max_pairs);
@@ -661,8 +717,12 @@ static void tc_pass(const DeviceInfo& di, const CUtensorMap& tmX, const CUtensor
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        KRAG_CUDA(cudaLaunchKernelEx(&cfg, dense_tc2_kernel<NQ>, tmX, tmQh, n_rows, kblocks, n_ptiles, xnorm, alive,
-                                     (const float*)w.thr, w.cand_count, w.cand_rows, cap));
+        if (bf16)
+            KRAG_CUDA(cudaLaunchKernelEx(&cfg, dense_tc2_kernel<NQ, true>, tmXh, tmQh, n_rows, kb2, n_ptiles, xnorm, alive,
+                                         (const float*)w.thr, w.cand_count, w.cand_rows, cap));
+        else
+            KRAG_CUDA(cudaLaunchKernelEx(&cfg, dense_tc2_kernel<NQ, false>, tmX, tmQh, n_rows, kb2, n_ptiles, xnorm, alive,
+                                         (const float*)w.thr, w.cand_count, w.cand_rows, cap));
     } else {
         dense_tc_kernel<NQ, false><<<grid_m, TC_THREADS, Cfg::SMEM, st>>>(tmX, tmQ, n_rows, kblocks, n_tiles, 1, xnorm, alive, w.thr,
                                                                           w.cand_count, w.cand_rows, cap, nullptr, 0);
@@ -677,7 +737,9 @@ static void tc_pass(const DeviceInfo& di, const CUtensorMap& tmX, const CUtensor
     count_launch();
     launch_merge(w.exact_keys, 1, cap, nq, P, cap, cap, keys_out, st);
     // 5. certificate
-    certify_kernel<<<(nq * 32 + 255) / 256, 256, 0, st>>>(q, dpad, nq, P, w.thr, w.cand_count, cap, keys_out, xn_max_bits, w.flags);
+    // the threshold came from TF32 values and the pruning from bf16 ones: the certificate uses the sum of both error bounds
+    const float eps_rel = bf16 ? (0.00390625f + 0.001953125f + 0.00048828125f) : (0.001953125f + 0.000244140625f);
+    certify_kernel<<<(nq * 32 + 255) / 256, 256, 0, st>>>(q, dpad, nq, P, w.thr, w.cand_count, cap, keys_out, xn_max_bits, eps_rel, w.flags);
     KRAG_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -687,8 +749,10 @@ int64_t dense_tc_fallback_queries() { return g_tc_fallback_queries; }
 
 bool launch_dense_tc(const DeviceInfo& di, const float* X, int64_t n_rows, int dpad, const uint32_t* alive,
                      const float* xnorm, const uint32_t* xn_max_bits, const float* q, int batch, int P, uint32_t ord_base,
-                     void* workspace, size_t workspace_bytes, uint64_t* part, uint64_t* keys_out, cudaStream_t st)
+                     void* workspace, size_t workspace_bytes, uint64_t* part, uint64_t* keys_out, cudaStream_t st,
+                     const uint16_t* Xh)
 {
+    if (Xh != nullptr && dpad % (2 * TC_KBLOCK) != 0) Xh = nullptr;   // bf16 k-blocks are 64 elements wide
     if (n_rows < TC_MIN_ROWS || n_rows >= (1ll << 31) || xnorm == nullptr) return false;
     const int cap = tc_cap(P);
     const int64_t S = tc_sample_tiles(n_rows) * TC_TILE_M;
@@ -704,9 +768,9 @@ bool launch_dense_tc(const DeviceInfo& di, const float* X, int64_t n_rows, int d
         CUtensorMap tmQ;
         if (!make_map(&tmQ, qb, nq, dpad, NQ)) return false;
         uint64_t* ko = keys_out + (size_t)b0 * P;
-        if (NQ == 64) tc_pass<64>(di, tmX, tmQ, X, n_rows, dpad, xnorm, xn_max_bits, alive, qb, nq, P, ord_base, w, cap, S, ko, st);
-        else if (NQ == 128) tc_pass<128>(di, tmX, tmQ, X, n_rows, dpad, xnorm, xn_max_bits, alive, qb, nq, P, ord_base, w, cap, S, ko, st);
-        else tc_pass<256>(di, tmX, tmQ, X, n_rows, dpad, xnorm, xn_max_bits, alive, qb, nq, P, ord_base, w, cap, S, ko, st);
+        if (NQ == 64) tc_pass<64>(di, tmX, tmQ, X, n_rows, dpad, xnorm, xn_max_bits, alive, qb, nq, P, ord_base, w, cap, S, ko, Xh, st);
+        else if (NQ == 128) tc_pass<128>(di, tmX, tmQ, X, n_rows, dpad, xnorm, xn_max_bits, alive, qb, nq, P, ord_base, w, cap, S, ko, Xh, st);
+        else tc_pass<256>(di, tmX, tmQ, X, n_rows, dpad, xnorm, xn_max_bits, alive, qb, nq, P, ord_base, w, cap, S, ko, Xh, st);
         // uncertified queries (rare) are re-run on the exact scan kernel -- still on the GPU
         KRAG_CUDA(cudaMemcpyAsync(flags.data(), w.flags, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
         KRAG_CUDA(cudaStreamSynchronize(st));

@@ -78,3 +78,34 @@ def test_tc_certificate_fallback_on_adversarial_data(ctx_tc, oracle):
         assert fb >= 1
     finally:
         ix.drop()
+
+
+@pytest.fixture(scope="module")
+def ctx_bf16():
+    from kaito_b200 import _native
+    c = _native.Context(device_id=0, dense_mode=_native.DENSE_TC_BF16)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("batch,P", [(64, 30), (256, 30), (32, 300)])
+def test_bf16_shadow_pruning_still_returns_exact_fp32(ctx_bf16, oracle, batch, P):
+    """opt-in mode: the tensor-core PRUNE pass reads a bf16 shadow of the corpus; the returned distances are exact
+    fp32 re-scores of the fp32 rows and must equal the oracle bit for bit; appends keep the shadow in sync"""
+    from kaito_b200 import _native
+    n, d = 300_000, 128
+    x = oracle.synth_dense(n, d, seed=5)
+    q = oracle.synth_queries(x, batch, seed=batch + 1)
+    ix = ctx_bf16.create_index(f"bf16_{batch}_{P}", d)
+    try:
+        ix.add(np.arange(200_000, dtype=np.uint64), x[:200_000])
+        ix.add(np.arange(200_000, n, dtype=np.uint64), x[200_000:])
+        fb0 = _native.load().krag_tc_fallback_queries()
+        dist, ordn = ix.search_dense(q, P)
+        fb = _native.load().krag_tc_fallback_queries() - fb0
+        rd, ro = oracle.dense_topk(x, q, P)
+        assert np.array_equal(ordn, ro) and np.array_equal(dist, rd)
+        assert fb <= max(1, batch // 10), fb
+        assert _native.last_dense_kernel()[1] == 4      # the bf16 cta_group::2 kernel really ran
+    finally:
+        ix.drop()
