@@ -42,6 +42,17 @@ constexpr int GM_STAGES = 3;
 constexpr int GM_THREADS = 192;
 constexpr size_t GM_SMEM = (size_t)GM_STAGES * GM_STAGE_BYTES + 1024 + 256;
 
+// 256-bit global accesses (sm_100): one full 32-byte sector per thread and instruction
+__device__ __forceinline__ void st_global_v8(float* p, const float* o)
+{
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
+}
+__device__ __forceinline__ void ld_global_v8(const float* p, float* r)
+{
+    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7]) : "l"(p));
+}
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
 __global__ void __launch_bounds__(GM_THREADS, 1)
@@ -155,17 +166,25 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     float* crow = C + (size_t)row * N + n0 + c0;
                     const float* rrow = residual ? residual + (size_t)row * N + n0 + c0 : nullptr;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
-                        float4 o;
-                        o.x = __uint_as_float(v[j + 0]) + b4.x; o.y = __uint_as_float(v[j + 1]) + b4.y;
-                        o.z = __uint_as_float(v[j + 2]) + b4.z; o.w = __uint_as_float(v[j + 3]) + b4.w;
-                        if (act_gelu) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
-                        if (rrow) {
-                            const float4 r4 = *reinterpret_cast<const float4*>(rrow + j);
-                            o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+                    for (int j = 0; j < 32; j += 8) {   // 32-byte (full-sector) vector accesses: a thread owns a row segment
+                        float o[8];
+#pragma unroll
+                        for (int t = 0; t < 8; t += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j + t));
+                            o[t + 0] = __uint_as_float(v[j + t + 0]) + b4.x; o[t + 1] = __uint_as_float(v[j + t + 1]) + b4.y;
+                            o[t + 2] = __uint_as_float(v[j + t + 2]) + b4.z; o[t + 3] = __uint_as_float(v[j + t + 3]) + b4.w;
                         }
-                        *reinterpret_cast<float4*>(crow + j) = o;
+                        if (act_gelu) {
+#pragma unroll
+                            for (int t = 0; t < 8; ++t) o[t] = gelu_erf(o[t]);
+                        }
+                        if (rrow) {
+                            float r[8];
+                            ld_global_v8(rrow + j, r);
+#pragma unroll
+                            for (int t = 0; t < 8; ++t) o[t] += r[t];
+                        }
+                        st_global_v8(crow + j, o);
                     }
                 }
             }
@@ -319,17 +338,25 @@ gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     float* crow = C + (size_t)row * N + n0 + c0;
                     const float* rrow = residual ? residual + (size_t)row * N + n0 + c0 : nullptr;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j));
-                        float4 o;
-                        o.x = __uint_as_float(v[j + 0]) + b4.x; o.y = __uint_as_float(v[j + 1]) + b4.y;
-                        o.z = __uint_as_float(v[j + 2]) + b4.z; o.w = __uint_as_float(v[j + 3]) + b4.w;
-                        if (act_gelu) { o.x = gelu_erf(o.x); o.y = gelu_erf(o.y); o.z = gelu_erf(o.z); o.w = gelu_erf(o.w); }
-                        if (rrow) {
-                            const float4 r4 = *reinterpret_cast<const float4*>(rrow + j);
-                            o.x += r4.x; o.y += r4.y; o.z += r4.z; o.w += r4.w;
+                    for (int j = 0; j < 32; j += 8) {   // 32-byte (full-sector) vector accesses: a thread owns a row segment
+                        float o[8];
+#pragma unroll
+                        for (int t = 0; t < 8; t += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j + t));
+                            o[t + 0] = __uint_as_float(v[j + t + 0]) + b4.x; o[t + 1] = __uint_as_float(v[j + t + 1]) + b4.y;
+                            o[t + 2] = __uint_as_float(v[j + t + 2]) + b4.z; o[t + 3] = __uint_as_float(v[j + t + 3]) + b4.w;
                         }
-                        *reinterpret_cast<float4*>(crow + j) = o;
+                        if (act_gelu) {
+#pragma unroll
+                            for (int t = 0; t < 8; ++t) o[t] = gelu_erf(o[t]);
+                        }
+                        if (rrow) {
+                            float r[8];
+                            ld_global_v8(rrow + j, r);
+#pragma unroll
+                            for (int t = 0; t < 8; ++t) o[t] += r[t];
+                        }
+                        st_global_v8(crow + j, o);
                     }
                 }
             }
