@@ -197,6 +197,21 @@ int32_t krag_index_read_rows(krag_index* idx, int64_t row0, int64_t n, float* ou
 int32_t krag_index_read_postings(krag_index* idx, uint32_t term, int64_t cap, uint32_t* docs_out, float* scores_out,
                                  int64_t* n_out);
 
+/* ----------------------------------------- peer-memory candidate exchange (one process per GPU, one box) */
+/* The all-gather + merge of the per-shard candidate lists done by our own kernels over NVLink peer memory:
+ * every rank creates a mailbox (cudaMalloc + CUDA IPC handle), the host exchanges the 64-byte handles (any
+ * side channel; kaito_b200/sharded.py uses torch.distributed.all_gather_object), every rank connects, and
+ * krag_dev_exchange_merge then (1) stores this rank's lists [n_lists, batch, P] into all mailboxes with P2P
+ * writes + a system-scope release flag and (2) waits for all ranks' flags and merges G*P -> P locally.
+ * No counterpart in the reference (single replica). */
+typedef struct krag_p2p krag_p2p;
+int32_t krag_p2p_create(krag_ctx* ctx, int32_t rank, int32_t world, int32_t max_batch, int32_t max_P, krag_p2p** out,
+                        uint8_t* handle_out /*[64]*/);
+int32_t krag_p2p_connect(krag_p2p* p, const uint8_t* handles /*[world][64], own entry ignored*/);
+int32_t krag_dev_exchange_merge(krag_p2p* p, int32_t n_lists, int32_t batch, int32_t P, const uint64_t* d_local_keys,
+                                uint64_t* d_merged_out /*[n_lists, batch, P]*/, void* stream);
+int32_t krag_p2p_destroy(krag_p2p* p);
+
 /* ------------------------------------------------------------- embedding forward (K5) */
 /* replaces: LocalHuggingFaceEmbedding (embedding/huggingface_local_embedding.py:34-53) -> sentence-
  * transformers BertModel forward, CLS pooling, L2 normalisation.  Tokenisation (WordPiece) stays in

@@ -32,6 +32,7 @@ SYMBOLS = [
     "krag_synth_fill", "krag_index_read_rows", "krag_index_read_postings", "krag_tc_fallback_queries",
     "krag_debug_tc_dump", "krag_last_dense_kernel", "krag_embedder_create", "krag_embedder_load_tensor",
     "krag_embedder_finalize", "krag_embed", "krag_embed_dev", "krag_embedder_destroy", "krag_debug_gemm_tf32",
+    "krag_p2p_create", "krag_p2p_connect", "krag_dev_exchange_merge", "krag_p2p_destroy",
 ]
 
 
@@ -108,6 +109,10 @@ def load() -> C.CDLL:
     L.krag_embed_dev.argtypes = [vp, i32, vp, vp, vp, i32, vp]
     L.krag_embedder_destroy.argtypes = [vp]
     L.krag_debug_gemm_tf32.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, i32, vp]
+    L.krag_p2p_create.argtypes = [vp, i32, i32, i32, i32, C.POINTER(vp), vp]
+    L.krag_p2p_connect.argtypes = [vp, vp]
+    L.krag_dev_exchange_merge.argtypes = [vp, i32, i32, i32, vp, vp, vp]
+    L.krag_p2p_destroy.argtypes = [vp]
     L.krag_tc_fallback_queries.restype = i64
     L.krag_last_dense_kernel.argtypes = [C.POINTER(C.c_float), C.POINTER(i32), C.POINTER(i64), C.POINTER(i64)]
     L.krag_debug_tc_dump.argtypes = [vp, i32, vp, vp, i64, C.POINTER(i64), C.POINTER(i32)]
@@ -185,6 +190,29 @@ class Context:
         check(self._L.krag_dev_fuse(self._h, batch, P, k, ptr(d_dense), ptr(d_bm25), vw, tw, mode, ptr(d_allow),
                                     ptr(d_final), ptr(d_dense_out), ptr(d_sparse_out), ptr(d_rank), ptr(d_ord),
                                     ptr(d_count), ptr(stream)))
+
+
+class P2PExchange:
+    """krag_p2p: candidate-list all-gather + merge over NVLink peer memory (our kernels, not NCCL)."""
+
+    def __init__(self, ctx: "Context", rank: int, world: int, max_batch: int, max_P: int):
+        self._L = ctx._L
+        h = C.c_void_p()
+        self.handle = np.zeros(64, np.uint8)
+        check(self._L.krag_p2p_create(ctx._h, rank, world, max_batch, max_P, C.byref(h), ptr(self.handle)))
+        self._h, self.world = h, world
+
+    def connect(self, handles: np.ndarray):
+        handles = np.ascontiguousarray(handles, np.uint8).reshape(self.world, 64)
+        check(self._L.krag_p2p_connect(self._h, ptr(handles)))
+
+    def exchange_merge(self, n_lists, batch, P, d_local, d_merged, stream=0):
+        check(self._L.krag_dev_exchange_merge(self._h, n_lists, batch, P, ptr(d_local), ptr(d_merged), ptr(stream)))
+
+    def destroy(self):
+        if self._h:
+            check(self._L.krag_p2p_destroy(self._h))
+            self._h = None
 
 
 class Embedder:

@@ -848,6 +848,81 @@ int32_t krag_debug_tc_dump(krag_index* ix, int32_t nq, const float* q, float* ou
     });
 }
 
+// ------------------------------------------------------------- peer-memory exchange (one process per GPU)
+struct krag_p2p {
+    krag_ctx* ctx; int rank, world, nl, max_batch, max_P; int64_t slot_words;
+    uint64_t* own = nullptr;                 // this rank's mailbox (cudaMalloc, IPC-exported)
+    std::vector<uint64_t*> peers;            // [world] device pointers: own + IPC-opened peers
+    uint64_t** d_peers = nullptr;            // device copy of the pointer table
+    unsigned long long seq = 0;
+};
+
+int32_t krag_p2p_create(krag_ctx* c, int32_t rank, int32_t world, int32_t max_batch, int32_t max_P, krag_p2p** out, uint8_t* handle_out /*[64]*/)
+{
+    return guarded([&] {
+        KRAG_REQUIRE(c && out && handle_out && world >= 1 && world <= 64 && rank >= 0 && rank < world, KRAG_E_INVALID, "bad argument");
+        KRAG_CUDA(cudaSetDevice(c->di.device));
+        krag_p2p* p = new krag_p2p();
+        p->ctx = c; p->rank = rank; p->world = world; p->nl = 2; p->max_batch = max_batch; p->max_P = max_P;
+        p->slot_words = (int64_t)2 * max_batch * max_P;
+        const size_t words = p2p_mailbox_words(world, 2, max_batch, max_P);
+        KRAG_CUDA(cudaMalloc(&p->own, words * 8));
+        KRAG_CUDA(cudaMemset(p->own, 0, words * 8));
+        cudaIpcMemHandle_t h;
+        KRAG_CUDA(cudaIpcGetMemHandle(&h, p->own));
+        static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        memcpy(handle_out, &h, 64);
+        p->peers.assign((size_t)world, nullptr);
+        p->peers[(size_t)rank] = p->own;
+        *out = p;
+    });
+}
+
+int32_t krag_p2p_connect(krag_p2p* p, const uint8_t* handles /*[world][64]*/)
+{
+    return guarded([&] {
+        KRAG_REQUIRE(p && handles, KRAG_E_INVALID, "null argument");
+        KRAG_CUDA(cudaSetDevice(p->ctx->di.device));
+        for (int r = 0; r < p->world; ++r) {
+            if (r == p->rank) continue;
+            cudaIpcMemHandle_t h;
+            memcpy(&h, handles + (size_t)r * 64, 64);
+            void* ptr = nullptr;
+            KRAG_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+            p->peers[(size_t)r] = (uint64_t*)ptr;
+        }
+        KRAG_CUDA(cudaMalloc(&p->d_peers, sizeof(uint64_t*) * (size_t)p->world));
+        KRAG_CUDA(cudaMemcpy(p->d_peers, p->peers.data(), sizeof(uint64_t*) * (size_t)p->world, cudaMemcpyHostToDevice));
+    });
+}
+
+int32_t krag_dev_exchange_merge(krag_p2p* p, int32_t n_lists, int32_t batch, int32_t P, const uint64_t* d_local, uint64_t* d_merged, void* stream)
+{
+    return guarded([&] {
+        KRAG_REQUIRE(p && p->d_peers && d_local && d_merged, KRAG_E_INVALID, "bad argument / not connected");
+        KRAG_REQUIRE(n_lists >= 1 && n_lists <= 2 && batch >= 1 && (int64_t)n_lists * batch * P <= p->slot_words, KRAG_E_INVALID,
+                     "exchange exceeds the mailbox the ranks agreed on");
+        check_P(P);
+        KRAG_CUDA(cudaSetDevice(p->ctx->di.device));
+        ++p->seq;
+        launch_p2p_exchange_merge(p->d_peers, p->own, p->rank, p->world, p->slot_words, p->seq, n_lists, batch, P, d_local, d_merged,
+                                  (cudaStream_t)stream);
+    });
+}
+
+int32_t krag_p2p_destroy(krag_p2p* p)
+{
+    return guarded([&] {
+        KRAG_REQUIRE(p, KRAG_E_INVALID, "null argument");
+        cudaSetDevice(p->ctx->di.device);
+        cudaDeviceSynchronize();
+        for (int r = 0; r < p->world; ++r) if (r != p->rank && p->peers[(size_t)r]) cudaIpcCloseMemHandle(p->peers[(size_t)r]);
+        if (p->d_peers) cudaFree(p->d_peers);
+        if (p->own) cudaFree(p->own);
+        delete p;
+    });
+}
+
 // ---------------------------------------------------------------------- K5 embedder
 struct krag_embedder { krag_ctx* ctx; Embedder* e; };
 

@@ -53,6 +53,11 @@ bool dense_tc_debug_dump(const DeviceInfo& di, const float* X, int64_t n_rows, i
 // per query: n_lists lists of list_len keys (element (l,i) at in[b*batch_stride + l*list_stride + i]) -> the P smallest
 void launch_merge(const uint64_t* keys_in, int n_lists, int list_len, int batch, int P, int64_t list_stride,
                   int64_t batch_stride, uint64_t* keys_out, cudaStream_t st, const uint64_t* thr_hint = nullptr);
+// peer-memory exchange: push local lists [nl, batch, P] into every rank's mailbox, then merge G*P -> P locally
+size_t p2p_mailbox_words(int world, int nl, int max_batch, int max_P);
+void launch_p2p_exchange_merge(uint64_t* const* d_mailboxes, uint64_t* own_mailbox, int rank, int world, int64_t slot_words,
+                               unsigned long long seq, int nl, int batch, int P, const uint64_t* local, uint64_t* merged,
+                               cudaStream_t st);
 // append zero-score fillers to short BM25 lists (bm25s argpartition semantics)
 void launch_bm25_fill(uint64_t* keys /*[batch,P]*/, int batch, int P, const uint32_t* alive, int64_t n_rows,
                       uint32_t ord_base, cudaStream_t st);

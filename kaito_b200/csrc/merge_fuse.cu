@@ -2,6 +2,7 @@
 // weighted fusion (HybridRetriever._fuse, presets/ragengine/vector_store/retriever/
 // hybrid_retriever.py:132-166).  Tiny, latency-bound kernels: one CTA per query.
 #include <math_constants.h>
+#include <stdio.h>
 
 #include "engine.h"
 #include "select.cuh"
@@ -51,6 +52,92 @@ void launch_merge(const uint64_t* keys_in, int n_lists, int list_len, int batch,
                   int64_t batch_stride, uint64_t* keys_out, cudaStream_t st, const uint64_t* thr_hint)
 {
     merge_kernel<<<batch, MG_THREADS, 0, st>>>(keys_in, n_lists, list_len, P, list_stride, batch_stride, keys_out, thr_hint);
+    KRAG_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+// ------------------------------------------------------ peer-memory exchange (multi-GPU, one process per GPU)
+// Replaces "NCCL all-gather, then merge" by two kernels of our own over NVLink peer memory:
+//   p2p_push_kernel : block r copies this rank's candidate lists straight into rank r's mailbox (P2P stores through
+//                     the IPC-mapped pointer), then publishes a sequence number with a system-scope release;
+//   p2p_merge_kernel: spins (system-scope acquire) until every rank's sequence number has arrived in the LOCAL
+//                     mailbox, then merges G*P -> P per (list, query) out of local memory.
+// Mailbox layout (u64 words): flags[world] padded to 32 words, then data[2 slots][world][nl*B*P].  Two slots
+// alternate with the sequence parity: a rank can run at most one exchange ahead of its slowest peer.
+constexpr int P2P_HDR = 32;
+__global__ void __launch_bounds__(1024)
+p2p_push_kernel(const uint64_t* __restrict__ local, int64_t n_words, uint64_t* const* __restrict__ mailboxes, int my_rank,
+                int world, int64_t slot_words, unsigned long long seq)
+{
+    uint64_t* mb = mailboxes[blockIdx.x];                                   // destination rank = blockIdx.x (peer or self)
+    uint64_t* dst = mb + P2P_HDR + ((seq & 1ull) * world + my_rank) * slot_words;
+    const uint4* s4 = reinterpret_cast<const uint4*>(local);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (int64_t i = threadIdx.x; i < n_words / 2; i += blockDim.x) d4[i] = s4[i];
+    if ((n_words & 1) && threadIdx.x == 0) dst[n_words - 1] = local[n_words - 1];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(mb + my_rank), "l"(seq) : "memory");
+    }
+}
+
+__global__ void __launch_bounds__(MG_THREADS)
+p2p_merge_kernel(uint64_t* __restrict__ mailbox, int world, int64_t slot_words, unsigned long long seq, int nl, int batch, int P,
+                 uint64_t* __restrict__ out /*[nl][batch][P]*/)
+{
+    __shared__ uint64_t s_buf[MG_CAP];
+    __shared__ int s_count;
+    __shared__ uint64_t s_thr;
+    const int tid = threadIdx.x;
+    const int l = blockIdx.y, q = blockIdx.x;
+    if (tid < world) {                                                       // wait for every rank's lists of this exchange
+        const long long t0 = clock64();
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mailbox + tid) : "memory");
+            if (v < seq && clock64() - t0 > 20000000000ll) { printf("p2p_merge: rank %d never arrived (seq %llu)\n", tid, seq); __trap(); }
+        } while (v < seq);
+    }
+    SelectBuf sel{s_buf, &s_count, &s_thr, MG_CAP};
+    select_init(sel, tid);
+    __syncthreads();
+    const uint64_t* data = mailbox + P2P_HDR + (seq & 1ull) * world * slot_words;
+    const int64_t total = (int64_t)world * P;
+    const int epoch = (MG_CAP - P) / MG_THREADS;
+    uint64_t thr = KEY_PAD;
+    int it = 0;
+    for (int64_t i0 = 0; i0 < total; i0 += MG_THREADS, ++it) {
+        const int64_t i = i0 + tid;
+        if (i < total) {
+            const int r = (int)(i / P), j = (int)(i - (int64_t)r * P);
+            const uint64_t key = data[(int64_t)r * slot_words + ((int64_t)l * batch + q) * P + j];
+            if (key != KEY_PAD) select_push(sel, key, thr);
+        }
+        if ((it + 1) % epoch == 0) {
+            __syncthreads();
+            if (s_count + epoch * MG_THREADS > MG_CAP) select_prune<MG_THREADS>(sel, P, tid, 0);
+            thr = s_thr;
+        }
+    }
+    select_prune<MG_THREADS>(sel, P, tid, 0);
+    select_store<MG_THREADS>(sel, P, out + ((int64_t)l * batch + q) * P, tid);
+}
+
+size_t p2p_mailbox_words(int world, int nl, int max_batch, int max_P)
+{
+    return (size_t)P2P_HDR + (size_t)2 * world * ((size_t)nl * max_batch * max_P);
+}
+
+void launch_p2p_exchange_merge(uint64_t* const* d_mailboxes, uint64_t* own_mailbox, int rank, int world, int64_t slot_words,
+                               unsigned long long seq, int nl, int batch, int P, const uint64_t* local, uint64_t* merged,
+                               cudaStream_t st)
+{
+    const int64_t n_words = (int64_t)nl * batch * P;
+    p2p_push_kernel<<<world, 1024, 0, st>>>(local, n_words, d_mailboxes, rank, world, slot_words, seq);
+    KRAG_CUDA(cudaGetLastError());
+    count_launch();
+    p2p_merge_kernel<<<dim3((unsigned)batch, (unsigned)nl), MG_THREADS, 0, st>>>(own_mailbox, world, slot_words, seq, nl, batch, P, merged);
     KRAG_CUDA(cudaGetLastError());
     count_launch();
 }

@@ -15,6 +15,8 @@ with gloo by the tests; the product always uses `NativeStages` (libkaito_rag, no
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -52,6 +54,24 @@ class NativeStages:
     def merge(self, gathered: torch.Tensor, n_lists: int, batch: int, P: int, out: torch.Tensor):
         self.ctx.dev_merge(n_lists, batch, P, gathered.data_ptr(), out.data_ptr(), self.stream())
 
+    # peer-memory exchange (our kernels over NVLink instead of NCCL all-gather + merge); ShardedRetriever sets it up
+    P2P_MAX_BATCH, P2P_MAX_P = 1024, 256      # mailbox slot = 2 lists x 1024 x 256 keys (4 MiB per rank and parity)
+
+    def p2p_setup(self, rank: int, world: int, group):
+        from . import _native
+        p = _native.P2PExchange(self.ctx, rank, world, self.P2P_MAX_BATCH, self.P2P_MAX_P)
+        handles = [None] * world
+        dist.all_gather_object(handles, p.handle.tobytes(), group=group)
+        p.connect(np.frombuffer(b"".join(handles), np.uint8).copy())   # the caller's all-reduce is the barrier
+        self._p2p = p
+
+    def p2p_fits(self, nl: int, B: int, P: int) -> bool:
+        return nl * B * P <= 2 * self.P2P_MAX_BATCH * self.P2P_MAX_P and P <= 1024
+
+    def exchange_merge(self, local: torch.Tensor, merged: torch.Tensor):
+        nl, B, P = local.shape
+        self._p2p.exchange_merge(nl, B, P, local.data_ptr(), merged.data_ptr(), self.stream())
+
     def fuse(self, batch, P, k, dense_keys, bm25_keys, vw, tw, mode, out):
         self.ctx.dev_fuse(batch, P, k, dense_keys.data_ptr(), None if bm25_keys is None else bm25_keys.data_ptr(), vw, tw,
                           mode, None, out["final"].data_ptr(), out["dense"].data_ptr(), out["sparse"].data_ptr(),
@@ -67,6 +87,7 @@ class ShardedRetriever:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.hybrid = False
         self._buf = {}
+        self._p2p_state = None
 
     # ------------------------------------------------------------------ index time
     def commit(self, vocab: int, n_local_rows: int):
@@ -88,6 +109,25 @@ class ShardedRetriever:
         return n_docs, total, base
 
     # ------------------------------------------------------------------ query time
+    def _use_p2p(self, nl: int, B: int, P: int) -> bool:
+        """Peer-memory exchange when the stages provide it (NativeStages on a multi-GPU box); KRAG_P2P=0 keeps NCCL.
+        Every rank takes the same decision: it depends only on (stages type, env, shapes) and setup is collective."""
+        if self._p2p_state is None:
+            ok = hasattr(self.stages, "p2p_setup") and self.device.type == "cuda" and os.environ.get("KRAG_P2P", "1") != "0"
+            if ok:
+                err = None
+                try:
+                    self.stages.p2p_setup(self.rank, self.world, self.group)
+                except Exception as e:  # no peer access on this box: keep the NCCL path, loudly
+                    err = e
+                flag = torch.tensor([0 if err is None else 1], dtype=torch.int32, device=self.device)
+                dist.all_reduce(flag, group=self.group)
+                if int(flag.item()):
+                    print(f"[kaito_b200] rank {self.rank}: peer-memory exchange unavailable ({err}); using NCCL all-gather", flush=True)
+                    ok = False
+            self._p2p_state = ok
+        return self._p2p_state and self.stages.p2p_fits(nl, B, P)
+
     def _tensor(self, name, shape, dtype):
         t = self._buf.get(name)
         if t is None or t.shape != torch.Size(shape) or t.dtype != dtype:
@@ -108,7 +148,10 @@ class ShardedRetriever:
         self.stages.dense_candidates(q, P, local[0])
         if hybrid:
             self.stages.bm25_candidates(terms, toff, B, P, local[1], toff_host)
-        if self.world > 1:
+        if self.world > 1 and self._use_p2p(nl, B, P):
+            merged = self._tensor("merged", (nl, B, P), torch.int64)
+            self.stages.exchange_merge(local, merged)          # P2P stores + flag-waiting merge (our kernels over NVLink)
+        elif self.world > 1:
             flat = self._tensor("gathered", (self.world * nl, B, P), torch.int64)
             dist.all_gather_into_tensor(flat, local, group=self.group)   # concatenation along dim 0
             gathered = flat.view(self.world, nl, B, P)

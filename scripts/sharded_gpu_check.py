@@ -41,8 +41,42 @@ for b in range(B):
     assert np.array_equal(got["ordinal"][b, :c], od), (rank, b, got["ordinal"][b, :c], od)
     assert np.array_equal(got["final"][b, :c], fin)
     assert np.array_equal(got2["ordinal"][b], do[0, :k])
+# the peer-memory exchange (default) and the NCCL all-gather path must agree, over repeated exchanges (mailbox parity
+# slots) and changing batch sizes
+sn = ShardedRetriever(NativeStages(ctx, ix), dev, ix.stats().dim_padded)
+sn.hybrid, sn._p2p_state = True, False
+assert world == 1 or sr._p2p_state is True, "peer-memory exchange did not come up"
+for it in range(6):
+    b = [B, 1, 5, B, 3, 7][it]
+    a1 = sr.retrieve(q[:b], qs[:b] if it % 2 == 0 else None, k)
+    a2 = sn.retrieve(q[:b], qs[:b] if it % 2 == 0 else None, k)
+    for key in ("ordinal", "final", "count"):
+        assert np.array_equal(a1[key], a2[key]), (rank, it, key)
+# exchange cost: retrieve_dev with both paths, batch 1 and 256 (device time, max over ranks)
+import time
+def timed(r, b, hybrid, iters=30):
+    qd = torch.from_numpy(np.pad(o.synth_queries(x, b, 9), ((0, 0), (0, r.dpad - d)))).to(dev)
+    tq = o.synth_query_terms(vocab, b, 10, rank_offset=30)
+    flat = np.concatenate(tq).astype(np.int32); toff_h = np.zeros(b + 1, np.int32); toff_h[1:] = np.cumsum([len(t) for t in tq])
+    terms, toff = torch.from_numpy(flat).to(dev), torch.from_numpy(toff_h).to(dev)
+    for _ in range(5):
+        r.retrieve_dev(qd, terms if hybrid else None, toff if hybrid else None, k, toff_host=toff_h)
+    torch.cuda.synchronize(); dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        r.retrieve_dev(qd, terms if hybrid else None, toff if hybrid else None, k, toff_host=toff_h)
+    e1.record(); torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / iters], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+if world > 1:
+    for b in (1, 256):
+        tp, tn = timed(sr, b, True), timed(sn, b, True)
+        if rank == 0:
+            print(f"exchange batch {b}: peer-memory {tp*1e3:.1f} us/step, NCCL all-gather + merges {tn*1e3:.1f} us/step")
 dist.barrier()
 if rank == 0:
-    print(f"sharded gpu check ok: world={world}, ids/finals bit-exact vs single-shard oracle")
+    print(f"sharded gpu check ok: world={world}, ids/finals bit-exact vs single-shard oracle; p2p == nccl path")
 ix.drop(); ctx.close()
 dist.destroy_process_group()

@@ -255,3 +255,26 @@ def test_full_size_properties(ctx_scan, oracle):
         assert np.array_equal(o1[0], ordn[0]) and np.array_equal(d1[0], dist[0])
     finally:
         ix.drop()
+
+
+@pytest.mark.gpu
+def test_peer_exchange_single_rank_roundtrip(ctx_scan):
+    """krag_p2p with world = 1: push into the own mailbox + flag-waiting merge must return the sorted lists unchanged,
+    across repeated exchanges (parity slots) and changing shapes. The world > 1 case is covered on a 2-GPU box by
+    scripts/sharded_gpu_check.py (peer-memory path == NCCL path == single-shard oracle)."""
+    import torch
+    from kaito_b200 import _native
+    p = _native.P2PExchange(ctx_scan, 0, 1, 64, 64)
+    p.connect(p.handle.copy())
+    rng = np.random.default_rng(5)
+    for it, (nl, B, P) in enumerate([(2, 7, 30), (1, 64, 64), (2, 1, 3), (2, 64, 64), (1, 5, 17)]):
+        keys = np.sort(rng.integers(0, 2**62, size=(nl, B, P), dtype=np.uint64), axis=-1)
+        keys[0, 0, P - 1] = np.uint64(2**64 - 1)      # a padded (short) list stays padded
+        d_in = torch.from_numpy(keys.view(np.int64)).cuda()
+        d_out = torch.empty_like(d_in)
+        p.exchange_merge(nl, B, P, d_in.data_ptr(), d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out.cpu().numpy().view(np.uint64), keys), it
+    with pytest.raises(_native.KragError):
+        p.exchange_merge(2, 64, 65, d_in.data_ptr(), d_out.data_ptr(), 0)   # larger than the agreed mailbox
+    p.destroy()
