@@ -238,6 +238,11 @@ int32_t krag_embedder_destroy(krag_embedder* e);
  * N % 128 == 0, K % 32 == 0.  Test hook. */
 int32_t krag_debug_gemm_tf32(krag_ctx* ctx, int32_t M, int32_t N, int32_t K, const float* A, const float* B,
                              const float* bias, const float* residual, int32_t gelu, float* C_out);
+/* Y = LayerNorm(A . B^T + bias (+residual)) * gamma + beta through K5's linear-layer dispatcher (for a handful of rows:
+ * 128 x 32 split-K tiles + the reduce/LayerNorm kernel).  Test hook. */
+int32_t krag_debug_linear_ln(krag_ctx* ctx, int32_t M, int32_t N, int32_t K, const float* A, const float* B,
+                             const float* bias, const float* residual, const float* ln_gamma, const float* ln_beta,
+                             float eps, float* Y_out);
 /* queries whose tensor-core result failed the exactness certificate and were re-run on the
  * exact scan kernel (process-wide counter) */
 int64_t krag_tc_fallback_queries(void);

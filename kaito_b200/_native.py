@@ -32,7 +32,7 @@ SYMBOLS = [
     "krag_synth_fill", "krag_index_read_rows", "krag_index_read_postings", "krag_tc_fallback_queries",
     "krag_debug_tc_dump", "krag_last_dense_kernel", "krag_embedder_create", "krag_embedder_load_tensor",
     "krag_embedder_finalize", "krag_embed", "krag_embed_dev", "krag_embedder_destroy", "krag_debug_gemm_tf32",
-    "krag_p2p_create", "krag_p2p_connect", "krag_dev_exchange_merge", "krag_p2p_destroy",
+    "krag_debug_linear_ln", "krag_p2p_create", "krag_p2p_connect", "krag_dev_exchange_merge", "krag_p2p_destroy",
 ]
 
 
@@ -109,6 +109,7 @@ def load() -> C.CDLL:
     L.krag_embed_dev.argtypes = [vp, i32, vp, vp, vp, i32, vp]
     L.krag_embedder_destroy.argtypes = [vp]
     L.krag_debug_gemm_tf32.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, i32, vp]
+    L.krag_debug_linear_ln.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, C.c_float, vp]
     L.krag_p2p_create.argtypes = [vp, i32, i32, i32, i32, C.POINTER(vp), vp]
     L.krag_p2p_connect.argtypes = [vp, vp]
     L.krag_dev_exchange_merge.argtypes = [vp, i32, i32, i32, vp, vp, vp]
@@ -269,6 +270,18 @@ def debug_gemm_tf32(ctx: "Context", A, B, bias, residual=None, gelu=False) -> np
     out = np.empty((A.shape[0], B.shape[0]), np.float32)
     check(load().krag_debug_gemm_tf32(ctx._h, A.shape[0], B.shape[0], A.shape[1], ptr(A), ptr(B), ptr(bias), ptr(residual),
                                       1 if gelu else 0, ptr(out)))
+    return out
+
+
+def debug_linear_ln(ctx: "Context", A, B, bias, residual, gamma, beta, eps=1e-12) -> np.ndarray:
+    A = np.ascontiguousarray(A, np.float32); B = np.ascontiguousarray(B, np.float32)
+    bias = np.ascontiguousarray(bias, np.float32); gamma = np.ascontiguousarray(gamma, np.float32)
+    beta = np.ascontiguousarray(beta, np.float32)
+    if residual is not None:
+        residual = np.ascontiguousarray(residual, np.float32)
+    out = np.empty((A.shape[0], B.shape[0]), np.float32)
+    check(load().krag_debug_linear_ln(ctx._h, A.shape[0], B.shape[0], A.shape[1], ptr(A), ptr(B), ptr(bias), ptr(residual),
+                                      ptr(gamma), ptr(beta), eps, ptr(out)))
     return out
 
 

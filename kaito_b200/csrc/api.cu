@@ -980,22 +980,42 @@ int32_t krag_embedder_destroy(krag_embedder* h)
         delete h;
     });
 }
+static void debug_linear(krag_ctx* c, int32_t M, int32_t N, int32_t K, const float* A, const float* B, const float* bias,
+                         const float* residual, int32_t gelu, const float* ln_g, const float* ln_b, float eps, float* out)
+{
+    KRAG_REQUIRE(c && A && B && bias && out && M >= 1 && N % 128 == 0 && K % 32 == 0, KRAG_E_INVALID, "bad argument (N % 128, K % 32)");
+    KRAG_CUDA(cudaSetDevice(c->di.device));
+    float *dA, *dB, *db, *dr = nullptr, *dC, *dY = nullptr, *dg = nullptr, *dlb = nullptr, *ws;
+    const size_t ws_floats = (size_t)4 << 20;
+    KRAG_CUDA(cudaMalloc(&dA, 4 * (size_t)M * K)); KRAG_CUDA(cudaMalloc(&dB, 4 * (size_t)N * K)); KRAG_CUDA(cudaMalloc(&db, 4 * (size_t)N));
+    KRAG_CUDA(cudaMalloc(&dC, 4 * (size_t)M * N)); KRAG_CUDA(cudaMalloc(&ws, 4 * ws_floats));
+    KRAG_CUDA(cudaMemcpy(dA, A, 4 * (size_t)M * K, cudaMemcpyHostToDevice)); KRAG_CUDA(cudaMemcpy(dB, B, 4 * (size_t)N * K, cudaMemcpyHostToDevice));
+    KRAG_CUDA(cudaMemcpy(db, bias, 4 * (size_t)N, cudaMemcpyHostToDevice));
+    if (residual) { KRAG_CUDA(cudaMalloc(&dr, 4 * (size_t)M * N)); KRAG_CUDA(cudaMemcpy(dr, residual, 4 * (size_t)M * N, cudaMemcpyHostToDevice)); }
+    if (ln_g) {
+        KRAG_CUDA(cudaMalloc(&dg, 4 * (size_t)N)); KRAG_CUDA(cudaMalloc(&dlb, 4 * (size_t)N)); KRAG_CUDA(cudaMalloc(&dY, 4 * (size_t)M * N));
+        KRAG_CUDA(cudaMemcpy(dg, ln_g, 4 * (size_t)N, cudaMemcpyHostToDevice)); KRAG_CUDA(cudaMemcpy(dlb, ln_b, 4 * (size_t)N, cudaMemcpyHostToDevice));
+    }
+    launch_linear(c->di, dA, dB, M, N, K, db, dr, gelu != 0, dC, dg, dlb, eps, dY, ws, ws_floats, c->admin);
+    KRAG_CUDA(cudaStreamSynchronize(c->admin));
+    KRAG_CUDA(cudaMemcpy(out, ln_g ? dY : dC, 4 * (size_t)M * N, cudaMemcpyDeviceToHost));
+    cudaFree(dA); cudaFree(dB); cudaFree(db); cudaFree(dC); cudaFree(ws);
+    if (dr) cudaFree(dr);
+    if (dg) { cudaFree(dg); cudaFree(dlb); cudaFree(dY); }
+}
+
 int32_t krag_debug_gemm_tf32(krag_ctx* c, int32_t M, int32_t N, int32_t K, const float* A, const float* B, const float* bias,
                              const float* residual, int32_t gelu, float* C_out)
 {
+    return guarded([&] { debug_linear(c, M, N, K, A, B, bias, residual, gelu, nullptr, nullptr, 0.f, C_out); });
+}
+
+int32_t krag_debug_linear_ln(krag_ctx* c, int32_t M, int32_t N, int32_t K, const float* A, const float* B, const float* bias,
+                             const float* residual, const float* ln_gamma, const float* ln_beta, float eps, float* Y_out)
+{
     return guarded([&] {
-        KRAG_REQUIRE(c && A && B && bias && C_out && M >= 1 && N % 128 == 0 && K % 32 == 0, KRAG_E_INVALID, "bad argument (N % 128, K % 32)");
-        KRAG_CUDA(cudaSetDevice(c->di.device));
-        float *dA, *dB, *db, *dr = nullptr, *dC;
-        KRAG_CUDA(cudaMalloc(&dA, 4 * (size_t)M * K)); KRAG_CUDA(cudaMalloc(&dB, 4 * (size_t)N * K)); KRAG_CUDA(cudaMalloc(&db, 4 * (size_t)N));
-        KRAG_CUDA(cudaMalloc(&dC, 4 * (size_t)M * N));
-        KRAG_CUDA(cudaMemcpy(dA, A, 4 * (size_t)M * K, cudaMemcpyHostToDevice)); KRAG_CUDA(cudaMemcpy(dB, B, 4 * (size_t)N * K, cudaMemcpyHostToDevice));
-        KRAG_CUDA(cudaMemcpy(db, bias, 4 * (size_t)N, cudaMemcpyHostToDevice));
-        if (residual) { KRAG_CUDA(cudaMalloc(&dr, 4 * (size_t)M * N)); KRAG_CUDA(cudaMemcpy(dr, residual, 4 * (size_t)M * N, cudaMemcpyHostToDevice)); }
-        launch_gemm_tf32(c->di, dA, dB, M, N, K, db, dr, gelu != 0, dC, c->admin);
-        KRAG_CUDA(cudaStreamSynchronize(c->admin));
-        KRAG_CUDA(cudaMemcpy(C_out, dC, 4 * (size_t)M * N, cudaMemcpyDeviceToHost));
-        cudaFree(dA); cudaFree(dB); cudaFree(db); cudaFree(dC); if (dr) cudaFree(dr);
+        KRAG_REQUIRE(ln_gamma && ln_beta, KRAG_E_INVALID, "null LayerNorm parameters");
+        debug_linear(c, M, N, K, A, B, bias, residual, 0, ln_gamma, ln_beta, eps, Y_out);
     });
 }
 

@@ -379,6 +379,151 @@ gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
 }
 
+// ---------------------------------------------------------------- small-M GEMM: 128 x BN tiles, split-K
+// A handful of query tokens (batch-1 latency; the per-rank slice of a batch on 8 GPUs) gives the persistent kernels
+// above 6..24 tiles for 148 SMs, each CTA streaming up to 1.5 MB of weights through a serial K loop.  This kernel
+// cuts the output into 128 x BN tiles (BN = 32 or 64) AND the K range into `splits` slices, one CTA each, so that
+// ~148 CTAs pull the weight matrix concurrently; when M < 128 only round8(M) activation rows are staged (the other
+// MMA rows compute on stale shared memory and are never stored).  splits == 1: bias / GELU / residual epilogue
+// straight to C; splits > 1: raw fp32 partials to ws[split][M][N], summed in split order by splitk_reduce_kernel
+// (deterministic), which also applies bias / residual / LayerNorm.
+template <int BN> struct GskCfg {
+    static constexpr int B_BYTES = BN * GM_KB * 4;
+    static constexpr int STAGE_BYTES = GM_SLAB + B_BYTES;          // one k-block per stage: 20 KB / 24 KB
+    static constexpr int STAGES = 8;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GM_THREADS, 1)
+gemm_sk_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int kb_per_split,
+                    int a_rows, int b_evict_first, const float* __restrict__ bias, const float* __restrict__ residual, int act_gelu,
+                    float* __restrict__ C, float* __restrict__ ws)
+{
+    using Cfg = GskCfg<BN>;
+    extern __shared__ unsigned char gm_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gm_smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* tail = smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
+    uint64_t* empty_bar = full_bar + Cfg::STAGES;
+    uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * BN, m0 = blockIdx.y * GM_TILE, split = blockIdx.z;
+    const int kb0 = split * kb_per_split;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(tfull_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint32_t tx = (uint32_t)(a_rows * GM_KB * 4 + Cfg::B_BYTES);
+            for (int i = 0; i < kb_per_split; ++i) {
+                const int stage = i % Cfg::STAGES;
+                const uint32_t phase = (uint32_t)((i / Cfg::STAGES) & 1);
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                unsigned char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
+                mbar_expect_tx(&full_bar[stage], tx);
+                const int k0 = (kb0 + i) * GM_KB;
+                tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0, TMA_EVICT_LAST);
+                tma_load_2d(sa + GM_SLAB, &tmB, &full_bar[stage], k0, n0, b_evict_first ? TMA_EVICT_FIRST : TMA_EVICT_LAST);
+            }
+        }
+    } else if (warp == 1) {
+        constexpr uint32_t idesc = umma_idesc_tf32(GM_TILE, BN);
+        const uint64_t desc0 = umma_desc_sw128(smem_u32(smem));
+        const uint32_t lo0 = (uint32_t)desc0;
+        for (int i = 0; i < kb_per_split; ++i) {
+            const int stage = i % Cfg::STAGES;
+            const uint32_t phase = (uint32_t)((i / Cfg::STAGES) & 1);
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t a_lo = lo0 + (uint32_t)((stage * Cfg::STAGE_BYTES) >> 4);
+                const uint32_t b_lo = a_lo + (uint32_t)(GM_SLAB >> 4);
+#pragma unroll
+                for (int k = 0; k < GM_KB / 8; ++k) {
+                    const uint64_t ad = (desc0 & 0xFFFFFFFF00000000ull) | (uint64_t)(a_lo + 2 * k);
+                    const uint64_t bd = (desc0 & 0xFFFFFFFF00000000ull) | (uint64_t)(b_lo + 2 * k);
+                    umma_tf32(tmem_base, ad, bd, idesc, (uint32_t)((i | k) != 0));
+                }
+                umma_commit(&empty_bar[stage]);
+                if (i == kb_per_split - 1) umma_commit(tfull_bar);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int lg = warp & 3;
+        const int row = m0 + lg * 32 + lane;
+        mbar_wait(tfull_bar, 0);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16);
+        const bool direct = gridDim.z == 1;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_x32(taddr + c0, v);
+            tmem_wait_ld();
+            if (row < M) {
+                if (direct) {
+                    float* crow = C + (size_t)row * N + n0 + c0;
+                    const float* rrow = residual ? residual + (size_t)row * N + n0 + c0 : nullptr;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        float o[8];
+#pragma unroll
+                        for (int t = 0; t < 8; t += 4) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j + t));
+                            o[t + 0] = __uint_as_float(v[j + t + 0]) + b4.x; o[t + 1] = __uint_as_float(v[j + t + 1]) + b4.y;
+                            o[t + 2] = __uint_as_float(v[j + t + 2]) + b4.z; o[t + 3] = __uint_as_float(v[j + t + 3]) + b4.w;
+                        }
+                        if (act_gelu) {
+#pragma unroll
+                            for (int t = 0; t < 8; ++t) o[t] = gelu_erf(o[t]);
+                        }
+                        if (rrow) {
+                            float r[8];
+                            ld_global_v8(rrow + j, r);
+#pragma unroll
+                            for (int t = 0; t < 8; ++t) o[t] += r[t];
+                        }
+                        st_global_v8(crow + j, o);
+                    }
+                } else {
+                    float* wrow = ws + ((size_t)split * M + row) * N + n0 + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        float o[8];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) o[t] = __uint_as_float(v[j + t]);
+                        st_global_v8(wrow + j, o);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    }
+}
+
 // --------------------------------------------------------------------------- fp32 row kernels
 __device__ __forceinline__ float warp_sum(float v)
 {
@@ -432,6 +577,69 @@ embed_ln_kernel(const int32_t* __restrict__ tok, const int32_t* __restrict__ pos
 // ------------------------------------------------------------------------------- attention
 // packed variable-length sequences: qkv [n_tok, 3d] (Q | K | V, heads contiguous inside each), out [n_tok, d].
 // grid (ceil(max_len / 16), heads, batch); 8 warps, 2 query rows per warp; keys processed in chunks of 64.
+// split-K epilogue: out[row] = f(sum_s ws[s][row] + bias) (+GELU) (+residual), optionally followed by LayerNorm over
+// the row (N <= 1024).  One 256-thread block per row, one float4 column group per thread: the `splits` partial loads
+// of a thread are independent (all in flight at once) -- with a few rows this kernel is pure load latency.
+// `residual` and `out` may alias (a thread reads its residual elements before it writes them).
+constexpr int SK_MAX_SPLITS = 8;
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N, const float* __restrict__ bias, const float* residual,
+                     int act_gelu, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps, float* out)
+{
+    __shared__ float s_red[2][8];
+    const int row = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const size_t plane = (size_t)M * N;
+    const float* w0 = ws + (size_t)row * N;
+    auto element = [&](int c) {
+        float4 p[SK_MAX_SPLITS];
+#pragma unroll
+        for (int sp = 0; sp < SK_MAX_SPLITS; ++sp)
+            if (sp < splits) p[sp] = *reinterpret_cast<const float4*>(w0 + (size_t)sp * plane + c);
+        float4 s = p[0];
+#pragma unroll
+        for (int sp = 1; sp < SK_MAX_SPLITS; ++sp)
+            if (sp < splits) { s.x += p[sp].x; s.y += p[sp].y; s.z += p[sp].z; s.w += p[sp].w; }
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c));
+        s.x += b4.x; s.y += b4.y; s.z += b4.z; s.w += b4.w;
+        if (act_gelu) { s.x = gelu_erf(s.x); s.y = gelu_erf(s.y); s.z = gelu_erf(s.z); s.w = gelu_erf(s.w); }
+        if (residual) {
+            const float4 r = *reinterpret_cast<const float4*>(residual + (size_t)row * N + c);
+            s.x += r.x; s.y += r.y; s.z += r.z; s.w += r.w;
+        }
+        return s;
+    };
+    if (ln_g == nullptr) {
+        for (int c = tid * 4; c < N; c += 1024) *reinterpret_cast<float4*>(out + (size_t)row * N + c) = element(c);
+        return;
+    }
+    const int c = tid * 4;                         // N <= 1024: at most one column group per thread
+    const bool on = c < N;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (on) v = element(c);
+    float sum = warp_sum((v.x + v.y) + (v.z + v.w));
+    if (lane == 0) s_red[0][warp] = sum;
+    __syncthreads();
+    sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += s_red[0][w];
+    const float mean = sum / (float)N;
+    const float a = v.x - mean, b = v.y - mean, cc = v.z - mean, dd = v.w - mean;
+    float var = on ? (a * a + b * b) + (cc * cc + dd * dd) : 0.f;
+    var = warp_sum(var);
+    if (lane == 0) s_red[1][warp] = var;
+    __syncthreads();
+    var = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) var += s_red[1][w];
+    const float rstd = rsqrtf(var / (float)N + eps);
+    if (on) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(ln_g + c)), be = __ldg(reinterpret_cast<const float4*>(ln_b + c));
+        float4 o;
+        o.x = a * rstd * g.x + be.x; o.y = b * rstd * g.y + be.y; o.z = cc * rstd * g.z + be.z; o.w = dd * rstd * g.w + be.w;
+        *reinterpret_cast<float4*>(out + (size_t)row * N + c) = o;
+    }
+}
+
 constexpr int AT_ROWS = 16;
 constexpr int AT_CHUNK = 64;
 __global__ void __launch_bounds__(256)
@@ -835,6 +1043,60 @@ void launch_gemm_tf32(const DeviceInfo& di, const float* A, const float* B, int 
 }
 
 
+// small-M path: 128 x BN tiles x split-K slices, ~one CTA per SM (see gemm_sk_tf32_kernel)
+template <int BN>
+static void launch_gemm_sk(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int m_tiles, int splits, int kb_per_split, int a_rows,
+                           const float* bias, const float* residual, bool gelu, float* C, float* ws, cudaStream_t st)
+{
+    static bool attr = false;
+    if (!attr) { KRAG_CUDA(cudaFuncSetAttribute(gemm_sk_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GskCfg<BN>::SMEM)); attr = true; }
+    gemm_sk_tf32_kernel<BN><<<dim3((unsigned)(N / BN), (unsigned)m_tiles, (unsigned)splits), GM_THREADS, GskCfg<BN>::SMEM, st>>>(
+        tmA, tmB, M, N, kb_per_split, a_rows, m_tiles == 1 ? 1 : 0, bias, residual, gelu ? 1 : 0, C, ws);
+    KRAG_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+void launch_linear(const DeviceInfo& di, const float* A, const float* B, int M, int N, int K, const float* bias, const float* residual,
+                   bool gelu, float* C, const float* ln_g, const float* ln_b, float eps, float* Y, float* ws, size_t ws_floats,
+                   cudaStream_t st)
+{
+    static int use_sk = -1;
+    if (use_sk < 0) { const char* ev = getenv("KRAG_GEMM_SPLITK"); use_sk = (ev == nullptr || ev[0] != '0') ? 1 : 0; }
+    const int m_tiles = (M + GM_TILE - 1) / GM_TILE;
+    const int tiles128 = m_tiles * (N / GM_TILE);
+    if (use_sk && ws && tiles128 < di.sm_count / 2 && N % 64 == 0 && K % GM_KB == 0 && (!ln_g || N <= 1024)) {
+        const int BN = m_tiles == 1 ? 32 : 64;
+        const int ctas = m_tiles * (N / BN), kblocks = K / GM_KB;
+        int splits = 1;
+        if (ctas <= di.sm_count / 3) {              // 72 CTAs with the whole K range beat 144 + a reduce kernel
+            const int want = di.sm_count / ctas < SK_MAX_SPLITS ? di.sm_count / ctas : SK_MAX_SPLITS;
+            for (int s = want; s >= 2; --s)
+                if (kblocks % s == 0 && kblocks / s >= 4 && (size_t)s * M * N <= ws_floats) { splits = s; break; }
+        }
+        const int a_rows = m_tiles == 1 ? ((M + 7) / 8) * 8 : GM_TILE;
+        CUtensorMap tmA, tmB;
+        emb_map(&tmA, A, M, K, a_rows);
+        emb_map(&tmB, B, N, K, BN);
+        float* direct_out = C;
+        if (BN == 32) launch_gemm_sk<32>(tmA, tmB, M, N, m_tiles, splits, kblocks / splits, a_rows, bias, residual, gelu, direct_out, ws, st);
+        else launch_gemm_sk<64>(tmA, tmB, M, N, m_tiles, splits, kblocks / splits, a_rows, bias, residual, gelu, direct_out, ws, st);
+        if (splits > 1) {
+            splitk_reduce_kernel<<<M, 256, 0, st>>>(ws, splits, M, N, bias, residual, gelu ? 1 : 0, ln_g, ln_b, eps, ln_g ? Y : C);
+            KRAG_CUDA(cudaGetLastError());
+            count_launch();
+            return;
+        }
+    } else {
+        launch_gemm_tf32(di, A, B, M, N, K, bias, residual, gelu, C, st);
+    }
+    if (ln_g) {
+        layernorm_kernel<<<(M * 32 + 255) / 256, 256, 0, st>>>(C, Y, ln_g, ln_b, M, N, eps);
+        KRAG_CUDA(cudaGetLastError());
+        count_launch();
+    }
+}
+
+
 struct Embedder {
     DeviceInfo di;
     BertConfig cfg;
@@ -849,6 +1111,8 @@ struct Embedder {
     int cap_tok = 0, cap_batch = 0;
     int32_t *d_tok = nullptr, *d_pos = nullptr, *d_off = nullptr;
     float *x = nullptr, *x2 = nullptr, *qkv = nullptr, *ctx = nullptr, *ffn = nullptr, *out = nullptr;
+    float* ws = nullptr;                  // split-K partials (small token counts)
+    static constexpr size_t WS_FLOATS = (size_t)4 << 20;
 };
 
 static float* emb_get(Embedder* e, const std::string& name, int64_t n)
@@ -905,6 +1169,7 @@ void embedder_finalize(Embedder* e)
                               "output.dense.weight", "output.dense.bias", "output.LayerNorm.weight", "output.LayerNorm.bias"})
             emb_get(e, lname(l, s), 0);
     }
+    if (!e->ws) KRAG_CUDA(cudaMalloc(&e->ws, sizeof(float) * Embedder::WS_FLOATS));
     e->finalized = true;
 }
 
@@ -916,6 +1181,7 @@ void embedder_destroy(Embedder* e)
     for (float* p : e->bqkv) cudaFree(p);
     for (void* p : {(void*)e->d_tok, (void*)e->d_pos, (void*)e->d_off, (void*)e->x, (void*)e->x2, (void*)e->qkv, (void*)e->ctx, (void*)e->ffn, (void*)e->out})
         if (p) cudaFree(p);
+    if (e->ws) cudaFree(e->ws);
     if (e->st) cudaStreamDestroy(e->st);
     delete e;
 }
@@ -980,9 +1246,9 @@ void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int3
     }
     static int use_flash = -1;
     if (use_flash < 0) { const char* ev = getenv("KRAG_ATTN_FLASH"); use_flash = (ev == nullptr || ev[0] != '0') ? 1 : 0; }
-    const int ln_grid = (n_tok * 32 + 255) / 256;
     for (int l = 0; l < c.layers; ++l) {
-        launch_gemm_tf32(e->di, e->x, e->wqkv[(size_t)l], n_tok, 3 * d, d, e->bqkv[(size_t)l], nullptr, false, e->qkv, st);
+        launch_linear(e->di, e->x, e->wqkv[(size_t)l], n_tok, 3 * d, d, e->bqkv[(size_t)l], nullptr, false, e->qkv, nullptr, nullptr, 0.f,
+                      nullptr, e->ws, Embedder::WS_FLOATS, st);
         if (max_len <= 32)
             attention_tiled_kernel<32><<<dim3((unsigned)batch, (unsigned)c.heads), 128, ats_smem32, st>>>(e->qkv, e->d_off, e->ctx, d, c.heads);
         else if (max_len <= ATS_MAX)
@@ -995,18 +1261,15 @@ void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int3
                 e->qkv, e->d_off, e->ctx, d, c.heads, max_len);
         KRAG_CUDA(cudaGetLastError());
         count_launch();
-        launch_gemm_tf32(e->di, e->ctx, e->t[lname(l, "attention.output.dense.weight")], n_tok, d, d,
-                         e->t[lname(l, "attention.output.dense.bias")], e->x, false, e->x2, st);
-        layernorm_kernel<<<ln_grid, 256, 0, st>>>(e->x2, e->x, e->t[lname(l, "attention.output.LayerNorm.weight")],
-                                                  e->t[lname(l, "attention.output.LayerNorm.bias")], n_tok, d, c.eps);
-        count_launch();
-        launch_gemm_tf32(e->di, e->x, e->t[lname(l, "intermediate.dense.weight")], n_tok, c.inter, d,
-                         e->t[lname(l, "intermediate.dense.bias")], nullptr, true, e->ffn, st);
-        launch_gemm_tf32(e->di, e->ffn, e->t[lname(l, "output.dense.weight")], n_tok, d, c.inter, e->t[lname(l, "output.dense.bias")],
-                         e->x, false, e->x2, st);
-        layernorm_kernel<<<ln_grid, 256, 0, st>>>(e->x2, e->x, e->t[lname(l, "output.LayerNorm.weight")],
-                                                  e->t[lname(l, "output.LayerNorm.bias")], n_tok, d, c.eps);
-        count_launch();
+        // O projection (+bias +residual) -> LayerNorm; FFN1 (+bias, GELU); FFN2 (+bias +residual) -> LayerNorm
+        launch_linear(e->di, e->ctx, e->t[lname(l, "attention.output.dense.weight")], n_tok, d, d, e->t[lname(l, "attention.output.dense.bias")],
+                      e->x, false, e->x2, e->t[lname(l, "attention.output.LayerNorm.weight")], e->t[lname(l, "attention.output.LayerNorm.bias")],
+                      c.eps, e->x, e->ws, Embedder::WS_FLOATS, st);
+        launch_linear(e->di, e->x, e->t[lname(l, "intermediate.dense.weight")], n_tok, c.inter, d, e->t[lname(l, "intermediate.dense.bias")],
+                      nullptr, true, e->ffn, nullptr, nullptr, 0.f, nullptr, e->ws, Embedder::WS_FLOATS, st);
+        launch_linear(e->di, e->ffn, e->t[lname(l, "output.dense.weight")], n_tok, d, c.inter, e->t[lname(l, "output.dense.bias")], e->x, false,
+                      e->x2, e->t[lname(l, "output.LayerNorm.weight")], e->t[lname(l, "output.LayerNorm.bias")], c.eps, e->x, e->ws,
+                      Embedder::WS_FLOATS, st);
     }
     };   // run_layers
     static int use_graph = -1;

@@ -102,6 +102,11 @@ int embedder_hidden(const Embedder* e);
 void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int32_t* tok_offsets, float* out_host,
                       float* out_dev = nullptr, int ld_out = 0, cudaStream_t consumer = nullptr);
 // C[M,N] = A[M,K] . B[N,K]^T + bias (+gelu) (+residual), fp32 in/out, TF32 tensor cores; device pointers
+// Linear layer: C = A . B^T + bias (+GELU) (+residual); with ln_g the row LayerNorm of that goes to Y (C is scratch).
+// Picks CTA pairs / 128x128 tiles / 128xBN split-K tiles by problem size; ws = split-K workspace (may be null).
+void launch_linear(const DeviceInfo& di, const float* A, const float* B, int M, int N, int K, const float* bias, const float* residual,
+                   bool gelu, float* C, const float* ln_g, const float* ln_b, float eps, float* Y, float* ws, size_t ws_floats,
+                   cudaStream_t st);
 void launch_gemm_tf32(const DeviceInfo& di, const float* A, const float* B, int M, int N, int K, const float* bias,
                       const float* residual, bool gelu, float* C, cudaStream_t st);
 
