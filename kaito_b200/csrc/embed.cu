@@ -387,27 +387,31 @@ gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // MMA rows compute on stale shared memory and are never stored).  splits == 1: bias / GELU / residual epilogue
 // straight to C; splits > 1: raw fp32 partials to ws[split][M][N], summed in split order by splitk_reduce_kernel
 // (deterministic), which also applies bias / residual / LayerNorm.
+// Stages are packed: round8(M) activation rows (a_bytes) + BN weight rows per k-block, so that for a handful of
+// tokens the whole K slice of a CTA (16..24 k-blocks of ~6 KB) is in flight at once and two CTAs fit on an SM.  The
+// MMA still reads a 128-row A operand from each stage base; the bytes past a_bytes belong to later stages (or the
+// 16 KB slack after the last one) and only feed accumulator rows that are never stored.
+constexpr int GSK_MAX_STAGES = 32;
 template <int BN> struct GskCfg {
     static constexpr int B_BYTES = BN * GM_KB * 4;
-    static constexpr int STAGE_BYTES = GM_SLAB + B_BYTES;          // one k-block per stage: 20 KB / 24 KB
-    static constexpr int STAGES = 8;
-    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
 };
+static inline size_t gsk_smem_bytes(int n_stages, int stage_bytes) { return 2048 + (size_t)n_stages * stage_bytes + GM_SLAB; }
 
 template <int BN>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 gemm_sk_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int kb_per_split,
-                    int a_rows, int b_evict_first, const float* __restrict__ bias, const float* __restrict__ residual, int act_gelu,
-                    float* __restrict__ C, float* __restrict__ ws)
+                    int a_bytes, int n_stages, int b_evict_first, const float* __restrict__ bias, const float* __restrict__ residual,
+                    int act_gelu, float* __restrict__ C, float* __restrict__ ws)
 {
     using Cfg = GskCfg<BN>;
     extern __shared__ unsigned char gm_smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gm_smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* tail = smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);
-    uint64_t* empty_bar = full_bar + Cfg::STAGES;
-    uint64_t* tfull_bar = empty_bar + Cfg::STAGES;
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gm_smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(base);
+    uint64_t* empty_bar = full_bar + GSK_MAX_STAGES;
+    uint64_t* tfull_bar = empty_bar + GSK_MAX_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+    unsigned char* smem = base + 1024;
+    const int stage_bytes = a_bytes + Cfg::B_BYTES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BN, m0 = blockIdx.y * GM_TILE, split = blockIdx.z;
@@ -416,7 +420,7 @@ gemm_sk_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int s = 0; s < n_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(tfull_bar, 1);
         fence_barrier_init();
     }
@@ -424,37 +428,38 @@ gemm_sk_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    pdl_launch_dependents();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                        // everything above overlapped the previous kernel's tail
 
     if (warp == 0) {
         if (lane == 0) {
-            const uint32_t tx = (uint32_t)(a_rows * GM_KB * 4 + Cfg::B_BYTES);
+            const uint32_t tx = (uint32_t)stage_bytes;
+            int stage = 0; uint32_t phase = 0;
             for (int i = 0; i < kb_per_split; ++i) {
-                const int stage = i % Cfg::STAGES;
-                const uint32_t phase = (uint32_t)((i / Cfg::STAGES) & 1);
                 mbar_wait(&empty_bar[stage], phase ^ 1);
-                unsigned char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
+                unsigned char* sa = smem + (size_t)stage * stage_bytes;
                 mbar_expect_tx(&full_bar[stage], tx);
                 const int k0 = (kb0 + i) * GM_KB;
                 tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0, TMA_EVICT_LAST);
-                tma_load_2d(sa + GM_SLAB, &tmB, &full_bar[stage], k0, n0, b_evict_first ? TMA_EVICT_FIRST : TMA_EVICT_LAST);
+                tma_load_2d(sa + a_bytes, &tmB, &full_bar[stage], k0, n0, b_evict_first ? TMA_EVICT_FIRST : TMA_EVICT_LAST);
+                if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
         constexpr uint32_t idesc = umma_idesc_tf32(GM_TILE, BN);
         const uint64_t desc0 = umma_desc_sw128(smem_u32(smem));
         const uint32_t lo0 = (uint32_t)desc0;
+        int stage = 0; uint32_t phase = 0;
         for (int i = 0; i < kb_per_split; ++i) {
-            const int stage = i % Cfg::STAGES;
-            const uint32_t phase = (uint32_t)((i / Cfg::STAGES) & 1);
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t a_lo = lo0 + (uint32_t)((stage * Cfg::STAGE_BYTES) >> 4);
-                const uint32_t b_lo = a_lo + (uint32_t)(GM_SLAB >> 4);
+                const uint32_t a_lo = lo0 + (uint32_t)((stage * stage_bytes) >> 4);
+                const uint32_t b_lo = a_lo + (uint32_t)(a_bytes >> 4);
 #pragma unroll
                 for (int k = 0; k < GM_KB / 8; ++k) {
                     const uint64_t ad = (desc0 & 0xFFFFFFFF00000000ull) | (uint64_t)(a_lo + 2 * k);
@@ -465,6 +470,7 @@ gemm_sk_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 if (i == kb_per_split - 1) umma_commit(tfull_bar);
             }
             __syncwarp();
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
     } else {
         const int lg = warp & 3;
@@ -549,6 +555,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ g, const float* __restrict__ b,
                  int rows, int d, float eps)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (r >= rows) return;
     warp_layernorm_row(x + (size_t)r * d, y + (size_t)r * d, g, b, d, eps, lane);
@@ -561,6 +569,8 @@ embed_ln_kernel(const int32_t* __restrict__ tok, const int32_t* __restrict__ pos
                 const float* __restrict__ b, float* __restrict__ x, int n_tok, int d, int vocab, float eps)
 {
     extern __shared__ float e_sm[];   // [8][d]
+    pdl_launch_dependents();
+    pdl_wait();
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int t = blockIdx.x * 8 + w;
     if (t >= n_tok) return;
@@ -587,6 +597,8 @@ splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N, con
                      int act_gelu, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps, float* out)
 {
     __shared__ float s_red[2][8];
+    pdl_launch_dependents();
+    pdl_wait();
     const int row = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const size_t plane = (size_t)M * N;
     const float* w0 = ws + (size_t)row * N;
@@ -745,6 +757,8 @@ attention_tiled_kernel(const float* __restrict__ qkv, const int32_t* __restrict_
     float* s_kT = s_qT + 64 * LD;      // [dh][LD]   k transposed: s_kT[c][key]
     float* s_v = s_kT + 64 * LD;       // [S2][64]   v: s_v[key][c]
     float* s_pT = s_v + S2 * 64;       // [S2][LD]   probabilities transposed: s_pT[key][r]
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = blockIdx.x, h = blockIdx.y;
     const int t0 = seq_off[b], len = seq_off[b + 1] - t0;
     const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
@@ -952,6 +966,8 @@ __global__ void __launch_bounds__(256)
 cls_normalize_kernel(const float* __restrict__ x, const int32_t* __restrict__ seq_off, float* __restrict__ out, int batch, int d,
                      int ld_out)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (b >= batch) return;
     const float* row = x + (size_t)seq_off[b] * d;
@@ -962,6 +978,27 @@ cls_normalize_kernel(const float* __restrict__ x, const int32_t* __restrict__ se
 }
 
 // ------------------------------------------------------------------------------------ host
+static bool pdl_enabled()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("KRAG_PDL"); v = (e == nullptr || e[0] != '0') ? 1 : 0; }
+    return v == 1;
+}
+// launch with programmatic stream serialization (see pdl_wait in tc_ptx.cuh); only for kernels that call pdl_wait()
+template <typename... KArgs, typename... Args>
+static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    KRAG_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+    count_launch();
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1049,11 +1086,17 @@ static void launch_gemm_sk(const CUtensorMap& tmA, const CUtensorMap& tmB, int M
                            const float* bias, const float* residual, bool gelu, float* C, float* ws, cudaStream_t st)
 {
     static bool attr = false;
-    if (!attr) { KRAG_CUDA(cudaFuncSetAttribute(gemm_sk_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GskCfg<BN>::SMEM)); attr = true; }
-    gemm_sk_tf32_kernel<BN><<<dim3((unsigned)(N / BN), (unsigned)m_tiles, (unsigned)splits), GM_THREADS, GskCfg<BN>::SMEM, st>>>(
-        tmA, tmB, M, N, kb_per_split, a_rows, m_tiles == 1 ? 1 : 0, bias, residual, gelu ? 1 : 0, C, ws);
-    KRAG_CUDA(cudaGetLastError());
-    count_launch();
+    if (!attr) { KRAG_CUDA(cudaFuncSetAttribute(gemm_sk_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
+    const int a_bytes = a_rows * GM_KB * 4, stage_bytes = a_bytes + GskCfg<BN>::B_BYTES;
+    // a few activation rows: keep a CTA under half an SM's shared memory (two CTAs per SM, the next kernel's CTAs
+    // can become resident while this one drains); full 128-row tiles take the whole SM
+    const int budget = (a_rows <= 32 ? 96 : 196) * 1024;
+    int n_stages = budget / stage_bytes;
+    n_stages = n_stages > GSK_MAX_STAGES ? GSK_MAX_STAGES : n_stages;
+    n_stages = n_stages > kb_per_split ? kb_per_split : n_stages;
+    launch_pdl(gemm_sk_tf32_kernel<BN>, dim3((unsigned)(N / BN), (unsigned)m_tiles, (unsigned)splits), dim3(GM_THREADS),
+               gsk_smem_bytes(n_stages, stage_bytes), st, tmA, tmB, M, N, kb_per_split, a_bytes, n_stages, m_tiles == 1 ? 1 : 0, bias, residual,
+               gelu ? 1 : 0, C, ws);
 }
 
 void launch_linear(const DeviceInfo& di, const float* A, const float* B, int M, int N, int K, const float* bias, const float* residual,
@@ -1081,18 +1124,15 @@ void launch_linear(const DeviceInfo& di, const float* A, const float* B, int M, 
         if (BN == 32) launch_gemm_sk<32>(tmA, tmB, M, N, m_tiles, splits, kblocks / splits, a_rows, bias, residual, gelu, direct_out, ws, st);
         else launch_gemm_sk<64>(tmA, tmB, M, N, m_tiles, splits, kblocks / splits, a_rows, bias, residual, gelu, direct_out, ws, st);
         if (splits > 1) {
-            splitk_reduce_kernel<<<M, 256, 0, st>>>(ws, splits, M, N, bias, residual, gelu ? 1 : 0, ln_g, ln_b, eps, ln_g ? Y : C);
-            KRAG_CUDA(cudaGetLastError());
-            count_launch();
+            launch_pdl(splitk_reduce_kernel, dim3((unsigned)M), dim3(256), 0, st, ws, splits, M, N, bias, residual, gelu ? 1 : 0, ln_g, ln_b, eps,
+                       ln_g ? Y : C);
             return;
         }
     } else {
         launch_gemm_tf32(di, A, B, M, N, K, bias, residual, gelu, C, st);
     }
     if (ln_g) {
-        layernorm_kernel<<<(M * 32 + 255) / 256, 256, 0, st>>>(C, Y, ln_g, ln_b, M, N, eps);
-        KRAG_CUDA(cudaGetLastError());
-        count_launch();
+        launch_pdl(layernorm_kernel, dim3((unsigned)((M * 32 + 255) / 256)), dim3(256), 0, st, C, Y, ln_g, ln_b, M, N, eps);
     }
 }
 
@@ -1226,12 +1266,10 @@ void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int3
     // The forward is ~7 kernels per layer; for a handful of query tokens it is bound by launch gaps and kernel
     // prologues, so each (n_tok, batch, max_len) shape is captured into a CUDA graph the second time it is seen.
     auto run_layers = [&]() {
-    embed_ln_kernel<<<(n_tok + 7) / 8, 256, (size_t)8 * d * 4, st>>>(
-        e->d_tok, e->d_pos, e->t["embeddings.word_embeddings.weight"], e->t["embeddings.position_embeddings.weight"],
-        e->t["embeddings.token_type_embeddings.weight"], e->t["embeddings.LayerNorm.weight"], e->t["embeddings.LayerNorm.bias"], e->x,
-        n_tok, d, c.vocab, c.eps);
-    KRAG_CUDA(cudaGetLastError());
-    count_launch();
+    launch_pdl(embed_ln_kernel, dim3((unsigned)((n_tok + 7) / 8)), dim3(256), (size_t)8 * d * 4, st, e->d_tok, e->d_pos,
+               e->t["embeddings.word_embeddings.weight"], e->t["embeddings.position_embeddings.weight"],
+               e->t["embeddings.token_type_embeddings.weight"], e->t["embeddings.LayerNorm.weight"], e->t["embeddings.LayerNorm.bias"], e->x,
+               n_tok, d, c.vocab, c.eps);
     const int dh = d / c.heads;
     const size_t at_smem = sizeof(float) * ((size_t)AT_ROWS * dh + (size_t)dh * (AT_CHUNK + 1) + (size_t)AT_CHUNK * dh + (size_t)AT_ROWS * max_len);
     const size_t ats_smem32 = sizeof(float) * ((size_t)2 * 64 * (32 + 4) + (size_t)32 * 64 + (size_t)32 * (32 + 4));
@@ -1249,18 +1287,20 @@ void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int3
     for (int l = 0; l < c.layers; ++l) {
         launch_linear(e->di, e->x, e->wqkv[(size_t)l], n_tok, 3 * d, d, e->bqkv[(size_t)l], nullptr, false, e->qkv, nullptr, nullptr, 0.f,
                       nullptr, e->ws, Embedder::WS_FLOATS, st);
-        if (max_len <= 32)
-            attention_tiled_kernel<32><<<dim3((unsigned)batch, (unsigned)c.heads), 128, ats_smem32, st>>>(e->qkv, e->d_off, e->ctx, d, c.heads);
-        else if (max_len <= ATS_MAX)
-            attention_tiled_kernel<64><<<dim3((unsigned)batch, (unsigned)c.heads), 128, ats_smem64, st>>>(e->qkv, e->d_off, e->ctx, d, c.heads);
-        else if (use_flash)
-            attention_flash_kernel<<<dim3((unsigned)((max_len + 63) / 64), (unsigned)c.heads, (unsigned)batch), 128, ats_smem64, st>>>(
-                e->qkv, e->d_off, e->ctx, d, c.heads);
-        else
-            attention_kernel<<<dim3((unsigned)((max_len + AT_ROWS - 1) / AT_ROWS), (unsigned)c.heads, (unsigned)batch), 256, at_smem, st>>>(
-                e->qkv, e->d_off, e->ctx, d, c.heads, max_len);
-        KRAG_CUDA(cudaGetLastError());
-        count_launch();
+        if (max_len <= 32) {
+            launch_pdl(attention_tiled_kernel<32>, dim3((unsigned)batch, (unsigned)c.heads), dim3(128), ats_smem32, st, e->qkv, e->d_off, e->ctx, d, c.heads);
+        } else if (max_len <= ATS_MAX) {
+            launch_pdl(attention_tiled_kernel<64>, dim3((unsigned)batch, (unsigned)c.heads), dim3(128), ats_smem64, st, e->qkv, e->d_off, e->ctx, d, c.heads);
+        } else {
+            if (use_flash)
+                attention_flash_kernel<<<dim3((unsigned)((max_len + 63) / 64), (unsigned)c.heads, (unsigned)batch), 128, ats_smem64, st>>>(
+                    e->qkv, e->d_off, e->ctx, d, c.heads);
+            else
+                attention_kernel<<<dim3((unsigned)((max_len + AT_ROWS - 1) / AT_ROWS), (unsigned)c.heads, (unsigned)batch), 256, at_smem, st>>>(
+                    e->qkv, e->d_off, e->ctx, d, c.heads, max_len);
+            KRAG_CUDA(cudaGetLastError());
+            count_launch();
+        }
         // O projection (+bias +residual) -> LayerNorm; FFN1 (+bias, GELU); FFN2 (+bias +residual) -> LayerNorm
         launch_linear(e->di, e->ctx, e->t[lname(l, "attention.output.dense.weight")], n_tok, d, d, e->t[lname(l, "attention.output.dense.bias")],
                       e->x, false, e->x2, e->t[lname(l, "attention.output.LayerNorm.weight")], e->t[lname(l, "attention.output.LayerNorm.bias")],

@@ -154,4 +154,10 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar)   // arrives on `
 }
 
 
+
+// programmatic dependent launch: let the next kernel of the stream become resident and run its prologue while this
+// grid drains; every thread of a kernel launched that way calls pdl_wait() before it touches global memory written by
+// its predecessors (and before it may exit, so that completion stays transitive along the stream)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 }  // namespace krag
