@@ -76,8 +76,12 @@ def env_config() -> dict:
     }
 
 
-def create_app(store: vs.VectorStore, cfg: dict | None = None) -> FastAPI:
+def create_app(store: vs.VectorStore, cfg: dict | None = None, llm=None) -> FastAPI:
     cfg = cfg or env_config()
+    from . import chat as _chat
+    chat_cfg = {**_chat.chat_config(), **{k: v for k, v in cfg.items() if k in _chat.chat_config()}}
+    if llm is None and chat_cfg.get("llm_inference_url"):
+        llm = _chat.LLMClient(chat_cfg["llm_inference_url"], chat_cfg["llm_access_secret"], chat_cfg["llm_context_window"])
     app = FastAPI(title="KAITO RAGEngine service (B200-native)")
     reg = CollectorRegistry()
     lat = lambda n, d, labels=("status",): Histogram(n, d, labelnames=list(labels), registry=reg)  # noqa: E731
@@ -169,12 +173,12 @@ def create_app(store: vs.VectorStore, cfg: dict | None = None) -> FastAPI:
         return run("retrieve", go)
 
     @app.post("/v1/chat/completions")
-    async def chat_completions(request: dict):   # main.py:326-353
-        if not cfg.get("llm_inference_url"):
+    def chat_completions(request: dict):   # main.py:326-353; RAG or pass-through: kaito_b200/chat.py
+        if llm is None:
             M["chat"][1].labels("failure").inc()
             raise HTTPException(status_code=503, detail="LLM inference URL is not configured; chat completions are unavailable. "
                                                         "Use /retrieve for retrieval-only deployments.")
-        raise HTTPException(status_code=501, detail="chat completion proxying is not part of this build (SURVEY.md section 8 f3)")
+        return run("chat", lambda: store.chat_completion(request, llm, chat_cfg))
 
     @app.get("/indexes", response_model=list[str])
     def list_indexes():
@@ -227,20 +231,39 @@ def create_app(store: vs.VectorStore, cfg: dict | None = None) -> FastAPI:
     return app
 
 
+def resolve_model_dir(model_id: str) -> str | None:
+    """A local Hugging Face snapshot of `model_id` (config.json + vocab.txt + weights): the path itself, KRAG_MODEL_DIR,
+    or the hub cache layout the reference image pre-populates ($HF_HOME/hub/models--ORG--NAME/snapshots/<rev>)."""
+    import glob
+    cands = [os.getenv("KRAG_MODEL_DIR"), model_id]
+    hf_home = os.getenv("HF_HOME") or os.path.join(os.path.expanduser("~"), ".cache", "huggingface")
+    cands += sorted(glob.glob(os.path.join(hf_home, "hub", "models--" + model_id.replace("/", "--"), "snapshots", "*")), reverse=True)
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, "config.json")) and os.path.isfile(os.path.join(c, "vocab.txt")):
+            return c
+    return None
+
+
 def main():
     """entry point of the image's `python3 main.py` shim (preset_rag.go:186): port 5000, /health probes."""
     import uvicorn
     from . import _native
-    from .embedding import HashingEmbedding
+    from .embedding import GpuBertEmbedding, HashingEmbedding
     cfg = env_config()
     if cfg["vector_db_type"] not in ("faiss", "krag"):
         raise SystemExit(f"VECTOR_DB_TYPE={cfg['vector_db_type']} is not served by this image (faiss-compatible engine only)")
+    if cfg["embedding_source"] != "local":
+        raise SystemExit("remote embedding endpoints are not served by this image; use embedding.local (GPU BERT forward)")
     engine = _native.Context(device_id=cfg["device_id"])
-    # the GPU BERT forward (K5) is not built yet: the service refuses to pretend it has a language model
-    if os.getenv("KRAG_ALLOW_HASHING_EMBEDDING") != "1":
-        raise SystemExit("no embedding model available: K5 (bge forward) is not built; set KRAG_ALLOW_HASHING_EMBEDDING=1 "
-                         "to start with the deterministic hashing embedder (functional tests only)")
-    app = create_app(vs.VectorStore(HashingEmbedding(384), engine), cfg)
+    model_dir = resolve_model_dir(cfg["embedding_model"])
+    if model_dir:
+        embed = GpuBertEmbedding.from_pretrained(engine, model_dir)          # K5: bge forward on the GPU
+    elif os.getenv("KRAG_ALLOW_HASHING_EMBEDDING") == "1":
+        embed = HashingEmbedding(384)                                        # functional tests only, not a language model
+    else:
+        raise SystemExit(f"embedding model '{cfg['embedding_model']}' not found locally (no network in the pod): mount a "
+                         "Hugging Face snapshot and set KRAG_MODEL_DIR, or KRAG_ALLOW_HASHING_EMBEDDING=1 for functional tests")
+    app = create_app(vs.VectorStore(embed, engine), cfg)
     uvicorn.run(app, host="0.0.0.0", port=5000)
 
 

@@ -206,6 +206,21 @@ class VectorStore:
         except Exception as e:  # same envelope as base.py:972-978
             raise HTTPException(500, f"Retrieve failed: {e}")
 
+    # ------------------------------------------------- /v1/chat/completions
+    def dense_candidates(self, index_name: str, query: str, top_k: int) -> list[tuple[_Node, float]]:
+        """index.as_retriever(similarity_top_k=top_k) of the chat engine (base.py:376-391): exact dense kNN, faiss
+        scores = squared L2 distances, ascending."""
+        st = self.index_map[index_name]
+        q = np.asarray(self.embed_model.get_query_embedding(query), np.float32).reshape(1, -1)
+        k = max(1, min(top_k, sum(1 for n in st.nodes if n.alive)))
+        dist, ordn = st.index.search_dense(q, k)
+        return [(st.nodes[int(o)], float(d)) for d, o in zip(dist[0], ordn[0]) if o >= 0]
+
+    def chat_completion(self, request: dict, llm, cfg: dict | None = None) -> dict:
+        """base.py:180-477 -- see kaito_b200/chat.py"""
+        from . import chat
+        return chat.chat_completion(self, llm, request, cfg)
+
     # ------------------------------------------------------------------- CRUD
     def list_indexes(self) -> list[str]:
         return list(self.index_map.keys())

@@ -60,6 +60,9 @@ class OracleIndex:
             out["final"][b, :len(od)] = fin; out["ordinal"][b, :len(od)] = od; out["count"][b] = len(od)
         return out
 
+    def search_dense(self, q, k):
+        return self.o.dense_topk(self.x, np.asarray(q, np.float32).reshape(-1, self.dim), k, self._alive())
+
     def drop(self):
         pass
 
