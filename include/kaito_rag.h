@@ -45,6 +45,10 @@ extern "C" {
 
 #define KRAG_FUSION_REFERENCE 0  /* vec_score = L2^2 itself (hybrid_retriever.py:139-142,158-166) */
 #define KRAG_FUSION_SIMILARITY 1 /* vec_score = 1 - L2^2/2 (not the reference) */
+/* OR-ed into fusion_mode: apply krag_retrieve's allow bitmap INSIDE the dense and BM25 kernels (every one of the P
+ * candidates of both lists satisfies the filter) instead of the reference's post-filter of the keyword list only
+ * (hybrid_retriever.py:227-235; its dense side cannot filter at all).  Not the reference. */
+#define KRAG_FILTER_PUSHDOWN 0x100
 
 #define KRAG_DENSE_AUTO 0   /* exact fp32 scan for small batches, tensor-core path for large */
 #define KRAG_DENSE_SCAN 1   /* K1: exact fp32 CUDA-core scan */
@@ -157,6 +161,7 @@ int32_t krag_search_bm25(krag_index* idx, int32_t batch, const uint32_t* q_terms
  * Outputs are [batch, k]; out_count[batch] gives the valid prefix per query.
  *   out_final  fp64 fused score (dense-only fallback: the L2^2)
  *   out_dense  L2^2 or NaN;  out_sparse BM25 score or NaN;  out_rank BM25 rank or -1
+ * fusion_mode | KRAG_FILTER_PUSHDOWN: the bitmap restricts both candidate scans instead (also in the vector-only case).
  */
 int32_t krag_retrieve(krag_index* idx, int32_t batch, const float* q,
                       const uint32_t* q_terms, const int32_t* q_term_offsets,

@@ -189,9 +189,11 @@ const uint32_t* alive_ptr(const krag_index* ix) { return ix->has_dead ? ix->aliv
 void check_P(int P) { KRAG_REQUIRE(P >= 1 && P <= KRAG_MAX_POOL, KRAG_E_INVALID, "candidate pool must be in [1, 1024]"); }
 
 // dense candidates for device-resident padded queries
-void dense_candidates_dev(krag_index* ix, Slot* s, const float* d_q, int batch, int P, uint64_t* d_keys, cudaStream_t st)
+void dense_candidates_dev(krag_index* ix, Slot* s, const float* d_q, int batch, int P, uint64_t* d_keys, cudaStream_t st,
+                          const uint32_t* eligible = nullptr)
 {
     krag_ctx* c = ix->ctx;
+    const uint32_t* alive = eligible ? eligible : alive_ptr(ix);     // rows the scan may return (tombstones [& filter])
     if (ix->n_rows == 0) {
         KRAG_CUDA(cudaMemsetAsync(d_keys, 0xFF, sizeof(uint64_t) * (size_t)batch * P, st));
         return;
@@ -204,18 +206,18 @@ void dense_candidates_dev(krag_index* ix, Slot* s, const float* d_q, int batch, 
     if (use_tc && dense_tc_supported(c->di, ix->dpad)) {
         size_t ws = dense_tc_workspace_bytes(c->di, ix->n_rows, P);
         s->tc_ws.reserve((int64_t)ws, 0, st);
-        if (launch_dense_tc(c->di, ix->X.p, ix->n_rows, ix->dpad, alive_ptr(ix), ix->xnorm.p, ix->xn_max.p, d_q, batch, P,
+        if (launch_dense_tc(c->di, ix->X.p, ix->n_rows, ix->dpad, alive, ix->xnorm.p, ix->xn_max.p, d_q, batch, P,
                             (uint32_t)ix->ord_base, s->tc_ws.p, ws, s->part.p, d_keys, st,
                             mode == KRAG_DENSE_TC_BF16 ? ix->Xh.p : nullptr))
             return;
     }
     KRAG_REQUIRE(mode != KRAG_DENSE_TC || !dense_tc_wants(ix->n_rows, 16), KRAG_E_UNSUPPORTED, "tensor-core dense path unavailable for this index/device");
-    launch_dense_scan(c->di, ix->X.p, ix->n_rows, ix->dpad, alive_ptr(ix), d_q, batch, P, (uint32_t)ix->ord_base,
+    launch_dense_scan(c->di, ix->X.p, ix->n_rows, ix->dpad, alive, d_q, batch, P, (uint32_t)ix->ord_base,
                       s->part.p, d_keys, st);
 }
 
 void bm25_candidates_dev(krag_index* ix, Slot* s, const uint32_t* d_terms, const int32_t* d_toff, int n_terms_total, int batch,
-                         int P, uint64_t* d_keys, cudaStream_t st)
+                         int P, uint64_t* d_keys, cudaStream_t st, const uint32_t* eligible = nullptr)
 {
     KRAG_REQUIRE(ix->committed, KRAG_E_STATE, "index has no committed postings (call krag_index_commit)");
     if (n_terms_total < 0) {   // caller did not provide the host copy of the offsets: read the total back (4 bytes)
@@ -226,7 +228,7 @@ void bm25_candidates_dev(krag_index* ix, Slot* s, const uint32_t* d_terms, const
     }
     s->part.reserve((int64_t)bm25_part_elems(ix->committed_rows, batch, P), 0, st);
     s->bm25_res.reserve((int64_t)(n_terms_total > 0 ? n_terms_total : 1) * 16, 0, st);
-    launch_bm25(ix->ctx->di, ix->post, ix->committed_rows, alive_ptr(ix), d_terms, d_toff, n_terms_total, s->bm25_res.p, batch, P,
+    launch_bm25(ix->ctx->di, ix->post, ix->committed_rows, eligible ? eligible : alive_ptr(ix), d_terms, d_toff, n_terms_total, s->bm25_res.p, batch, P,
                 (uint32_t)ix->ord_base, s->part.p, d_keys, st);
 }
 
@@ -664,15 +666,25 @@ int32_t krag_retrieve(krag_index* ix, int32_t batch, const float* q, const uint3
         Slot* s = lease.s;
         cudaStream_t st = s->st;
         const bool hybrid = q_terms != nullptr && q_toff != nullptr && ix->committed;
+        const bool pushdown = (fusion_mode & KRAG_FILTER_PUSHDOWN) != 0 && keyword_allow_bitmap != nullptr;
+        fusion_mode &= 0xFF;
+        const uint32_t* eligible = nullptr;
+        if (pushdown) {   // eligible = allow & alive, consumed by K1/K2/K3 in place of the tombstone bitmap
+            const int64_t words = (ix->n_rows + 31) / 32;
+            s->allow.reserve(words > 0 ? words : 1, 0, st);
+            KRAG_CUDA(cudaMemcpyAsync(s->allow.p, keyword_allow_bitmap, sizeof(uint32_t) * (size_t)words, cudaMemcpyHostToDevice, st));
+            if (ix->has_dead && words > 0) launch_bitmap_and(s->allow.p, ix->alive_d.p, words, st);
+            eligible = s->allow.p;
+        }
         const float* dq = upload_queries(ix, s, q, batch);
         s->dense_keys.reserve((int64_t)batch * P, 0, st);
-        dense_candidates_dev(ix, s, dq, batch, P, s->dense_keys.p, st);
+        dense_candidates_dev(ix, s, dq, batch, P, s->dense_keys.p, st, eligible);
         const uint32_t* d_allow = nullptr;
         if (hybrid) {
             upload_terms(s, q_terms, q_toff, batch);
             s->bm25_keys.reserve((int64_t)batch * P, 0, st);
-            bm25_candidates_dev(ix, s, s->terms.p, s->toff.p, q_toff[batch], batch, P, s->bm25_keys.p, st);
-            if (keyword_allow_bitmap) {
+            bm25_candidates_dev(ix, s, s->terms.p, s->toff.p, q_toff[batch], batch, P, s->bm25_keys.p, st, eligible);
+            if (keyword_allow_bitmap && !pushdown) {
                 // bitmap is over local rows; fuse tests global ordinals -> shift by ord_base words is only
                 // valid when ord_base % 32 == 0; the host path is single-shard (ord_base == 0)
                 KRAG_REQUIRE(ix->ord_base == 0, KRAG_E_UNSUPPORTED, "keyword filter on host path requires ordinal_base 0");

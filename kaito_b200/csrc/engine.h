@@ -58,6 +58,7 @@ size_t p2p_mailbox_words(int world, int nl, int max_batch, int max_P);
 void launch_p2p_exchange_merge(uint64_t* const* d_mailboxes, uint64_t* own_mailbox, int rank, int world, int64_t slot_words,
                                unsigned long long seq, int nl, int batch, int P, const uint64_t* local, uint64_t* merged,
                                cudaStream_t st);
+void launch_bitmap_and(uint32_t* dst, const uint32_t* other, int64_t words, cudaStream_t st);
 // append zero-score fillers to short BM25 lists (bm25s argpartition semantics)
 void launch_bm25_fill(uint64_t* keys /*[batch,P]*/, int batch, int P, const uint32_t* alive, int64_t n_rows,
                       uint32_t ord_base, cudaStream_t st);

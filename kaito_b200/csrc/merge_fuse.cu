@@ -142,6 +142,19 @@ void launch_p2p_exchange_merge(uint64_t* const* d_mailboxes, uint64_t* own_mailb
     count_launch();
 }
 
+// ------------------------------------------------------------------- filter pushdown: eligible = allow & alive
+__global__ void __launch_bounds__(256) bitmap_and_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ other, int64_t words)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < words) dst[i] &= other[i];
+}
+void launch_bitmap_and(uint32_t* dst, const uint32_t* other, int64_t words, cudaStream_t st)
+{
+    bitmap_and_kernel<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(dst, other, words);
+    KRAG_CUDA(cudaGetLastError());
+    count_launch();
+}
+
 // ------------------------------------------------------------------- BM25 zero fill
 // bm25s ranks all N documents (argpartition over the full score vector), so a query that
 // matches fewer than P documents still returns P entries: the rest score 0.  With the

@@ -22,6 +22,7 @@ import numpy as np
 
 from . import text as _text
 
+FILTER_PUSHDOWN = 0x100   # kaito_rag.h KRAG_FILTER_PUSHDOWN
 RAG_MAX_TOP_K = int(os.getenv("RAG_MAX_TOP_K", 300))  # config.py:127
 
 
@@ -90,7 +91,8 @@ class HybridRetriever:
     """hybrid_retriever.py:60-237: pool size, weights, keyword post-filter, fuse -- on the GPU."""
 
     def __init__(self, state: _IndexState, embed_model, max_results: int = 10, candidate_multiplier: float = 3.0,
-                 vector_weight: float = 0.7, text_weight: float = 0.3, metadata_filter: dict | None = None):
+                 vector_weight: float = 0.7, text_weight: float = 0.3, metadata_filter: dict | None = None,
+                 filter_pushdown: bool = False):
         total = vector_weight + text_weight
         self._vector_weight = vector_weight / total
         self._text_weight = text_weight / total
@@ -99,6 +101,9 @@ class HybridRetriever:
         self._candidate_multiplier = max(1.0, candidate_multiplier)
         self._candidate_pool_size = int(max_results * self._candidate_multiplier)
         self._metadata_filter = metadata_filter
+        # False (reference): only the keyword list is post-filtered (:227-235).  True: the bitmap restricts the dense and
+        # the BM25 scan on the GPU, so every result satisfies the filter (not the reference).
+        self._filter_pushdown = filter_pushdown
 
     def _allow_bitmap(self):
         if not self._metadata_filter:
@@ -115,9 +120,11 @@ class HybridRetriever:
         q = np.asarray(self._embed.get_query_embedding(query), np.float32).reshape(1, -1)
         # BM25 unavailable (empty docstore / nothing committed) -> vector-only fallback (:113-121, :216-218)
         terms = [st.vocab.query_terms(query)] if st.committed else None
+        allow = self._allow_bitmap() if (terms is not None or self._filter_pushdown) else None
         out = st.index.retrieve(q, terms, self._max_results, cand_mult=self._candidate_multiplier,
                                 vector_weight=self._vector_weight, text_weight=self._text_weight,
-                                keyword_allow_bitmap=self._allow_bitmap() if terms is not None else None)
+                                fusion_mode=FILTER_PUSHDOWN if (self._filter_pushdown and allow is not None) else 0,
+                                keyword_allow_bitmap=allow)
         c = int(out["count"][0])
         return [(st.nodes[int(o)], float(s)) for o, s in zip(out["ordinal"][0, :c], out["final"][0, :c])]
 
@@ -131,6 +138,7 @@ class VectorStore:
         self.dimension = embed_model.get_embedding_dimension()   # faiss_store.py:28
         self.index_map: dict[str, _IndexState] = {}
         self.splitter = SentenceSplitter()
+        self.filter_pushdown = os.getenv("KRAG_FILTER_PUSHDOWN", "0") == "1"
         # many readers / one writer (aiorwlock in the reference, base.py:77-79); the engine enforces the same
         # discipline per index internally, this lock protects the host-side docstore
         self._lock = threading.RLock()
@@ -194,7 +202,8 @@ class VectorStore:
                 raise HTTPException(400, "Query string cannot be empty.")
             top_k = min(max_node_count, RAG_MAX_TOP_K)
             st = self.index_map[index_name]
-            retriever = HybridRetriever(st, self.embed_model, max_results=top_k, metadata_filter=metadata_filter)
+            retriever = HybridRetriever(st, self.embed_model, max_results=top_k, metadata_filter=metadata_filter,
+                                        filter_pushdown=self.filter_pushdown)
             t0 = time.time()
             nodes = retriever.retrieve(query)
             self.last_retrieve_seconds = time.time() - t0

@@ -46,13 +46,19 @@ class OracleIndex:
         P = o.pool_size(k, cand_mult)
         B = len(q)
         out = {"final": np.zeros((B, k)), "ordinal": np.full((B, k), -1, np.int64), "count": np.zeros(B, np.int32)}
+        alive = self._alive()
+        if fusion_mode & 0x100 and keyword_allow_bitmap is not None:       # filter pushdown: eligible = allow & alive
+            words = (len(self.ids) + 31) // 32
+            alive = np.asarray(keyword_allow_bitmap[:words], np.uint32) & (alive if alive is not None else np.uint32(0xFFFFFFFF))
+            keyword_allow_bitmap = None
+        fusion_mode &= 0xFF
         for b in range(B):
-            dd, do = o.dense_topk(self.x, q[b:b + 1], P, self._alive())
+            dd, do = o.dense_topk(self.x, q[b:b + 1], P, alive)
             if q_terms_list is None or self.post is None:
                 n = min(k, int((do[0] >= 0).sum()))
                 out["final"][b, :n] = dd[0, :n]; out["ordinal"][b, :n] = do[0, :n]; out["count"][b] = n
                 continue
-            bs, bo = o.bm25_query(self.post, q_terms_list[b], P, self._alive())
+            bs, bo = o.bm25_query(self.post, q_terms_list[b], P, alive)
             if keyword_allow_bitmap is not None:
                 keep = np.array([o_ >= 0 and (keyword_allow_bitmap[o_ >> 5] >> (o_ & 31)) & 1 for o_ in bo], bool)
                 bs, bo = bs[keep], bo[keep]

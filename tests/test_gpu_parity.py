@@ -278,3 +278,49 @@ def test_peer_exchange_single_rank_roundtrip(ctx_scan):
     with pytest.raises(_native.KragError):
         p.exchange_merge(2, 64, 65, d_in.data_ptr(), d_out.data_ptr(), 0)   # larger than the agreed mailbox
     p.destroy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dense_mode,batch", [(1, 3), (0, 40)])
+def test_filter_pushdown_bit_exact(oracle, dense_mode, batch):
+    """KRAG_FILTER_PUSHDOWN: the allow bitmap (AND tombstones) is honoured inside K1 / K2 / K3 -- compared with the
+    oracle run on eligible = allow & alive for both lists (ids and fused scores bit-exact); 3% and 60% selectivity."""
+    from kaito_b200 import _native
+    o = oracle
+    n, d, vocab, k = 300_000 if dense_mode == 0 else 60_000, 128, 5000, 10
+    x = o.synth_dense(n, d, 21)
+    off, ids, tf, dl = o.synth_sparse(n, vocab, 22)
+    q = o.synth_queries(x, batch, 23)
+    qs = o.synth_query_terms(vocab, batch, 24, rank_offset=30)
+    c = _native.Context(0, dense_mode=dense_mode)
+    try:
+        ix = c.create_index("pd", d)
+        ix.add(np.arange(n, dtype=np.uint64), x, off, ids, tf, dl)
+        dead = set(range(0, n, 7))
+        ix.remove(np.array(sorted(dead), np.uint64))
+        ix.commit(vocab)
+        live = np.ones(n, bool); live[list(dead)] = False
+        keep = np.repeat(live, np.diff(off))
+        off2 = np.concatenate([[0], np.cumsum(np.where(live, np.diff(off), 0))]).astype(np.int64)
+        df = np.bincount(ids[keep], minlength=vocab).astype(np.uint32)
+        post = o.bm25_build(off2, ids[keep], tf[keep], dl, vocab, df, int(live.sum()), int(dl[live].astype(np.int64).sum()))
+        alive = o.alive_bitmap(n, dead)
+        rng = np.random.default_rng(9)
+        P = o.pool_size(k)
+        for frac in (0.03, 0.6):
+            allow = np.packbits(rng.random(((n + 31) // 32) * 32) < frac, bitorder="little").view(np.uint32)
+            got = ix.retrieve(q, qs, k, fusion_mode=_native.FILTER_PUSHDOWN, keyword_allow_bitmap=allow)
+            got_v = ix.retrieve(q, None, k, fusion_mode=_native.FILTER_PUSHDOWN, keyword_allow_bitmap=allow)
+            elig = allow & alive
+            for b in range(batch):
+                dd, do = o.dense_topk(x, q[b:b + 1], P, elig)
+                bs, bo = o.bm25_query(post, qs[b], P, elig)
+                fin, de, sp, rk, od = o.fuse(dd[0], do[0], bs, bo, k)
+                cnt = int(got["count"][b])
+                assert cnt == len(od) and np.array_equal(got["ordinal"][b, :cnt], od), (frac, b)
+                assert np.array_equal(got["final"][b, :cnt], fin)
+                assert all((elig[o_ >> 5] >> (o_ & 31)) & 1 for o_ in got["ordinal"][b, :cnt])
+                assert np.array_equal(got_v["ordinal"][b, :k], do[0, :k]) and np.array_equal(got_v["final"][b, :k], dd[0, :k].astype(np.float64))
+        ix.drop()
+    finally:
+        c.close()

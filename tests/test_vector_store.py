@@ -51,12 +51,19 @@ def _check_suite(store):
     # keyword-side metadata filter (hybrid_retriever.py:227-235)
     r_f = store.retrieve("test_index", "document retrieval", max_node_count=3, metadata_filter={"type": "recipe"})
     assert r_f["count"] <= 3
+    # filter pushdown (KRAG_FILTER_PUSHDOWN, not the reference): the bitmap restricts both scans, so every result matches
+    store.filter_pushdown = True
+    r_p = store.retrieve("test_index", "document retrieval", max_node_count=3, metadata_filter={"type": "recipe"})
+    n_match = sum(1 for d in DOCS if (d.get("metadata") or {}).get("type") == "recipe")
+    assert r_p["count"] == min(3, n_match) and all((x["metadata"] or {}).get("type") == "recipe" for x in r_p["results"])
+    assert store.retrieve("test_index", "document retrieval", max_node_count=3, metadata_filter={"type": "nothing"})["count"] == 0
+    store.filter_pushdown = False
     # delete
     d = store.delete_documents("test_index", [ids[0], "nope"])
     assert d == {"deleted_doc_ids": [ids[0]], "not_found_doc_ids": ["nope"]}
     r2 = store.retrieve("test_index", "What is the first document?", max_node_count=5)
     assert ids[0] not in [x["doc_id"] for x in r2["results"]]
-    return r, r_f, r2
+    return r, r_f, r2, r_p
 
 
 def test_store_suite_cpu(cpu_store):
