@@ -248,6 +248,10 @@ int32_t krag_debug_gemm_tf32(krag_ctx* ctx, int32_t M, int32_t N, int32_t K, con
 int32_t krag_debug_linear_ln(krag_ctx* ctx, int32_t M, int32_t N, int32_t K, const float* A, const float* B,
                              const float* bias, const float* residual, const float* ln_gamma, const float* ln_beta,
                              float eps, float* Y_out);
+/* Switch the dense kernel policy (KRAG_DENSE_*) of the context this index lives in.  Switching to KRAG_DENSE_TC_BF16
+ * builds the index's bf16 shadow if it does not exist yet (one conversion pass over the fp32 rows); switching away
+ * keeps the shadow unless release_shadow != 0.  Results never change: every mode returns exact fp32 distances. */
+int32_t krag_index_set_dense_mode(krag_index* idx, int32_t dense_mode, int32_t release_shadow);
 /* queries whose tensor-core result failed the exactness certificate and were re-run on the
  * exact scan kernel (process-wide counter) */
 int64_t krag_tc_fallback_queries(void);

@@ -33,7 +33,7 @@ SYMBOLS = [
     "krag_synth_fill", "krag_index_read_rows", "krag_index_read_postings", "krag_tc_fallback_queries",
     "krag_debug_tc_dump", "krag_last_dense_kernel", "krag_embedder_create", "krag_embedder_load_tensor",
     "krag_embedder_finalize", "krag_embed", "krag_embed_dev", "krag_embedder_destroy", "krag_debug_gemm_tf32",
-    "krag_debug_linear_ln", "krag_p2p_create", "krag_p2p_connect", "krag_dev_exchange_merge", "krag_p2p_destroy",
+    "krag_debug_linear_ln", "krag_index_set_dense_mode", "krag_p2p_create", "krag_p2p_connect", "krag_dev_exchange_merge", "krag_p2p_destroy",
 ]
 
 
@@ -111,6 +111,7 @@ def load() -> C.CDLL:
     L.krag_embedder_destroy.argtypes = [vp]
     L.krag_debug_gemm_tf32.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, i32, vp]
     L.krag_debug_linear_ln.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, C.c_float, vp]
+    L.krag_index_set_dense_mode.argtypes = [vp, i32, i32]
     L.krag_p2p_create.argtypes = [vp, i32, i32, i32, i32, C.POINTER(vp), vp]
     L.krag_p2p_connect.argtypes = [vp, vp]
     L.krag_dev_exchange_merge.argtypes = [vp, i32, i32, i32, vp, vp, vp]
@@ -345,6 +346,10 @@ class Index:
 
     def persist(self, path: str):
         check(self._L.krag_index_persist(self._h, path.encode()))
+
+    def set_dense_mode(self, dense_mode: int, release_shadow: bool = False):
+        """KRAG_DENSE_*; DENSE_TC_BF16 builds the bf16 shadow on first use (results stay exact fp32 in every mode)"""
+        check(self._L.krag_index_set_dense_mode(self._h, dense_mode, 1 if release_shadow else 0))
 
     def search_dense(self, q, k: int):
         q = np.ascontiguousarray(q, np.float32).reshape(-1, self.dim)

@@ -272,7 +272,7 @@ void ensure_capacity(krag_index* ix, int64_t rows, int64_t nnz, cudaStream_t st)
 {
     ix->X.reserve(rows * ix->dpad, ix->n_rows * ix->dpad, st);
     ix->xnorm.reserve(rows, ix->n_rows, st);
-    if (ix->ctx->cfg.dense_mode == KRAG_DENSE_TC_BF16) ix->Xh.reserve(rows * ix->dpad, ix->n_rows * ix->dpad, st);
+    if (ix->ctx->cfg.dense_mode == KRAG_DENSE_TC_BF16 || ix->Xh.p) ix->Xh.reserve(rows * ix->dpad, ix->n_rows * ix->dpad, st);
     if (ix->xn_max.p == nullptr) {
         ix->xn_max.reserve(1, 0, st);
         KRAG_CUDA(cudaMemsetAsync(ix->xn_max.p, 0, sizeof(uint32_t), st));
@@ -822,6 +822,23 @@ int32_t krag_index_read_postings(krag_index* ix, uint32_t term, int64_t cap, uin
         int64_t m = cnt < cap ? cnt : cap;
         if (m > 0 && docs_out) KRAG_CUDA(cudaMemcpy(docs_out, ix->post.doc + be[0], sizeof(uint32_t) * (size_t)m, cudaMemcpyDeviceToHost));
         if (m > 0 && scores_out) KRAG_CUDA(cudaMemcpy(scores_out, ix->post.score + be[0], sizeof(float) * (size_t)m, cudaMemcpyDeviceToHost));
+    });
+}
+
+int32_t krag_index_set_dense_mode(krag_index* ix, int32_t dense_mode, int32_t release_shadow)
+{
+    return guarded([&] {
+        KRAG_REQUIRE(ix && dense_mode >= KRAG_DENSE_AUTO && dense_mode <= KRAG_DENSE_TC_BF16, KRAG_E_INVALID, "bad argument");
+        std::unique_lock<std::shared_mutex> lk(ix->mu);
+        KRAG_CUDA(cudaSetDevice(ix->ctx->di.device));
+        cudaStream_t st = ix->ctx->admin;
+        if (dense_mode == KRAG_DENSE_TC_BF16 && ix->Xh.p == nullptr && ix->X.p != nullptr) {
+            ix->Xh.reserve(ix->X.cap, 0, st);                     // same capacity as the fp32 rows: later appends convert in place
+            launch_f32_to_bf16(ix->X.p, ix->Xh.p, ix->n_rows * ix->dpad, st);
+        }
+        if (dense_mode != KRAG_DENSE_TC_BF16 && release_shadow) ix->Xh.release();
+        KRAG_CUDA(cudaStreamSynchronize(st));
+        ix->ctx->cfg.dense_mode = dense_mode;
     });
 }
 

@@ -109,3 +109,34 @@ def test_bf16_shadow_pruning_still_returns_exact_fp32(ctx_bf16, oracle, batch, P
         assert _native.last_dense_kernel()[1] == 4      # the bf16 cta_group::2 kernel really ran
     finally:
         ix.drop()
+
+
+def test_dense_mode_switch_builds_shadow_on_demand(oracle):
+    """krag_index_set_dense_mode: AUTO (TF32 over fp32) -> TC_BF16 builds the shadow from the resident rows, later appends
+    keep it in sync, switching back releases it; the results are bit-identical in every mode."""
+    from kaito_b200 import _native
+    n, d, batch, P = 300_000, 128, 64, 30
+    x = oracle.synth_dense(n, d, seed=8)
+    q = oracle.synth_queries(x, batch, seed=9)
+    c = _native.Context(device_id=0)
+    try:
+        ix = c.create_index("switch", d)
+        ix.add(np.arange(280_000, dtype=np.uint64), x[:280_000])
+        rd, ro = oracle.dense_topk(x[:280_000], q, P)
+        d0, o0 = ix.search_dense(q, P)
+        assert _native.last_dense_kernel()[1] == 3 and np.array_equal(o0, ro) and np.array_equal(d0, rd)
+        bytes0 = ix.stats().device_bytes
+        ix.set_dense_mode(_native.DENSE_TC_BF16)
+        assert ix.stats().device_bytes > bytes0
+        d1, o1 = ix.search_dense(q, P)
+        assert _native.last_dense_kernel()[1] == 4 and np.array_equal(o1, ro) and np.array_equal(d1, rd)
+        ix.add(np.arange(280_000, n, dtype=np.uint64), x[280_000:])           # append with the shadow present
+        rd2, ro2 = oracle.dense_topk(x, q, P)
+        d2, o2 = ix.search_dense(q, P)
+        assert _native.last_dense_kernel()[1] == 4 and np.array_equal(o2, ro2) and np.array_equal(d2, rd2)
+        ix.set_dense_mode(_native.DENSE_AUTO, release_shadow=True)
+        d3, o3 = ix.search_dense(q, P)
+        assert _native.last_dense_kernel()[1] == 3 and np.array_equal(o3, ro2) and np.array_equal(d3, rd2)
+        ix.drop()
+    finally:
+        c.close()
