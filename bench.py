@@ -413,7 +413,7 @@ def run_ours(args):
     # OPT-IN leg, reported beside (never instead of) the default: the same step with K2's prune pass reading a bf16
     # shadow of the corpus (+50% memory, built here by one conversion pass); returned distances stay exact fp32.
     optin = None
-    if args.dense_mode == 0 and not args.no_optin and kern_id in (2, 3):
+    if args.dense_mode == 0 and not args.no_optin and kern_id in (2, 3, 5):
         t_sh = time.perf_counter()
         ix.set_dense_mode(_native.DENSE_TC_BF16)
         t_sh = time.perf_counter() - t_sh
@@ -451,6 +451,7 @@ def run_ours(args):
         kname = {1: "K1 dense_scan_kernel (exact fp32 L2^2 scan + fused top-P)",
                  2: "K2 dense_tc_kernel (tcgen05 cta_group::1 TF32 prune pass; exact fp32 rescoring follows)",
                  3: "K2 dense_tc2_kernel (tcgen05 cta_group::2 TF32 prune pass, CTA pairs; exact fp32 rescoring follows)",
+                 5: "K2 dense_tc2cvt_kernel (tcgen05 cta_group::2 kind::f16 prune pass; fp32 corpus rows staged by TMA and rounded to bf16 in shared memory -- no shadow copy, 4 B/element from HBM; exact fp32 rescoring follows)",
                  4: "K2 dense_tc2_kernel<bf16> (OPT-IN: prune pass over a bf16 shadow of the corpus, kind::f16; exact fp32 rescoring of the fp32 corpus follows)"}
         qps = B * args.steps / (ms_dev * 1e-3)
         qps_e2e = B * args.steps / (ms_e2e * 1e-3)

@@ -52,9 +52,12 @@ extern "C" {
 
 #define KRAG_DENSE_AUTO 0   /* exact fp32 scan for small batches, tensor-core path for large */
 #define KRAG_DENSE_SCAN 1   /* K1: exact fp32 CUDA-core scan */
-#define KRAG_DENSE_TC 2     /* K2: tcgen05 TF32 candidates + exact fp32 rescoring */
+#define KRAG_DENSE_TC 2     /* K2: tcgen05 prune pass (fp32 rows rounded to bf16 in shared memory, kind::f16; TF32 when the
+                               padded dimension is not a multiple of 64) + exact fp32 rescoring */
 #define KRAG_DENSE_TC_BF16 3 /* K2 pruning on a bf16 SHADOW copy of the corpus (+50% memory); the returned distances are
                                still exact fp32 re-scores of the fp32 corpus and carry the same exactness certificate */
+
+#define KRAG_DENSE_TC_TF32 4 /* K2 with the fp32 rows consumed directly as TF32 (kind::tf32): the earlier default, kept for comparison */
 
 typedef struct krag_ctx krag_ctx;
 typedef struct krag_index krag_index;

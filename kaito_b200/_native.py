@@ -21,7 +21,7 @@ KRAG_MAX_TOP_K = 300
 KRAG_MAX_POOL = 1024
 FUSION_REFERENCE, FUSION_SIMILARITY = 0, 1
 FILTER_PUSHDOWN = 0x100   # OR into fusion_mode: the allow bitmap restricts the dense and BM25 scans themselves
-DENSE_AUTO, DENSE_SCAN, DENSE_TC, DENSE_TC_BF16 = 0, 1, 2, 3
+DENSE_AUTO, DENSE_SCAN, DENSE_TC, DENSE_TC_BF16, DENSE_TC_TF32 = 0, 1, 2, 3, 4
 
 # every symbol include/kaito_rag.h declares (tests check the export table against this)
 SYMBOLS = [

@@ -201,17 +201,17 @@ void dense_candidates_dev(krag_index* ix, Slot* s, const float* d_q, int batch, 
     KRAG_REQUIRE(ix->ord_base + ix->n_rows <= 0xFFFFFFFFll, KRAG_E_UNSUPPORTED, "global ordinal exceeds 32 bits");
     s->part.reserve((int64_t)dense_scan_part_elems(c->di, P), 0, st);
     int mode = c->cfg.dense_mode;
-    bool use_tc = (mode == KRAG_DENSE_TC) || (mode == KRAG_DENSE_TC_BF16 && dense_tc_wants(ix->n_rows, batch)) ||
+    bool use_tc = (mode == KRAG_DENSE_TC) || (mode == KRAG_DENSE_TC_TF32) || (mode == KRAG_DENSE_TC_BF16 && dense_tc_wants(ix->n_rows, batch)) ||
                   (mode == KRAG_DENSE_AUTO && dense_tc_wants(ix->n_rows, batch));
     if (use_tc && dense_tc_supported(c->di, ix->dpad)) {
         size_t ws = dense_tc_workspace_bytes(c->di, ix->n_rows, P);
         s->tc_ws.reserve((int64_t)ws, 0, st);
         if (launch_dense_tc(c->di, ix->X.p, ix->n_rows, ix->dpad, alive, ix->xnorm.p, ix->xn_max.p, d_q, batch, P,
                             (uint32_t)ix->ord_base, s->tc_ws.p, ws, s->part.p, d_keys, st,
-                            mode == KRAG_DENSE_TC_BF16 ? ix->Xh.p : nullptr))
+                            mode == KRAG_DENSE_TC_BF16 ? ix->Xh.p : nullptr, mode != KRAG_DENSE_TC_TF32))
             return;
     }
-    KRAG_REQUIRE(mode != KRAG_DENSE_TC || !dense_tc_wants(ix->n_rows, 16), KRAG_E_UNSUPPORTED, "tensor-core dense path unavailable for this index/device");
+    KRAG_REQUIRE((mode != KRAG_DENSE_TC && mode != KRAG_DENSE_TC_TF32) || !dense_tc_wants(ix->n_rows, 16), KRAG_E_UNSUPPORTED, "tensor-core dense path unavailable for this index/device");
     launch_dense_scan(c->di, ix->X.p, ix->n_rows, ix->dpad, alive, d_q, batch, P, (uint32_t)ix->ord_base,
                       s->part.p, d_keys, st);
 }
@@ -828,7 +828,7 @@ int32_t krag_index_read_postings(krag_index* ix, uint32_t term, int64_t cap, uin
 int32_t krag_index_set_dense_mode(krag_index* ix, int32_t dense_mode, int32_t release_shadow)
 {
     return guarded([&] {
-        KRAG_REQUIRE(ix && dense_mode >= KRAG_DENSE_AUTO && dense_mode <= KRAG_DENSE_TC_BF16, KRAG_E_INVALID, "bad argument");
+        KRAG_REQUIRE(ix && dense_mode >= KRAG_DENSE_AUTO && dense_mode <= KRAG_DENSE_TC_TF32, KRAG_E_INVALID, "bad argument");
         std::unique_lock<std::shared_mutex> lk(ix->mu);
         KRAG_CUDA(cudaSetDevice(ix->ctx->di.device));
         cudaStream_t st = ix->ctx->admin;

@@ -452,6 +452,239 @@ dense_tc2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
 }
 
+// ------------------------------------------------- K2, default: fp32 rows -> bf16 IN SHARED MEMORY -> kind::f16
+// The TF32 pass above runs at 97-99% tensor-pipe activity with the SM clock held at 1.2-1.3 GHz by the power cap:
+// it is bound by tensor energy, not by HBM.  This variant keeps the corpus fp32 in HBM (no shadow copy, same
+// 4 bytes/element of traffic) but halves the tensor work: TMA lands the fp32 k-blocks in a staging ring, four
+// converter warps round them to bf16 (cvt.rn.bf16x2, the same rounding as the shadow mode) straight into the
+// 128B-swizzled operand ring, and the pair's MMAs are kind::f16 (K = 16).  The pass becomes HBM-bound.
+// Pruning only, as before: candidates are re-scored in exact fp32 and certified with the bf16 error bound.
+//   warp 0: corpus TMA (fp32 staging ring, per CTA)      warp 1: MMA issuer (pair leader)
+//   warp 2: query TMA (bf16 queries, operand ring)       warps 3-10: epilogue      warps 11-13: converters, warp w owns
+//   operand stage w: the three conversions in flight hide each other's shared-memory and barrier latency
+constexpr int TCV_THREADS = 448;
+constexpr int TCV_A_STAGES = 8;            // fp32 staging k-blocks (16 KB each): 128 KB of corpus in flight per SM covers the HBM latency
+constexpr int TCV_B_STAGES = 3;            // bf16 operand k-blocks: 16 KB corpus + this CTA's half of the queries
+template <int NQ> struct TcvCfg {
+    static constexpr int QH_BYTES = (NQ / 2) * 128;                    // 64 bf16 per row
+    static constexpr int B_STAGE = TC_A_BYTES + QH_BYTES;
+    static constexpr int TMEM_COLS = (2 * NQ < 32) ? 32 : 2 * NQ;
+    static constexpr int BAR_BYTES = 256;
+    static constexpr size_t SMEM = (size_t)TCV_A_STAGES * TC_A_BYTES + (size_t)TCV_B_STAGES * B_STAGE + 1024 + BAR_BYTES + NQ * 4;
+};
+
+template <int NQ>
+__global__ void __launch_bounds__(TCV_THREADS, 1)
+dense_tc2cvt_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmQh, int64_t n_rows,
+                    int kblocks /*fp32 k-blocks, even*/, int64_t n_ptiles, const float* __restrict__ xnorm,
+                    const uint32_t* __restrict__ alive, const float* __restrict__ thr_g, uint32_t* __restrict__ cand_count,
+                    uint32_t* __restrict__ cand_rows, int cap)
+{
+    using Cfg = TcvCfg<NQ>;
+    extern __shared__ unsigned char tc_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* ring_a = smem;                                            // fp32 staging
+    unsigned char* ring_b = smem + (size_t)TCV_A_STAGES * TC_A_BYTES;        // bf16 operands
+    unsigned char* tail = ring_b + (size_t)TCV_B_STAGES * Cfg::B_STAGE;
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(tail);                    // per CTA
+    uint64_t* a_empty = a_full + TCV_A_STAGES;                               // per CTA, the converter warp that read the slot
+    uint64_t* b_full = a_empty + TCV_A_STAGES;                               // leader only: 2 query producers + 2 converter warps + tx
+    uint64_t* b_empty = b_full + TCV_B_STAGES;                               // per CTA (multicast commit)
+    uint64_t* tfull_bar = b_empty + TCV_B_STAGES;                            // per CTA [2]
+    uint64_t* tempty_bar = tfull_bar + 2;                                    // leader only [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    float* s_thr = reinterpret_cast<float*>(tail + Cfg::BAR_BYTES);
+    static_assert((2 * TCV_A_STAGES + 2 * TCV_B_STAGES + 4) * 8 + 8 <= Cfg::BAR_BYTES, "barrier area too small");
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int kb2 = kblocks >> 1;                                            // bf16 k-blocks per tile
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmX);
+        tma_prefetch_desc(&tmQh);
+        for (int s = 0; s < TCV_A_STAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < TCV_B_STAGES; ++s) { mbar_init(&b_full[s], 4); mbar_init(&b_empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 16); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    for (int j = threadIdx.x; j < NQ; j += TCV_THREADS) s_thr[j] = 0.5f * thr_g[j];
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== corpus producer: fp32 k-blocks of this CTA's 128 rows =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t pt = pair; pt < n_ptiles; pt += n_pairs) {
+                const int row0 = (int)(pt * (2 * TC_TILE_M) + rank * TC_TILE_M);
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    mbar_wait(&a_empty[stage], phase ^ 1);
+                    mbar_expect_tx(&a_full[stage], TC_A_BYTES);
+                    tma_load_2d(ring_a + (size_t)stage * TC_A_BYTES, &tmX, &a_full[stage], kb * TC_KBLOCK, row0, TMA_EVICT_FIRST);
+                    if (++stage == TCV_A_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== query producer: this CTA's half of the bf16 query rows =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int64_t pt = pair; pt < n_ptiles; pt += n_pairs) {
+                for (int jb = 0; jb < kb2; ++jb) {
+                    mbar_wait(&b_empty[stage], phase ^ 1);
+                    if (rank == 0) mbar_expect_tx(&b_full[stage], 2 * Cfg::QH_BYTES);
+                    else mbar_arrive_remote(&b_full[stage], 0);
+                    tma_load_2d_2sm(ring_b + (size_t)stage * Cfg::B_STAGE + TC_A_BYTES, &tmQh, &b_full[stage], jb * 64, (int)rank * (NQ / 2),
+                                    TMA_EVICT_LAST);
+                    if (++stage == TCV_B_STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0) {
+            // ===================== MMA issuer (pair leader) =====================
+            constexpr uint32_t idesc = umma_idesc_bf16(2 * TC_TILE_M, NQ);
+            const uint64_t desc0 = umma_desc_sw128(smem_u32(ring_b));
+            const uint32_t lo0 = (uint32_t)desc0;
+            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            for (int64_t pt = pair; pt < n_ptiles; pt += n_pairs) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NQ);
+                for (int jb = 0; jb < kb2; ++jb) {
+                    mbar_wait(&b_full[stage], phase);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t a_lo = lo0 + (uint32_t)((stage * Cfg::B_STAGE) >> 4);
+                        const uint32_t q_lo = a_lo + (uint32_t)(TC_A_BYTES >> 4);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)      // UMMA K = 16 bf16 (32 bytes = 2 descriptor units)
+                            umma_2sm<true>(d_tmem, desc_with_lo(desc0, a_lo + 2 * k), desc_with_lo(desc0, q_lo + 2 * k), idesc,
+                                           (uint32_t)((jb | k) != 0));
+                        umma_commit_2sm(&b_empty[stage]);
+                        if (jb == kb2 - 1) umma_commit_2sm(&tfull_bar[acc]);
+                    }
+                    __syncwarp();
+                    if (++stage == TCV_B_STAGES) { stage = 0; phase ^= 1; }
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1;
+            }
+        }
+    } else if (warp >= 11) {
+        // ===================== converters: two fp32 staging k-blocks -> one bf16 operand k-block =====================
+        static_assert(TCV_B_STAGES == 3 && TCV_A_STAGES == 8, "converter warp w owns operand stage w; staging ring of 8");
+        const int w = warp - 11;                                // operand stage owned by this warp
+        const int c = lane & 7;                                 // 16-byte chunk of the fp32 row
+        // rows handled by a lane: base {0,4,1,5}[lane >> 3] + 2 (it & 1) + 8 (it >> 1).  The two rows of a half-warp differ in
+        // bit 2, so their swizzled 64-byte bf16 halves fall into opposite bank halves (conflict-free 64-bit stores)
+        const int rr = (((lane >> 3) & 1) << 2) | (lane >> 4);
+        const int64_t my_tiles = (n_ptiles - pair + n_pairs - 1) / n_pairs;
+        const int64_t total = my_tiles * kb2;                   // bf16 k-blocks this CTA converts
+        unsigned char* dst = ring_b + (size_t)w * Cfg::B_STAGE;
+        uint32_t pbe = 1;                                       // parity to wait for on b_empty[w]
+        for (int64_t g = w; g < total; g += TCV_B_STAGES) {
+            mbar_wait(&b_empty[w], pbe);                        // the MMAs that read this operand stage have retired
+            pbe ^= 1;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int64_t i = 2 * g + h;                    // fp32 k-block counter of this CTA
+                const int sa = (int)(i & 7);
+                mbar_wait(&a_full[sa], (uint32_t)((i >> 3) & 1));
+                const unsigned char* src = ring_a + (size_t)sa * TC_A_BYTES;
+                const int cd = (h << 2) | (c >> 1);             // 16-byte chunk of the bf16 row
+#pragma unroll
+                for (int b8 = 0; b8 < 4; ++b8) {
+                    float4 v[8];
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int r = rr + 2 * (it & 1) + 8 * (b8 * 4 + (it >> 1));
+                        v[it] = *reinterpret_cast<const float4*>(src + r * 128 + ((c ^ (r & 7)) << 4));
+                    }
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int r = rr + 2 * (it & 1) + 8 * (b8 * 4 + (it >> 1));
+                        const __nv_bfloat162 lo = __floats2bfloat162_rn(v[it].x, v[it].y), hi = __floats2bfloat162_rn(v[it].z, v[it].w);
+                        uint2 o;
+                        o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+                        *reinterpret_cast<uint2*>(dst + r * 128 + ((cd ^ (r & 7)) << 4) + ((c & 1) << 3)) = o;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_empty[sa]);        // staging slot read: TMA may refill it
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA's async proxy
+            __syncwarp();
+            if (lane == 0) { if (rank == 0) mbar_arrive(&b_full[w]); else mbar_arrive_remote(&b_full[w], 0); }
+        }
+    } else {
+        // ===================== epilogue (warps 3-10): as dense_tc2_kernel =====================
+        const int lg = warp & 3;
+        const int col_half = (warp - 3) >> 2;
+        const int row_in_tile = lg * 32 + lane;
+        int acc = 0; uint32_t acc_phase = 0;
+        for (int64_t pt = pair; pt < n_ptiles; pt += n_pairs) {
+            const int64_t row = pt * (2 * TC_TILE_M) + rank * TC_TILE_M + row_in_tile;
+            float xn = CUDART_INF_F;
+            if (row < n_rows && (alive == nullptr || bit_test(alive, (uint32_t)row))) xn = xnorm[row];
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * NQ);
+            const float half_xn = 0.5f * xn;
+#pragma unroll 1
+            for (int c0 = col_half * (NQ / 2); c0 < (col_half + 1) * (NQ / 2); c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_x32(taddr + c0, v);
+                tmem_wait_ld();
+                float t[32];
+                float mx = -CUDART_INF_F;
+#pragma unroll
+                for (int j4 = 0; j4 < 32; j4 += 4) {
+                    const float4 h = *reinterpret_cast<const float4*>(s_thr + c0 + j4);
+                    t[j4 + 0] = __uint_as_float(v[j4 + 0]) + h.x;
+                    t[j4 + 1] = __uint_as_float(v[j4 + 1]) + h.y;
+                    t[j4 + 2] = __uint_as_float(v[j4 + 2]) + h.z;
+                    t[j4 + 3] = __uint_as_float(v[j4 + 3]) + h.w;
+                    mx = fmaxf(mx, fmaxf(fmaxf(t[j4 + 0], t[j4 + 1]), fmaxf(t[j4 + 2], t[j4 + 3])));
+                }
+                if (mx > half_xn) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (t[j] > half_xn) {
+                            const uint32_t pos = atomicAdd(&cand_count[c0 + j], 1u);
+                            if (pos < (uint32_t)cap) cand_rows[(size_t)(c0 + j) * cap + pos] = (uint32_t)row;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (rank == 0) mbar_arrive(&tempty_bar[acc]);
+                else mbar_arrive_remote(&tempty_bar[acc], 0);
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)Cfg::TMEM_COLS) : "memory");
+    }
+}
+
 // ------------------------------------------------------------- row norms (index time)
 __global__ void __launch_bounds__(256)
 row_norms_kernel(const float* __restrict__ X, int64_t row0, int64_t n, int dpad, float* __restrict__ xnorm,
@@ -655,10 +888,10 @@ template <int NQ>
 static void tc_pass(const DeviceInfo& di, const CUtensorMap& tmX, const CUtensorMap& tmQ, const float* X, int64_t n_rows,
                     int dpad, const float* xnorm, const uint32_t* xn_max_bits, const uint32_t* alive, const float* q,
                     int nq, int P, uint32_t ord_base, const TcWorkspace& w, int cap, int64_t S, uint64_t* keys_out,
-                    const uint16_t* Xh, cudaStream_t st)
+                    const uint16_t* Xh, bool cvt, cudaStream_t st)
 {
     using Cfg = TcCfg<NQ>;
-    const bool bf16 = Xh != nullptr;
+    const bool bf16 = Xh != nullptr || cvt;      // bf16 operands in the prune pass (shadow copy, or converted on chip)
     static bool attr_set = false;
     if (!attr_set) {
         KRAG_CUDA(cudaFuncSetAttribute(dense_tc_kernel<NQ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
@@ -690,8 +923,33 @@ static void tc_pass(const DeviceInfo& di, const CUtensorMap& tmX, const CUtensor
     KRAG_CUDA(cudaMemsetAsync(w.cand_count, 0, 256 * 4, st));
     // 3. main pass: stream the corpus once, prune on the tensor cores
     if (bf16) launch_f32_to_bf16(q, w.q_bf16, (int64_t)nq * dpad, st);
-    dense_timer_begin(st, bf16 ? 4 : (tc_use_2cta() ? 3 : 2), n_rows * (int64_t)dpad * (bf16 ? 2 : 4), 2 * (int64_t)NQ * n_rows * dpad);
-    if (tc_use_2cta() || bf16) {
+    dense_timer_begin(st, cvt ? 5 : (bf16 ? 4 : (tc_use_2cta() ? 3 : 2)), n_rows * (int64_t)dpad * ((bf16 && !cvt) ? 2 : 4),
+                      2 * (int64_t)NQ * n_rows * dpad);
+    if (cvt) {
+        using CfgV = TcvCfg<NQ>;
+        static bool attrv_set = false;
+        if (!attrv_set) {
+            KRAG_CUDA(cudaFuncSetAttribute(dense_tc2cvt_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CfgV::SMEM));
+            attrv_set = true;
+        }
+        CUtensorMap tmQh;
+        if (!make_map(&tmQh, (const void*)w.q_bf16, nq, dpad, NQ / 2, true))
+            throw CudaError{cudaErrorUnknown, "cuTensorMapEncodeTiled(Q half, bf16)", __FILE__, __LINE__};
+        const int64_t n_ptiles = (n_rows + 2 * TC_TILE_M - 1) / (2 * TC_TILE_M);
+        const int64_t max_pairs = di.sm_count / 2;
+        const int n_pairs = (int)(n_ptiles < max_pairs ? n_ptiles : max_pairs);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(2 * n_pairs));
+        cfg.blockDim = dim3(TCV_THREADS);
+        cfg.dynamicSmemBytes = CfgV::SMEM;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        KRAG_CUDA(cudaLaunchKernelEx(&cfg, dense_tc2cvt_kernel<NQ>, tmX, tmQh, n_rows, kblocks, n_ptiles, xnorm, alive,
+                                     (const float*)w.thr, w.cand_count, w.cand_rows, cap));
+    } else if (tc_use_2cta() || bf16) {
         using Cfg2 = Tc2Cfg<NQ>;
         static bool attr2_set = false;
         if (!attr2_set) {
@@ -744,15 +1002,25 @@ static void tc_pass(const DeviceInfo& di, const CUtensorMap& tmX, const CUtensor
     count_launch();
 }
 
+static bool tc_use_cvt()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("KRAG_TC_CVT"); v = (e == nullptr || e[0] != '0') ? 1 : 0; }
+    return v == 1;
+}
+
 static int64_t g_tc_fallback_queries = 0;
 int64_t dense_tc_fallback_queries() { return g_tc_fallback_queries; }
 
 bool launch_dense_tc(const DeviceInfo& di, const float* X, int64_t n_rows, int dpad, const uint32_t* alive,
                      const float* xnorm, const uint32_t* xn_max_bits, const float* q, int batch, int P, uint32_t ord_base,
                      void* workspace, size_t workspace_bytes, uint64_t* part, uint64_t* keys_out, cudaStream_t st,
-                     const uint16_t* Xh)
+                     const uint16_t* Xh, bool allow_cvt)
 {
     if (Xh != nullptr && dpad % (2 * TC_KBLOCK) != 0) Xh = nullptr;   // bf16 k-blocks are 64 elements wide
+    // default prune pass: fp32 rows converted to bf16 in shared memory (no shadow); KRAG_TC_CVT=0 keeps the TF32 pass
+    const bool cvt = Xh == nullptr && allow_cvt && tc_use_cvt() && tc_use_2cta() && dpad % (2 * TC_KBLOCK) == 0 &&
+                     di.smem_optin >= TcvCfg<256>::SMEM;
     if (n_rows < TC_MIN_ROWS || n_rows >= (1ll << 31) || xnorm == nullptr) return false;
     const int cap = tc_cap(P);
     const int64_t S = tc_sample_tiles(n_rows) * TC_TILE_M;
@@ -768,9 +1036,9 @@ bool launch_dense_tc(const DeviceInfo& di, const float* X, int64_t n_rows, int d
         CUtensorMap tmQ;
         if (!make_map(&tmQ, qb, nq, dpad, NQ)) return false;
         uint64_t* ko = keys_out + (size_t)b0 * P;
-        if (NQ == 64) tc_pass<64>(di, tmX, tmQ, X, n_rows, dpad, xnorm, xn_max_bits, alive, qb, nq, P, ord_base, w, cap, S, ko, Xh, st);
-        else if (NQ == 128) tc_pass<128>(di, tmX, tmQ, X, n_rows, dpad, xnorm, xn_max_bits, alive, qb, nq, P, ord_base, w, cap, S, ko, Xh, st);
-        else tc_pass<256>(di, tmX, tmQ, X, n_rows, dpad, xnorm, xn_max_bits, alive, qb, nq, P, ord_base, w, cap, S, ko, Xh, st);
+        if (NQ == 64) tc_pass<64>(di, tmX, tmQ, X, n_rows, dpad, xnorm, xn_max_bits, alive, qb, nq, P, ord_base, w, cap, S, ko, Xh, cvt, st);
+        else if (NQ == 128) tc_pass<128>(di, tmX, tmQ, X, n_rows, dpad, xnorm, xn_max_bits, alive, qb, nq, P, ord_base, w, cap, S, ko, Xh, cvt, st);
+        else tc_pass<256>(di, tmX, tmQ, X, n_rows, dpad, xnorm, xn_max_bits, alive, qb, nq, P, ord_base, w, cap, S, ko, Xh, cvt, st);
         // uncertified queries (rare) are re-run on the exact scan kernel -- still on the GPU
         KRAG_CUDA(cudaMemcpyAsync(flags.data(), w.flags, sizeof(int32_t) * (size_t)nq, cudaMemcpyDeviceToHost, st));
         KRAG_CUDA(cudaStreamSynchronize(st));

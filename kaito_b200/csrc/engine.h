@@ -41,7 +41,8 @@ void launch_row_norms(const float* X, int64_t row0, int64_t n, int dpad, float* 
 bool launch_dense_tc(const DeviceInfo& di, const float* X, int64_t n_rows, int dpad, const uint32_t* alive,
                      const float* xnorm, const uint32_t* xn_max_bits, const float* q, int batch, int P,
                      uint32_t ord_base, void* workspace, size_t workspace_bytes, uint64_t* part, uint64_t* keys_out,
-                     cudaStream_t st, const uint16_t* Xh = nullptr /* optional bf16 shadow of X for the prune pass */);
+                     cudaStream_t st, const uint16_t* Xh = nullptr /* optional bf16 shadow of X for the prune pass */,
+                     bool allow_cvt = true /* fp32 rows rounded to bf16 on chip (kind::f16) instead of kind::tf32 */);
 void launch_f32_to_bf16(const float* in, uint16_t* out, int64_t n_elems, cudaStream_t st);
 int64_t dense_tc_fallback_queries();   // queries re-run on K1 because the exactness certificate failed
 // diagnostics: a[j][r] = |x_r|^2 - 2 x_r.q_j for ALL rows through the tensor-core kernel (tests only)

@@ -8,10 +8,12 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def ctx_tc():
+@pytest.fixture(scope="module", params=["cvt", "tf32"])
+def ctx_tc(request):
+    """K2 forced for every batch size: the default prune pass (fp32 rows rounded to bf16 in shared memory, kind::f16) and
+    the direct TF32 pass (kind::tf32) it replaced"""
     from kaito_b200 import _native
-    c = _native.Context(device_id=0, dense_mode=_native.DENSE_TC)
+    c = _native.Context(device_id=0, dense_mode=_native.DENSE_TC if request.param == "cvt" else _native.DENSE_TC_TF32)
     yield c
     c.close()
 
@@ -124,7 +126,7 @@ def test_dense_mode_switch_builds_shadow_on_demand(oracle):
         ix.add(np.arange(280_000, dtype=np.uint64), x[:280_000])
         rd, ro = oracle.dense_topk(x[:280_000], q, P)
         d0, o0 = ix.search_dense(q, P)
-        assert _native.last_dense_kernel()[1] == 3 and np.array_equal(o0, ro) and np.array_equal(d0, rd)
+        assert _native.last_dense_kernel()[1] == 5 and np.array_equal(o0, ro) and np.array_equal(d0, rd)   # default: convert-in-smem pass
         bytes0 = ix.stats().device_bytes
         ix.set_dense_mode(_native.DENSE_TC_BF16)
         assert ix.stats().device_bytes > bytes0
@@ -136,7 +138,7 @@ def test_dense_mode_switch_builds_shadow_on_demand(oracle):
         assert _native.last_dense_kernel()[1] == 4 and np.array_equal(o2, ro2) and np.array_equal(d2, rd2)
         ix.set_dense_mode(_native.DENSE_AUTO, release_shadow=True)
         d3, o3 = ix.search_dense(q, P)
-        assert _native.last_dense_kernel()[1] == 3 and np.array_equal(o3, ro2) and np.array_equal(d3, rd2)
+        assert _native.last_dense_kernel()[1] == 5 and np.array_equal(o3, ro2) and np.array_equal(d3, rd2)
         ix.drop()
     finally:
         c.close()
