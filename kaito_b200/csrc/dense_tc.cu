@@ -712,17 +712,27 @@ void launch_row_norms(const float* X, int64_t row0, int64_t n, int dpad, float* 
 constexpr int ST_THREADS = 512;
 constexpr int ST_CAP = 2048;
 __global__ void __launch_bounds__(ST_THREADS)
-sample_threshold_kernel(const float* __restrict__ dump, int64_t S, int m, int nq_valid, float* __restrict__ thr)
+sample_threshold_kernel(const float* __restrict__ dump, int64_t S, int m, int nq_valid, float* __restrict__ thr,
+                        float* __restrict__ part_vals /* != null: grid (NQ, parts), write this part's m smallest values */)
 {
     __shared__ uint64_t s_buf[ST_CAP];
     __shared__ int s_count;
     __shared__ uint64_t s_thr;
     const int tid = threadIdx.x, j = blockIdx.x;
-    if (j >= nq_valid) { if (tid == 0) thr[j] = -CUDART_INF_F; return; }   // padded query: admits nothing
+    const int parts = gridDim.y, part = blockIdx.y;
+    if (j >= nq_valid) {                                                    // padded query: admits nothing
+        if (part_vals) { for (int i = tid; i < m; i += ST_THREADS) part_vals[((int64_t)j * parts + part) * m + i] = CUDART_INF_F; }
+        else if (tid == 0) thr[j] = -CUDART_INF_F;
+        return;
+    }
     SelectBuf sel{s_buf, &s_count, &s_thr, ST_CAP};
     select_init(sel, tid);
     __syncthreads();
-    const float* col = dump + (int64_t)j * S;
+    // this block's slice of the query's samples (two-level selection: `parts` blocks per query, then one more pass
+    // of this kernel over their parts * m survivors)
+    const int64_t lo = S * part / parts, hi = S * (part + 1) / parts;
+    const float* col = dump + (int64_t)j * S + lo;
+    S = hi - lo;
     const int epoch = (ST_CAP - m) / ST_THREADS;
     uint64_t t = KEY_PAD;
     int it = 0;
@@ -736,7 +746,12 @@ sample_threshold_kernel(const float* __restrict__ dump, int64_t S, int m, int nq
         }
     }
     select_prune<ST_THREADS>(sel, m, tid, 0);
-    if (tid == 0) thr[j] = (s_count >= m) ? key_value_asc(s_buf[m - 1]) : CUDART_INF_F;
+    if (part_vals) {
+        for (int i = tid; i < m; i += ST_THREADS)
+            part_vals[((int64_t)j * parts + part) * m + i] = (i < s_count) ? key_value_asc(s_buf[i]) : CUDART_INF_F;
+    } else if (tid == 0) {
+        thr[j] = (s_count >= m) ? key_value_asc(s_buf[m - 1]) : CUDART_INF_F;
+    }
 }
 
 // ------------------------------------------------------------------ exact rescoring
@@ -917,7 +932,14 @@ static void tc_pass(const DeviceInfo& di, const CUtensorMap& tmX, const CUtensor
     int m = (int)((double)tc_target(P, bf16) * (double)sampled_rows / (double)n_rows + 0.5);
     if (m < 4) m = 4;
     if (m > 1024) m = 1024;
-    sample_threshold_kernel<<<NQ, ST_THREADS, 0, st>>>(w.dump, S, m, nq, w.thr);
+    // two-level: 8 blocks per query keep their m smallest, a second pass takes the m-th smallest of the 8 m survivors
+    // (the survivors are parked in the exact_keys area, which is not in use before the rescoring)
+    constexpr int ST_PARTS = 8;
+    float* part_vals = reinterpret_cast<float*>(w.exact_keys);
+    sample_threshold_kernel<<<dim3(NQ, ST_PARTS), ST_THREADS, 0, st>>>(w.dump, S, m, nq, nullptr, part_vals);
+    KRAG_CUDA(cudaGetLastError());
+    count_launch();
+    sample_threshold_kernel<<<dim3(NQ, 1), ST_THREADS, 0, st>>>(part_vals, (int64_t)ST_PARTS * m, m, nq, w.thr, nullptr);
     KRAG_CUDA(cudaGetLastError());
     count_launch();
     KRAG_CUDA(cudaMemsetAsync(w.cand_count, 0, 256 * 4, st));
