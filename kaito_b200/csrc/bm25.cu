@@ -17,6 +17,8 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <vector>
+
 #include "engine.h"
 #include "select.cuh"
 
@@ -124,19 +126,41 @@ __global__ void tile_index_kernel(const uint32_t* __restrict__ sorted_terms, con
         if (p == e - 1) for (int64_t tl = tile_d + 1; tl <= n_tiles; ++tl) row[tl] = (uint32_t)(e - b);
     }
 }
+// device scratch of the index build: everything allocated through it is freed on scope exit (also when a CUDA call
+// throws half-way), except what keep() hands over to the Postings
+struct DevScratch {
+    std::vector<void*> ptrs;
+    template <typename T> T* alloc(size_t n)
+    {
+        void* p = nullptr;
+        KRAG_CUDA(cudaMalloc(&p, sizeof(T) * (n ? n : 1)));
+        ptrs.push_back(p);
+        return static_cast<T*>(p);
+    }
+    void free_now(void* p)
+    {
+        for (auto& q : ptrs) if (q == p && q) { cudaFree(q); q = nullptr; }
+    }
+    template <typename T> T* keep(T* p)
+    {
+        for (auto& q : ptrs) if (q == static_cast<void*>(p)) q = nullptr;
+        return p;
+    }
+    ~DevScratch() { for (void* p : ptrs) if (p) cudaFree(p); }
+};
+
 static void build_tile_index(const uint32_t* sorted_terms, const uint32_t* post_doc, const int64_t* off, int64_t nnz_live,
                              int64_t vocab, int64_t n_rows, Postings& out, cudaStream_t st)
 {
-    int32_t *flag = nullptr, *scan = nullptr, *slot = nullptr;
-    KRAG_CUDA(cudaMalloc(&flag, sizeof(int32_t) * (size_t)(vocab + 1)));
-    KRAG_CUDA(cudaMalloc(&scan, sizeof(int32_t) * (size_t)(vocab + 1)));
-    KRAG_CUDA(cudaMalloc(&slot, sizeof(int32_t) * (size_t)vocab));
+    DevScratch sc;
+    int32_t* flag = sc.alloc<int32_t>((size_t)(vocab + 1));
+    int32_t* scan = sc.alloc<int32_t>((size_t)(vocab + 1));
+    int32_t* slot = sc.alloc<int32_t>((size_t)vocab);
     tile_flag_kernel<<<256, 256, 0, st>>>(off, vocab, flag);
     count_launch();
     size_t bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, bytes, flag, scan, (int)(vocab + 1), st);
-    void* tmp = nullptr;
-    KRAG_CUDA(cudaMalloc(&tmp, bytes ? bytes : 16));
+    void* tmp = sc.alloc<unsigned char>(bytes);
     cub::DeviceScan::ExclusiveSum(tmp, bytes, flag, scan, (int)(vocab + 1), st);
     count_launch();
     tile_slot_kernel<<<256, 256, 0, st>>>(flag, scan, vocab, slot);
@@ -144,11 +168,10 @@ static void build_tile_index(const uint32_t* sorted_terms, const uint32_t* post_
     int32_t n_slots = 0;
     KRAG_CUDA(cudaMemcpyAsync(&n_slots, scan + vocab, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     KRAG_CUDA(cudaStreamSynchronize(st));
-    KRAG_CUDA(cudaFree(tmp)); KRAG_CUDA(cudaFree(flag)); KRAG_CUDA(cudaFree(scan));
+    sc.free_now(tmp); sc.free_now(flag); sc.free_now(scan);
     int64_t n_tiles = (n_rows + BM25_TILE_DOCS - 1) / BM25_TILE_DOCS;
     if (n_tiles < 1) n_tiles = 1;
-    uint32_t* tile_off = nullptr;
-    KRAG_CUDA(cudaMalloc(&tile_off, sizeof(uint32_t) * (size_t)((int64_t)(n_slots > 0 ? n_slots : 1) * (n_tiles + 1))));
+    uint32_t* tile_off = sc.alloc<uint32_t>((size_t)((int64_t)(n_slots > 0 ? n_slots : 1) * (n_tiles + 1)));
     if (n_slots > 0) {
         tile_index_kernel<<<148 * 8, 256, 0, st>>>(sorted_terms, post_doc, off, slot, nnz_live, n_tiles, tile_off);
         KRAG_CUDA(cudaGetLastError());
@@ -156,6 +179,7 @@ static void build_tile_index(const uint32_t* sorted_terms, const uint32_t* post_
     }
     if (out.tile_slot) cudaFree(out.tile_slot);
     if (out.tile_off) cudaFree(out.tile_off);
+    sc.keep(slot); sc.keep(tile_off);
     out.tile_slot = slot; out.tile_off = tile_off; out.n_slots = n_slots; out.n_tiles = n_tiles;
 }
 
@@ -164,42 +188,33 @@ void build_postings(const uint32_t* term_ids, const uint16_t* term_tf, const uin
                     double avgdl, int64_t n_docs_rows, Postings& out, cudaStream_t st)
 {
     // local df (live docs only) -> exclusive scan -> offsets
-    uint32_t* df_local = nullptr;
-    int64_t* off = nullptr;
-    KRAG_CUDA(cudaMalloc(&df_local, sizeof(uint32_t) * (size_t)(vocab + 1)));
+    DevScratch sc;
+    uint32_t* df_local = sc.alloc<uint32_t>((size_t)(vocab + 1));
     KRAG_CUDA(cudaMemsetAsync(df_local, 0, sizeof(uint32_t) * (size_t)(vocab + 1), st));
     launch_df_histogram(term_ids, entry_doc, alive, nnz, df_local, st);
-    KRAG_CUDA(cudaMalloc(&off, sizeof(int64_t) * (size_t)(vocab + 1)));
-    int64_t* tmp64 = nullptr;
-    KRAG_CUDA(cudaMalloc(&tmp64, sizeof(int64_t) * (size_t)(vocab + 1)));
+    int64_t* off = sc.alloc<int64_t>((size_t)(vocab + 1));
+    int64_t* tmp64 = sc.alloc<int64_t>((size_t)(vocab + 1));
     df_to_i64_kernel<<<256, 256, 0, st>>>(df_local, vocab, tmp64);
     count_launch();
     size_t scan_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, tmp64, off, (int)(vocab + 1), st);
-    void* scan_tmp = nullptr;
-    KRAG_CUDA(cudaMalloc(&scan_tmp, scan_bytes ? scan_bytes : 16));
+    void* scan_tmp = sc.alloc<unsigned char>(scan_bytes);
     cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, tmp64, off, (int)(vocab + 1), st);
     count_launch();
     int64_t nnz_live = 0;
     KRAG_CUDA(cudaMemcpyAsync(&nnz_live, off + vocab, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     KRAG_CUDA(cudaStreamSynchronize(st));
-    KRAG_CUDA(cudaFree(scan_tmp));
-    KRAG_CUDA(cudaFree(tmp64));
-    KRAG_CUDA(cudaFree(df_local));
+    sc.free_now(scan_tmp); sc.free_now(tmp64); sc.free_now(df_local);
 
-    uint32_t* post_doc = nullptr;
-    float* post_score = nullptr;
-    KRAG_CUDA(cudaMalloc(&post_doc, sizeof(uint32_t) * (size_t)(nnz_live > 0 ? nnz_live : 1)));
-    KRAG_CUDA(cudaMalloc(&post_score, sizeof(float) * (size_t)(nnz_live > 0 ? nnz_live : 1)));
+    uint32_t* post_doc = sc.alloc<uint32_t>((size_t)(nnz_live > 0 ? nnz_live : 1));
+    float* post_score = sc.alloc<float>((size_t)(nnz_live > 0 ? nnz_live : 1));
 
     if (nnz > 0) {
         // stable LSD radix sort by term id keeps documents ascending inside every term
-        uint32_t *k_in = nullptr, *k_out = nullptr;
-        uint64_t *v_in = nullptr, *v_out = nullptr;
-        KRAG_CUDA(cudaMalloc(&k_in, sizeof(uint32_t) * (size_t)nnz));
-        KRAG_CUDA(cudaMalloc(&k_out, sizeof(uint32_t) * (size_t)nnz));
-        KRAG_CUDA(cudaMalloc(&v_in, sizeof(uint64_t) * (size_t)nnz));
-        KRAG_CUDA(cudaMalloc(&v_out, sizeof(uint64_t) * (size_t)nnz));
+        uint32_t* k_in = sc.alloc<uint32_t>((size_t)nnz);
+        uint32_t* k_out = sc.alloc<uint32_t>((size_t)nnz);
+        uint64_t* v_in = sc.alloc<uint64_t>((size_t)nnz);
+        uint64_t* v_out = sc.alloc<uint64_t>((size_t)nnz);
         pack_sort_values_kernel<<<148 * 8, 256, 0, st>>>(term_ids, term_tf, entry_doc, alive, nnz, (uint32_t)vocab,
                                                         k_in, v_in);
         count_launch();
@@ -207,8 +222,7 @@ void build_postings(const uint32_t* term_ids, const uint16_t* term_tf, const uin
         while (((int64_t)1 << end_bit) <= vocab) ++end_bit;  // keys range over [0, vocab]
         size_t sort_bytes = 0;
         cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, k_in, k_out, v_in, v_out, nnz, 0, end_bit, st);
-        void* sort_tmp = nullptr;
-        KRAG_CUDA(cudaMalloc(&sort_tmp, sort_bytes ? sort_bytes : 16));
+        void* sort_tmp = sc.alloc<unsigned char>(sort_bytes);
         cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, k_in, k_out, v_in, v_out, nnz, 0, end_bit, st);
         count_launch();
         if (nnz_live > 0) {
@@ -218,24 +232,22 @@ void build_postings(const uint32_t* term_ids, const uint16_t* term_tf, const uin
             build_tile_index(k_out, post_doc, off, nnz_live, vocab, n_docs_rows, out, st);
         }
         KRAG_CUDA(cudaStreamSynchronize(st));
-        KRAG_CUDA(cudaFree(sort_tmp));
-        KRAG_CUDA(cudaFree(k_in)); KRAG_CUDA(cudaFree(k_out));
-        KRAG_CUDA(cudaFree(v_in)); KRAG_CUDA(cudaFree(v_out));
+        sc.free_now(sort_tmp);
+        sc.free_now(k_in); sc.free_now(k_out); sc.free_now(v_in); sc.free_now(v_out);
     }
     if (nnz_live == 0 || nnz == 0) {   // no postings: every term is "rare" with an empty list
-        int32_t* slot = nullptr;
-        KRAG_CUDA(cudaMalloc(&slot, sizeof(int32_t) * (size_t)vocab));
+        int32_t* slot = sc.alloc<int32_t>((size_t)vocab);
         KRAG_CUDA(cudaMemset(slot, 0xFF, sizeof(int32_t) * (size_t)vocab));
-        uint32_t* toff = nullptr;
-        KRAG_CUDA(cudaMalloc(&toff, 16));
+        uint32_t* toff = sc.alloc<uint32_t>(4);
         if (out.tile_slot) cudaFree(out.tile_slot);
         if (out.tile_off) cudaFree(out.tile_off);
-        out.tile_slot = slot; out.tile_off = toff; out.n_slots = 0;
+        out.tile_slot = sc.keep(slot); out.tile_off = sc.keep(toff); out.n_slots = 0;
         out.n_tiles = (n_docs_rows + BM25_TILE_DOCS - 1) / BM25_TILE_DOCS < 1 ? 1 : (n_docs_rows + BM25_TILE_DOCS - 1) / BM25_TILE_DOCS;
     }
     if (out.off) cudaFree(out.off);
     if (out.doc) cudaFree(out.doc);
     if (out.score) cudaFree(out.score);
+    sc.keep(off); sc.keep(post_doc); sc.keep(post_score);
     out.off = off; out.doc = post_doc; out.score = post_score; out.vocab = vocab; out.nnz = nnz_live;
 }
 

@@ -28,6 +28,7 @@
 
 #include <stdlib.h>
 
+#include <atomic>
 #include <mutex>
 #include <vector>
 
@@ -1031,8 +1032,8 @@ static bool tc_use_cvt()
     return v == 1;
 }
 
-static int64_t g_tc_fallback_queries = 0;
-int64_t dense_tc_fallback_queries() { return g_tc_fallback_queries; }
+static std::atomic<int64_t> g_tc_fallback_queries{0};   // searches run concurrently (reader lock)
+int64_t dense_tc_fallback_queries() { return g_tc_fallback_queries.load(); }
 
 bool launch_dense_tc(const DeviceInfo& di, const float* X, int64_t n_rows, int dpad, const uint32_t* alive,
                      const float* xnorm, const uint32_t* xn_max_bits, const float* q, int batch, int P, uint32_t ord_base,
