@@ -17,6 +17,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
+#include <stdlib.h>
 #include <vector>
 
 #include "engine.h"
@@ -256,7 +257,16 @@ constexpr int BQ_THREADS = 256;   // a term contributes ~200 postings to a 16384
 constexpr int BQ_MAX_TERMS = 32;    // query terms resolved per pass; longer queries loop
 constexpr int BQ_MAX_SLABS = 96;    // 512-posting slabs per pass
 constexpr int BQ_PREFETCH = 8;      // slabs held in registers at a time
-constexpr int BQ_GROUP = 8;         // consecutive doc tiles handled by one work item (same query): one resolve, one select, one store
+constexpr int BQ_GROUP_MAX = 32;    // upper bound of the group size (shared-memory table)
+// consecutive doc tiles handled by one work item (same query): one resolve, one select, one store.  Runtime value
+// (KRAG_BM25_GROUP, default 8): larger groups mean fewer per-item sorts/stores and tighter own thresholds, smaller
+// ones more items to balance over the 444 resident CTAs
+static int bq_group()
+{
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("KRAG_BM25_GROUP"); int g = e ? atoi(e) : 8; v = g < 1 ? 1 : (g > BQ_GROUP_MAX ? BQ_GROUP_MAX : g); }
+    return v;
+}
 
 // A "slab" is up to 512 consecutive postings of one query term that fall into this CTA's doc
 // range (frequent terms: looked up in the tile index; rare terms: the whole <= 256-entry list,
@@ -268,7 +278,7 @@ bm25_tile_kernel(const int64_t* __restrict__ post_off, const uint32_t* __restric
                  const uint32_t* __restrict__ tile_off, int64_t n_tiles_idx, int64_t vocab,
                  const uint32_t* __restrict__ q_terms, const int32_t* __restrict__ q_term_offsets,
                  const int32_t* __restrict__ q_slot, const int64_t* __restrict__ q_base, const int32_t* __restrict__ q_rare_len,
-                 int64_t n_rows, const uint32_t* __restrict__ alive, int P, int cap, uint32_t ord_base, int batch, int n_tiles,
+                 int64_t n_rows, const uint32_t* __restrict__ alive, int P, int cap, uint32_t ord_base, int batch, int n_tiles, int group,
                  uint64_t* __restrict__ part /*[batch][n_groups][P]*/, unsigned long long* __restrict__ g_thr /*[batch]*/)
 {
     extern __shared__ __align__(16) unsigned char bsm[];
@@ -283,7 +293,7 @@ bm25_tile_kernel(const int64_t* __restrict__ post_off, const uint32_t* __restric
     __shared__ int s_nslab, s_next_term, s_next_off;
     __shared__ int32_t s_slot[BQ_MAX_TERMS], s_rare[BQ_MAX_TERMS];
     __shared__ int64_t s_base[BQ_MAX_TERMS];
-    __shared__ uint32_t s_toff[BQ_MAX_TERMS][BQ_GROUP + 1];
+    __shared__ uint32_t s_toff[BQ_MAX_TERMS][BQ_GROUP_MAX + 1];
 
     const int tid = threadIdx.x;
     // the accumulators are zeroed once: every touched entry is reset by the claim step
@@ -295,11 +305,11 @@ bm25_tile_kernel(const int64_t* __restrict__ post_off, const uint32_t* __restric
     // buffer (and its threshold) carries over from tile to tile, and one top-P list is stored per item.
     // g_thr[q] (min over finished items of their P-th best key -- an upper bound of the global P-th best) prunes
     // almost every candidate of later items before it reaches the select buffer.
-    const int n_groups = (n_tiles + BQ_GROUP - 1) / BQ_GROUP;
+    const int n_groups = (n_tiles + group - 1) / group;
     const int64_t n_items = (int64_t)n_groups * batch;
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int tg = (int)(item / batch), qi = (int)(item - (int64_t)tg * batch);
-    const int tile0 = tg * BQ_GROUP, gcount = min(BQ_GROUP, n_tiles - tile0);
+    const int tile0 = tg * group, gcount = min(group, n_tiles - tile0);
     const int tb = q_term_offsets[qi], te = q_term_offsets[qi + 1];
     const bool single_chunk = (te - tb <= BQ_MAX_TERMS);
     __syncthreads();   // previous item fully stored
@@ -506,7 +516,7 @@ size_t bm25_part_elems(int64_t n_rows, int batch, int P)
 {
     int64_t n_tiles = (n_rows + BM25_TILE_DOCS - 1) / BM25_TILE_DOCS;
     if (n_tiles < 1) n_tiles = 1;
-    const int64_t n_groups = (n_tiles + BQ_GROUP - 1) / BQ_GROUP;
+    const int64_t n_groups = (n_tiles + bq_group() - 1) / bq_group();
     return (size_t)n_groups * batch * P + (size_t)batch;   // + per-query threshold hints
 }
 
@@ -533,7 +543,7 @@ void launch_bm25(const DeviceInfo& di, const Postings& post, int64_t n_rows, con
         KRAG_CUDA(cudaFuncSetAttribute(bm25_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         attr_set = true;
     }
-    const int64_t n_groups = (n_tiles + BQ_GROUP - 1) / BQ_GROUP;
+    const int64_t n_groups = (n_tiles + bq_group() - 1) / bq_group();
     unsigned long long* g_thr = reinterpret_cast<unsigned long long*>(part + (size_t)n_groups * batch * P);
     KRAG_CUDA(cudaMemsetAsync(g_thr, 0xFF, sizeof(unsigned long long) * (size_t)batch, st));
     const int64_t n_items = n_groups * batch;
@@ -542,7 +552,7 @@ void launch_bm25(const DeviceInfo& di, const Postings& post, int64_t n_rows, con
     const int grid = (int)(n_items < max_grid ? n_items : max_grid);
     bm25_tile_kernel<<<grid, BQ_THREADS, smem, st>>>(post.off, post.doc, post.score, post.tile_slot, post.tile_off,
                                                      post.n_tiles, post.vocab, q_terms, q_term_offsets, q_slot, q_base, q_rare, n_rows,
-                                                     alive, P, cap, ord_base, batch, (int)n_tiles, part, g_thr);
+                                                     alive, P, cap, ord_base, batch, (int)n_tiles, bq_group(), part, g_thr);
     KRAG_CUDA(cudaGetLastError());
     count_launch();
     launch_merge(part, (int)n_groups, P, batch, P, /*list_stride=*/P, /*batch_stride=*/n_groups * P, keys_out, st,

@@ -1108,7 +1108,11 @@ void launch_linear(const DeviceInfo& di, const float* A, const float* B, int M, 
     const int m_tiles = (M + GM_TILE - 1) / GM_TILE;
     const int tiles128 = m_tiles * (N / GM_TILE);
     if (use_sk && ws && tiles128 < di.sm_count / 2 && N % 64 == 0 && K % GM_KB == 0 && (!ln_g || N <= 1024)) {
-        const int BN = m_tiles == 1 ? 32 : 64;
+        // long-K layers over several activation tiles (FFN2 for tens of queries): 128 x 128 tiles halve the operand
+        // re-reads through L2 (the binding resource with 4-byte operands); split-K restores the CTA count
+        static int use_wide = -1;
+        if (use_wide < 0) { const char* ev = getenv("KRAG_SK_WIDE"); use_wide = (ev == nullptr || ev[0] != '0') ? 1 : 0; }
+        const int BN = m_tiles == 1 ? 32 : ((use_wide && K >= 2048 && N % 128 == 0) ? 128 : 64);
         const int ctas = m_tiles * (N / BN), kblocks = K / GM_KB;
         int splits = 1;
         if (ctas <= di.sm_count / 3) {              // 72 CTAs with the whole K range beat 144 + a reduce kernel
@@ -1122,6 +1126,7 @@ void launch_linear(const DeviceInfo& di, const float* A, const float* B, int M, 
         emb_map(&tmB, B, N, K, BN);
         float* direct_out = C;
         if (BN == 32) launch_gemm_sk<32>(tmA, tmB, M, N, m_tiles, splits, kblocks / splits, a_rows, bias, residual, gelu, direct_out, ws, st);
+        else if (BN == 128) launch_gemm_sk<128>(tmA, tmB, M, N, m_tiles, splits, kblocks / splits, a_rows, bias, residual, gelu, direct_out, ws, st);
         else launch_gemm_sk<64>(tmA, tmB, M, N, m_tiles, splits, kblocks / splits, a_rows, bias, residual, gelu, direct_out, ws, st);
         if (splits > 1) {
             launch_pdl(splitk_reduce_kernel, dim3((unsigned)M), dim3(256), 0, st, ws, splits, M, N, bias, residual, gelu ? 1 : 0, ln_g, ln_b, eps,

@@ -14,7 +14,8 @@ pytestmark = pytest.mark.gpu
                                            # small-M split-K path (128 x 32 tiles, M <= 128; 128 x 64 tiles above)
                                            (1, 768, 768, False, False), (16, 2304, 768, False, False), (16, 3072, 768, True, False),
                                            (100, 768, 3072, False, True), (128, 384, 384, False, True), (7, 1024, 4096, False, True),
-                                           (512, 768, 768, False, True), (400, 768, 3072, False, True), (512, 2304, 768, False, False)])
+                                           (512, 768, 768, False, True), (400, 768, 3072, False, True), (512, 2304, 768, False, False),
+                                           (1024, 768, 3072, False, True), (600, 1024, 4096, False, False)])
 def test_gemm_tf32_matches_numpy(ctx, M, N, K, gelu, res):
     from kaito_b200 import _native
     g = np.random.default_rng(M + N + K)
