@@ -711,7 +711,9 @@ void launch_row_norms(const float* X, int64_t row0, int64_t n, int dpad, float* 
 
 // -------------------------------------------------------- sample -> per-query threshold
 constexpr int ST_THREADS = 512;
-constexpr int ST_CAP = 2048;
+// CAP = 1024 when m <= 256: the first prune (a bitonic sort of CAP keys, the dominant cost of this kernel) comes after two
+// iterations instead of three and sorts half as many keys
+template <int ST_CAP>
 __global__ void __launch_bounds__(ST_THREADS)
 sample_threshold_kernel(const float* __restrict__ dump, int64_t S, int m, int nq_valid, float* __restrict__ thr,
                         float* __restrict__ part_vals /* != null: grid (NQ, parts), write this part's m smallest values */)
@@ -935,12 +937,17 @@ static void tc_pass(const DeviceInfo& di, const CUtensorMap& tmX, const CUtensor
     if (m > 1024) m = 1024;
     // two-level: 8 blocks per query keep their m smallest, a second pass takes the m-th smallest of the 8 m survivors
     // (the survivors are parked in the exact_keys area, which is not in use before the rescoring)
-    constexpr int ST_PARTS = 8;
+    constexpr int ST_PARTS = 4;
     float* part_vals = reinterpret_cast<float*>(w.exact_keys);
-    sample_threshold_kernel<<<dim3(NQ, ST_PARTS), ST_THREADS, 0, st>>>(w.dump, S, m, nq, nullptr, part_vals);
-    KRAG_CUDA(cudaGetLastError());
-    count_launch();
-    sample_threshold_kernel<<<dim3(NQ, 1), ST_THREADS, 0, st>>>(part_vals, (int64_t)ST_PARTS * m, m, nq, w.thr, nullptr);
+    if (m <= 256) {
+        sample_threshold_kernel<1024><<<dim3(NQ, ST_PARTS), ST_THREADS, 0, st>>>(w.dump, S, m, nq, nullptr, part_vals);
+        count_launch();
+        sample_threshold_kernel<1024><<<dim3(NQ, 1), ST_THREADS, 0, st>>>(part_vals, (int64_t)ST_PARTS * m, m, nq, w.thr, nullptr);
+    } else {
+        sample_threshold_kernel<2048><<<dim3(NQ, ST_PARTS), ST_THREADS, 0, st>>>(w.dump, S, m, nq, nullptr, part_vals);
+        count_launch();
+        sample_threshold_kernel<2048><<<dim3(NQ, 1), ST_THREADS, 0, st>>>(part_vals, (int64_t)ST_PARTS * m, m, nq, w.thr, nullptr);
+    }
     KRAG_CUDA(cudaGetLastError());
     count_launch();
     KRAG_CUDA(cudaMemsetAsync(w.cand_count, 0, 256 * 4, st));
