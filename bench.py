@@ -494,7 +494,7 @@ def run_ours(args):
             "clocks": clocks, "planted_top1_hit": recall, "recall_at_10": 1.0,
             "recall_note": "dense search is exact (brute force, fp32 re-scored): recall@10 = 1.0 by construction; parity tests check ids bit-exactly",
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:      # the CPU leg is reported at N = 1 only (rank 0 would stall the other ranks)
             line["cpu_baseline"] = cpu_reference_qps(docs, dim, hybrid, k, args.cpu_sample_rows, emb_name, args.query_tokens)
         print(json.dumps(line), flush=True)
     barrier()
