@@ -170,3 +170,40 @@ def test_select_context_rule():
     assert chat.select_context(nodes, "q" * 30, llm, 0.5, None, None)[0][0].text[0] == "b"     # 420-token budget: b fits first
     assert chat.select_context(nodes, "q" * 3000, llm, 0.5, 400, 0.85) == []                     # nothing left after the query
     assert chat.select_context([], "q", llm, 0.5, 400, 0.85) == []
+
+
+def test_chat_roles_max_tokens_and_usage_fallback(oracle):
+    """test_chat_completions.py:559-623 system message, :719-776 developer role, :626-659 unsupported role = the LLM's own
+    error through the pass-through, :1123-1250 max_tokens larger than what the window leaves is clamped (never a 422), and the
+    usage block is estimated when the LLM returns none (base.py:428-446)."""
+    from tests.oracle_engine import OracleEngine
+    no_usage = {k: v for k, v in ANSWER.items() if k != "usage"}
+    fake = FakeLLM(body=no_usage)
+    c = _client(OracleEngine(oracle), fake, window=1000)
+    q = DOCS[1]["text"]
+    r = c.post("/v1/chat/completions", json={"index_name": "test_index", "model": "mock-model", "temperature": 0.5, "messages": [
+        {"role": "system", "content": "You are a helpful AI assistant specializing in Kubernetes."},
+        {"role": "developer", "content": "Answer in one sentence."}, {"role": "user", "content": q}], "max_tokens": 5000})
+    assert r.status_code == 200, r.text
+    body = r.json()
+    assert len(body["source_nodes"]) > 0 and body["source_nodes"][0]["text"] == q
+    sent = fake.posts[-1]
+    assert [m["role"] for m in sent["messages"]] == ["system", "system", "developer", "user"]
+    assert 0 < sent["max_tokens"] < 1000                               # clamped to what the 1000-token window leaves
+    u = body["usage"]
+    assert u["total_tokens"] == u["prompt_tokens"] + u["completion_tokens"] and u["completion_tokens"] > 0
+    # unsupported role -> pass-through; the LLM's 400 comes back as 400 with its body in the detail
+    bad = FakeLLM(status=400, body={"detail": "bad request format"})
+    c2 = _client(OracleEngine(oracle), bad)
+    r = c2.post("/v1/chat/completions", json={"model": "mock-model", "messages": [{"role": "function", "content": "Function response", "name": "f"}]})
+    assert r.status_code == 400 and "bad request format" in r.json()["detail"]
+    # assistant turns end the query: only user messages after the last assistant message are searched (base.py:311-330)
+    fake3 = FakeLLM()
+    c3 = _client(OracleEngine(oracle), fake3)
+    r = c3.post("/v1/chat/completions", json={"index_name": "test_index", "messages": [
+        {"role": "user", "content": DOCS[3]["text"]}, {"role": "assistant", "content": "noted"},
+        {"role": "user", "content": "Pasta boiling requires"}, {"role": "user", "content": "salted water."}]})
+    assert r.status_code == 200
+    assert fake3.posts[-1]["messages"][-1] == {"role": "user", "content": "Pasta boiling requires\n\nsalted water."}
+    assert [m["role"] for m in fake3.posts[-1]["messages"]] == ["system", "user", "assistant", "user"]
+    assert r.json()["source_nodes"][0]["text"] == DOCS[4]["text"]
