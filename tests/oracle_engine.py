@@ -29,6 +29,7 @@ class OracleIndex:
         return self.o.alive_bitmap(len(self.ids), self.dead) if self.dead else None
 
     def commit(self, vocab):
+        self.vocab = vocab
         o, n = self.o, len(self.ids)
         live = np.array([i not in self.dead for i in range(n)])
         df = np.zeros(vocab, np.uint32)
@@ -69,6 +70,11 @@ class OracleIndex:
     def search_dense(self, q, k):
         return self.o.dense_topk(self.x, np.asarray(q, np.float32).reshape(-1, self.dim), k, self._alive())
 
+    def persist(self, path):
+        import os
+        np.savez(os.path.join(path, "oracle_index.npz"), x=self.x, ids=self.ids, off=self.off, tid=self.tid, tf=self.tf, dl=self.dl,
+                 dead=np.array(sorted(self.dead), np.int64), vocab=np.int64(getattr(self, "vocab", 0)))
+
     def drop(self):
         pass
 
@@ -79,3 +85,13 @@ class OracleEngine:
 
     def create_index(self, name, dim):
         return OracleIndex(self.o, name, dim)
+
+    def load_index(self, name, path):
+        import os
+        z = np.load(os.path.join(path, "oracle_index.npz"))
+        ix = OracleIndex(self.o, name, z["x"].shape[1])
+        ix.x, ix.ids, ix.off, ix.tid, ix.tf, ix.dl = z["x"], z["ids"], z["off"], z["tid"], z["tf"], z["dl"]
+        ix.dead = set(int(d) for d in z["dead"])
+        if int(z["vocab"]) > 0:
+            ix.commit(int(z["vocab"]))
+        return ix

@@ -1,0 +1,126 @@
+"""PostStart / PreStop shims (deploy/app/ragengine/lifecycle/hooks.py) against a live service: the snapshot protocol the
+controller's hooks rely on (pkg/ragengine/manifests/manifests.go:116-134; presets/ragengine/lifecycle/manager.py:126-326):
+  <persist_dir>/systemsnapshots/<ts>_pod-<uid8>/<index>/..., metadata.json {index_names, version}, LATEST -> newest snapshot,
+restore of every index of LATEST at start.  CPU: uvicorn in a thread over the oracle engine double."""
+import importlib.util
+import json
+import os
+import socket
+import threading
+import time
+
+import pytest
+
+from kaito_b200.embedding import HashingEmbedding
+from kaito_b200.service import create_app, resolve_model_dir
+from kaito_b200.vector_store import VectorStore
+
+HOOKS = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "deploy", "app", "ragengine", "lifecycle", "hooks.py")
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _serve(app, port):
+    import uvicorn
+    server = uvicorn.Server(uvicorn.Config(app, host="127.0.0.1", port=port, log_level="error"))
+    th = threading.Thread(target=server.run, daemon=True)
+    th.start()
+    for _ in range(100):
+        try:
+            socket.create_connection(("127.0.0.1", port), timeout=0.2).close()
+            return server, th
+        except OSError:
+            time.sleep(0.05)
+    raise RuntimeError("server did not start")
+
+
+def _load_hooks(monkeypatch, port, persist_dir, uid):
+    monkeypatch.setenv("RAG_SERVICE_URL", f"http://127.0.0.1:{port}")
+    monkeypatch.setenv("DEFAULT_VECTOR_DB_PERSIST_DIR", str(persist_dir))
+    monkeypatch.setenv("POD_UID", uid)
+    spec = importlib.util.spec_from_file_location(f"hooks_{uid}", HOOKS)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)          # BASE / ROOT are read from the environment at import, as in the pod
+    return mod
+
+
+def test_prestop_snapshot_and_poststart_restore(oracle, tmp_path, monkeypatch):
+    from starlette.testclient import TestClient
+    from tests.oracle_engine import OracleEngine
+    port = _free_port()
+    store = VectorStore(HashingEmbedding(64), OracleEngine(oracle))
+    app = create_app(store, {"persist_dir": str(tmp_path), "llm_inference_url": None})
+    server, th = _serve(app, port)
+    try:
+        c = TestClient(app)
+        docs = [{"text": "First document about retrieval engines"}, {"text": "Second document about Kubernetes operators", "metadata": {"k": "v"}}]
+        assert c.post("/index", json={"index_name": "idx_a", "documents": docs}).status_code == 200
+        assert c.post("/index", json={"index_name": "idx b", "documents": docs[:1]}).status_code == 200     # name needing URL quoting
+        before = c.post("/retrieve", json={"index_name": "idx_a", "query": "Kubernetes operators", "max_node_count": 2}).json()
+
+        hooks = _load_hooks(monkeypatch, port, tmp_path, "0123456789abcdef")
+        hooks.prestop()
+        root = tmp_path / "systemsnapshots"
+        snaps = [d for d in os.listdir(root) if d != "LATEST"]
+        assert len(snaps) == 1 and snaps[0].endswith("_pod-01234567")
+        meta = json.load(open(root / "LATEST" / "metadata.json"))
+        assert meta == {"index_names": ["idx_a", "idx b"], "version": 1}
+        assert os.path.realpath(root / "LATEST") == os.path.realpath(root / snaps[0])
+        assert os.path.isfile(root / snaps[0] / "idx_a" / "docstore.json")
+
+        # a fresh pod: empty service, PostStart restores every index named in LATEST/metadata.json
+        for name in ("idx_a", "idx b"):
+            assert c.delete(f"/indexes/{name}").status_code == 200
+        assert c.get("/indexes").json() == []
+        hooks.poststart()
+        assert sorted(c.get("/indexes").json()) == ["idx b", "idx_a"]
+        after = c.post("/retrieve", json={"index_name": "idx_a", "query": "Kubernetes operators", "max_node_count": 2}).json()
+        assert after == before
+        assert c.get("/indexes/idx_a/documents").json()["total_items"] == 2
+
+        # retention: only the newest 5 snapshots are kept (manager.py keeps 5)
+        for i in range(6):
+            os.makedirs(root / f"2000010{i}-000000_pod-old{i}")
+        hooks.prestop()
+        kept = sorted(d for d in os.listdir(root) if d != "LATEST")
+        assert len(kept) == 5 and os.path.realpath(root / "LATEST") == os.path.realpath(root / kept[-1])
+    finally:
+        server.should_exit = True
+        th.join(timeout=5)
+
+
+def test_poststart_without_snapshot_is_a_noop(oracle, tmp_path, monkeypatch, capsys):
+    from tests.oracle_engine import OracleEngine
+    port = _free_port()
+    app = create_app(VectorStore(HashingEmbedding(64), OracleEngine(oracle)), {"persist_dir": str(tmp_path), "llm_inference_url": None})
+    server, th = _serve(app, port)
+    try:
+        hooks = _load_hooks(monkeypatch, port, tmp_path, "ffff")
+        hooks.poststart()
+        assert "no snapshot to restore" in capsys.readouterr().out
+        hooks.prestop()                                   # no indexes: nothing is written
+        assert not os.path.exists(tmp_path / "systemsnapshots" / "LATEST")
+    finally:
+        server.should_exit = True
+        th.join(timeout=5)
+
+
+def test_resolve_model_dir(tmp_path, monkeypatch):
+    """service.resolve_model_dir: explicit KRAG_MODEL_DIR, MODEL_ID as a path, hub cache layout; None when nothing is local"""
+    def snap(p):
+        os.makedirs(p)
+        for f in ("config.json", "vocab.txt"):
+            open(os.path.join(p, f), "w").write("{}")
+        return str(p)
+    monkeypatch.delenv("KRAG_MODEL_DIR", raising=False)
+    monkeypatch.setenv("HF_HOME", str(tmp_path / "hf"))
+    assert resolve_model_dir("BAAI/bge-small-en-v1.5") is None
+    hub = snap(tmp_path / "hf" / "hub" / "models--BAAI--bge-small-en-v1.5" / "snapshots" / "abc123")
+    assert resolve_model_dir("BAAI/bge-small-en-v1.5") == hub
+    local = snap(tmp_path / "mymodel")
+    assert resolve_model_dir(local) == local
+    monkeypatch.setenv("KRAG_MODEL_DIR", snap(tmp_path / "explicit"))
+    assert resolve_model_dir("BAAI/bge-small-en-v1.5") == str(tmp_path / "explicit")
