@@ -26,19 +26,29 @@ static std::atomic<int64_t> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
+// "last dense kernel" diagnostics (krag_last_dense_kernel, read by bench.py).  Process-wide and last-writer-wins: with
+// concurrent searches the numbers describe one of them; the mutex only keeps the record itself consistent.
+static std::mutex g_t_mu;
 static cudaEvent_t g_t0 = nullptr, g_t1 = nullptr;
 static int g_t_kernel = 0;
 static int64_t g_t_bytes = 0, g_t_flops = 0;
 static bool g_t_valid = false;
 void dense_timer_begin(cudaStream_t st, int kernel_id, int64_t bytes, int64_t flops)
 {
+    std::lock_guard<std::mutex> lk(g_t_mu);
     if (!g_t0) { cudaEventCreate(&g_t0); cudaEventCreate(&g_t1); }
     g_t_kernel = kernel_id; g_t_bytes = bytes; g_t_flops = flops; g_t_valid = false;
     cudaEventRecord(g_t0, st);
 }
-void dense_timer_end(cudaStream_t st) { cudaEventRecord(g_t1, st); g_t_valid = true; }
+void dense_timer_end(cudaStream_t st)
+{
+    std::lock_guard<std::mutex> lk(g_t_mu);
+    cudaEventRecord(g_t1, st);
+    g_t_valid = true;
+}
 bool dense_timer_read(float* ms, int* kernel_id, int64_t* bytes, int64_t* flops)
 {
+    std::lock_guard<std::mutex> lk(g_t_mu);
     if (!g_t_valid || cudaEventSynchronize(g_t1) != cudaSuccess || cudaEventElapsedTime(ms, g_t0, g_t1) != cudaSuccess) return false;
     *kernel_id = g_t_kernel; *bytes = g_t_bytes; *flops = g_t_flops;
     return true;
@@ -469,8 +479,14 @@ int32_t krag_index_add(krag_index* ix, int64_t n, const uint64_t* node_ids, cons
         cudaStream_t st = ix->ctx->admin;
         KRAG_REQUIRE(ix->n_rows == 0 || sparse == ix->has_sparse, KRAG_E_STATE,
                      "an index is either hybrid (term lists for every node) or dense-only");
-        for (int64_t i = 0; i < n; ++i)
-            KRAG_REQUIRE(ix->id2row.find(node_ids[i]) == ix->id2row.end(), KRAG_E_INVALID, "duplicate node id");
+        {
+            std::unordered_map<uint64_t, int64_t> batch;   // ids must be new to the index AND unique inside the call
+            batch.reserve((size_t)n);
+            for (int64_t i = 0; i < n; ++i) {
+                KRAG_REQUIRE(ix->id2row.find(node_ids[i]) == ix->id2row.end(), KRAG_E_INVALID, "duplicate node id");
+                KRAG_REQUIRE(batch.emplace(node_ids[i], i).second, KRAG_E_INVALID, "duplicate node id inside the batch");
+            }
+        }
         const int64_t add_nnz = sparse ? term_offsets[n] - term_offsets[0] : 0;
         KRAG_REQUIRE(!sparse || (term_offsets[0] == 0 && add_nnz >= 0), KRAG_E_INVALID, "term_offsets must start at 0");
         ensure_capacity(ix, ix->n_rows + n, sparse ? ix->nnz + add_nnz : -1, st);
@@ -561,6 +577,7 @@ int32_t krag_index_commit(krag_index* ix, int64_t vocab)
 {
     return guarded([&] {
         KRAG_REQUIRE(ix, KRAG_E_INVALID, "null index");
+        KRAG_REQUIRE(vocab >= 1 && vocab <= (int64_t)1 << 31, KRAG_E_INVALID, "vocab must be in [1, 2^31]");
         std::unique_lock<std::shared_mutex> lk(ix->mu);
         KRAG_CUDA(cudaSetDevice(ix->ctx->di.device));
         std::vector<uint32_t> df((size_t)vocab);
