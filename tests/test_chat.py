@@ -207,3 +207,25 @@ def test_chat_roles_max_tokens_and_usage_fallback(oracle):
     assert fake3.posts[-1]["messages"][-1] == {"role": "user", "content": "Pasta boiling requires\n\nsalted water."}
     assert [m["role"] for m in fake3.posts[-1]["messages"]] == ["system", "user", "assistant", "user"]
     assert r.json()["source_nodes"][0]["text"] == DOCS[4]["text"]
+
+
+def test_select_context_against_reference_golden():
+    """tests/golden/context_selection_reference.json was produced by executing the reference's own
+    ContextSelectionProcessor._postprocess_nodes (oracle/gen_golden_context.py); our restatement must pick the same
+    nodes in the same order for every recorded case (budget arithmetic, stable distance order, threshold, greedy skip)."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "context_selection_reference.json")
+    fx = json.load(open(path))
+    assert fx["meta"]["addition_prompt_tokens"] == chat.ADDITION_PROMPT_TOKENS
+
+    class N:
+        def __init__(self, text, nid):
+            self.text, self.nid = text, nid
+
+    assert len(fx["cases"]) >= 30 and sum(1 for c in fx["cases"] if c["selected"]) >= 15
+    for c in fx["cases"]:
+        llm = chat.LLMClient(None, context_window=c["window"])
+        llm._encoder_failed = True                       # the fixture's count_tokens is the len/3 fallback
+        nodes = [(N("t" * L, i), s) for i, (L, s) in enumerate(zip(c["text_lens"], c["scores"]))]
+        got = chat.select_context(nodes, "q" * c["query_len"], llm, c["ratio"], c["max_tokens"], c["threshold"])
+        assert [n.nid for n, _ in got] == c["selected"], c
