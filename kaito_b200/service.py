@@ -56,6 +56,40 @@ class RetrieveRequest(BaseModel):
     metadata_filter: dict | None = None
 
 
+class NodeWithScore(BaseModel):          # models.py:63-71; the reference's retrieve leaves the three optional scores unset
+    doc_id: str
+    node_id: str
+    text: str
+    score: float
+    dense_score: float | None = None
+    sparse_score: float | None = None
+    source: str | None = None            # "both", "dense_only", "sparse_only"
+    metadata: dict | None = None
+
+
+class RetrieveResponse(BaseModel):
+    query: str
+    results: list[NodeWithScore]
+    count: int
+
+
+class ListDocumentsResponse(BaseModel):
+    documents: list[Document]
+    count: int
+    total_items: int
+
+
+class UpdateDocumentResponse(BaseModel):
+    updated_documents: list[Document]
+    unchanged_documents: list[Document]
+    not_found_documents: list[Document]
+
+
+class DeleteDocumentResponse(BaseModel):
+    deleted_doc_ids: list[str]
+    not_found_doc_ids: list[str]
+
+
 class HealthStatus(BaseModel):
     status: str
     detail: str | None = None
@@ -160,7 +194,7 @@ def create_app(store: vs.VectorStore, cfg: dict | None = None, llm=None) -> Fast
             return [Document(doc_id=i, text=d.text, metadata=d.metadata) for i, d in zip(ids, request.documents)]
         return run("index", go)
 
-    @app.post("/retrieve")
+    @app.post("/retrieve", response_model=RetrieveResponse)
     def retrieve_from_index(request: RetrieveRequest):   # main.py:742-771
         def go():
             out = store.retrieve(request.index_name, request.query, request.max_node_count, request.metadata_filter)
@@ -184,7 +218,7 @@ def create_app(store: vs.VectorStore, cfg: dict | None = None, llm=None) -> Fast
     def list_indexes():
         return run("indexes", store.list_indexes)
 
-    @app.get("/indexes/{index_name}/documents")
+    @app.get("/indexes/{index_name}/documents", response_model=ListDocumentsResponse)
     def list_documents(index_name: str, limit: int = Query(10, ge=1, le=100), offset: int = Query(0, ge=0),
                        max_text_length: int | None = Query(1000, ge=1), metadata_filter: str | None = Query(None)):
         def go():
@@ -197,11 +231,11 @@ def create_app(store: vs.VectorStore, cfg: dict | None = None, llm=None) -> Fast
             return store.list_documents_in_index(unquote(index_name), limit, offset, max_text_length, mf)
         return run("documents", go)
 
-    @app.post("/indexes/{index_name}/documents")
+    @app.post("/indexes/{index_name}/documents", response_model=UpdateDocumentResponse)
     def update_documents(index_name: str, request: UpdateDocumentRequest):
         return run("update", lambda: store.update_documents(unquote(index_name), [d.model_dump() for d in request.documents]))
 
-    @app.post("/indexes/{index_name}/documents/delete")
+    @app.post("/indexes/{index_name}/documents/delete", response_model=DeleteDocumentResponse)
     def delete_documents(index_name: str, request: DeleteDocumentRequest):
         return run("delete_doc", lambda: store.delete_documents(unquote(index_name), request.doc_ids))
 

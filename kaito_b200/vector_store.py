@@ -104,6 +104,7 @@ class HybridRetriever:
         # False (reference): only the keyword list is post-filtered (:227-235).  True: the bitmap restricts the dense and
         # the BM25 scan on the GPU, so every result satisfies the filter (not the reference).
         self._filter_pushdown = filter_pushdown
+        self.last_components: list[dict] = []
 
     def _allow_bitmap(self):
         if not self._metadata_filter:
@@ -126,6 +127,12 @@ class HybridRetriever:
                                 fusion_mode=FILTER_PUSHDOWN if (self._filter_pushdown and allow is not None) else 0,
                                 keyword_allow_bitmap=allow)
         c = int(out["count"][0])
+        self.last_components = []
+        if "dense" in out and "sparse" in out:          # per-result L2^2 / BM25 score as computed by the fuse kernel (NaN = absent)
+            for d, s in zip(out["dense"][0, :c], out["sparse"][0, :c]):
+                hd, hs = not np.isnan(d), not np.isnan(s)
+                self.last_components.append({"dense_score": float(d) if hd else None, "sparse_score": float(s) if hs else None,
+                                             "source": "both" if hd and hs else ("dense_only" if hd else "sparse_only")})
         return [(st.nodes[int(o)], float(s)) for o, s in zip(out["ordinal"][0, :c], out["final"][0, :c])]
 
 
@@ -139,6 +146,7 @@ class VectorStore:
         self.index_map: dict[str, _IndexState] = {}
         self.splitter = SentenceSplitter()
         self.filter_pushdown = os.getenv("KRAG_FILTER_PUSHDOWN", "0") == "1"
+        self.component_scores = os.getenv("KRAG_COMPONENT_SCORES", "0") == "1"
         # many readers / one writer (aiorwlock in the reference, base.py:77-79); the engine enforces the same
         # discipline per index internally, this lock protects the host-side docstore
         self._lock = threading.RLock()
@@ -209,6 +217,9 @@ class VectorStore:
             self.last_retrieve_seconds = time.time() - t0
             results = [{"doc_id": n.ref_doc_id or n.node_id, "node_id": n.node_id, "text": n.text, "score": s,
                         "metadata": n.metadata if n.metadata else None} for n, s in nodes]
+            if self.component_scores:       # KRAG_COMPONENT_SCORES=1: fill the optional fields of models.NodeWithScore
+                for r, extra in zip(results, retriever.last_components):
+                    r.update(extra)
             return {"query": query, "results": results, "count": len(results)}
         except HTTPException:
             raise

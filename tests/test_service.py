@@ -31,8 +31,9 @@ def _exercise(client, tmp_path):
     body = r.json()
     assert body["query"] == "another test document" and body["count"] == len(body["results"]) <= 2
     assert {x["doc_id"] for x in body["results"]} <= {doc1["doc_id"], doc2["doc_id"]}
-    for x in body["results"]:
-        assert set(x) >= {"doc_id", "node_id", "text", "score", "metadata"}
+    for x in body["results"]:   # models.NodeWithScore: the reference serialises the three optional scores as null
+        assert set(x) == {"doc_id", "node_id", "text", "score", "metadata", "dense_score", "sparse_score", "source"}
+        assert x["dense_score"] is None and x["sparse_score"] is None and x["source"] is None
     assert client.post("/retrieve", json={"index_name": "nope", "query": "q"}).status_code == 404
     assert client.post("/retrieve", json={"index_name": "nope", "query": "q"}).json() == {"detail": "No such index: 'nope' exists."}
     assert client.post("/retrieve", json={"index_name": "test_index", "query": "  "}).json() == {"detail": "Query string cannot be empty."}
@@ -73,3 +74,20 @@ def test_service_gpu(ctx, oracle, tmp_path):
     assert client.post("/load/test_index", params={"path": p}).status_code == 409
     assert client.post("/load/test_index", params={"path": p, "overwrite": "true"}).status_code == 200
     assert client.delete("/indexes/test_index").status_code == 200
+
+
+def test_wire_models_match_reference_schemas():
+    """tests/golden/wire_models_reference.json holds the JSON schemas of the reference's own pydantic models
+    (presets/ragengine/models.py executed by oracle/gen_golden_models.py): same fields, required sets, types, defaults and
+    limits on every request/response model of the routes this service keeps."""
+    import json
+    import os
+    from kaito_b200 import service
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wire_models_reference.json")))["models"]
+    keep = ("type", "default", "minimum", "maximum", "anyOf", "items", "$ref")
+    assert len(fx) == 11
+    for name, ref in fx.items():
+        sch = getattr(service, name).model_json_schema()
+        assert sorted(sch.get("required", [])) == ref["required"], name
+        props = {k: {kk: vv for kk, vv in v.items() if kk in keep} for k, v in sch.get("properties", {}).items()}
+        assert props == ref["properties"], (name, props, ref["properties"])
