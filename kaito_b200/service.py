@@ -110,6 +110,75 @@ def env_config() -> dict:
     }
 
 
+# --------------------------------------------------------------- Prometheus metrics (metrics/prometheus_metrics.py:27-330)
+# Every metric the reference registers -- name, kind, labels, buckets -- including the rag_hybrid_* family it defines for its
+# dashboards but never observes (kept registered so that scrapes and dashboards see the same series set).
+_B_DEFAULT = None
+_B_SCORE = (0.1, 0.2, 0.3, 0.35, 0.4, 0.45, 0.5, 0.6, 0.7, 0.8, 0.9, 1.0)
+_B_HSCORE = (0.1, 0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 0.9, 0.95, 1.0)
+_B_CAND = (0, 1, 2, 3, 5, 10, 20, 50, 100)
+_B_CNT = (0, 1, 2, 3, 5, 10, 20, 50)
+METRIC_SPEC = [
+    ("rag_embedding_latency_seconds", "H", ("status", "mode"), _B_DEFAULT, "Time to embed in seconds"),
+    ("rag_embedding_requests", "C", ("status", "mode"), None, "Count of successful/failed embed requests"),
+    ("rag_chat_latency_seconds", "H", ("status",), _B_DEFAULT, "Time to call '/v1/chat/completions' API in seconds"),
+    ("rag_chat_requests", "C", ("status",), None, "Count of successful/failed calling '/v1/chat/completions' requests"),
+    ("rag_index_latency_seconds", "H", ("status",), _B_DEFAULT, "Time to call '/index' API in seconds"),
+    ("rag_index_requests", "C", ("status",), None, "Count of successful/failed calling '/index' requests"),
+    ("rag_indexes_latency_seconds", "H", ("status",), _B_DEFAULT, "Time to call '/indexes' API in seconds"),
+    ("rag_indexes_requests", "C", ("status",), None, "Count of successful/failed calling '/indexes' requests"),
+    ("rag_indexes_document_latency_seconds", "H", ("status",), _B_DEFAULT, "Time to call get '/indexes/{index_name}/documents' API in seconds"),
+    ("rag_indexes_document_requests", "C", ("status",), None, "Count of successful/failed calling get '/indexes/{index_name}/documents' requests"),
+    ("rag_indexes_update_document_latency_seconds", "H", ("status",), _B_DEFAULT, "Time to call post '/indexes/{index_name}/documents' API in seconds"),
+    ("rag_indexes_update_document_requests", "C", ("status",), None, "Count of successful/failed calling post '/indexes/{index_name}/documents' requests"),
+    ("rag_indexes_retrieve_latency_seconds", "H", ("status",), _B_DEFAULT, "Time to call post '/retrieve' API in seconds"),
+    ("rag_indexes_retrieve_requests", "C", ("status",), None, "Count of successful/failed calling post '/retrieve' requests"),
+    ("rag_indexes_delete_document_latency_seconds", "H", ("status",), _B_DEFAULT, "Time to call '/indexes/{index_name}/documents/delete' API in seconds"),
+    ("rag_indexes_delete_document_requests", "C", ("status",), None, "Count of successful/failed calling '/indexes/{index_name}/documents/delete' requests"),
+    ("rag_persist_latency_seconds", "H", ("status",), _B_DEFAULT, "Time to call '/persist/{index_name}' API in seconds"),
+    ("rag_persist_requests", "C", ("status",), None, "Count of successful/failed calling '/persist/{index_name}' requests"),
+    ("rag_load_latency_seconds", "H", ("status",), _B_DEFAULT, "Time to call '/load/{index_name}' API in seconds"),
+    ("rag_load_requests", "C", ("status",), None, "Count of successful/failed calling '/load/{index_name}' requests"),
+    ("rag_delete_index_latency_seconds", "H", ("status",), _B_DEFAULT, "Time to call delete '/indexes/{index_name}' API in seconds"),
+    ("rag_delete_index_requests", "C", ("status",), None, "Count of successful/failed calling delete '/indexes/{index_name}' requests"),
+    ("e2e_request", "C", ("status",), None, "Total number of all processed requests"),
+    ("e2e_request_latency_seconds", "H", ("status",), _B_DEFAULT, "End to end request latency in seconds"),
+    ("num_requests_running", "G", (), None, "Number of requests currently being processed"),
+    ("rag_vector_store_operation_latency_seconds", "H", ("operation", "status"), (0.005, 0.01, 0.025, 0.05, 0.1, 0.25, 0.5, 1.0, 2.5, 5.0, 10.0),
+     "Latency of vector store backend operations (insert, query, delete)"),
+    ("rag_retrieve_result_count", "H", (), (0, 1, 2, 3, 5, 10, 20, 50, 100, 200, 300), "Number of document chunks returned per retrieve call"),
+    ("rag_lowest_source_score", "H", (), _B_SCORE, "Score of the lowest scoring source node (typically the most relevant)"),
+    ("rag_avg_source_score", "H", (), _B_SCORE, "Average score of all retrieved source documents in RAG queries"),
+    ("rag_hybrid_search_mode", "C", ("search_mode",), None, "Number of retrieve calls by search mode"),
+    ("rag_hybrid_retrieve_latency_seconds", "H", (), (0.005, 0.01, 0.025, 0.05, 0.1, 0.25, 0.5, 1.0, 2.5, 5.0),
+     "End-to-end latency of hybrid retrieve (dense+sparse encode, query, fusion)"),
+    ("rag_hybrid_retrieve_latency_avg_seconds", "G", (), None, "Running average latency of hybrid retrieve calls (sum / count)"),
+    ("rag_hybrid_top_score", "H", (), _B_HSCORE, "Highest (best) fused score among results per hybrid retrieve call"),
+    ("rag_hybrid_median_score", "H", (), _B_HSCORE, "Median fused score of results per hybrid retrieve call"),
+    ("rag_hybrid_score_spread", "H", (), (0.0, 0.05, 0.1, 0.15, 0.2, 0.3, 0.4, 0.5, 0.7, 1.0), "Score spread (max - min) per hybrid retrieve call"),
+    ("rag_hybrid_top_k_requested", "H", (), (1, 2, 3, 5, 10, 20, 50, 100), "The top_k value requested per hybrid retrieve call"),
+    ("rag_hybrid_sparse_top_k", "H", (), (3, 6, 9, 15, 30, 60, 150, 300), "The sparse_top_k (prefetch) value used per hybrid retrieve call"),
+    ("rag_hybrid_dense_candidates", "H", (), _B_CAND, "Number of dense (vector) candidate nodes returned before fusion"),
+    ("rag_hybrid_sparse_candidates", "H", (), _B_CAND, "Number of sparse (BM25) candidate nodes returned before fusion"),
+    ("rag_hybrid_overlap_count", "H", (), _B_CNT, "Number of final result nodes that appear in BOTH dense and sparse results"),
+    ("rag_hybrid_dense_only_count", "H", (), _B_CNT, "Number of final result nodes that came from dense (vector) search only"),
+    ("rag_hybrid_sparse_only_count", "H", (), _B_CNT, "Number of final result nodes that came from sparse (BM25) search only"),
+]
+
+
+def build_metrics(reg: CollectorRegistry) -> dict:
+    out = {}
+    for name, kind, labels, buckets, doc in METRIC_SPEC:
+        if kind == "H":
+            kw = {} if buckets is None else {"buckets": buckets}
+            out[name] = Histogram(name, doc, labelnames=list(labels), registry=reg, **kw)
+        elif kind == "C":
+            out[name] = Counter(name, doc, labelnames=list(labels), registry=reg)
+        else:
+            out[name] = Gauge(name, doc, registry=reg)
+    return out
+
+
 def create_app(store: vs.VectorStore, cfg: dict | None = None, llm=None) -> FastAPI:
     cfg = cfg or env_config()
     from . import chat as _chat
@@ -118,43 +187,38 @@ def create_app(store: vs.VectorStore, cfg: dict | None = None, llm=None) -> Fast
         llm = _chat.LLMClient(chat_cfg["llm_inference_url"], chat_cfg["llm_access_secret"], chat_cfg["llm_context_window"])
     app = FastAPI(title="KAITO RAGEngine service (B200-native)")
     reg = CollectorRegistry()
-    lat = lambda n, d, labels=("status",): Histogram(n, d, labelnames=list(labels), registry=reg)  # noqa: E731
-    cnt = lambda n, d, labels=("status",): Counter(n, d, labelnames=list(labels), registry=reg)    # noqa: E731
-    M = {
-        "index": (lat("rag_index_latency_seconds", "Time to call '/index' API in seconds"), cnt("rag_index_requests", "index requests")),
-        "indexes": (lat("rag_indexes_latency_seconds", "list indexes latency"), cnt("rag_indexes_requests", "list indexes requests")),
-        "documents": (lat("rag_indexes_document_latency_seconds", "list documents latency"), cnt("rag_indexes_document_requests", "list documents requests")),
-        "update": (lat("rag_indexes_update_document_latency_seconds", "update latency"), cnt("rag_indexes_update_document_requests", "update requests")),
-        "retrieve": (lat("rag_indexes_retrieve_latency_seconds", "retrieve latency"), cnt("rag_indexes_retrieve_requests", "retrieve requests")),
-        "delete_doc": (lat("rag_indexes_delete_document_latency_seconds", "delete doc latency"), cnt("rag_indexes_delete_document_requests", "delete doc requests")),
-        "persist": (lat("rag_persist_latency_seconds", "persist latency"), cnt("rag_persist_requests", "persist requests")),
-        "load": (lat("rag_load_latency_seconds", "load latency"), cnt("rag_load_requests", "load requests")),
-        "delete": (lat("rag_delete_index_latency_seconds", "delete index latency"), cnt("rag_delete_index_requests", "delete index requests")),
-        "chat": (lat("rag_chat_latency_seconds", "chat latency"), cnt("rag_chat_requests", "chat requests")),
-    }
-    e2e_total = Counter("e2e_request", "Total requests", labelnames=["status", "method", "path"], registry=reg)
-    e2e_lat = Histogram("e2e_request_latency_seconds", "End to end latency", labelnames=["status", "method", "path"], registry=reg)
-    running = Gauge("num_requests_running", "Number of requests currently being processed", registry=reg)
-    vs_lat = Histogram("rag_vector_store_operation_latency_seconds", "vector store op latency", labelnames=["operation", "status"], registry=reg)
-    res_count = Histogram("rag_retrieve_result_count", "results per retrieve", registry=reg, buckets=[0, 1, 2, 5, 10, 20, 50, 100, 300])
-    low_score = Histogram("rag_lowest_source_score", "lowest score", registry=reg)
-    avg_score = Histogram("rag_avg_source_score", "average score", registry=reg)
-    emb_lat = Histogram("rag_embedding_latency_seconds", "Time to embed in seconds", labelnames=["status", "mode"], registry=reg)
+    mx = build_metrics(reg)
+    M = {"index": ("rag_index_latency_seconds", "rag_index_requests"), "indexes": ("rag_indexes_latency_seconds", "rag_indexes_requests"),
+         "documents": ("rag_indexes_document_latency_seconds", "rag_indexes_document_requests"),
+         "update": ("rag_indexes_update_document_latency_seconds", "rag_indexes_update_document_requests"),
+         "retrieve": ("rag_indexes_retrieve_latency_seconds", "rag_indexes_retrieve_requests"),
+         "delete_doc": ("rag_indexes_delete_document_latency_seconds", "rag_indexes_delete_document_requests"),
+         "persist": ("rag_persist_latency_seconds", "rag_persist_requests"), "load": ("rag_load_latency_seconds", "rag_load_requests"),
+         "delete": ("rag_delete_index_latency_seconds", "rag_delete_index_requests"), "chat": ("rag_chat_latency_seconds", "rag_chat_requests")}
+    M = {k: (mx[h], mx[c]) for k, (h, c) in M.items()}
+    e2e_total, e2e_lat, running = mx["e2e_request"], mx["e2e_request_latency_seconds"], mx["num_requests_running"]
+    vs_lat, res_count = mx["rag_vector_store_operation_latency_seconds"], mx["rag_retrieve_result_count"]
+    low_score, avg_score = mx["rag_lowest_source_score"], mx["rag_avg_source_score"]
+    emb_lat, emb_cnt = mx["rag_embedding_latency_seconds"], mx["rag_embedding_requests"]
     app.state.store, app.state.registry = store, reg
 
+    TRACKED = ("/index", "/indexes", "/persist", "/load", "/retrieve", "/v1/chat/completions")
+
     @app.middleware("http")
-    async def track_requests(request: Request, call_next):   # main.py:97-128
+    async def track_requests(request: Request, call_next):   # main.py:97-128: tracked paths only; status = the handler returned
+        if not any(request.url.path.startswith(p) for p in TRACKED):
+            return await call_next(request)
         running.inc()
         t0 = time.perf_counter()
-        status = "500"
+        status = "failure"
         try:
             resp = await call_next(request)
-            status = str(resp.status_code)
+            status = "success"
             return resp
         finally:
             running.dec()
-            e2e_total.labels(status, request.method, request.url.path).inc()
-            e2e_lat.labels(status, request.method, request.url.path).observe(time.perf_counter() - t0)
+            e2e_lat.labels(status).observe(time.perf_counter() - t0)
+            e2e_total.labels(status).inc()
 
     def run(kind, fn):
         """observe latency/status like the reference's per-route try/finally blocks"""
@@ -191,6 +255,7 @@ def create_app(store: vs.VectorStore, cfg: dict | None = None, llm=None) -> Fast
             t0 = time.perf_counter()
             ids = store.index_documents(request.index_name, docs)
             emb_lat.labels("success", "local").observe(time.perf_counter() - t0)
+            emb_cnt.labels("success", "local").inc()
             return [Document(doc_id=i, text=d.text, metadata=d.metadata) for i, d in zip(ids, request.documents)]
         return run("index", go)
 

@@ -91,3 +91,31 @@ def test_wire_models_match_reference_schemas():
         assert sorted(sch.get("required", [])) == ref["required"], name
         props = {k: {kk: vv for kk, vv in v.items() if kk in keep} for k, v in sch.get("properties", {}).items()}
         assert props == ref["properties"], (name, props, ref["properties"])
+
+
+def test_prometheus_metrics_match_reference_registry(oracle):
+    """tests/golden/prometheus_metrics_reference.json lists every metric the reference registers (name, kind, labels, buckets;
+    produced by executing its prometheus_metrics.py): the service registers exactly that set, and the middleware labels
+    e2e requests with success/failure on the tracked paths only (main.py:97-128)."""
+    import json
+    import os
+    from prometheus_client.metrics import MetricWrapperBase
+    from kaito_b200 import service
+    from tests.oracle_engine import OracleEngine
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "prometheus_metrics_reference.json")))
+    app = create_app(VectorStore(HashingEmbedding(64), OracleEngine(oracle)), dict(CFG))
+    mx = service.build_metrics(__import__("prometheus_client").CollectorRegistry())
+    got = {}
+    for name, m in mx.items():
+        assert isinstance(m, MetricWrapperBase)
+        kind = type(m).__name__
+        ub = m._kwargs.get("buckets") if kind == "Histogram" else None
+        got[m._name] = {"kind": kind, "labels": list(m._labelnames),
+                        "buckets": None if kind != "Histogram" else [float(b) for b in (ub if ub is not None else m.DEFAULT_BUCKETS) if b != float("inf")]}
+    assert got == fx["metrics"]
+    c = TestClient(app)
+    c.get("/health"); c.get("/metrics")                                   # untracked paths
+    c.post("/retrieve", json={"index_name": "nope", "query": "q"})        # tracked; the handler returned (404) -> "success"
+    text = c.get("/metrics").text
+    assert 'e2e_request_total{status="success"} 1.0' in text and 'path=' not in text
+    assert "rag_hybrid_top_k_requested_bucket" in text                    # registered like the reference's, never observed
