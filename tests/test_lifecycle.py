@@ -5,6 +5,7 @@ restore of every index of LATEST at start.  CPU: uvicorn in a thread over the or
 import importlib.util
 import json
 import os
+import re
 import socket
 import threading
 import time
@@ -62,31 +63,87 @@ def test_prestop_snapshot_and_poststart_restore(oracle, tmp_path, monkeypatch):
         before = c.post("/retrieve", json={"index_name": "idx_a", "query": "Kubernetes operators", "max_node_count": 2}).json()
 
         hooks = _load_hooks(monkeypatch, port, tmp_path, "0123456789abcdef")
-        hooks.prestop()
+        monkeypatch.setenv("POD_NAME", "ragengine-0")
+        assert hooks.prestop() == 0
         root = tmp_path / "systemsnapshots"
-        snaps = [d for d in os.listdir(root) if d != "LATEST"]
-        assert len(snaps) == 1 and snaps[0].endswith("_pod-01234567")
-        meta = json.load(open(root / "LATEST" / "metadata.json"))
-        assert meta == {"index_names": ["idx_a", "idx b"], "version": 1}
-        assert os.path.realpath(root / "LATEST") == os.path.realpath(root / snaps[0])
+        snaps = os.listdir(root)
+        assert len(snaps) == 1 and re.fullmatch(r"\d{4}-\d\d-\d\dT\d\d-\d\d-\d\d_pod-01234567", snaps[0])      # manager.py:229-232
+        meta = json.load(open(root / snaps[0] / "metadata.json"))
+        assert set(meta) == {"timestamp", "pod_name", "pod_uid", "index_names", "version"}                         # manager.py:268-274
+        assert meta["index_names"] == ["idx_a", "idx b"] and meta["version"] == 1 and meta["pod_uid"] == "01234567" and meta["pod_name"] == "ragengine-0"
+        assert os.readlink(tmp_path / "LATEST") == os.path.join("systemsnapshots", snaps[0])                       # relative, at the base dir
         assert os.path.isfile(root / snaps[0] / "idx_a" / "docstore.json")
 
         # a fresh pod: empty service, PostStart restores every index named in LATEST/metadata.json
         for name in ("idx_a", "idx b"):
             assert c.delete(f"/indexes/{name}").status_code == 200
         assert c.get("/indexes").json() == []
-        hooks.poststart()
+        assert hooks.poststart() == 0
         assert sorted(c.get("/indexes").json()) == ["idx b", "idx_a"]
         after = c.post("/retrieve", json={"index_name": "idx_a", "query": "Kubernetes operators", "max_node_count": 2}).json()
         assert after == before
         assert c.get("/indexes/idx_a/documents").json()["total_items"] == 2
 
-        # retention: only the newest 5 snapshots are kept (manager.py keeps 5)
+        # LATEST lost: PostStart falls back to the newest snapshot directory and recreates the link (manager.py:153-178)
+        os.remove(tmp_path / "LATEST")
+        assert c.delete("/indexes/idx_a").status_code == 200
+        assert hooks.poststart() == 0 and "idx_a" in c.get("/indexes").json()
+        assert os.readlink(tmp_path / "LATEST") == os.path.join("systemsnapshots", snaps[0])
+
+        # retention: only the newest 5 snapshots are kept
         for i in range(6):
-            os.makedirs(root / f"2000010{i}-000000_pod-old{i}")
-        hooks.prestop()
-        kept = sorted(d for d in os.listdir(root) if d != "LATEST")
-        assert len(kept) == 5 and os.path.realpath(root / "LATEST") == os.path.realpath(root / kept[-1])
+            os.makedirs(root / f"2000-01-0{i + 1}T00-00-00_pod-old{i}")
+        time.sleep(1.1)                                    # snapshot names have one-second resolution
+        assert hooks.prestop() == 0
+        kept = sorted(os.listdir(root))
+        assert len(kept) == 5 and os.path.realpath(tmp_path / "LATEST") == os.path.realpath(root / kept[-1])
+    finally:
+        server.should_exit = True
+        th.join(timeout=5)
+
+
+REF_MANAGER = "/root/reference/presets/ragengine/lifecycle/manager.py"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_MANAGER), reason="reference tree not present (it never is on the GPU box)")
+def test_reference_lifecycle_manager_drives_this_service(oracle, tmp_path, monkeypatch):
+    """Drop-in check with the reference in the loop: its own PreStop/PostStart handlers (lifecycle/manager.py, executed
+    unmodified, only pointed at the test server) persist and restore this service's indexes, and snapshots written by
+    either implementation restore under the other."""
+    from starlette.testclient import TestClient
+    from tests.oracle_engine import OracleEngine
+    port = _free_port()
+    url = f"http://127.0.0.1:{port}"
+    app = create_app(VectorStore(HashingEmbedding(64), OracleEngine(oracle)), {"persist_dir": str(tmp_path), "llm_inference_url": None})
+    server, th = _serve(app, port)
+    try:
+        spec = importlib.util.spec_from_file_location("ref_lifecycle_manager", REF_MANAGER)
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+        ref.wait_for_service.__defaults__ = (url + "/indexes", 60)
+        for fn in (ref.get_indexes, ref.load_index, ref.persist_index):
+            fn.__defaults__ = (url,)
+        import types
+        monkeypatch.setattr(ref, "time", types.SimpleNamespace(sleep=lambda s: None, time=time.time))   # its 0.5 s rate limiting
+        monkeypatch.setenv("POD_UID", "feedfacecafe")
+        c = TestClient(app)
+        docs = [{"text": "First document about retrieval engines"}, {"text": "Second document about Kubernetes operators"}]
+        assert c.post("/index", json={"index_name": "idx_a", "documents": docs}).status_code == 200
+        before = c.post("/retrieve", json={"index_name": "idx_a", "query": "retrieval engines", "max_node_count": 2}).json()
+        # reference PreStop -> our PostStart
+        assert ref.prestop_handler(str(tmp_path)) == 0
+        assert c.delete("/indexes/idx_a").status_code == 200
+        hooks = _load_hooks(monkeypatch, port, tmp_path, "feedfacecafe")
+        assert hooks.poststart() == 0
+        assert c.post("/retrieve", json={"index_name": "idx_a", "query": "retrieval engines", "max_node_count": 2}).json() == before
+        # our PreStop -> reference PostStart
+        time.sleep(1.1)
+        assert hooks.prestop() == 0
+        assert c.delete("/indexes/idx_a").status_code == 200
+        assert ref.poststart_handler(str(tmp_path)) == 0
+        assert c.get("/indexes").json() == ["idx_a"]
+        assert c.post("/retrieve", json={"index_name": "idx_a", "query": "retrieval engines", "max_node_count": 2}).json() == before
+        assert len(os.listdir(tmp_path / "systemsnapshots")) == 2
     finally:
         server.should_exit = True
         th.join(timeout=5)
@@ -99,10 +156,10 @@ def test_poststart_without_snapshot_is_a_noop(oracle, tmp_path, monkeypatch, cap
     server, th = _serve(app, port)
     try:
         hooks = _load_hooks(monkeypatch, port, tmp_path, "ffff")
-        hooks.poststart()
-        assert "no snapshot to restore" in capsys.readouterr().out
-        hooks.prestop()                                   # no indexes: nothing is written
-        assert not os.path.exists(tmp_path / "systemsnapshots" / "LATEST")
+        assert hooks.poststart() == 0
+        assert "No previous snapshots found" in capsys.readouterr().out
+        assert hooks.prestop() == 0                       # no indexes: the empty snapshot directory is removed again
+        assert not os.path.lexists(tmp_path / "LATEST") and os.listdir(tmp_path / "systemsnapshots") == []
     finally:
         server.should_exit = True
         th.join(timeout=5)
