@@ -119,3 +119,21 @@ def test_prometheus_metrics_match_reference_registry(oracle):
     text = c.get("/metrics").text
     assert 'e2e_request_total{status="success"} 1.0' in text and 'path=' not in text
     assert "rag_hybrid_top_k_requested_bucket" in text                    # registered like the reference's, never observed
+
+
+def test_env_defaults_match_reference_config(monkeypatch):
+    """tests/golden/config_reference.json = defaults of the reference's config.py (executed with the variables unset)."""
+    import json
+    import os
+    from kaito_b200 import chat, service, vector_store
+    d = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config_reference.json")))["defaults"]
+    for k in list(os.environ):
+        if k.startswith(("RAG_", "LLM_", "EMBEDDING_", "LOCAL_EMBEDDING", "VECTOR_DB", "DEFAULT_VECTOR_DB", "MODEL_ID")):
+            monkeypatch.delenv(k)
+    e, c = service.env_config(), chat.chat_config()
+    assert (e["embedding_source"], e["embedding_model"], e["vector_db_type"], e["persist_dir"], e["llm_inference_url"]) == \
+        (d["EMBEDDING_SOURCE_TYPE"], d["LOCAL_EMBEDDING_MODEL_ID"], d["VECTOR_DB_TYPE"], d["DEFAULT_VECTOR_DB_PERSIST_DIR"], d["LLM_INFERENCE_URL"])
+    assert (c["llm_access_secret"], c["llm_context_window"], c["similarity_threshold"], c["context_token_fill_ratio"], c["node_token_approximation"]) == \
+        (d["LLM_ACCESS_SECRET"], d["LLM_CONTEXT_WINDOW"], d["RAG_SIMILARITY_THRESHOLD"], d["RAG_DEFAULT_CONTEXT_TOKEN_FILL_RATIO"],
+         d["RAG_DOCUMENT_NODE_TOKEN_APPROXIMATION"])
+    assert vector_store.RAG_MAX_TOP_K == d["RAG_MAX_TOP_K"] == service.RAG_MAX_TOP_K
