@@ -181,3 +181,32 @@ def test_resolve_model_dir(tmp_path, monkeypatch):
     assert resolve_model_dir(local) == local
     monkeypatch.setenv("KRAG_MODEL_DIR", snap(tmp_path / "explicit"))
     assert resolve_model_dir("BAAI/bge-small-en-v1.5") == str(tmp_path / "explicit")
+
+
+REF_GO = "/root/reference/pkg/ragengine"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_GO), reason="reference tree not present")
+def test_deploy_tree_satisfies_the_controllers_pod_contract():
+    """The literals the unmodified controller puts into the pod spec (pkg/ragengine/manifests/manifests.go:116-134, 146-279;
+    pkg/ragengine/controllers/preset_rag.go:33-64, 186) resolve inside deploy/: hook script path and verbs, `python3 main.py` in
+    the image WORKDIR, port and probe path, and the environment variables the hooks read."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    man = open(os.path.join(REF_GO, "manifests", "manifests.go")).read()
+    pre = open(os.path.join(REF_GO, "controllers", "preset_rag.go")).read()
+    hook_path = re.search(r'"(/app/ragengine/lifecycle/hooks\.py)"', man).group(1)
+    assert os.path.isfile(os.path.join(root, "deploy", hook_path.lstrip("/")))
+    assert "python3 /app/ragengine/lifecycle/hooks.py prestop" in man and '"poststart"' in man
+    hooks_src = open(os.path.join(root, "deploy", hook_path.lstrip("/"))).read()
+    for verb in ("poststart", "prestop"):
+        assert f'"{verb}"' in hooks_src
+    for env in ("POD_NAME", "POD_UID", "DEFAULT_VECTOR_DB_PERSIST_DIR"):
+        assert f'Name:  "{env}"' in man or f'Name: "{env}"' in man
+        assert env in hooks_src
+    assert 'utils.ShellCmd("python3 main.py")' in pre and os.path.isfile(os.path.join(root, "deploy", "app", "ragengine", "main.py"))
+    dockerfile = open(os.path.join(root, "deploy", "Dockerfile")).read()
+    assert "WORKDIR /app/ragengine" in dockerfile and "python3 main.py" in dockerfile and "EXPOSE 5000" in dockerfile
+    port = int(re.search(r"PortInferenceServer\s*=\s*(\d+)", pre).group(1))
+    probe = re.search(r'ProbePath\s*=\s*"([^"]+)"', pre).group(1)
+    svc = open(os.path.join(root, "kaito_b200", "service.py")).read()
+    assert f"port={port}" in svc and f'@app.get("{probe}"' in svc
