@@ -1,6 +1,7 @@
-"""Embedding-model interface of the host (mirrors embedding/base.py:21-31 BaseEmbeddingModel) and a
-deterministic hashing embedder used by tests and the demo service until the GPU BERT forward (K5) lands.
-The production embedder for the CRD's `embedding.local.modelID` is K5."""
+"""Embedding-model interface of the host (mirrors embedding/base.py:21-31 BaseEmbeddingModel).
+`GpuBertEmbedding` is the production embedder for the CRD's `embedding.local.modelID` (K5, the BERT forward in
+libkaito_rag); `HashingEmbedding` is a deterministic stand-in without weights for the host-logic
+tests (no checkpoints are available offline) and never the default of the service."""
 from __future__ import annotations
 
 import hashlib
