@@ -229,3 +229,21 @@ def test_select_context_against_reference_golden():
         nodes = [(N("t" * L, i), s) for i, (L, s) in enumerate(zip(c["text_lens"], c["scores"]))]
         got = chat.select_context(nodes, "q" * c["query_len"], llm, c["ratio"], c["max_tokens"], c["threshold"])
         assert [n.nid for n, _ in got] == c["selected"], c
+
+
+def test_chat_llm_500_and_assistant_history(oracle):
+    """test_chat_completions.py:779-813: the LLM answering 500 on the RAG path surfaces as 500 with "An unexpected error
+    occurred" in the detail; :816-875: an assistant turn with content is history, the last user message is the query."""
+    from tests.oracle_engine import OracleEngine
+    c = _client(OracleEngine(oracle), FakeLLM(status=500, body={"error": "Internal server error"}))
+    r = c.post("/v1/chat/completions", json={"index_name": "test_index", "model": "mock-model",
+                                            "messages": [{"role": "user", "content": DOCS[6]["text"]}]})
+    assert r.status_code == 500 and "An unexpected error occurred" in r.json()["detail"]
+    fake = FakeLLM()
+    c = _client(OracleEngine(oracle), fake)
+    r = c.post("/v1/chat/completions", json={"index_name": "test_index", "model": "mock-model", "messages": [
+        {"role": "user", "content": "Hello"}, {"role": "assistant", "content": "Hello! How can I help you?"},
+        {"role": "user", "content": DOCS[7]["text"]}]})
+    assert r.status_code == 200 and r.json()["choices"][0]["message"]["content"] == ANSWER["choices"][0]["message"]["content"]
+    assert [m["role"] for m in fake.posts[-1]["messages"]] == ["system", "user", "assistant", "user"]
+    assert fake.posts[-1]["messages"][-1]["content"] == DOCS[7]["text"]
