@@ -131,15 +131,16 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("n", [2001, 64])
-def test_two_shards_equal_single_shard_oracle(n):
+@pytest.mark.parametrize("world,n", [(2, 2001), (2, 64), (3, 1000)])
+def test_shards_equal_single_shard_oracle(world, n):
+    """world_size 2 (odd and tiny corpora) and 3 (uneven shards, three-way gather/merge)"""
     from oracle import oracle as o
     o.build()
     mgr = mp.Manager()
     ret = mgr.dict()
-    mp.spawn(_worker, args=(2, _free_port(), n, 48, 300, 7, ret), nprocs=2, join=True)
-    assert ret.get(0) == "ok", ret.get(0)
-    assert ret.get(1) == "ok", ret.get(1)
+    mp.spawn(_worker, args=(world, _free_port(), n, 48, 300, 7, ret), nprocs=world, join=True)
+    for r in range(world):
+        assert ret.get(r) == "ok", ret.get(r)
 
 
 def test_shard_range_partition():
