@@ -46,3 +46,27 @@ def test_product_package_never_imports_oracle():
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, f
                 assert "libkrag_oracle" not in txt and not re.search(r'#include\s*"[^"]*oracle', txt), f
+
+
+def test_header_is_plain_c99_and_links(tmp_path):
+    """include/kaito_rag.h is consumed by cgo: it must compile as C99 (no C++-isms, no torch/CUDA types) and a C program
+    calling an entry point must link against libkaito_rag.so (no compute call: there is no GPU here)."""
+    import shutil
+    import subprocess
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "abi.c"
+    src.write_text('#include "kaito_rag.h"\n#include <stdio.h>\n'
+                   'int main(void) { krag_config c; krag_stats_t s; (void)c; (void)s;\n'
+                   '  printf("%lld %s\\n", (long long)krag_tc_fallback_queries(), KRAG_KEY_PAD == 0xFFFFFFFFFFFFFFFFull ? "pad" : "?");\n'
+                   '  return 0; }\n')
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(root, "include"), "-fsyntax-only", str(src)],
+                   check=True)
+    exe = tmp_path / "abi"
+    lib_dir = os.path.join(root, "kaito_b200")
+    subprocess.run([gcc, "-std=c99", "-I", os.path.join(root, "include"), str(src), "-o", str(exe), "-L", lib_dir, "-lkaito_rag",
+                    "-Wl,-rpath," + lib_dir], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert out.strip() == "0 pad"
