@@ -70,3 +70,24 @@ def test_header_is_plain_c99_and_links(tmp_path):
                     "-Wl,-rpath," + lib_dir], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
     assert out.strip() == "0 pad"
+
+
+def test_c_example_builds_and_fails_loudly_without_a_gpu(tmp_path):
+    """examples/krag_demo.c (the cgo-equivalent call sequence in plain C) compiles as pedantic C99 and links; on a machine
+    without an sm_100 GPU it stops at krag_init with KRAG_E_NO_DEVICE -- there is no CPU path to fall back to."""
+    import shutil
+    import subprocess
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    lib_dir = os.path.join(ROOT, "kaito_b200")
+    exe = tmp_path / "krag_demo"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "krag_demo.c"), "-o", str(exe), "-L", lib_dir, "-lkaito_rag", "-Wl,-rpath," + lib_dir, "-lm"],
+                   check=True)
+    import torch
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert r.returncode == 0 and r.stdout.startswith("#0 node 2 ")          # the query is node 2's own vector
+    else:
+        assert r.returncode == 1 and "-> -2" in r.stderr and "no CPU fallback" in r.stderr
