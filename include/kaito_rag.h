@@ -241,6 +241,22 @@ int32_t krag_embed_dev(krag_embedder* e, int32_t batch, const int32_t* tok_ids, 
                        int32_t ld_out, void* stream);
 int32_t krag_embedder_destroy(krag_embedder* e);
 
+/* ------------------------------------------------- host-side text analysis (no GPU involved; ASCII input) */
+/* The analysis chains the reference runs in native third-party code, for hosts that are not Python (a cgo host links the
+ * same functions the Python host uses for ASCII text; kaito_b200/text.py is the Unicode-complete restatement and the spec).
+ * krag_text_analyze: bm25s.tokenize(text, stopwords="english", stemmer=Snowball english) as used by
+ *   BM25Retriever.from_defaults (hybrid_retriever.py:122-125): lower-case, \w\w+ tokens, 33 stop words dropped, Porter2 stems.
+ *   Writes the stems separated by '\n' into out (if *out_len <= cap) and always reports the needed length and the token count.
+ * krag_wordpiece_*: BertTokenizer (uncased) of the bge models (huggingface_local_embedding.py:34-53): BasicTokenizer +
+ *   greedy longest-match WordPiece; vocab = the lines of vocab.txt joined by '\n'; encode_batch writes, per text,
+ *   [CLS] ids[: max_len - 2] [SEP] into out_ids[i * max_len ...] and its length into out_n[i] (texts are threaded). */
+typedef struct krag_wordpiece krag_wordpiece;
+int32_t krag_text_analyze(const char* text, int64_t len, char* out, int64_t cap, int64_t* out_len, int32_t* n_terms);
+int32_t krag_wordpiece_create(const char* vocab, int64_t len, int32_t lower_case, krag_wordpiece** out);
+int32_t krag_wordpiece_encode_batch(const krag_wordpiece* w, int64_t n, const char* texts, const int64_t* offsets /*[n+1]*/,
+                                    int32_t max_len, int32_t* out_ids /*[n * max_len]*/, int32_t* out_n /*[n]*/);
+int32_t krag_wordpiece_destroy(krag_wordpiece* w);
+
 /* ------------------------------------------------------------------- diagnostics */
 /* C[M,N] = A[M,K] . B[N,K]^T + bias (+erf-GELU) (+residual) through K5's tcgen05 TF32 GEMM; host buffers.
  * N % 128 == 0, K % 32 == 0.  Test hook. */

@@ -102,7 +102,7 @@ class GpuBertEmbedding(BaseEmbeddingModel):
         return np.concatenate(out)
 
     def get_text_embedding_batch(self, texts):
-        return self._embed_tokens([self.tokenizer.encode(t) for t in texts])
+        return self._embed_tokens(self.tokenizer.encode_batch(list(texts)))
 
     def get_text_embedding(self, text: str):
         return self.get_text_embedding_batch([text])[0]

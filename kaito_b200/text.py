@@ -179,9 +179,45 @@ def stem(word: str) -> str:
 
 
 # ------------------------------------------------------------------------------ tokenise
-def tokenize(text: str) -> list[str]:
-    """bm25s-style tokens of one text: lower-case, \\w\\w+ words, stop words removed, stemmed."""
+def tokenize_py(text: str) -> list[str]:
+    """bm25s-style tokens of one text: lower-case, \\w\\w+ words, stop words removed, stemmed.  Pure Python: the
+    Unicode-complete restatement and the spec of the native path."""
     return [stem(t) for t in TOKEN_PATTERN.findall(text.lower()) if t not in STOPWORDS_EN]
+
+
+_lib = None
+
+
+def _native_lib():
+    """libkaito_rag.so for the host-side analysis functions (csrc/text_native.cpp); False when it cannot be loaded -- the
+    analysis is host code, so unlike the search path it may run in pure Python."""
+    global _lib
+    if _lib is None:
+        try:
+            from . import _native
+            _lib = _native.load()
+        except Exception:
+            _lib = False
+    return _lib
+
+
+def tokenize(text: str) -> list[str]:
+    """tokenize_py, through the native analyser (same output, ~20x faster) when the text is ASCII."""
+    L = _native_lib()
+    if not L or not text.isascii():
+        return tokenize_py(text)
+    import ctypes as C
+    raw = text.encode("ascii")
+    cap = len(raw) + 16                       # stems are never longer than their tokens plus one 'e' per token... see below
+    n_len, n_tok = C.c_int64(0), C.c_int32(0)
+    buf = C.create_string_buffer(cap)
+    if L.krag_text_analyze(raw, len(raw), buf, cap, C.byref(n_len), C.byref(n_tok)) != 0:
+        return tokenize_py(text)
+    if n_len.value > cap:                     # (a token of >= 2 chars yields a stem of at most len + 1 chars and a separator)
+        cap = n_len.value
+        buf = C.create_string_buffer(cap)
+        L.krag_text_analyze(raw, len(raw), buf, cap, C.byref(n_len), C.byref(n_tok))
+    return buf.raw[: n_len.value].decode("ascii").split("\n") if n_tok.value else []
 
 
 class Vocabulary:
@@ -238,10 +274,29 @@ class WordPieceTokenizer:
     tokenizer through sentence-transformers (embedding/huggingface_local_embedding.py:34-53)."""
 
     def __init__(self, vocab: dict[str, int] | list[str], do_lower_case: bool = True, max_length: int = 512):
+        tokens = None
         if not isinstance(vocab, dict):
-            vocab = {t: i for i, t in enumerate(vocab)}
+            tokens = list(vocab)
+            vocab = {t: i for i, t in enumerate(tokens)}
         self.vocab, self.lower, self.max_length = vocab, do_lower_case, max_length
         self.unk, self.cls, self.sep = vocab["[UNK]"], vocab["[CLS]"], vocab["[SEP]"]
+        # native encoder (csrc/text_native.cpp) for ASCII text; needs the ordered token list and tokens without newlines
+        self._nat = None
+        L = _native_lib()
+        if L and tokens is not None and all("\n" not in t for t in tokens):
+            import ctypes as C
+            blob = "\n".join(tokens).encode("utf-8")
+            h = C.c_void_p()
+            if L.krag_wordpiece_create(blob, len(blob), 1 if do_lower_case else 0, C.byref(h)) == 0:
+                self._nat = h
+
+    def __del__(self):
+        if getattr(self, "_nat", None):
+            try:
+                _native_lib().krag_wordpiece_destroy(self._nat)
+            except Exception:
+                pass
+            self._nat = None
 
     @classmethod
     def from_file(cls, path: str, **kw):
@@ -295,6 +350,30 @@ class WordPieceTokenizer:
             start = end
         return ids
 
-    def encode(self, text: str) -> list[int]:
+    def encode_py(self, text: str) -> list[int]:
         ids = [i for w in self._basic(text) for i in self._wordpiece(w)]
         return [self.cls] + ids[: self.max_length - 2] + [self.sep]
+
+    def encode(self, text: str) -> list[int]:
+        return self.encode_batch([text])[0]
+
+    def encode_batch(self, texts: list[str]) -> list[list[int]]:
+        """ids of every text; ASCII texts go through the native, multi-threaded encoder in one call, the rest through encode_py"""
+        out: list = [None] * len(texts)
+        idx = [i for i, t in enumerate(texts) if self._nat is not None and t.isascii()]
+        if idx:
+            import ctypes as C
+            raws = [texts[i].encode("ascii") for i in idx]
+            offs = np.zeros(len(raws) + 1, np.int64)
+            np.cumsum([len(r) for r in raws], out=offs[1:])
+            ids = np.empty((len(raws), self.max_length), np.int32)
+            cnt = np.empty(len(raws), np.int32)
+            rc = _native_lib().krag_wordpiece_encode_batch(self._nat, len(raws), b"".join(raws), offs.ctypes.data_as(C.c_void_p),
+                                                           self.max_length, ids.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p))
+            if rc == 0:
+                for j, i in enumerate(idx):
+                    out[i] = ids[j, : cnt[j]].tolist()
+        for i, t in enumerate(texts):
+            if out[i] is None:
+                out[i] = self.encode_py(t)
+        return out
