@@ -109,3 +109,36 @@ class GpuBertEmbedding(BaseEmbeddingModel):
 
     def get_query_embedding(self, query: str):
         return self.get_text_embedding((self.query_instruction or "") + query)
+
+
+class RemoteEmbeddingModel(BaseEmbeddingModel):
+    """`embedding.remote` of the CRD (embedding/remote_embedding.py:24-76): POST {"inputs": text} with a bearer token to
+    REMOTE_EMBEDDING_URL, the reply is the embedding as a JSON list.  Host-side HTTP only -- the retrieval kernels take the
+    vectors exactly as with the local model."""
+
+    def __init__(self, model_url: str, api_key: str, transport=None):
+        self.model_url, self.api_key, self._transport = model_url, api_key, transport
+        self._client = None
+
+    def _http(self):
+        if self._client is None:
+            import httpx
+            kw = {"transport": self._transport} if self._transport is not None else {}
+            self._client = httpx.Client(timeout=300.0, **kw)
+        return self._client
+
+    def get_text_embedding(self, text: str):
+        import httpx
+        headers = {"Authorization": f"Bearer {self.api_key}", "Content-Type": "application/json"}
+        try:
+            r = self._http().post(self.model_url, headers=headers, json={"inputs": text})
+            r.raise_for_status()
+            emb = r.json()
+        except httpx.HTTPError as e:
+            raise RuntimeError(f"Failed to get embedding from remote model: {e}")
+        if not isinstance(emb, list):
+            raise ValueError("Unexpected response format. Expected a list.")
+        return np.asarray(emb, np.float32)
+
+    def get_embedding_dimension(self) -> int:
+        return len(self.get_text_embedding("This is a dummy sentence."))

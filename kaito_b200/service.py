@@ -103,6 +103,8 @@ def env_config() -> dict:
     return {
         "embedding_source": g("EMBEDDING_SOURCE_TYPE") or g("EMBEDDING_TYPE") or "local",
         "embedding_model": g("LOCAL_EMBEDDING_MODEL_ID") or g("MODEL_ID") or "BAAI/bge-small-en-v1.5",
+        "remote_embedding_url": g("REMOTE_EMBEDDING_URL", "http://localhost:5000/embedding"),
+        "remote_embedding_access_secret": g("REMOTE_EMBEDDING_ACCESS_SECRET", "default-access-secret"),
         "vector_db_type": g("VECTOR_DB_TYPE", "faiss"),
         "persist_dir": g("DEFAULT_VECTOR_DB_PERSIST_DIR", "storage"),
         "llm_inference_url": g("LLM_INFERENCE_URL"),
@@ -200,6 +202,7 @@ def create_app(store: vs.VectorStore, cfg: dict | None = None, llm=None) -> Fast
     vs_lat, res_count = mx["rag_vector_store_operation_latency_seconds"], mx["rag_retrieve_result_count"]
     low_score, avg_score = mx["rag_lowest_source_score"], mx["rag_avg_source_score"]
     emb_lat, emb_cnt = mx["rag_embedding_latency_seconds"], mx["rag_embedding_requests"]
+    emb_mode = "remote" if str(cfg.get("embedding_source", "local")).lower() == "remote" else "local"   # MODE_LOCAL / MODE_REMOTE
     app.state.store, app.state.registry = store, reg
 
     TRACKED = ("/index", "/indexes", "/persist", "/load", "/retrieve", "/v1/chat/completions")
@@ -254,8 +257,8 @@ def create_app(store: vs.VectorStore, cfg: dict | None = None, llm=None) -> Fast
             docs = [{"text": d.text, "metadata": d.metadata or {}} for d in request.documents]
             t0 = time.perf_counter()
             ids = store.index_documents(request.index_name, docs)
-            emb_lat.labels("success", "local").observe(time.perf_counter() - t0)
-            emb_cnt.labels("success", "local").inc()
+            emb_lat.labels("success", emb_mode).observe(time.perf_counter() - t0)
+            emb_cnt.labels("success", emb_mode).inc()
             return [Document(doc_id=i, text=d.text, metadata=d.metadata) for i, d in zip(ids, request.documents)]
         return run("index", go)
 
@@ -351,11 +354,15 @@ def main():
     cfg = env_config()
     if cfg["vector_db_type"] not in ("faiss", "krag"):
         raise SystemExit(f"VECTOR_DB_TYPE={cfg['vector_db_type']} is not served by this image (faiss-compatible engine only)")
-    if cfg["embedding_source"] != "local":
-        raise SystemExit("remote embedding endpoints are not served by this image; use embedding.local (GPU BERT forward)")
+    source = cfg["embedding_source"].lower()
+    if source not in ("local", "remote"):
+        raise SystemExit("Invalid Embedding Type Specified (Must be Local or Remote)")          # main.py:133-141
     engine = _native.Context(device_id=cfg["device_id"])
-    model_dir = resolve_model_dir(cfg["embedding_model"])
-    if model_dir:
+    model_dir = resolve_model_dir(cfg["embedding_model"]) if source == "local" else None
+    if source == "remote":
+        from .embedding import RemoteEmbeddingModel
+        embed = RemoteEmbeddingModel(cfg["remote_embedding_url"], cfg["remote_embedding_access_secret"])
+    elif model_dir:
         embed = GpuBertEmbedding.from_pretrained(engine, model_dir)          # K5: bge forward on the GPU
     elif os.getenv("KRAG_ALLOW_HASHING_EMBEDDING") == "1":
         embed = HashingEmbedding(384)                                        # functional tests only, not a language model

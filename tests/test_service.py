@@ -137,3 +137,34 @@ def test_env_defaults_match_reference_config(monkeypatch):
         (d["LLM_ACCESS_SECRET"], d["LLM_CONTEXT_WINDOW"], d["RAG_SIMILARITY_THRESHOLD"], d["RAG_DEFAULT_CONTEXT_TOKEN_FILL_RATIO"],
          d["RAG_DOCUMENT_NODE_TOKEN_APPROXIMATION"])
     assert vector_store.RAG_MAX_TOP_K == d["RAG_MAX_TOP_K"] == service.RAG_MAX_TOP_K
+
+
+def test_remote_embedding_model(oracle):
+    """embedding.remote of the CRD (embedding/remote_embedding.py:24-76): {"inputs": text} with a bearer token, the reply is
+    the vector; the store indexes and retrieves with it, the embedding metrics carry mode="remote", failures surface."""
+    import json
+    import httpx
+    import numpy as np
+    from kaito_b200.embedding import RemoteEmbeddingModel
+    from tests.oracle_engine import OracleEngine
+    local = HashingEmbedding(32)
+    seen = []
+
+    def handler(request: httpx.Request):
+        body = json.loads(request.content)
+        seen.append((request.headers["authorization"], body))
+        if body["inputs"] == "boom":
+            return httpx.Response(503, json={"error": "down"})
+        return httpx.Response(200, json=[float(x) for x in local.get_text_embedding(body["inputs"])])
+
+    emb = RemoteEmbeddingModel("http://embedder/embedding", "tok3n", transport=httpx.MockTransport(handler))
+    assert emb.get_embedding_dimension() == 32 and seen[0] == ("Bearer tok3n", {"inputs": "This is a dummy sentence."})
+    with pytest.raises(RuntimeError, match="Failed to get embedding from remote model"):
+        emb.get_text_embedding("boom")
+    app = create_app(VectorStore(emb, OracleEngine(oracle)), {**CFG, "embedding_source": "remote"})
+    c = TestClient(app)
+    assert c.post("/index", json={"index_name": "r", "documents": [{"text": "alpha beta"}, {"text": "gamma delta"}]}).status_code == 200
+    r = c.post("/retrieve", json={"index_name": "r", "query": "gamma delta", "max_node_count": 1}).json()
+    assert r["count"] == 1
+    assert np.allclose(emb.get_query_embedding("gamma delta"), local.get_text_embedding("gamma delta"))
+    assert 'rag_embedding_requests_total{mode="remote",status="success"} 1.0' in c.get("/metrics").text
