@@ -266,7 +266,19 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------- our arm
+def trace(msg):
+    """phase markers on stderr (KRAG_BENCH_TRACE=1): which phase a rank was in when a run dies"""
+    if os.environ.get("KRAG_BENCH_TRACE", "0") != "0":
+        sys.stderr.write(f"[bench rank {os.environ.get('RANK', '0')} +{time.perf_counter() - _T0:7.2f}s] {msg}\n")
+        sys.stderr.flush()
+
+
+_T0 = time.perf_counter()
+
+
 def run_ours(args):
+    import faulthandler
+    faulthandler.enable(all_threads=True)      # a SIGABRT/SIGSEGV inside a native library prints the Python stacks
     import torch
     import torch.distributed as dist
     from kaito_b200 import _native
@@ -297,6 +309,7 @@ def run_ours(args):
         sr.commit(VOCAB, n_local)
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build
+    trace(f"index built in {t_build:.1f}s")
     st = ix.stats()
 
     # queries: half planted (perturbed corpus rows of rank 0's shard), half random; same on every rank
@@ -371,8 +384,10 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     l0 = ctx.launch_count()
+    trace("timed ms_dev")
     ms_dev = timed(step_dev, args.steps, args.warmup)
     launches = (ctx.launch_count() - l0) // (args.steps + args.warmup) * args.steps
+    trace("timed ms_e2e")
     ms_e2e = timed(step_e2e, args.steps, args.warmup)
     # batch-1 (latency mode)
     q1, t1 = qpad[:1], None
@@ -390,34 +405,44 @@ def run_ours(args):
             return sr.retrieve(None, terms_list[:1] if hybrid else None, k, embedder=embedder, tokens=(flat_tok1, tok_off1))
         return sr.retrieve(qh[:1], terms_list[:1] if hybrid else None, k)
 
+    trace("timed ms_b1")
     ms_b1 = timed(step_b1, args.steps * 4, args.warmup)
+    trace("timed ms_b1_e2e")
     ms_b1_e2e = timed(step_b1_e2e, args.steps * 4, args.warmup)
     ms_embed = ms_embed1 = None
     if embedder:
+        trace("timed ms_embed")
         ms_embed = timed(lambda: sr.embed_into(embedder, flat_tok, tok_off, qpad), args.steps, args.warmup)
+        trace("timed ms_embed1")
         ms_embed1 = timed(lambda: embedder.embed_dev(flat_tok1, tok_off1, q1.data_ptr(), st.dim_padded, stages.stream()), args.steps * 4, args.warmup)
         qpad[:, :dim] = qt      # restore the planted/random query vectors for the stage timings below
     # dominant kernel: the dense candidate stage alone; the library brackets the kernel itself with
     # CUDA events on the launching stream (krag_last_dense_kernel), read after each timed region
     keys = torch.empty((B, P), dtype=torch.int64, device=dev)
+    trace("timed ms_dense")
     ms_dense = timed(lambda: stages.dense_candidates(qpad, P, keys), args.steps, args.warmup)
     kern_ms, kern_id, kern_bytes, kern_flops = _native.last_dense_kernel()
+    trace("timed ms_dense1")
     ms_dense1 = timed(lambda: stages.dense_candidates(q1, P, keys[:1]), args.steps * 4, args.warmup)
     kern1_ms, kern1_id, kern1_bytes, _ = _native.last_dense_kernel()
     ms_bm25 = None
     if hybrid:
+        trace("timed ms_bm25")
         ms_bm25 = timed(lambda: stages.bm25_candidates(d_terms, d_toff, B, P, keys, offs), args.steps, args.warmup)
     fallbacks = int(_native.load().krag_tc_fallback_queries())
     clocks = sampler.stop() if rank == 0 else None
 
     # OPT-IN leg, reported beside (never instead of) the default: the same step with K2's prune pass reading a bf16
     # shadow of the corpus (+50% memory, built here by one conversion pass); returned distances stay exact fp32.
+    trace("default legs done")
     optin = None
     if args.dense_mode == 0 and not args.no_optin and kern_id in (2, 3, 5):
         t_sh = time.perf_counter()
         ix.set_dense_mode(_native.DENSE_TC_BF16)
         t_sh = time.perf_counter() - t_sh
+        trace("timed ms_opt")
         ms_opt = timed(step_dev, args.steps, args.warmup)
+        trace("timed ms_opt_dense")
         ms_opt_dense = timed(lambda: stages.dense_candidates(qpad, P, keys), args.steps, args.warmup)
         ko_ms, ko_id, ko_bytes, _ = _native.last_dense_kernel()
         optin = {"what": "KRAG_DENSE_TC_BF16: K2 prune pass over a bf16 shadow of the fp32 corpus (+50% memory); exact fp32 rescoring "
@@ -429,6 +454,7 @@ def run_ours(args):
         ix.set_dense_mode(args.dense_mode, release_shadow=True)
 
     # sanity inside the bench: planted rows come back as nearest neighbour (dense list), recall vs exact scan
+    trace("optin done")
     recall = None
     if rank == 0 and world == 1 and B >= 2:
         m = min(16, B // 2)
@@ -502,6 +528,7 @@ def run_ours(args):
         if not args.no_cpu_baseline and world == 1:      # the CPU leg is reported at N = 1 only (rank 0 would stall the other ranks)
             line["cpu_baseline"] = cpu_reference_qps(docs, dim, hybrid, k, args.cpu_sample_rows, emb_name, args.query_tokens)
         print(json.dumps(line), flush=True)
+    trace("line printed; teardown")
     barrier()
     if embedder:
         embedder.destroy()

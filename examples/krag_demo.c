@@ -47,7 +47,7 @@ int main(void)
     const uint32_t q_terms[2] = {3, 4};
     const int32_t q_off[2] = {0, 2};
     double final_[K]; float dense[K], sparse[K]; int32_t rank[K], count = 0; int64_t ord[K];
-    CHECK(krag_retrieve(ix, 1, vecs + 2 * DIM, q_terms, q_off, K, 3.0, 0.7, 0.3, KRAG_FUSION_REFERENCE, NULL,
+    CHECK(krag_retrieve(ix, 1, vecs + 2 * DIM, q_terms, q_off, K, 3.0, 0.7, 0.3, KRAG_FUSION_REFERENCE, NULL, 0,
                         final_, dense, sparse, rank, ord, &count));
     for (int i = 0; i < count; ++i)
         printf("#%d node %lld  final %.6f  l2sq %.6f  bm25 %.6f (rank %d)\n", i, (long long)ord[i], final_[i], dense[i], sparse[i], (int)rank[i]);

@@ -158,7 +158,8 @@ int32_t krag_search_bm25(krag_index* idx, int32_t batch, const uint32_t* q_terms
 /*
  * The whole HybridRetriever._aretrieve (hybrid_retriever.py:205-237) for a batch:
  * dense top-P, BM25 top-P, keyword-side metadata post-filter (optional bitmap of
- * allowed LOCAL rows, 1 bit per row; NULL = no filter), _fuse, top-k.
+ * allowed LOCAL rows, 1 bit per row, at least (n_rows + 31) / 32 words -- fewer is KRAG_E_INVALID; NULL = no filter),
+ * _fuse, top-k.
  *   P = int(k * max(1, cand_mult)).  q_terms == NULL or an uncommitted index selects
  *   the reference's vector-only fallback (:216-218): dense top-P cut to k.
  * Outputs are [batch, k]; out_count[batch] gives the valid prefix per query.
@@ -169,7 +170,7 @@ int32_t krag_search_bm25(krag_index* idx, int32_t batch, const uint32_t* q_terms
 int32_t krag_retrieve(krag_index* idx, int32_t batch, const float* q,
                       const uint32_t* q_terms, const int32_t* q_term_offsets,
                       int32_t k, double cand_mult, double vector_weight, double text_weight, int32_t fusion_mode,
-                      const uint32_t* keyword_allow_bitmap,
+                      const uint32_t* keyword_allow_bitmap, int64_t keyword_allow_words /* u32 words held by the bitmap */,
                       double* out_final, float* out_dense, float* out_sparse, int32_t* out_rank,
                       int64_t* out_ordinals, int32_t* out_count);
 

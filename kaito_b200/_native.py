@@ -96,7 +96,7 @@ def load() -> C.CDLL:
     L.krag_index_load.argtypes = [vp, C.c_char_p, C.c_char_p, C.POINTER(vp)]
     L.krag_search_dense.argtypes = [vp, i32, vp, i32, vp, vp]
     L.krag_search_bm25.argtypes = [vp, i32, vp, vp, i32, vp, vp]
-    L.krag_retrieve.argtypes = [vp, i32, vp, vp, vp, i32, f64, f64, f64, i32, vp, vp, vp, vp, vp, vp, vp]
+    L.krag_retrieve.argtypes = [vp, i32, vp, vp, vp, i32, f64, f64, f64, i32, vp, i64, vp, vp, vp, vp, vp, vp]
     L.krag_dev_dense_candidates.argtypes = [vp, i32, vp, i32, vp, vp]
     L.krag_dev_bm25_candidates.argtypes = [vp, i32, vp, vp, vp, i32, vp, vp]
     L.krag_dev_merge.argtypes = [vp, i32, i32, i32, vp, vp, vp]
@@ -397,7 +397,8 @@ class Index:
             "ordinal": np.empty((b, k), np.int64), "count": np.empty(b, np.int32),
         }
         check(self._L.krag_retrieve(self._h, b, ptr(q), ptr(flat), ptr(offs), k, cand_mult, vector_weight, text_weight,
-                                    fusion_mode, ptr(keyword_allow_bitmap), ptr(out["final"]), ptr(out["dense"]),
+                                    fusion_mode, ptr(keyword_allow_bitmap),
+                                    0 if keyword_allow_bitmap is None else keyword_allow_bitmap.size, ptr(out["final"]), ptr(out["dense"]),
                                     ptr(out["sparse"]), ptr(out["rank"]), ptr(out["ordinal"]), ptr(out["count"])))
         return out
 

@@ -163,6 +163,7 @@ struct krag_index {
     DevArray<uint16_t> ttf;
     DevArray<uint32_t> dlen;
     int64_t nnz = 0;
+    uint32_t max_term_id = 0;       // largest term id ever added (commit requires vocab > max_term_id)
     // committed postings
     Postings post;
     DevArray<uint32_t> entry_doc;  // scratch kept between commit_local and commit_global
@@ -305,8 +306,10 @@ void commit_local_impl(krag_index* ix, int64_t vocab, uint32_t* df_out, int64_t*
     uint32_t* df = nullptr;
     KRAG_CUDA(cudaMalloc(&df, sizeof(uint32_t) * (size_t)vocab));
     KRAG_CUDA(cudaMemsetAsync(df, 0, sizeof(uint32_t) * (size_t)vocab, st));
+    // term ids >= vocab would make the df kernel write out of bounds: the largest id is tracked on the host at add time
+    KRAG_REQUIRE(ix->nnz == 0 || vocab > (int64_t)ix->max_term_id, KRAG_E_INVALID,
+                 "vocab must exceed the largest term id added to the index");
     if (ix->nnz > 0) {
-        // reject term ids >= vocab up front (host check of the max would need a reduction; df kernel would write OOB)
         launch_df_histogram(ix->tid.p, ix->entry_doc.p, alive_ptr(ix), ix->nnz, df, st);
     }
     KRAG_CUDA(cudaMemcpyAsync(df_out, df, sizeof(uint32_t) * (size_t)vocab, cudaMemcpyDeviceToHost, st));
@@ -328,7 +331,11 @@ void commit_global_impl(krag_index* ix, int64_t vocab, const uint32_t* df_global
 {
     cudaStream_t st = ix->ctx->admin;
     KRAG_REQUIRE(ord_base >= 0 && ord_base + ix->n_rows <= 0xFFFFFFFFll, KRAG_E_UNSUPPORTED, "global ordinal exceeds 32 bits");
-    KRAG_REQUIRE(n_docs_global > 0 || ix->n_rows == 0, KRAG_E_INVALID, "n_docs_global must be positive");
+    // n_docs_global == 0 is legal: every document deleted (the reference's docstore is then empty and its retriever
+    // falls back to vector-only, hybrid_retriever.py:113-121); the postings come out empty and avgdl is irrelevant
+    KRAG_REQUIRE(n_docs_global >= 0 && total_len_global >= 0, KRAG_E_INVALID, "n_docs_global / total_len_global must be >= 0");
+    KRAG_REQUIRE(ix->nnz == 0 || vocab > (int64_t)ix->max_term_id, KRAG_E_INVALID,
+                 "vocab must exceed the largest term id added to the index");
     // idf on the host with glibc log(): the same libm call chain as the reference's math.log
     std::vector<float> idf((size_t)vocab);
     for (int64_t t = 0; t < vocab; ++t) {
@@ -511,6 +518,9 @@ int32_t krag_index_add(krag_index* ix, int64_t n, const uint64_t* node_ids, cons
                                       cudaMemcpyHostToDevice, st));
             KRAG_CUDA(cudaMemcpyAsync(ix->dlen.p + ix->n_rows, doc_len, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice, st));
             if (add_nnz > 0) {
+                uint32_t mx = ix->max_term_id;
+                for (int64_t i = 0; i < add_nnz; ++i) mx = term_ids[i] > mx ? term_ids[i] : mx;
+                ix->max_term_id = mx;
                 KRAG_CUDA(cudaMemcpyAsync(ix->tid.p + ix->nnz, term_ids, sizeof(uint32_t) * (size_t)add_nnz, cudaMemcpyHostToDevice, st));
                 KRAG_CUDA(cudaMemcpyAsync(ix->ttf.p + ix->nnz, term_tf, sizeof(uint16_t) * (size_t)add_nnz, cudaMemcpyHostToDevice, st));
             }
@@ -663,8 +673,8 @@ int32_t krag_search_bm25(krag_index* ix, int32_t batch, const uint32_t* q_terms,
 
 int32_t krag_retrieve(krag_index* ix, int32_t batch, const float* q, const uint32_t* q_terms, const int32_t* q_toff,
                       int32_t k, double cand_mult, double vector_weight, double text_weight, int32_t fusion_mode,
-                      const uint32_t* keyword_allow_bitmap, double* out_final, float* out_dense, float* out_sparse,
-                      int32_t* out_rank, int64_t* out_ord, int32_t* out_count)
+                      const uint32_t* keyword_allow_bitmap, int64_t keyword_allow_words, double* out_final, float* out_dense,
+                      float* out_sparse, int32_t* out_rank, int64_t* out_ord, int32_t* out_count)
 {
     return guarded([&] {
         KRAG_REQUIRE(ix && q && out_final && out_dense && out_sparse && out_rank && out_ord && out_count && batch >= 1,
@@ -678,6 +688,10 @@ int32_t krag_retrieve(krag_index* ix, int32_t batch, const float* q, const uint3
         const int P = (int)((double)k * mult);
         check_P(P);
         std::shared_lock<std::shared_mutex> lk(ix->mu);
+        // the bitmap is read (n_rows + 31) / 32 words deep: the caller states how many it holds, so a bitmap built
+        // before a concurrent krag_index_add is refused instead of over-read
+        KRAG_REQUIRE(keyword_allow_bitmap == nullptr || keyword_allow_words >= (ix->n_rows + 31) / 32, KRAG_E_INVALID,
+                     "keyword_allow_bitmap holds fewer words than the index has rows / 32");
         KRAG_CUDA(cudaSetDevice(ix->ctx->di.device));
         SlotLease lease(ix->ctx);
         Slot* s = lease.s;
@@ -802,6 +816,7 @@ int32_t krag_synth_fill(krag_index* ix, int64_t n, int64_t row_base, uint64_t se
             ix->ttf.p = tf; ix->ttf.cap = nnz > 0 ? nnz : 1;
             ix->dlen.p = dl; ix->dlen.cap = n > 0 ? n : 1;
             ix->nnz = nnz;
+            ix->max_term_id = (uint32_t)(vocab - 1);     // the generator draws ids in [0, vocab)
             ix->has_sparse = true;
         }
         mark_alive(ix, 0, n, st);

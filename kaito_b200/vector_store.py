@@ -70,6 +70,70 @@ class SentenceSplitter:
         return out
 
 
+class RWLock:
+    """Many readers / one writer, writers preferred (aiorwlock.RWLock of the reference, base.py:77-79, with threads
+    instead of tasks: FastAPI runs the sync handlers of this service in a thread pool)."""
+
+    def __init__(self):
+        self._cv = threading.Condition(threading.Lock())
+        self._readers, self._writer, self._waiting_writers = 0, None, 0
+        self._depth = 0                      # the writer may re-enter (update -> insert)
+
+    class _Guard:
+        def __init__(self, acquire, release):
+            self._a, self._r = acquire, release
+
+        def __enter__(self):
+            self._a()
+
+        def __exit__(self, *exc):
+            self._r()
+
+    def _acquire_read(self):
+        me = threading.get_ident()
+        with self._cv:
+            if self._writer == me:           # the writer reads its own state
+                self._depth += 1
+                return
+            while self._writer is not None or self._waiting_writers:
+                self._cv.wait()
+            self._readers += 1
+
+    def _release_read(self):
+        with self._cv:
+            if self._writer == threading.get_ident():
+                self._depth -= 1
+                return
+            self._readers -= 1
+            if self._readers == 0:
+                self._cv.notify_all()
+
+    def _acquire_write(self):
+        me = threading.get_ident()
+        with self._cv:
+            if self._writer == me:
+                self._depth += 1
+                return
+            self._waiting_writers += 1
+            while self._writer is not None or self._readers:
+                self._cv.wait()
+            self._waiting_writers -= 1
+            self._writer, self._depth = me, 1
+
+    def _release_write(self):
+        with self._cv:
+            self._depth -= 1
+            if self._depth == 0:
+                self._writer = None
+                self._cv.notify_all()
+
+    def reader(self):
+        return RWLock._Guard(self._acquire_read, self._release_read)
+
+    def writer(self):
+        return RWLock._Guard(self._acquire_write, self._release_write)
+
+
 class _Node:
     __slots__ = ("node_id", "ref_doc_id", "text", "metadata", "ordinal", "alive")
 
@@ -85,6 +149,28 @@ class _IndexState:
         self.nodes: list[_Node] = []             # by ordinal (== insertion order == engine row)
         self.ref_docs: dict[str, dict] = {}      # doc_id -> {"text", "metadata", "nodes": [ordinal]}
         self.committed = False
+        self._filter_cache: dict[str, tuple[int, np.ndarray]] = {}   # filter json -> (nodes covered, allow bitmap)
+
+    def allow_bitmap(self, metadata_filter: dict) -> np.ndarray:
+        """1 bit per node (ordinal order) whose metadata equals the filter on every key (hybrid_retriever.py:227-235).
+        Cached per filter and extended incrementally: a filtered request costs O(new nodes since the last one with the
+        same filter), not O(all nodes)."""
+        key = json.dumps(metadata_filter, sort_keys=True, default=str)
+        n = len(self.nodes)
+        done, bm = self._filter_cache.get(key, (0, np.zeros(0, np.uint32)))
+        if done < n or bm.size != (n + 31) // 32:
+            nb = np.zeros((n + 31) // 32, np.uint32)
+            nb[: bm.size] = bm[: nb.size]
+            items = list(metadata_filter.items())
+            for o in range(done, n):
+                md = self.nodes[o].metadata or {}
+                if all(md.get(k) == v for k, v in items):
+                    nb[o >> 5] |= np.uint32(1 << (o & 31))
+            bm = nb
+            if len(self._filter_cache) > 256:
+                self._filter_cache.clear()
+            self._filter_cache[key] = (n, bm)
+        return bm
 
 
 class HybridRetriever:
@@ -109,12 +195,7 @@ class HybridRetriever:
     def _allow_bitmap(self):
         if not self._metadata_filter:
             return None
-        nodes = self._state.nodes
-        bm = np.zeros((len(nodes) + 31) // 32, np.uint32)
-        for n in nodes:
-            if all((n.metadata or {}).get(k) == v for k, v in self._metadata_filter.items()):
-                bm[n.ordinal >> 5] |= np.uint32(1 << (n.ordinal & 31))
-        return bm
+        return self._state.allow_bitmap(self._metadata_filter)
 
     def retrieve(self, query: str) -> list[tuple[_Node, float]]:
         st = self._state
@@ -147,14 +228,16 @@ class VectorStore:
         self.splitter = SentenceSplitter()
         self.filter_pushdown = os.getenv("KRAG_FILTER_PUSHDOWN", "0") == "1"
         self.component_scores = os.getenv("KRAG_COMPONENT_SCORES", "0") == "1"
-        # many readers / one writer (aiorwlock in the reference, base.py:77-79); the engine enforces the same
-        # discipline per index internally, this lock protects the host-side docstore
-        self._lock = threading.RLock()
+        # many readers / one writer (aiorwlock in the reference, base.py:77-79).  The engine enforces the same
+        # discipline per index internally; this lock keeps the host-side docstore (nodes, ref_docs, vocabulary)
+        # consistent with the engine rows for the whole of a retrieve / chat / persist, as the reference's reader
+        # lock does (base.py:917-919)
+        self._rw = RWLock()
 
     # ------------------------------------------------------------------ /index
     def index_documents(self, index_name: str, documents: list[dict]) -> list[str]:
         """base.py:90-97: create on first use, else append with per-document dedupe (:99-131)."""
-        with self._lock:
+        with self._rw.writer():
             st = self.index_map.get(index_name)
             if st is None:
                 st = _IndexState(self.engine.create_index(index_name, self.dimension))
@@ -170,30 +253,47 @@ class VectorStore:
                 self._insert(st, fresh)
             return ids
 
-    def _insert(self, st: _IndexState, docs):
-        node_ids, texts, offs, tids, tfs, dls, new_nodes = [], [], [0], [], [], [], []
+    def _insert(self, st: _IndexState, docs, replace: bool = False):
+        """Chunk, analyse, embed and append `docs`; the host docstore is published only after the embedder and the
+        engine accepted the whole batch, so a failure (remote embedder error, 501 for code splitting, engine error)
+        leaves neither a listed-but-unretrievable document nor ordinals that a later insert would reuse."""
+        for _, _, metadata in docs:                                     # validate the whole batch before any work
+            if metadata.get("split_type") == "code" and not self.code_splitter_available(metadata):
+                raise HTTPException(501, "code splitting (tree-sitter) is not available in this build")
+        node_ids, texts, offs, tids, tfs, dls, new_nodes, new_refs = [], [], [0], [], [], [], [], {}
         base = len(st.nodes)
         for doc_id, text, metadata in docs:
-            if metadata.get("split_type") == "code":
-                raise HTTPException(501, "code splitting (tree-sitter) is not available in this build")
             ords = []
-            for i, chunk in enumerate(self.splitter.split(text)):
+            for i, chunk in enumerate(self.split_document(text, metadata)):
                 ordinal = base + len(new_nodes)
                 new_nodes.append(_Node(f"{doc_id}-{i}", doc_id, chunk, metadata, ordinal))
                 et = embed_text(chunk, metadata)
                 texts.append(et)
-                t_ids, t_tf, dl = st.vocab.doc_terms(et)
+                t_ids, t_tf, dl = st.vocab.doc_terms(et)     # may grow the vocabulary: unused ids are harmless
                 tids.append(t_ids); tfs.append(t_tf); dls.append(dl)
                 offs.append(offs[-1] + len(t_ids))
                 node_ids.append(ordinal)
                 ords.append(ordinal)
-            st.ref_docs[doc_id] = {"text": text, "metadata": metadata, "nodes": ords}
+            new_refs[doc_id] = {"text": text, "metadata": metadata, "nodes": ords}
         vecs = np.asarray(self.embed_model.get_text_embedding_batch(texts), np.float32)
         st.index.add(np.asarray(node_ids, np.uint64), vecs, np.asarray(offs, np.int64),
                      np.concatenate(tids) if tids else np.zeros(0, np.uint32),
                      np.concatenate(tfs) if tfs else np.zeros(0, np.uint16), np.asarray(dls, np.uint32))
+        # the rows are in the engine: publish.  (A failing commit below leaves the index "uncommitted": /retrieve takes
+        # the reference's vector-only fallback until the next successful commit.)
         st.nodes.extend(new_nodes)
+        old = {d: st.ref_docs.get(d) for d in new_refs} if replace else {}
+        st.ref_docs.update(new_refs)
+        st.committed = False
         self._commit(st)
+        return old
+
+    def code_splitter_available(self, metadata: dict) -> bool:
+        return False
+
+    def split_document(self, text: str, metadata: dict) -> list[str]:
+        """CustomTransformer.__call__ (custom_transformer.py:34-55): SentenceSplitter() unless split_type == "code"."""
+        return self.splitter.split(text)
 
     def _commit(self, st: _IndexState):
         # the reference rebuilds BM25 on every query (hybrid_retriever.py:104-130); here once per mutation
@@ -213,10 +313,11 @@ class VectorStore:
             retriever = HybridRetriever(st, self.embed_model, max_results=top_k, metadata_filter=metadata_filter,
                                         filter_pushdown=self.filter_pushdown)
             t0 = time.time()
-            nodes = retriever.retrieve(query)
+            with self._rw.reader():         # base.py:917-919: reader lock around the retrieval
+                nodes = retriever.retrieve(query)
+                results = [{"doc_id": n.ref_doc_id or n.node_id, "node_id": n.node_id, "text": n.text, "score": s,
+                            "metadata": n.metadata if n.metadata else None} for n, s in nodes]
             self.last_retrieve_seconds = time.time() - t0
-            results = [{"doc_id": n.ref_doc_id or n.node_id, "node_id": n.node_id, "text": n.text, "score": s,
-                        "metadata": n.metadata if n.metadata else None} for n, s in nodes]
             if self.component_scores:       # KRAG_COMPONENT_SCORES=1: fill the optional fields of models.NodeWithScore
                 for r, extra in zip(results, retriever.last_components):
                     r.update(extra)
@@ -230,11 +331,12 @@ class VectorStore:
     def dense_candidates(self, index_name: str, query: str, top_k: int) -> list[tuple[_Node, float]]:
         """index.as_retriever(similarity_top_k=top_k) of the chat engine (base.py:376-391): exact dense kNN, faiss
         scores = squared L2 distances, ascending."""
-        st = self.index_map[index_name]
         q = np.asarray(self.embed_model.get_query_embedding(query), np.float32).reshape(1, -1)
-        k = max(1, min(top_k, sum(1 for n in st.nodes if n.alive)))
-        dist, ordn = st.index.search_dense(q, k)
-        return [(st.nodes[int(o)], float(d)) for d, o in zip(dist[0], ordn[0]) if o >= 0]
+        with self._rw.reader():
+            st = self.index_map[index_name]
+            k = max(1, min(top_k, sum(1 for n in st.nodes if n.alive)))
+            dist, ordn = st.index.search_dense(q, k)
+            return [(st.nodes[int(o)], float(d)) for d, o in zip(dist[0], ordn[0]) if o >= 0]
 
     def chat_completion(self, request: dict, llm, cfg: dict | None = None) -> dict:
         """base.py:180-477 -- see kaito_b200/chat.py"""
@@ -271,7 +373,7 @@ class VectorStore:
     def delete_documents(self, index_name: str, doc_ids: list[str]):
         if index_name not in self.index_map:
             raise HTTPException(404, f"No such index: '{index_name}' exists.")
-        with self._lock:
+        with self._rw.writer():
             st = self.index_map[index_name]
             deleted, missing, rows = [], [], []
             for d in doc_ids:
@@ -292,7 +394,7 @@ class VectorStore:
         """base.py:529-561 semantics: by doc_id; unchanged text -> unchanged, else delete + re-insert."""
         if index_name not in self.index_map:
             raise HTTPException(404, f"No such index: '{index_name}' exists.")
-        with self._lock:
+        with self._rw.writer():
             st = self.index_map[index_name]
             updated, unchanged, missing = [], [], []
             for doc in documents:
@@ -302,15 +404,21 @@ class VectorStore:
                 elif rec["text"] == doc["text"] and (doc.get("metadata") or {}) == rec["metadata"]:
                     unchanged.append(doc)
                 else:
-                    self.delete_documents(index_name, [doc["doc_id"]])
-                    self._insert(st, [(doc["doc_id"], doc["text"], doc.get("metadata") or {})])
+                    # new rows first, old rows tombstoned only once the replacement is in: a failing embed/add leaves
+                    # the document as it was (the reference deletes first, base.py:529-561, and can lose it)
+                    old_rows = list(rec["nodes"])
+                    self._insert(st, [(doc["doc_id"], doc["text"], doc.get("metadata") or {})], replace=True)
+                    for o in old_rows:
+                        st.nodes[o].alive = False
+                    st.index.remove(np.asarray(old_rows, np.uint64))
+                    self._commit(st)
                     updated.append(doc)
             return {"updated_documents": updated, "unchanged_documents": unchanged, "not_found_documents": missing}
 
     def delete_index(self, index_name: str):
         if index_name not in self.index_map:
             raise HTTPException(404, f"No such index: '{index_name}' exists.")
-        with self._lock:
+        with self._rw.writer():
             self.index_map.pop(index_name).index.drop()
 
     # -------------------------------------------------------- persist / load
@@ -318,33 +426,43 @@ class VectorStore:
         """base.py:779-809. Own format: the engine snapshot + docstore.json."""
         if index_name not in self.index_map:
             raise HTTPException(404, f"No such index: '{index_name}' exists.")
-        st = self.index_map[index_name]
-        os.makedirs(path, exist_ok=True)
-        st.index.persist(path)
-        with open(os.path.join(path, "docstore.json"), "w") as f:
-            json.dump({"version": 1, "vocab": st.vocab.terms, "ref_docs": st.ref_docs,
-                       "nodes": [[n.node_id, n.ref_doc_id, n.text, n.metadata, n.alive] for n in st.nodes]}, f)
+        with self._rw.reader():             # engine snapshot and docstore.json describe the same state
+            st = self.index_map[index_name]
+            os.makedirs(path, exist_ok=True)
+            st.index.persist(path)
+            with open(os.path.join(path, "docstore.json"), "w") as f:
+                json.dump({"version": 1, "vocab": st.vocab.terms, "ref_docs": st.ref_docs,
+                           "nodes": [[n.node_id, n.ref_doc_id, n.text, n.metadata, n.alive] for n in st.nodes]}, f)
 
     def load(self, index_name: str, path: str, overwrite: bool = False):
         """base.py:811-868."""
         if index_name in self.index_map and not overwrite:
             raise HTTPException(409, f"Index '{index_name}' already exists. Use a different name or delete the existing index first.")
+        if not os.path.exists(path):        # base.py:841-845
+            raise HTTPException(404, f"Path does not exist: {path}")
         try:
             with open(os.path.join(path, "docstore.json")) as f:
                 ds = json.load(f)
-            with self._lock:
-                if index_name in self.index_map:
-                    self.index_map.pop(index_name).index.drop()
-                st = _IndexState(self.engine.load_index(index_name, path))
-                for t in ds["vocab"]:
-                    st.vocab.add(t)
-                st.ref_docs = ds["ref_docs"]
-                for i, (nid, rid, text, meta, alive) in enumerate(ds["nodes"]):
-                    n = _Node(nid, rid, text, meta, i)
-                    n.alive = alive
-                    st.nodes.append(n)
-                st.committed = True
-                self.index_map[index_name] = st
+            with self._rw.writer():
+                # load beside the live index (under a scratch engine name) and swap only on success: a corrupt snapshot
+                # must not destroy what is being served (the reference replaces index_map[name] after the load, :847-860)
+                fresh = _IndexState(self.engine.load_index(index_name, path))
+                try:
+                    for t in ds["vocab"]:
+                        fresh.vocab.add(t)
+                    fresh.ref_docs = ds["ref_docs"]
+                    for i, (nid, rid, text, meta, alive) in enumerate(ds["nodes"]):
+                        n = _Node(nid, rid, text, meta, i)
+                        n.alive = alive
+                        fresh.nodes.append(n)
+                    fresh.committed = True
+                except Exception:
+                    fresh.index.drop()
+                    raise
+                old = self.index_map.get(index_name)
+                self.index_map[index_name] = fresh
+                if old is not None:
+                    old.index.drop()
         except HTTPException:
             raise
         except Exception as e:

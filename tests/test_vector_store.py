@@ -108,3 +108,125 @@ def test_store_persist_load_gpu(ctx, tmp_path):
     b = store.retrieve("p2", "keyword retrieval with BM25", 4)
     assert a["results"] == b["results"]
     store.delete_index("p"); store.delete_index("p2")
+
+
+# ------------------------------------------------------------------ round-1 advisor findings
+def _sole_document_lifecycle(store):
+    """index one doc, update it, delete it (the sequence of test/rage2e/rag_test.go), then reload an all-dead snapshot"""
+    ids = store.index_documents("solo", [{"text": "the only document of this index", "metadata": {"v": 1}}])
+    u = store.update_documents("solo", [{"doc_id": ids[0], "text": "the only document, second edition", "metadata": {"v": 2}}])
+    assert [d["doc_id"] for d in u["updated_documents"]] == ids and not u["not_found_documents"]
+    r = store.retrieve("solo", "second edition of the only document", 3)
+    assert r["count"] == 1 and r["results"][0]["text"] == "the only document, second edition" and r["results"][0]["metadata"] == {"v": 2}
+    listed = store.list_documents_in_index("solo")
+    assert listed["total_items"] == 1 and listed["documents"][0]["text"].endswith("second edition")
+    d = store.delete_documents("solo", ids)
+    assert d == {"deleted_doc_ids": ids, "not_found_doc_ids": []}
+    assert store.retrieve("solo", "anything at all", 3)["count"] == 0          # every row tombstoned: nothing comes back
+    assert store.list_documents_in_index("solo")["total_items"] == 0
+    return ids
+
+
+def test_sole_document_update_delete_cpu(cpu_store, tmp_path):
+    _sole_document_lifecycle(cpu_store)
+    cpu_store.persist("solo", str(tmp_path / "s"))
+    cpu_store.load("solo2", str(tmp_path / "s"))                 # a snapshot whose rows are all dead loads
+    assert cpu_store.retrieve("solo2", "anything", 3)["count"] == 0
+
+
+@pytest.mark.gpu
+def test_sole_document_update_delete_gpu(ctx, tmp_path):
+    store = VectorStore(HashingEmbedding(64), ctx)
+    _sole_document_lifecycle(store)
+    store.persist("solo", str(tmp_path / "s"))
+    store.load("solo2", str(tmp_path / "s"))
+    assert store.retrieve("solo2", "anything", 3)["count"] == 0
+    again = store.index_documents("solo2", [{"text": "a fresh document after the purge"}])   # and the index keeps working
+    assert [x["doc_id"] for x in store.retrieve("solo2", "fresh document", 3)["results"]] == again
+    store.delete_index("solo"); store.delete_index("solo2")
+
+
+class _FlakyEmbedding(HashingEmbedding):
+    fail = False
+
+    def get_text_embedding_batch(self, texts):
+        if self.fail:
+            raise RuntimeError("embedding backend unavailable")
+        return super().get_text_embedding_batch(texts)
+
+
+def _failed_insert_leaves_no_trace(store, emb):
+    a = store.index_documents("tx", [{"text": "alpha doc about tensor cores"}])
+    emb.fail = True
+    with pytest.raises(RuntimeError):
+        store.index_documents("tx", [{"text": "beta doc about shared memory"}])
+    emb.fail = False
+    assert store.list_documents_in_index("tx")["total_items"] == 1           # the failed document is not listed
+    with pytest.raises(HTTPException) as e:                                   # 501 raised before any state is touched
+        store.index_documents("tx", [{"text": "delta doc"}, {"text": "def f(): pass", "metadata": {"split_type": "code", "language": "cobol"}}])
+    assert e.value.status_code == 501 and store.list_documents_in_index("tx")["total_items"] == 1
+    b = store.index_documents("tx", [{"text": "beta doc about shared memory"}])     # the retry indexes it
+    g = store.index_documents("tx", [{"text": "gamma doc about thread block clusters"}])
+    assert b[0] in [x["doc_id"] for x in store.retrieve("tx", "shared memory beta", 3)["results"]]
+    store.delete_documents("tx", b)                                           # deleting beta must not hit gamma's rows
+    got = [x["doc_id"] for x in store.retrieve("tx", "thread block clusters gamma", 3)["results"]]
+    assert g[0] in got and b[0] not in got and a[0] in got + a
+
+
+def test_failed_insert_leaves_no_trace_cpu(oracle):
+    from tests.oracle_engine import OracleEngine
+    emb = _FlakyEmbedding(64)
+    _failed_insert_leaves_no_trace(VectorStore(emb, OracleEngine(oracle)), emb)
+
+
+@pytest.mark.gpu
+def test_failed_insert_leaves_no_trace_gpu(ctx):
+    emb = _FlakyEmbedding(64)
+    store = VectorStore(emb, ctx)
+    _failed_insert_leaves_no_trace(store, emb)
+    store.delete_index("tx")
+
+
+def test_load_errors_match_reference_and_keep_the_live_index(cpu_store, tmp_path):
+    cpu_store.index_documents("live", DOCS)
+    before = cpu_store.retrieve("live", "BM25 keyword retrieval", 3)
+    with pytest.raises(HTTPException) as e:                                   # base.py:841-845
+        cpu_store.load("live", str(tmp_path / "nowhere"), overwrite=True)
+    assert e.value.status_code == 404 and e.value.detail == f"Path does not exist: {tmp_path / 'nowhere'}"
+    bad = tmp_path / "corrupt"
+    bad.mkdir()
+    (bad / "docstore.json").write_text("{\"version\": 1, \"vocab\": [], \"ref_docs\": {}, \"nodes\": []}")   # engine file missing
+    with pytest.raises(HTTPException) as e:
+        cpu_store.load("live", str(bad), overwrite=True)
+    assert e.value.status_code == 500 and e.value.detail.startswith("Loading failed:")
+    assert cpu_store.retrieve("live", "BM25 keyword retrieval", 3) == before   # the served index survived the failed load
+
+
+def test_filter_bitmap_cache_tracks_inserts(cpu_store):
+    cpu_store.index_documents("f", DOCS)
+    st = cpu_store.index_map["f"]
+    bm1 = st.allow_bitmap({"type": "recipe"}).copy()
+    assert bm1.tolist() == [1 << 2]
+    cpu_store.index_documents("f", [{"text": "another recipe with garlic", "metadata": {"type": "recipe"}}])
+    assert st.allow_bitmap({"type": "recipe"}).tolist() == [(1 << 2) | (1 << 5)]
+    assert st.allow_bitmap({"type": "recipe"}) is st.allow_bitmap({"type": "recipe"})    # served from the cache
+
+
+def test_rwlock_readers_share_writers_exclude():
+    import threading, time
+    from kaito_b200.vector_store import RWLock
+    rw, log = RWLock(), []
+    def reader(i):
+        with rw.reader():
+            log.append(("r+", i)); time.sleep(0.05); log.append(("r-", i))
+    def writer():
+        with rw.writer():
+            with rw.writer():                      # re-entrant for the owning thread
+                with rw.reader():
+                    log.append(("w+", 0)); time.sleep(0.05); log.append(("w-", 0))
+    ts = [threading.Thread(target=reader, args=(i,)) for i in range(3)] + [threading.Thread(target=writer)]
+    for t in ts: t.start()
+    for t in ts: t.join()
+    wi = log.index(("w+", 0))
+    assert log[wi + 1] == ("w-", 0)                                            # nothing interleaves with the writer
+    assert log[:2] == [("r+", 0), ("r+", 1)] or log[0][0] == "w+"              # readers overlap each other
