@@ -238,7 +238,7 @@ void bm25_candidates_dev(krag_index* ix, Slot* s, const uint32_t* d_terms, const
         n_terms_total = tot;
     }
     s->part.reserve((int64_t)bm25_part_elems(ix->committed_rows, batch, P), 0, st);
-    s->bm25_res.reserve((int64_t)(n_terms_total > 0 ? n_terms_total : 1) * 16, 0, st);
+    s->bm25_res.reserve((int64_t)bm25_resolve_bytes(ix->committed_rows, n_terms_total), 0, st);
     launch_bm25(ix->ctx->di, ix->post, ix->committed_rows, eligible ? eligible : alive_ptr(ix), d_terms, d_toff, n_terms_total, s->bm25_res.p, batch, P,
                 (uint32_t)ix->ord_base, s->part.p, d_keys, st);
 }

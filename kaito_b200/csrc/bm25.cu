@@ -120,8 +120,8 @@ __global__ void tile_index_kernel(const uint32_t* __restrict__ sorted_terms, con
         if (sl < 0) continue;
         const int64_t b = off[t], e = off[t + 1];
         const int64_t i = p - b;
-        const int64_t tile_d = post_doc[p] / BM25_TILE_DOCS;
-        const int64_t prev = (i == 0) ? -1 : (int64_t)(post_doc[p - 1] / BM25_TILE_DOCS);
+        const int64_t tile_d = post_doc[p] / BM25_SUB_DOCS;
+        const int64_t prev = (i == 0) ? -1 : (int64_t)(post_doc[p - 1] / BM25_SUB_DOCS);
         uint32_t* row = tile_off + (int64_t)sl * (n_tiles + 1);
         for (int64_t tl = prev + 1; tl <= tile_d; ++tl) row[tl] = (uint32_t)i;
         if (p == e - 1) for (int64_t tl = tile_d + 1; tl <= n_tiles; ++tl) row[tl] = (uint32_t)(e - b);
@@ -170,7 +170,7 @@ static void build_tile_index(const uint32_t* sorted_terms, const uint32_t* post_
     KRAG_CUDA(cudaMemcpyAsync(&n_slots, scan + vocab, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     KRAG_CUDA(cudaStreamSynchronize(st));
     sc.free_now(tmp); sc.free_now(flag); sc.free_now(scan);
-    int64_t n_tiles = (n_rows + BM25_TILE_DOCS - 1) / BM25_TILE_DOCS;
+    int64_t n_tiles = (n_rows + BM25_SUB_DOCS - 1) / BM25_SUB_DOCS;
     if (n_tiles < 1) n_tiles = 1;
     uint32_t* tile_off = sc.alloc<uint32_t>((size_t)((int64_t)(n_slots > 0 ? n_slots : 1) * (n_tiles + 1)));
     if (n_slots > 0) {
@@ -243,7 +243,7 @@ void build_postings(const uint32_t* term_ids, const uint16_t* term_tf, const uin
         if (out.tile_slot) cudaFree(out.tile_slot);
         if (out.tile_off) cudaFree(out.tile_off);
         out.tile_slot = sc.keep(slot); out.tile_off = sc.keep(toff); out.n_slots = 0;
-        out.n_tiles = (n_docs_rows + BM25_TILE_DOCS - 1) / BM25_TILE_DOCS < 1 ? 1 : (n_docs_rows + BM25_TILE_DOCS - 1) / BM25_TILE_DOCS;
+        out.n_tiles = (n_docs_rows + BM25_SUB_DOCS - 1) / BM25_SUB_DOCS < 1 ? 1 : (n_docs_rows + BM25_SUB_DOCS - 1) / BM25_SUB_DOCS;
     }
     if (out.off) cudaFree(out.off);
     if (out.doc) cudaFree(out.doc);
@@ -253,6 +253,10 @@ void build_postings(const uint32_t* term_ids, const uint16_t* term_tf, const uin
 }
 
 // -------------------------------------------------------------------------- query time
+// Two kernels.  bm25_warp_kernel (further down) is the one that runs: warp-autonomous sub-tiles, a sampled per-query
+// admission threshold, global candidate lists.  bm25_tile_kernel below is the first-generation CTA-per-tile kernel, kept as
+// the exact SAFETY NET for queries whose candidate list overflows (launched after every batch, it skips every query whose
+// overflow flag is 0) and selectable as a whole with KRAG_BM25_LEGACY=1.
 constexpr int BQ_THREADS = 256;   // a term contributes ~200 postings to a 16384-doc tile: 256-wide slabs keep the lanes busy
 constexpr int BQ_MAX_TERMS = 32;    // query terms resolved per pass; longer queries loop
 constexpr int BQ_MAX_SLABS = 96;    // 512-posting slabs per pass
@@ -279,8 +283,14 @@ bm25_tile_kernel(const int64_t* __restrict__ post_off, const uint32_t* __restric
                  const uint32_t* __restrict__ q_terms, const int32_t* __restrict__ q_term_offsets,
                  const int32_t* __restrict__ q_slot, const int64_t* __restrict__ q_base, const int32_t* __restrict__ q_rare_len,
                  int64_t n_rows, const uint32_t* __restrict__ alive, int P, int cap, uint32_t ord_base, int batch, int n_tiles, int group,
-                 uint64_t* __restrict__ part /*[batch][n_groups][P]*/, unsigned long long* __restrict__ g_thr /*[batch]*/)
+                 uint64_t* __restrict__ part /*[batch][n_groups][P]*/, unsigned long long* __restrict__ g_thr /*[batch]*/,
+                 const uint32_t* __restrict__ only_flag /* != null: only queries whose flag is set */)
 {
+    // the tile index has one column per BM25_SUB_DOCS docs; this kernel's tiles are BM25_SUBS_PER_TILE of them
+    auto idx_col = [&](int tile) -> int64_t {
+        const int64_t c = (int64_t)tile * BM25_SUBS_PER_TILE;
+        return c < n_tiles_idx ? c : n_tiles_idx;
+    };
     extern __shared__ __align__(16) unsigned char bsm[];
     float* acc = reinterpret_cast<float*>(bsm);                                          // [BM25_TILE_DOCS]
     uint64_t* sbuf = reinterpret_cast<uint64_t*>(bsm + (size_t)BM25_TILE_DOCS * 4);      // [cap]
@@ -309,6 +319,7 @@ bm25_tile_kernel(const int64_t* __restrict__ post_off, const uint32_t* __restric
     const int64_t n_items = (int64_t)n_groups * batch;
     for (int64_t item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int tg = (int)(item / batch), qi = (int)(item - (int64_t)tg * batch);
+    if (only_flag != nullptr && only_flag[qi] == 0) continue;      // uniform over the CTA, before any barrier of the item
     const int tile0 = tg * group, gcount = min(group, n_tiles - tile0);
     const int tb = q_term_offsets[qi], te = q_term_offsets[qi + 1];
     const bool single_chunk = (te - tb <= BQ_MAX_TERMS);
@@ -323,8 +334,8 @@ bm25_tile_kernel(const int64_t* __restrict__ post_off, const uint32_t* __restric
         const int32_t sl = q_slot[tb + tid];
         s_slot[tid] = sl; s_base[tid] = q_base[tb + tid]; s_rare[tid] = q_rare_len[tb + tid];
         if (sl >= 0) {
-            const uint32_t* row = tile_off + (int64_t)sl * (n_tiles_idx + 1) + tile0;
-            for (int g = 0; g <= gcount; ++g) s_toff[tid][g] = row[g];
+            const uint32_t* row = tile_off + (int64_t)sl * (n_tiles_idx + 1);
+            for (int g = 0; g <= gcount; ++g) s_toff[tid][g] = row[idx_col(tile0 + g)];
         }
     }
     __syncthreads();
@@ -344,7 +355,7 @@ bm25_tile_kernel(const int64_t* __restrict__ post_off, const uint32_t* __restric
             int64_t lo = 0; int len = 0;
             if (sl >= 0) {
                 const uint32_t* row = tile_off + (int64_t)sl * (n_tiles_idx + 1);
-                const uint32_t o0 = row[tile], o1 = row[tile + 1];
+                const uint32_t o0 = row[idx_col(tile)], o1 = row[idx_col(tile + 1)];
                 lo = q_base[c0 + tid] + o0; len = (int)(o1 - o0);
             } else if (sl == -1) {
                 lo = q_base[c0 + tid]; len = q_rare_len[c0 + tid];   // rare: whole list, filtered by doc range below
@@ -493,70 +504,430 @@ bm25_tile_kernel(const int64_t* __restrict__ post_off, const uint32_t* __restric
     }   // work items
 }
 
-// once per batch: (tile-index slot, posting base, rare length) of every query term position
-__global__ void bm25_resolve_kernel(const uint32_t* __restrict__ q_terms, int n_terms, const int64_t* __restrict__ post_off,
-                                    const int32_t* __restrict__ tile_slot, int64_t vocab, int32_t* __restrict__ q_slot,
-                                    int64_t* __restrict__ q_base, int32_t* __restrict__ q_rare_len)
+// ---------------------------------------------------------------------------------------------------------------------
+// K3, second generation: bm25_warp_kernel.
+//
+// The legacy kernel spends its time on per-(tile, query) bookkeeping -- ~17 CTA barriers, slab tables and a bitonic sort
+// per work item -- not on postings (ncu: DRAM 4.6 % busy, ~195 thread instructions per posting).  Here a WARP owns a
+// BM25_SUB_DOCS-document range ("sub-tile") with its fp32 accumulators in shared memory and walks the query's terms on its
+// own: no CTA barrier anywhere.  Documents are unique inside a term, so the lanes of a 32-posting round never collide;
+// rounds are issued in query-term order with a __syncwarp() in between, which fixes every document's fp32 summation
+// order to the oracle's (bit-exact).  All postings of a sub-tile (up to BW_ROUNDS rounds) are loaded into registers up
+// front -- the loads of all terms are in flight together -- then accumulated, then every touched document is claimed
+// once (atomicExch resets the accumulator) and, if it passes the query's admission threshold, appended to the query's
+// candidate list in global memory (one warp-aggregated atomic per round).  No per-item sort, no per-item list.
+//
+// Threshold: a first pass over every `stride`-th sub-tile (no threshold) fills the lists with a sample; the P-th best
+// sampled key is a VALID bound (P real documents are at least that good), so the main pass over all sub-tiles admits
+// ~stride * P documents per query instead of every touched one, and bm25_select_kernel takes the exact top-P of them.
+// A list that overflows (adversarial score layouts) raises the query's flag and the legacy kernel recomputes that query.
+//
+// Term -> posting range lookups: one u32 row of sub-tile boundaries per query term.  Frequent terms (> BM25_RARE_MAX
+// postings) have theirs in the persistent tile index; for the others bm25_resolve_kernel builds the row per batch from
+// the term's <= 2048 document ids (binary searches out of shared memory).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int BW_WARPS = 4;                 // warps per CTA: 4 x 16 KB accumulators, 3 CTAs per SM
+constexpr int BW_THREADS = BW_WARPS * 32;
+constexpr int BW_CHUNK = 8;                 // consecutive (sampled) sub-tiles of one query per work unit
+constexpr int BW_ROUNDS = 16;               // 32-posting rounds of a sub-tile held in registers
+
+// once per batch and query-term position: posting base, boundary row, and the legacy kernel's (slot, rare length)
+__global__ void __launch_bounds__(256)
+bm25_resolve_kernel(const uint32_t* __restrict__ q_terms, int n_terms, const int64_t* __restrict__ post_off,
+                    const uint32_t* __restrict__ post_doc, const int32_t* __restrict__ tile_slot,
+                    const uint32_t* __restrict__ tile_off, int64_t vocab, int64_t n_sub, uint32_t* __restrict__ scratch_rows,
+                    const uint32_t** __restrict__ q_row, int64_t* __restrict__ q_base, int32_t* __restrict__ q_slot,
+                    int32_t* __restrict__ q_rare_len)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint32_t s_doc[BM25_RARE_MAX];
+    const int i = blockIdx.x, tid = threadIdx.x;
     if (i >= n_terms) return;
     const uint32_t t = q_terms[i];
-    int32_t sl = -2; int64_t b = 0; int32_t rl = 0;
-    if ((int64_t)t < vocab) {
-        b = post_off[t];
-        sl = tile_slot[t];
-        if (sl < 0) { sl = -1; rl = (int32_t)(post_off[t + 1] - b); }
+    if ((int64_t)t >= vocab) {                                   // out-of-vocabulary id: contributes nothing
+        if (tid == 0) { q_row[i] = nullptr; q_base[i] = 0; q_slot[i] = -2; q_rare_len[i] = 0; }
+        return;
     }
-    q_slot[i] = sl; q_base[i] = b; q_rare_len[i] = rl;
+    const int64_t b = post_off[t];
+    const int df = (int)min((int64_t)0x7fffffff, post_off[t + 1] - b);
+    const int32_t sl = tile_slot[t];
+    if (sl >= 0) {
+        if (tid == 0) { q_row[i] = tile_off + (int64_t)sl * (n_sub + 1); q_base[i] = b; q_slot[i] = sl; q_rare_len[i] = 0; }
+        return;
+    }
+    // short list (df <= BM25_RARE_MAX): boundary row built here
+    for (int k = tid; k < df; k += 256) s_doc[k] = post_doc[b + k];
+    __syncthreads();
+    uint32_t* row = scratch_rows + (int64_t)i * (n_sub + 1);
+    for (int64_t sidx = tid; sidx <= n_sub; sidx += 256) {
+        const uint64_t target = (uint64_t)sidx * BM25_SUB_DOCS;  // first posting with doc >= target
+        int lo = 0, hi = df;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((uint64_t)s_doc[mid] < target) lo = mid + 1; else hi = mid; }
+        row[sidx] = (uint32_t)lo;
+    }
+    if (tid == 0) { q_row[i] = row; q_base[i] = b; q_slot[i] = -1; q_rare_len[i] = df; }
+}
+
+struct BwCtx {
+    const uint32_t* post_doc; const float* post_score; float* acc; const uint32_t* alive;
+    unsigned long long* cand_q; uint32_t* cnt_q; unsigned long long thr; uint32_t t0, ord_base; int capq, lane;
+};
+
+// rounds [u0, u0 + BW_ROUNDS) of the flattened (term, 32-posting round) sequence of one sub-tile -> registers.
+// Lane j < nt holds term j's (start, len, rounds, exclusive round prefix).
+template <bool kScores>
+__device__ __forceinline__ void bw_load_block(const BwCtx& c, int u0, int R, int64_t my_start, int my_len, int rj, int pre,
+                                              uint32_t (&d)[BW_ROUNDS], float (&sc)[BW_ROUNDS])
+{
+#pragma unroll
+    for (int u = 0; u < BW_ROUNDS; ++u) {
+        d[u] = 0xFFFFFFFFu; sc[u] = 0.f;
+        const int g = u0 + u;
+        if (g < R) {                                                      // warp-uniform
+            const unsigned m = __ballot_sync(0xffffffffu, pre <= g && g < pre + rj);   // exactly one term owns round g
+            const int j = __ffs(m) - 1;
+            const int64_t st = __shfl_sync(0xffffffffu, my_start, j);
+            const int ln = __shfl_sync(0xffffffffu, my_len, j);
+            const int pj = __shfl_sync(0xffffffffu, pre, j);
+            const int idx = (g - pj) * 32 + c.lane;
+            if (idx < ln) {
+                d[u] = __ldg(c.post_doc + st + idx);
+                if (kScores) sc[u] = __ldg(c.post_score + st + idx);
+            }
+        }
+    }
+}
+__device__ __forceinline__ void bw_accum_block(const BwCtx& c, int u0, int R, const uint32_t (&d)[BW_ROUNDS], const float (&sc)[BW_ROUNDS])
+{
+#pragma unroll
+    for (int u = 0; u < BW_ROUNDS; ++u) {
+        if (u0 + u < R) {
+            const uint32_t rel = d[u] - c.t0;
+            if (d[u] != 0xFFFFFFFFu && rel < (uint32_t)BM25_SUB_DOCS) c.acc[rel] += sc[u];
+            __syncwarp();                  // the next round may belong to the next term and touch the same document
+        }
+    }
+}
+__device__ __forceinline__ void bw_claim_block(const BwCtx& c, int u0, int R, const uint32_t (&d)[BW_ROUNDS])
+{
+#pragma unroll
+    for (int u = 0; u < BW_ROUNDS; ++u) {
+        if (u0 + u < R) {
+            bool hit = false;
+            unsigned long long key = 0;
+            const uint32_t rel = d[u] - c.t0;
+            if (d[u] != 0xFFFFFFFFu && rel < (uint32_t)BM25_SUB_DOCS) {
+                const float sum = atomicExch(&c.acc[rel], 0.f);           // first claimer takes the final score
+                if (sum > 0.f && (c.alive == nullptr || bit_test(c.alive, d[u]))) {
+                    key = make_key_desc(sum, c.ord_base + d[u]);
+                    hit = key <= c.thr;
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m) {                                                       // one atomic per round and warp
+                const int leader = __ffs(m) - 1;
+                uint32_t base_slot = 0;
+                if (c.lane == leader) base_slot = atomicAdd(c.cnt_q, (uint32_t)__popc(m));
+                base_slot = __shfl_sync(0xffffffffu, base_slot, leader);
+                if (hit) {
+                    const uint32_t slot = base_slot + (uint32_t)__popc(m & ((1u << c.lane) - 1u));
+                    if (slot < (uint32_t)c.capq) c.cand_q[slot] = key;     // past capq: counted, dropped -> overflow flag
+                }
+            }
+        }
+    }
+}
+
+// one phase (accumulate / claim) of one term chunk of one sub-tile
+template <bool kClaim>
+__device__ __forceinline__ void bw_phase(const BwCtx& c, int64_t my_start, int my_len, bool single_block_claim_from_regs,
+                                         uint32_t (&d)[BW_ROUNDS], float (&sc)[BW_ROUNDS], int& R_out)
+{
+    const int rj = (my_len + 31) >> 5;
+    int pre = rj;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pre, o); if (c.lane >= o) pre += v; }
+    const int R = __shfl_sync(0xffffffffu, pre, 31);
+    pre -= rj;
+    R_out = R;
+    if (!kClaim) {
+        for (int u0 = 0; u0 < R; u0 += BW_ROUNDS) {
+            bw_load_block<true>(c, u0, R, my_start, my_len, rj, pre, d, sc);
+            bw_accum_block(c, u0, R, d, sc);
+        }
+    } else {
+        if (single_block_claim_from_regs) { bw_claim_block(c, 0, R, d); return; }
+        for (int u0 = 0; u0 < R; u0 += BW_ROUNDS) {
+            bw_load_block<false>(c, u0, R, my_start, my_len, rj, pre, d, sc);
+            bw_claim_block(c, u0, R, d);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(BW_THREADS, 3)
+bm25_warp_kernel(const uint32_t* __restrict__ post_doc, const float* __restrict__ post_score,
+                 const int32_t* __restrict__ q_term_offsets, const uint32_t* const* __restrict__ q_row,
+                 const int64_t* __restrict__ q_base, int64_t n_rows, const uint32_t* __restrict__ alive, uint32_t ord_base,
+                 int batch, int n_s /* sub-tiles visited */, int stride /* every stride-th sub-tile */,
+                 const unsigned long long* __restrict__ thr_q /* null: admit everything */, unsigned long long* __restrict__ cand,
+                 uint32_t* __restrict__ cand_cnt, int capq, unsigned long long* __restrict__ unit_counter)
+{
+    extern __shared__ __align__(16) float bw_acc[];                        // [BW_WARPS][BM25_SUB_DOCS]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* acc = bw_acc + (size_t)warp * BM25_SUB_DOCS;
+    for (int i = lane; i < BM25_SUB_DOCS / 4; i += 32) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();                                                          // zeroed once: the claim step resets what it touches
+
+    const int n_chunks = (n_s + BW_CHUNK - 1) / BW_CHUNK;
+    const long long n_units = (long long)n_chunks * batch;
+    BwCtx c;
+    c.post_doc = post_doc; c.post_score = post_score; c.acc = acc; c.alive = alive; c.ord_base = ord_base; c.capq = capq; c.lane = lane;
+    uint32_t d[BW_ROUNDS]; float sc[BW_ROUNDS];
+    for (;;) {
+        unsigned long long unit = 0;
+        if (lane == 0) unit = atomicAdd(unit_counter, 1ull);               // dynamic: units differ a lot in postings
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if ((long long)unit >= n_units) break;
+        const int q = (int)(unit % (unsigned long long)batch), ch = (int)(unit / (unsigned long long)batch);
+        const int tb = q_term_offsets[q], te = q_term_offsets[q + 1];
+        if (te <= tb) continue;
+        c.thr = thr_q ? thr_q[q] : KEY_PAD;
+        c.cand_q = cand + (size_t)q * capq; c.cnt_q = cand_cnt + q;
+        const int s0 = ch * BW_CHUNK, ns = min(BW_CHUNK, n_s - s0);
+        if (te - tb <= 32) {
+            // common case: every term of the query lives in one lane; the boundary offsets of the whole chunk are
+            // fetched at once (independent loads), then the sub-tiles run without further index reads
+            const uint32_t* row = nullptr; int64_t base = 0;
+            if (lane < te - tb) { row = q_row[tb + lane]; base = q_base[tb + lane]; }
+            uint32_t olo[BW_CHUNK], ohi[BW_CHUNK];
+#pragma unroll
+            for (int i = 0; i < BW_CHUNK; ++i) {
+                olo[i] = 0; ohi[i] = 0;
+                if (row != nullptr && i < ns) { const int64_t sub = (int64_t)(s0 + i) * stride; olo[i] = row[sub]; ohi[i] = row[sub + 1]; }
+            }
+#pragma unroll 1
+            for (int i = 0; i < ns; ++i) {
+                uint32_t lo = 0, hi = 0;
+#pragma unroll
+                for (int k = 0; k < BW_CHUNK; ++k) if (k == i) { lo = olo[k]; hi = ohi[k]; }
+                c.t0 = (uint32_t)((int64_t)(s0 + i) * stride * BM25_SUB_DOCS);
+                const int64_t my_start = base + lo; const int my_len = (int)(hi - lo);
+                int R = 0;
+                bw_phase<false>(c, my_start, my_len, false, d, sc, R);
+                if (R == 0) continue;
+                __syncwarp();
+                bw_phase<true>(c, my_start, my_len, R <= BW_ROUNDS, d, sc, R);
+                __syncwarp();                                              // accumulators are zero again before the next sub-tile
+            }
+        } else {
+            // long queries: term chunks of 32; ALL chunks are accumulated (in query order) before any document is claimed
+            for (int i = 0; i < ns; ++i) {
+                const int64_t sub = (int64_t)(s0 + i) * stride;
+                c.t0 = (uint32_t)(sub * BM25_SUB_DOCS);
+                for (int phase = 0; phase < 2; ++phase) {
+                    for (int c0 = tb; c0 < te; c0 += 32) {
+                        int64_t my_start = 0; int my_len = 0;
+                        if (lane < te - c0) {
+                            const uint32_t* row = q_row[c0 + lane];
+                            if (row != nullptr) { const uint32_t lo = row[sub], hi = row[sub + 1]; my_start = q_base[c0 + lane] + lo; my_len = (int)(hi - lo); }
+                        }
+                        int R = 0;
+                        if (phase == 0) bw_phase<false>(c, my_start, my_len, false, d, sc, R);
+                        else bw_phase<true>(c, my_start, my_len, false, d, sc, R);
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    }
+}
+
+// per query: top-P of the candidate list.  mode 0 (after the sample pass): thr[q] = P-th best key (KEY_PAD when the sample
+// holds fewer than P documents), list emptied.  mode 1 (after the main pass): the sorted top-P to keys_out, or flag[q] = 1
+// when the list overflowed (the legacy kernel then recomputes the query; keys_out is left alone).
+constexpr int BS_THREADS = 512;
+constexpr int BS_CAP = 2048;   // >= KRAG_MAX_POOL + 2 * BS_THREADS
+__global__ void __launch_bounds__(BS_THREADS)
+bm25_select_kernel(const unsigned long long* __restrict__ cand, uint32_t* __restrict__ cand_cnt, int capq, int P, int mode,
+                   unsigned long long* __restrict__ thr_q, uint64_t* __restrict__ keys_out, uint32_t* __restrict__ flags)
+{
+    __shared__ uint64_t s_buf[BS_CAP];
+    __shared__ int s_count;
+    __shared__ uint64_t s_thr;
+    const int tid = threadIdx.x, q = blockIdx.x;
+    const uint32_t n_raw = cand_cnt[q];
+    if (mode == 1) {
+        if (tid == 0) flags[q] = n_raw > (uint32_t)capq ? 1u : 0u;
+        if (n_raw > (uint32_t)capq) return;                                // uniform
+    }
+    const int n = (int)min(n_raw, (uint32_t)capq);
+    SelectBuf sel{s_buf, &s_count, &s_thr, BS_CAP};
+    select_init(sel, tid);
+    __syncthreads();
+    const unsigned long long* src = cand + (size_t)q * capq;
+    const int epoch = (BS_CAP - P) / BS_THREADS;                           // >= 2 for P <= 1024
+    uint64_t thr = KEY_PAD;
+    int it = 0;
+    for (int i0 = 0; i0 < n; i0 += BS_THREADS, ++it) {
+        const int i = i0 + tid;
+        if (i < n) select_push(sel, src[i], thr);
+        if ((it + 1) % epoch == 0) {
+            __syncthreads();
+            if (s_count + epoch * BS_THREADS > BS_CAP) select_prune<BS_THREADS>(sel, P, tid, 0);
+            thr = s_thr;
+        }
+    }
+    select_prune<BS_THREADS>(sel, P, tid, 0);
+    if (mode == 0) {
+        if (tid == 0) { thr_q[q] = (s_count == P) ? s_buf[P - 1] : KEY_PAD; cand_cnt[q] = 0; }
+    } else {
+        select_store<BS_THREADS>(sel, P, keys_out + (size_t)q * P, tid);
+    }
 }
 
 static int bq_cap(int P) { return P <= 256 ? 512 : (P <= 512 ? 1024 : 2048); }   // cap - P >= BQ_THREADS; small caps keep 3 CTAs per SM
 
-size_t bm25_part_elems(int64_t n_rows, int batch, int P)
+static int env_int(const char* name, int dflt)
 {
-    int64_t n_tiles = (n_rows + BM25_TILE_DOCS - 1) / BM25_TILE_DOCS;
-    if (n_tiles < 1) n_tiles = 1;
-    const int64_t n_groups = (n_tiles + bq_group() - 1) / bq_group();
-    return (size_t)n_groups * batch * P + (size_t)batch;   // + per-query threshold hints
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+// candidate-list capacity per query: the main pass admits ~stride * P documents with stride = capq / (4 P)
+static int bw_capq(int P)
+{
+    const int forced = env_int("KRAG_BM25_CAPQ", -1);     // read per call: the tests force overflows with it
+    if (forced > 0) return forced < P ? P : forced;
+    int c = 32768;
+    while (c < 256 * P && c < 262144) c <<= 1;
+    return c;
+}
+static bool bw_legacy()
+{
+    return env_int("KRAG_BM25_LEGACY", 0) != 0;
+}
+
+struct BmLayout {   // carve-up of the caller's u64 workspace (`part`)
+    size_t legacy_part, g_thr, cand, thr, cnt_flags, counters, total;
+    int64_t n_tiles, n_groups;
+    int capq;
+};
+static BmLayout bm_layout(int64_t n_rows, int batch, int P)
+{
+    BmLayout L;
+    L.n_tiles = (n_rows + BM25_TILE_DOCS - 1) / BM25_TILE_DOCS;
+    if (L.n_tiles < 1) L.n_tiles = 1;
+    L.n_groups = (L.n_tiles + bq_group() - 1) / bq_group();
+    L.capq = bw_capq(P);
+    size_t o = 0;
+    L.legacy_part = o; o += (size_t)L.n_groups * batch * P;
+    L.g_thr = o; o += (size_t)batch;
+    L.cand = o; o += (size_t)batch * L.capq;
+    L.thr = o; o += (size_t)batch;
+    L.cnt_flags = o; o += (size_t)batch;          // u32 cnt[batch] then u32 flags[batch]
+    L.counters = o; o += 4;                       // work-unit counters of the two passes
+    L.total = o;
+    return L;
+}
+
+size_t bm25_part_elems(int64_t n_rows, int batch, int P) { return bm_layout(n_rows, batch, P).total; }
+
+size_t bm25_resolve_bytes(int64_t n_rows, int n_terms_total)
+{
+    const size_t n = (size_t)(n_terms_total > 0 ? n_terms_total : 1);
+    int64_t n_sub = (n_rows + BM25_SUB_DOCS - 1) / BM25_SUB_DOCS;
+    if (n_sub < 1) n_sub = 1;
+    return n * (8 + 8 + 4 + 4) + n * (size_t)(n_sub + 1) * 4 + 64;
 }
 
 void launch_bm25(const DeviceInfo& di, const Postings& post, int64_t n_rows, const uint32_t* alive,
                  const uint32_t* q_terms, const int32_t* q_term_offsets, int n_terms_total, void* resolve_ws, int batch, int P,
                  uint32_t ord_base, uint64_t* part, uint64_t* keys_out, cudaStream_t st)
 {
-    // resolve_ws: >= n_terms_total * 16 bytes
+    const size_t nt = (size_t)(n_terms_total > 0 ? n_terms_total : 1);
+    const int64_t n_sub = post.n_tiles;
+    // resolve_ws: bm25_resolve_bytes(n_rows, n_terms_total)
     int64_t* q_base = reinterpret_cast<int64_t*>(resolve_ws);
-    int32_t* q_slot = reinterpret_cast<int32_t*>(q_base + (n_terms_total > 0 ? n_terms_total : 1));
-    int32_t* q_rare = q_slot + (n_terms_total > 0 ? n_terms_total : 1);
+    const uint32_t** q_row = reinterpret_cast<const uint32_t**>(q_base + nt);
+    int32_t* q_slot = reinterpret_cast<int32_t*>(q_row + nt);
+    int32_t* q_rare = q_slot + nt;
+    uint32_t* scratch_rows = reinterpret_cast<uint32_t*>(q_rare + nt);
     if (n_terms_total > 0) {
-        bm25_resolve_kernel<<<(n_terms_total + 255) / 256, 256, 0, st>>>(q_terms, n_terms_total, post.off, post.tile_slot, post.vocab,
-                                                                         q_slot, q_base, q_rare);
+        bm25_resolve_kernel<<<n_terms_total, 256, 0, st>>>(q_terms, n_terms_total, post.off, post.doc, post.tile_slot, post.tile_off,
+                                                           post.vocab, n_sub, scratch_rows, q_row, q_base, q_slot, q_rare);
         KRAG_CUDA(cudaGetLastError());
         count_launch();
     }
-    int64_t n_tiles = (n_rows + BM25_TILE_DOCS - 1) / BM25_TILE_DOCS;
-    if (n_tiles < 1) n_tiles = 1;
-    const int cap = bq_cap(P);
-    const size_t smem = (size_t)BM25_TILE_DOCS * 4 + (size_t)cap * 8;
-    static bool attr_set = false;
-    if (!attr_set) {
-        KRAG_CUDA(cudaFuncSetAttribute(bm25_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        attr_set = true;
+    const BmLayout L = bm_layout(n_rows, batch, P);
+    unsigned long long* g_thr = reinterpret_cast<unsigned long long*>(part + L.g_thr);
+    unsigned long long* cand = reinterpret_cast<unsigned long long*>(part + L.cand);
+    unsigned long long* thr_q = reinterpret_cast<unsigned long long*>(part + L.thr);
+    uint32_t* cand_cnt = reinterpret_cast<uint32_t*>(part + L.cnt_flags);
+    uint32_t* flags = cand_cnt + batch;
+    unsigned long long* counters = reinterpret_cast<unsigned long long*>(part + L.counters);
+    const bool legacy_only = bw_legacy();
+    const bool complete = n_rows <= (int64_t)L.capq;     // one pass without threshold cannot overflow the lists
+    bool need_safety_net = legacy_only;
+
+    if (!legacy_only) {
+        static bool attr_set = false;
+        const size_t smem = (size_t)BW_WARPS * BM25_SUB_DOCS * 4;
+        if (!attr_set) {
+            KRAG_CUDA(cudaFuncSetAttribute(bm25_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        // cnt[batch] + flags[batch] (u32) and the counters are contiguous: one memset
+        KRAG_CUDA(cudaMemsetAsync(part + L.cnt_flags, 0, sizeof(uint64_t) * ((size_t)batch + 4), st));
+        auto pass = [&](int stride, const unsigned long long* thr, unsigned long long* counter) {
+            const int n_s = (int)((n_sub + stride - 1) / stride);
+            const long long units = (long long)((n_s + BW_CHUNK - 1) / BW_CHUNK) * batch;
+            const long long want = (units + BW_WARPS - 1) / BW_WARPS;
+            const long long max_grid = 3LL * di.sm_count;
+            const int grid = (int)(want < max_grid ? (want > 0 ? want : 1) : max_grid);
+            bm25_warp_kernel<<<grid, BW_THREADS, smem, st>>>(post.doc, post.score, q_term_offsets, q_row, q_base, n_rows, alive, ord_base,
+                                                             batch, n_s, stride, thr, cand, cand_cnt, L.capq, counter);
+            KRAG_CUDA(cudaGetLastError());
+            count_launch();
+        };
+        if (!complete) {
+            int stride = L.capq / (4 * P);
+            if (stride < 1) stride = 1;
+            if ((int64_t)stride > n_sub) stride = (int)n_sub;
+            pass(stride, nullptr, counters);                               // sample: every stride-th sub-tile, everything admitted
+            bm25_select_kernel<<<batch, BS_THREADS, 0, st>>>(cand, cand_cnt, L.capq, P, 0, thr_q, keys_out, flags);
+            KRAG_CUDA(cudaGetLastError());
+            count_launch();
+            pass(1, thr_q, counters + 1);                                  // main: all sub-tiles, key <= thr[q]
+            need_safety_net = true;
+        } else {
+            pass(1, nullptr, counters);
+        }
+        bm25_select_kernel<<<batch, BS_THREADS, 0, st>>>(cand, cand_cnt, L.capq, P, 1, thr_q, keys_out, flags);
+        KRAG_CUDA(cudaGetLastError());
+        count_launch();
     }
-    const int64_t n_groups = (n_tiles + bq_group() - 1) / bq_group();
-    unsigned long long* g_thr = reinterpret_cast<unsigned long long*>(part + (size_t)n_groups * batch * P);
-    KRAG_CUDA(cudaMemsetAsync(g_thr, 0xFF, sizeof(unsigned long long) * (size_t)batch, st));
-    const int64_t n_items = n_groups * batch;
-    const int per_sm = (smem <= 74 * 1024) ? 3 : 2;
-    const int64_t max_grid = (int64_t)per_sm * di.sm_count;
-    const int grid = (int)(n_items < max_grid ? n_items : max_grid);
-    bm25_tile_kernel<<<grid, BQ_THREADS, smem, st>>>(post.off, post.doc, post.score, post.tile_slot, post.tile_off,
-                                                     post.n_tiles, post.vocab, q_terms, q_term_offsets, q_slot, q_base, q_rare, n_rows,
-                                                     alive, P, cap, ord_base, batch, (int)n_tiles, bq_group(), part, g_thr);
-    KRAG_CUDA(cudaGetLastError());
-    count_launch();
-    launch_merge(part, (int)n_groups, P, batch, P, /*list_stride=*/P, /*batch_stride=*/n_groups * P, keys_out, st,
-                 reinterpret_cast<const uint64_t*>(g_thr));
+    if (need_safety_net) {
+        // legacy kernel: every query (KRAG_BM25_LEGACY=1) or only the queries whose list overflowed (normally none: its
+        // CTAs read one flag per work item and leave)
+        const int cap = bq_cap(P);
+        const size_t smem = (size_t)BM25_TILE_DOCS * 4 + (size_t)cap * 8;
+        static bool attr_set = false;
+        if (!attr_set) {
+            KRAG_CUDA(cudaFuncSetAttribute(bm25_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attr_set = true;
+        }
+        KRAG_CUDA(cudaMemsetAsync(g_thr, 0xFF, sizeof(unsigned long long) * (size_t)batch, st));
+        const int64_t n_items = L.n_groups * batch;
+        const int per_sm = (smem <= 74 * 1024) ? 3 : 2;
+        const int64_t max_grid = (int64_t)per_sm * di.sm_count;
+        const int grid = (int)(n_items < max_grid ? n_items : max_grid);
+        const uint32_t* only = legacy_only ? nullptr : flags;
+        bm25_tile_kernel<<<grid, BQ_THREADS, smem, st>>>(post.off, post.doc, post.score, post.tile_slot, post.tile_off,
+                                                         post.n_tiles, post.vocab, q_terms, q_term_offsets, q_slot, q_base, q_rare, n_rows,
+                                                         alive, P, cap, ord_base, batch, (int)L.n_tiles, bq_group(), part + L.legacy_part, g_thr, only);
+        KRAG_CUDA(cudaGetLastError());
+        count_launch();
+        launch_merge(part + L.legacy_part, (int)L.n_groups, P, batch, P, /*list_stride=*/P, /*batch_stride=*/L.n_groups * P, keys_out, st,
+                     reinterpret_cast<const uint64_t*>(g_thr), only);
+    }
     launch_bm25_fill(keys_out, batch, P, alive, n_rows, ord_base, st);
 }
 

@@ -52,8 +52,10 @@ bool dense_tc_debug_dump(const DeviceInfo& di, const float* X, int64_t n_rows, i
 
 // ---- merge / fuse (merge_fuse.cu)
 // per query: n_lists lists of list_len keys (element (l,i) at in[b*batch_stride + l*list_stride + i]) -> the P smallest
+// only_flag != null: queries whose flag is 0 are left untouched
 void launch_merge(const uint64_t* keys_in, int n_lists, int list_len, int batch, int P, int64_t list_stride,
-                  int64_t batch_stride, uint64_t* keys_out, cudaStream_t st, const uint64_t* thr_hint = nullptr);
+                  int64_t batch_stride, uint64_t* keys_out, cudaStream_t st, const uint64_t* thr_hint = nullptr,
+                  const uint32_t* only_flag = nullptr);
 // peer-memory exchange: push local lists [nl, batch, P] into every rank's mailbox, then merge G*P -> P locally
 size_t p2p_mailbox_words(int world, int nl, int max_batch, int max_P);
 void launch_p2p_exchange_merge(uint64_t* const* d_mailboxes, uint64_t* own_mailbox, int rank, int world, int64_t slot_words,
@@ -68,19 +70,23 @@ void launch_fuse(int batch, int P, int k, const uint64_t* dense_keys, const uint
                  int32_t* out_rank, int64_t* out_ord, int32_t* out_count, cudaStream_t st);
 
 // ---- K3: BM25 (bm25.cu)
-constexpr int BM25_TILE_DOCS = 16384;
+constexpr int BM25_SUB_DOCS = 4096;      // doc range of one tile-index column = one warp's shared-memory accumulator (K3)
+constexpr int BM25_SUBS_PER_TILE = 4;
+constexpr int BM25_TILE_DOCS = BM25_SUB_DOCS * BM25_SUBS_PER_TILE;   // doc range of one CTA in the legacy kernel (safety net)
 struct Postings {
     int64_t* off = nullptr;    // [vocab+1]
     uint32_t* doc = nullptr;   // [nnz] local rows ascending inside a term
     float* score = nullptr;    // [nnz]
     int64_t vocab = 0, nnz = 0;
     // tile index: for terms with more than BM25_RARE_MAX postings, the offset (relative to off[t]) of the
-    // first posting whose doc lies in each BM25_TILE_DOCS-sized doc range; removes per-query searches
-    int32_t* tile_slot = nullptr;   // [vocab]  slot of a frequent term, -1 for rare terms
+    // first posting whose doc lies in each BM25_SUB_DOCS-sized doc range; removes per-query searches.  Terms below the
+    // threshold get the same kind of row built per batch by bm25_resolve_kernel (a row costs 4 B per sub-tile, more than
+    // the postings of a short list)
+    int32_t* tile_slot = nullptr;   // [vocab]  slot of a frequent term, -1 for the others
     uint32_t* tile_off = nullptr;   // [n_slots][n_tiles + 1]
-    int64_t n_slots = 0, n_tiles = 0;
+    int64_t n_slots = 0, n_tiles = 0;   // n_tiles = number of BM25_SUB_DOCS ranges
 };
-constexpr int BM25_RARE_MAX = 256;
+constexpr int BM25_RARE_MAX = 2048;
 void launch_df_histogram(const uint32_t* term_ids, const uint32_t* entry_doc, const uint32_t* alive, int64_t nnz,
                          uint32_t* df, cudaStream_t st);
 void launch_expand_entry_doc(const int64_t* term_offsets, int64_t n_docs, uint32_t* entry_doc, cudaStream_t st);
@@ -89,6 +95,7 @@ void build_postings(const uint32_t* term_ids, const uint16_t* term_tf, const uin
                     const uint32_t* doc_len, const uint32_t* alive, int64_t nnz, int64_t vocab, const float* idf,
                     double avgdl, int64_t n_docs_rows, Postings& out, cudaStream_t st);
 size_t bm25_part_elems(int64_t n_rows, int batch, int P);
+size_t bm25_resolve_bytes(int64_t n_rows, int n_terms_total);   // size of launch_bm25's resolve_ws
 void launch_bm25(const DeviceInfo& di, const Postings& post, int64_t n_rows, const uint32_t* alive,
                  const uint32_t* q_terms, const int32_t* q_term_offsets, int n_terms_total, void* resolve_ws, int batch, int P,
                  uint32_t ord_base, uint64_t* part, uint64_t* keys_out, cudaStream_t st);

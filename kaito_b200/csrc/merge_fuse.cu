@@ -15,8 +15,10 @@ constexpr int MG_CAP = 2048;  // >= KRAG_MAX_POOL + MG_THREADS
 
 __global__ void __launch_bounds__(MG_THREADS)
 merge_kernel(const uint64_t* __restrict__ in, int n_lists, int list_len, int P, int64_t list_stride,
-             int64_t batch_stride, uint64_t* __restrict__ out, const uint64_t* __restrict__ thr_hint)
+             int64_t batch_stride, uint64_t* __restrict__ out, const uint64_t* __restrict__ thr_hint,
+             const uint32_t* __restrict__ only_flag)
 {
+    if (only_flag != nullptr && only_flag[blockIdx.x] == 0) return;   // uniform per block
     __shared__ uint64_t s_buf[MG_CAP];
     __shared__ int s_count;
     __shared__ uint64_t s_thr;
@@ -49,9 +51,9 @@ merge_kernel(const uint64_t* __restrict__ in, int n_lists, int list_len, int P, 
 }
 
 void launch_merge(const uint64_t* keys_in, int n_lists, int list_len, int batch, int P, int64_t list_stride,
-                  int64_t batch_stride, uint64_t* keys_out, cudaStream_t st, const uint64_t* thr_hint)
+                  int64_t batch_stride, uint64_t* keys_out, cudaStream_t st, const uint64_t* thr_hint, const uint32_t* only_flag)
 {
-    merge_kernel<<<batch, MG_THREADS, 0, st>>>(keys_in, n_lists, list_len, P, list_stride, batch_stride, keys_out, thr_hint);
+    merge_kernel<<<batch, MG_THREADS, 0, st>>>(keys_in, n_lists, list_len, P, list_stride, batch_stride, keys_out, thr_hint, only_flag);
     KRAG_CUDA(cudaGetLastError());
     count_launch();
 }
@@ -96,7 +98,7 @@ p2p_merge_kernel(uint64_t* __restrict__ mailbox, int world, int64_t slot_words, 
         unsigned long long v;
         do {
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mailbox + tid) : "memory");
-            if (v < seq && clock64() - t0 > 20000000000ll) { printf("p2p_merge: rank %d never arrived (seq %llu)\n", tid, seq); __trap(); }
+            if (v < seq && clock64() - t0 > 240000000000ll)   /* ~2 minutes: a peer that is this late is gone */ { printf("p2p_merge: rank %d never arrived (seq %llu)\n", tid, seq); __trap(); }
         } while (v < seq);
     }
     SelectBuf sel{s_buf, &s_count, &s_thr, MG_CAP};

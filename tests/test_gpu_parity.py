@@ -119,6 +119,56 @@ def test_bm25_zero_fill_and_tombstones(ctx_scan, oracle):
         ix.drop()
 
 
+def _bm25_batch_vs_oracle(ix, oracle, post, qs, pools, alive=None):
+    for P in pools:
+        score, ordn = ix.search_bm25(qs, P)
+        for b, qt in enumerate(qs):
+            rs, ro = oracle.bm25_query(post, qt[qt < post.off.size - 1], P, alive)
+            assert np.array_equal(ordn[b], ro), (b, P)
+            assert np.array_equal(score[b], rs), (b, P)
+
+
+@pytest.fixture(scope="module")
+def sparse_400k(ctx_scan, oracle):
+    """400k documents: 98 sub-tiles of 4096 docs, frequent terms (tile index rows), mid terms (rows built per batch by
+    bm25_resolve_kernel) and rare ones; two-pass path (sampled threshold, then the main pass)"""
+    n, vocab = 400_000, 60_000
+    ix, x, csr = _sparse_index(ctx_scan, oracle, n, vocab, d=32, seed=21)
+    post = oracle.bm25_build(*csr, vocab)
+    yield ix, post, n, vocab
+    ix.drop()
+
+
+def test_bm25_warp_kernel_two_pass_bit_exact(sparse_400k, oracle):
+    ix, post, n, vocab = sparse_400k
+    qs = oracle.synth_query_terms(vocab, 48, seed=5, rank_offset=20)
+    qs[0] = np.concatenate([qs[0], qs[0]])                        # every term twice
+    qs[1] = np.array([0, 1, 2, 3], np.uint32)                     # the most frequent terms: ~every document matches
+    qs[2] = np.array([vocab - 1, vocab - 2, vocab + 9], np.uint32)
+    g = np.random.default_rng(8)
+    qs[3] = g.integers(0, 2000, 45).astype(np.uint32)             # > 32 terms: chunked accumulate-all-then-claim path
+    _bm25_batch_vs_oracle(ix, oracle, post, qs, (30, 90, 900))
+
+
+def test_bm25_overflow_takes_the_exact_safety_net(sparse_400k, oracle, monkeypatch):
+    """a 64-entry candidate list overflows for every broad query: the overflow flag must route those queries through the
+    legacy exact kernel, the others stay on the warp kernel; results identical"""
+    ix, post, n, vocab = sparse_400k
+    qs = oracle.synth_query_terms(vocab, 12, seed=6, rank_offset=20)
+    qs[0] = np.array([vocab - 1], np.uint32)                      # a handful of matches: stays below the cap
+    monkeypatch.setenv("KRAG_BM25_CAPQ", "64")
+    _bm25_batch_vs_oracle(ix, oracle, post, qs, (30,))
+
+
+def test_bm25_legacy_kernel_still_exact(sparse_400k, oracle, monkeypatch):
+    """KRAG_BM25_LEGACY=1: the CTA-per-tile kernel alone (the safety net) on the 4096-doc tile index and 2048-posting short lists"""
+    ix, post, n, vocab = sparse_400k
+    qs = oracle.synth_query_terms(vocab, 10, seed=7, rank_offset=20)
+    qs[1] = np.random.default_rng(9).integers(0, 3000, 40).astype(np.uint32)
+    monkeypatch.setenv("KRAG_BM25_LEGACY", "1")
+    _bm25_batch_vs_oracle(ix, oracle, post, qs, (30, 300))
+
+
 @pytest.mark.parametrize("k", [1, 10, 40, 300])
 def test_retrieve_matches_oracle_pipeline(ctx_scan, oracle, k):
     n, vocab, d = 6000, 5000, 64

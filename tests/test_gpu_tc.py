@@ -142,3 +142,76 @@ def test_dense_mode_switch_builds_shadow_on_demand(oracle):
         ix.drop()
     finally:
         c.close()
+
+
+# ---------------------------------------------------------------- K2 at the shapes it is benchmarked on
+# bench.py runs K2 at d = 768 (24 fp32 / 12 bf16 k-blocks per tile: the staging ring wraps several times per tile and the
+# mbarrier phases flip, unlike d = 128) over millions of rows with NQ = 256.  These cases pin the whole pipeline (sample ->
+# threshold -> prune on tcgen05 -> exact rescoring -> certificate) bit-exact against the oracle at those shapes, for both
+# the default pass (kernel id 5, fp32 rows rounded to bf16 on chip) and the TF32 pass (id 3).
+_BIG = {}
+
+
+def _big_corpus(oracle, n, d, seed):
+    """rows generated on the device (krag_synth_fill), read back for the oracle; the oracle's answer for the widest pool is
+    computed once per (shape, batch) and shared by both kernel variants"""
+    key = (n, d, seed)
+    if key not in _BIG:
+        from kaito_b200 import _native
+        c = _native.Context(device_id=0, dense_mode=_native.DENSE_SCAN)
+        ix = c.create_index("big_src", d)
+        ix.synth_fill(n, row_base=0, seed=seed, vocab=0)
+        x = ix.read_rows(0, n)
+        ix.drop(); c.close()
+        _BIG[key] = {"x": x}
+    return _BIG[key]
+
+
+@pytest.mark.parametrize("n,d,batch,pools", [(1_000_000, 768, 256, (30, 900)), (1_000_000, 1024, 64, (30,))])
+def test_tc_pipeline_bit_exact_at_bench_shapes(ctx_tc, oracle, n, d, batch, pools):
+    from kaito_b200 import _native
+    ent = _big_corpus(oracle, n, d, seed=77)
+    x = ent["x"]
+    q = oracle.synth_queries(x, batch, seed=batch + d)
+    okey = ("oracle", batch, max(pools))
+    if okey not in ent:
+        ent[okey] = oracle.dense_topk(x, q, max(pools))
+    rd_all, ro_all = ent[okey]
+    ix = ctx_tc.create_index(f"tcbig_{d}_{batch}", d)
+    try:
+        ix.synth_fill(n, row_base=0, seed=77, vocab=0)
+        for P in pools:
+            fb0 = _native.load().krag_tc_fallback_queries()
+            dist, ordn = ix.search_dense(q, P)
+            fb = _native.load().krag_tc_fallback_queries() - fb0
+            kid = _native.last_dense_kernel()[1]
+            assert kid in (3, 5), kid                                   # the cta_group::2 pass that bench.py times
+            assert np.array_equal(ordn, ro_all[:, :P]), f"ids differ at P={P} (kernel {kid})"
+            assert np.array_equal(dist, rd_all[:, :P]), f"distances differ at P={P} (kernel {kid})"
+            assert fb <= batch // 20, f"{fb} of {batch} queries fell back to the exact scan on random data"
+    finally:
+        ix.drop()
+
+
+def test_tc_adversarial_duplicates_at_d768(ctx_tc, oracle):
+    """5000 near-duplicates of one row at d = 768: the query that hits them overflows its candidate list, the certificate
+    must fail for it and the exact scan must still return the oracle's answer; everything else stays on the tensor cores"""
+    from kaito_b200 import _native
+    n, d = 400_000, 768
+    ent = _big_corpus(oracle, 1_000_000, 768, seed=77)
+    x = ent["x"][:n].copy()
+    g = np.random.default_rng(5)
+    dup = g.choice(n, 5000, replace=False)
+    x[dup] = x[dup[0]] + 1e-5 * g.standard_normal((5000, d)).astype(np.float32)
+    q = np.concatenate([x[dup[:1]], oracle.synth_queries(x, 63, seed=6)])
+    ix = ctx_tc.create_index("tc_adv768", d)
+    try:
+        ix.add(np.arange(n, dtype=np.uint64), x)
+        fb0 = _native.load().krag_tc_fallback_queries()
+        dist, ordn = ix.search_dense(q, 30)
+        fb = _native.load().krag_tc_fallback_queries() - fb0
+        rd, ro = oracle.dense_topk(x, q, 30)
+        assert np.array_equal(ordn, ro) and np.array_equal(dist, rd)
+        assert 1 <= fb <= 8, fb
+    finally:
+        ix.drop()
