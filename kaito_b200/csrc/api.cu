@@ -1044,7 +1044,7 @@ int32_t krag_embedder_destroy(krag_embedder* h)
 static void debug_linear(krag_ctx* c, int32_t M, int32_t N, int32_t K, const float* A, const float* B, const float* bias,
                          const float* residual, int32_t gelu, const float* ln_g, const float* ln_b, float eps, float* out)
 {
-    KRAG_REQUIRE(c && A && B && bias && out && M >= 1 && N % 128 == 0 && K % 32 == 0, KRAG_E_INVALID, "bad argument (N % 128, K % 32)");
+    KRAG_REQUIRE(c && A && B && bias && out && M >= 1 && N % 128 == 0 && K % 64 == 0, KRAG_E_INVALID, "bad argument (N % 128, K % 64)");
     KRAG_CUDA(cudaSetDevice(c->di.device));
     float *dA, *dB, *db, *dr = nullptr, *dC, *dY = nullptr, *dg = nullptr, *dlb = nullptr, *ws;
     const size_t ws_floats = (size_t)4 << 20;
@@ -1057,7 +1057,7 @@ static void debug_linear(krag_ctx* c, int32_t M, int32_t N, int32_t K, const flo
         KRAG_CUDA(cudaMalloc(&dg, 4 * (size_t)N)); KRAG_CUDA(cudaMalloc(&dlb, 4 * (size_t)N)); KRAG_CUDA(cudaMalloc(&dY, 4 * (size_t)M * N));
         KRAG_CUDA(cudaMemcpy(dg, ln_g, 4 * (size_t)N, cudaMemcpyHostToDevice)); KRAG_CUDA(cudaMemcpy(dlb, ln_b, 4 * (size_t)N, cudaMemcpyHostToDevice));
     }
-    launch_linear(c->di, dA, dB, M, N, K, db, dr, gelu != 0, dC, dg, dlb, eps, dY, ws, ws_floats, c->admin);
+    launch_linear_f32(c->di, dA, dB, M, N, K, db, dr, gelu != 0, dC, dg, dlb, eps, dY, ws, ws_floats, c->admin);
     KRAG_CUDA(cudaStreamSynchronize(c->admin));
     KRAG_CUDA(cudaMemcpy(out, ln_g ? dY : dC, 4 * (size_t)M * N, cudaMemcpyDeviceToHost));
     cudaFree(dA); cudaFree(dB); cudaFree(db); cudaFree(dC); cudaFree(ws);

@@ -13,6 +13,7 @@
 // fp32 accumulation in TMEM, operands staged by TMA (fp32 weights/activations are consumed as TF32, no
 // conversion pass); bias / GELU / residual are fused into the TMEM epilogue.  LayerNorm, softmax and the
 // attention products are fp32 CUDA-core code (attention is 4 S^2 d: 2% of the flops at S = 32 queries).
+#include <cuda_fp16.h>
 #include <math_constants.h>
 #include <stdlib.h>
 
@@ -30,17 +31,27 @@
 namespace krag {
 
 // ------------------------------------------------------------------ GEMM: C = A . B^T (+bias)(gelu)(+res)
-// A [M, K] row-major (activations), B [N, K] row-major (nn.Linear weight), C [M, N] row-major, all fp32.
-// Persistent CTAs over 128 x 128 output tiles (n fastest so neighbouring CTAs share the A tile in L2);
-// one TMA warp, one MMA-issuing thread, four epilogue warps; stage = 2 k-blocks of 32 floats for A and B.
+// A [M, K] (activations), B [N, K] (nn.Linear weight), C [M, N], row-major.  The tensor cores see fp16 operands, the result
+// is fp32-accurate: every fp32 value v is carried as TWO fp16 numbers
+//     hi = fp16(v),   lo = fp16((v - hi) * 2^11)          v = hi + lo * 2^-11  to ~2^-22 relative
+// ("split" operands: producers write them next to / instead of the fp32 tensor, weights are split once at load time), and
+//     A . B^T  =  hi_A . hi_B^T  +  2^-11 (hi_A . lo_B^T + lo_A . hi_B^T)          (lo . lo term: 2^-22, dropped)
+// is three kind::f16 MMAs per K = 16 step into two TMEM accumulators (main term / correction terms, combined in the
+// epilogue; the scaling keeps the lo parts out of the fp16 subnormal range and the small terms out of the big
+// accumulator's rounding).  fp16 products are exact in fp32, so what is left is the accumulation order -- the same kind of
+// error an fp32 SIMT GEMM has.  Operand bytes per element are those of fp32 (2 + 2), the tensor work is 1.5x a TF32 GEMM's:
+// with these layer shapes the kernels stay bound by L2 -> shared-memory operand traffic, as the TF32 kernels they replace
+// were, but now meet the reference's fp32 arithmetic (TF32 carried 10 mantissa bits: ~5e-3 on the unit-norm embedding).
+// Persistent CTAs over 128 x 128 output tiles (n fastest so neighbouring CTAs share the A tile in L2); one TMA warp,
+// one MMA-issuing thread, four epilogue warps; stage = one k-block of 64 halfs of hi_A, lo_A, hi_B, lo_B.
 constexpr int GM_TILE = 128;
-constexpr int GM_KB = 32;                 // floats per k-block (128-byte swizzle row)
-constexpr int GM_KB_PER_STAGE = 2;
-constexpr int GM_SLAB = GM_TILE * GM_KB * 4;                     // 16 KB
-constexpr int GM_STAGE_BYTES = GM_KB_PER_STAGE * 2 * GM_SLAB;    // 64 KB
+constexpr int GH_KB = 64;                   // halfs per k-block (128-byte swizzle row)
+constexpr int GM_SLAB = GM_TILE * 128;      // 16 KB: 128 rows x 128 B
+constexpr int GM_STAGE_BYTES = 4 * GM_SLAB; // 64 KB
 constexpr int GM_STAGES = 3;
 constexpr int GM_THREADS = 192;
 constexpr size_t GM_SMEM = (size_t)GM_STAGES * GM_STAGE_BYTES + 1024 + 256;
+constexpr float GH_LO_SCALE = 2048.f, GH_LO_INV = 1.f / 2048.f;
 
 // 256-bit global accesses (sm_100): one full 32-byte sector per thread and instruction
 __device__ __forceinline__ void st_global_v8(float* p, const float* o)
@@ -55,9 +66,119 @@ __device__ __forceinline__ void ld_global_v8(const float* p, float* r)
 }
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
+// ---- split fp16 operands
+__device__ __forceinline__ uint16_t f2h_sat(float v)      // round to nearest even, finite saturation
+{
+    uint16_t h;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(h) : "f"(v));
+    return h;
+}
+__device__ __forceinline__ float h2f(uint16_t h)
+{
+    float f;
+    asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"(h));
+    return f;
+}
+__device__ __forceinline__ void split_f16(float v, uint16_t& hi, uint16_t& lo)
+{
+    hi = f2h_sat(v);
+    lo = f2h_sat((v - h2f(hi)) * GH_LO_SCALE);
+}
+// 8 consecutive elements -> one 16-byte store into each plane
+__device__ __forceinline__ void split_store8(const float* o, uint16_t* p_hi, uint16_t* p_lo)
+{
+    uint32_t a[4], b[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        uint16_t h0, l0, h1, l1;
+        split_f16(o[2 * t], h0, l0); split_f16(o[2 * t + 1], h1, l1);
+        a[t] = (uint32_t)h0 | ((uint32_t)h1 << 16); b[t] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+    }
+    *reinterpret_cast<uint4*>(p_hi) = make_uint4(a[0], a[1], a[2], a[3]);
+    *reinterpret_cast<uint4*>(p_lo) = make_uint4(b[0], b[1], b[2], b[3]);
+}
+__global__ void __launch_bounds__(256)
+split_f16_kernel(const float* __restrict__ in, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int64_t n8)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        float o[8];
+        const float4 x = reinterpret_cast<const float4*>(in)[2 * i], y = reinterpret_cast<const float4*>(in)[2 * i + 1];
+        o[0] = x.x; o[1] = x.y; o[2] = x.z; o[3] = x.w; o[4] = y.x; o[5] = y.y; o[6] = y.z; o[7] = y.w;
+        split_store8(o, hi + 8 * i, lo + 8 * i);
+    }
+}
+void launch_split_f16(const float* in, uint16_t* hi, uint16_t* lo, int64_t n, cudaStream_t st)   // n % 8 == 0
+{
+    const int64_t n8 = n / 8;
+    const int64_t want = (n8 + 255) / 256;
+    split_f16_kernel<<<(unsigned)(want < 148 * 16 ? (want > 0 ? want : 1) : 148 * 16), 256, 0, st>>>(in, hi, lo, n8);
+    KRAG_CUDA(cudaGetLastError());
+    count_launch();
+}
+
+// instruction descriptor for kind::f16 with fp16 operands (format 0), fp32 accumulate, both operands K-major
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N)
+{
+    return (1u << 4) /* D f32 */ | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// what a GEMM epilogue writes: fp32 C and / or the split planes of C (operand of the next GEMM)
+struct GemmOut {
+    float* c;            // [M, N] fp32 or null
+    uint16_t* hi;        // [M, N] split planes or null
+    uint16_t* lo;
+};
+
+// 32 accumulator columns of one row: v = main + 2^-11 corr (+bias)(gelu)(+residual) -> outputs
+__device__ __forceinline__ void gemm_epilogue_row32(const uint32_t* v0, const uint32_t* v1, const float* __restrict__ bias_c,
+                                                    const float* rrow, int act_gelu, const GemmOut& out, size_t off)
+{
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {   // 32-byte (full-sector) vector accesses: a thread owns a row segment
+        float o[8];
+#pragma unroll
+        for (int t = 0; t < 8; t += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias_c + j + t));
+            o[t + 0] = fmaf(__uint_as_float(v1[j + t + 0]), GH_LO_INV, __uint_as_float(v0[j + t + 0])) + b4.x;
+            o[t + 1] = fmaf(__uint_as_float(v1[j + t + 1]), GH_LO_INV, __uint_as_float(v0[j + t + 1])) + b4.y;
+            o[t + 2] = fmaf(__uint_as_float(v1[j + t + 2]), GH_LO_INV, __uint_as_float(v0[j + t + 2])) + b4.z;
+            o[t + 3] = fmaf(__uint_as_float(v1[j + t + 3]), GH_LO_INV, __uint_as_float(v0[j + t + 3])) + b4.w;
+        }
+        if (act_gelu) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) o[t] = gelu_erf(o[t]);
+        }
+        if (rrow) {
+            float r[8];
+            ld_global_v8(rrow + j, r);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) o[t] += r[t];
+        }
+        if (out.c) st_global_v8(out.c + off + j, o);
+        if (out.hi) split_store8(o, out.hi + off + j, out.lo + off + j);
+    }
+}
+
 __global__ void __launch_bounds__(GM_THREADS, 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-                 const float* __restrict__ bias, const float* __restrict__ residual, int act_gelu, float* __restrict__ C)
+gemm_f16s_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                 const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2, int M, int N, int K,
+                 const float* __restrict__ bias, const float* __restrict__ residual, int act_gelu, GemmOut out)
 {
     extern __shared__ unsigned char gm_smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(gm_smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -71,18 +192,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tiles = (M + GM_TILE - 1) / GM_TILE, n_tiles = N / GM_TILE;
     const int total = m_tiles * n_tiles;
-    const int kblocks = K / GM_KB;
-    const int stages_per_tile = (kblocks + GM_KB_PER_STAGE - 1) / GM_KB_PER_STAGE;
+    const int kblocks = K / GH_KB;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB1); tma_prefetch_desc(&tmB2);
         for (int s = 0; s < GM_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
         fence_barrier_init();
     }
-    if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+    if (warp == 1) {   // 2 buffers x (main 128 + correction 128) columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -94,52 +213,46 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int stage = 0; uint32_t phase = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             const int m0 = (t / n_tiles) * GM_TILE, n0 = (t % n_tiles) * GM_TILE;
-            for (int sk = 0; sk < stages_per_tile; ++sk) {
-                const int nkb = min(GM_KB_PER_STAGE, kblocks - sk * GM_KB_PER_STAGE);
+            for (int kb = 0; kb < kblocks; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (lane == 0) {
-                    unsigned char* sa = smem + (size_t)stage * GM_STAGE_BYTES;
-                    unsigned char* sb = sa + GM_KB_PER_STAGE * GM_SLAB;
-                    mbar_expect_tx(&full_bar[stage], nkb * 2 * GM_SLAB);
-                    for (int u = 0; u < nkb; ++u) {
-                        const int k0 = (sk * GM_KB_PER_STAGE + u) * GM_KB;
-                        tma_load_2d(sa + (size_t)u * GM_SLAB, &tmA, &full_bar[stage], k0, m0, TMA_EVICT_FIRST);
-                        tma_load_2d(sb + (size_t)u * GM_SLAB, &tmB, &full_bar[stage], k0, n0, TMA_EVICT_LAST);
-                    }
+                    unsigned char* s0 = smem + (size_t)stage * GM_STAGE_BYTES;
+                    mbar_expect_tx(&full_bar[stage], GM_STAGE_BYTES);
+                    const int k0 = kb * GH_KB;
+                    tma_load_2d(s0, &tmA1, &full_bar[stage], k0, m0, TMA_EVICT_FIRST);
+                    tma_load_2d(s0 + GM_SLAB, &tmA2, &full_bar[stage], k0, m0, TMA_EVICT_FIRST);
+                    tma_load_2d(s0 + 2 * GM_SLAB, &tmB1, &full_bar[stage], k0, n0, TMA_EVICT_LAST);
+                    tma_load_2d(s0 + 3 * GM_SLAB, &tmB2, &full_bar[stage], k0, n0, TMA_EVICT_LAST);
                 }
                 __syncwarp();
                 if (++stage == GM_STAGES) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = umma_idesc_tf32(GM_TILE, GM_TILE);
+        constexpr uint32_t idesc = umma_idesc_f16(GM_TILE, GM_TILE);
         const uint64_t desc0 = umma_desc_sw128(smem_u32(smem));
+        const uint64_t dhi = desc0 & 0xFFFFFFFF00000000ull;
         const uint32_t lo0 = (uint32_t)desc0;
         int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x) {
             mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
             tc_fence_after();
-            const uint32_t d_tmem = tmem_base + (uint32_t)(acc * GM_TILE);
-            for (int sk = 0; sk < stages_per_tile; ++sk) {
-                const int nkb = min(GM_KB_PER_STAGE, kblocks - sk * GM_KB_PER_STAGE);
+            const uint32_t d_main = tmem_base + (uint32_t)(acc * 2 * GM_TILE), d_corr = d_main + GM_TILE;
+            for (int kb = 0; kb < kblocks; ++kb) {
                 mbar_wait(&full_bar[stage], phase);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t a_lo = lo0 + (uint32_t)((stage * GM_STAGE_BYTES) >> 4);
-                    const uint32_t b_lo = a_lo + (uint32_t)((GM_KB_PER_STAGE * GM_SLAB) >> 4);
+                    const uint32_t a1 = lo0 + (uint32_t)((stage * GM_STAGE_BYTES) >> 4);
+                    const uint32_t a2 = a1 + (GM_SLAB >> 4), b1 = a1 + (2 * GM_SLAB >> 4), b2 = a1 + (3 * GM_SLAB >> 4);
 #pragma unroll
-                    for (int u = 0; u < GM_KB_PER_STAGE; ++u) {
-                        if (u < nkb) {
-#pragma unroll
-                            for (int k = 0; k < GM_KB / 8; ++k) {
-                                const uint64_t ad = (desc0 & 0xFFFFFFFF00000000ull) | (uint64_t)(a_lo + (uint32_t)((u * GM_SLAB) >> 4) + 2 * k);
-                                const uint64_t bd = (desc0 & 0xFFFFFFFF00000000ull) | (uint64_t)(b_lo + (uint32_t)((u * GM_SLAB) >> 4) + 2 * k);
-                                umma_tf32(d_tmem, ad, bd, idesc, (uint32_t)((sk | u | k) != 0));
-                            }
-                        }
+                    for (int k = 0; k < GH_KB / 16; ++k) {
+                        const uint32_t first = (uint32_t)((kb | k) != 0);
+                        umma_f16(d_main, dhi | (uint64_t)(a1 + 2 * k), dhi | (uint64_t)(b1 + 2 * k), idesc, first);
+                        umma_f16(d_corr, dhi | (uint64_t)(a1 + 2 * k), dhi | (uint64_t)(b2 + 2 * k), idesc, first);
+                        umma_f16(d_corr, dhi | (uint64_t)(a2 + 2 * k), dhi | (uint64_t)(b1 + 2 * k), idesc, 1u);
                     }
                     umma_commit(&empty_bar[stage]);
-                    if (sk == stages_per_tile - 1) umma_commit(&tfull_bar[acc]);
+                    if (kb == kblocks - 1) umma_commit(&tfull_bar[acc]);
                 }
                 __syncwarp();
                 if (++stage == GM_STAGES) { stage = 0; phase ^= 1; }
@@ -156,36 +269,16 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const int row = m0 + r_in;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * GM_TILE);
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 2 * GM_TILE);
 #pragma unroll 1
             for (int c0 = 0; c0 < GM_TILE; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld_x32(taddr + c0, v);
+                uint32_t v0[32], v1[32];
+                tmem_ld_x32(taddr + c0, v0);
+                tmem_ld_x32(taddr + GM_TILE + c0, v1);
                 tmem_wait_ld();
                 if (row < M) {
-                    float* crow = C + (size_t)row * N + n0 + c0;
-                    const float* rrow = residual ? residual + (size_t)row * N + n0 + c0 : nullptr;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {   // 32-byte (full-sector) vector accesses: a thread owns a row segment
-                        float o[8];
-#pragma unroll
-                        for (int t = 0; t < 8; t += 4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j + t));
-                            o[t + 0] = __uint_as_float(v[j + t + 0]) + b4.x; o[t + 1] = __uint_as_float(v[j + t + 1]) + b4.y;
-                            o[t + 2] = __uint_as_float(v[j + t + 2]) + b4.z; o[t + 3] = __uint_as_float(v[j + t + 3]) + b4.w;
-                        }
-                        if (act_gelu) {
-#pragma unroll
-                            for (int t = 0; t < 8; ++t) o[t] = gelu_erf(o[t]);
-                        }
-                        if (rrow) {
-                            float r[8];
-                            ld_global_v8(rrow + j, r);
-#pragma unroll
-                            for (int t = 0; t < 8; ++t) o[t] += r[t];
-                        }
-                        st_global_v8(crow + j, o);
-                    }
+                    const size_t off = (size_t)row * N + n0 + c0;
+                    gemm_epilogue_row32(v0, v1, bias + n0 + c0, residual ? residual + off : nullptr, act_gelu, out, off);
                 }
             }
             tc_fence_before();
@@ -199,19 +292,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     }
 }
 
 // ---------------------------------------------------------------- 2-CTA GEMM (cta_group::2, M = 256 per pair)
 // Same structure as dense_tc2_kernel (dense_tc.cu): a CTA pair owns a 256 x BN output tile; each CTA stages its
-// 128 activation rows and HALF of the BN weight rows, the pair's tensor cores share the operands
-// (per SM and 128-cycle MMA: 8 KB operand reads + 64 B/clk of TMA writes instead of 12 KB + 96 B/clk, which capped
-// the 1-CTA kernel at ~40% tensor-pipe activity on these shapes); one ring, 2 k-blocks per stage, one issuer thread.
+// 128 activation rows (hi and lo planes) and HALF of the BN weight rows (hi and lo), the pair's tensor cores share the
+// operands.  Both accumulators of the tile fill the pair's TMEM (2 x BN columns: BN = 256 -> all 512), so a tile's
+// epilogue is not overlapped with the next tile's MMAs; with 12..48 k-blocks per tile that costs a few percent.
 template <int BN> struct Gm2Cfg {
-    static constexpr int BH_BYTES = (BN / 2) * GM_KB * 4;              // this CTA's half of one weight k-block
-    static constexpr int STAGE_BYTES = GM_KB_PER_STAGE * (GM_SLAB + BH_BYTES);
-    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;          // 3 at BN = 256, 4 at BN = 128
+    static constexpr int BH_BYTES = (BN / 2) * 128;                    // this CTA's half of one weight k-block (one plane)
+    static constexpr int STAGE_BYTES = 2 * GM_SLAB + 2 * BH_BYTES;     // 64 KB at BN = 256, 48 KB at BN = 128
+    static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;          // 3 / 4
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
 };
@@ -219,8 +312,9 @@ constexpr int GM2_THREADS = 320;   // warp 0: TMA, warp 1: MMA issuer (leader), 
 
 template <int BN>
 __global__ void __launch_bounds__(GM2_THREADS, 1)
-gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBh, int M, int N, int K,
-                  const float* __restrict__ bias, const float* __restrict__ residual, int act_gelu, float* __restrict__ C)
+gemm2_f16s_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                  const __grid_constant__ CUtensorMap tmB1h, const __grid_constant__ CUtensorMap tmB2h, int M, int N, int K,
+                  const float* __restrict__ bias, const float* __restrict__ residual, int act_gelu, GemmOut out)
 {
     using Cfg = Gm2Cfg<BN>;
     extern __shared__ unsigned char gm_smem_raw[];
@@ -228,8 +322,8 @@ gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     unsigned char* tail = smem + (size_t)Cfg::STAGES * Cfg::STAGE_BYTES;
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(tail);             // leader only: 2 arrivals + tx bytes of both CTAs
     uint64_t* empty_bar = full_bar + Cfg::STAGES;                        // per CTA
-    uint64_t* tfull_bar = empty_bar + Cfg::STAGES;                       // per CTA [2]
-    uint64_t* tempty_bar = tfull_bar + 2;                                // leader only [2]: 16 arrivals
+    uint64_t* tfull_bar = empty_bar + Cfg::STAGES;                       // per CTA [1]
+    uint64_t* tempty_bar = tfull_bar + 2;                                // leader only [1]: 16 arrivals
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -237,14 +331,12 @@ gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
     const int m_ptiles = (M + 2 * GM_TILE - 1) / (2 * GM_TILE), n_tiles = N / BN;
     const int total = m_ptiles * n_tiles;
-    const int kblocks = K / GM_KB;
-    const int stages_per_tile = (kblocks + GM_KB_PER_STAGE - 1) / GM_KB_PER_STAGE;
+    const int kblocks = K / GH_KB;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmBh);
+        tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB1h); tma_prefetch_desc(&tmB2h);
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 16); }
+        mbar_init(&tfull_bar[0], 1); mbar_init(&tempty_bar[0], 16);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -261,19 +353,17 @@ gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int stage = 0; uint32_t phase = 0;
         for (int t = pair; t < total; t += n_pairs) {
             const int m0 = (t / n_tiles) * (2 * GM_TILE) + (int)rank * GM_TILE, n0 = (t % n_tiles) * BN + (int)rank * (BN / 2);
-            for (int sk = 0; sk < stages_per_tile; ++sk) {
-                const int nkb = min(GM_KB_PER_STAGE, kblocks - sk * GM_KB_PER_STAGE);
+            for (int kb = 0; kb < kblocks; ++kb) {
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 if (lane == 0) {
-                    unsigned char* sa = smem + (size_t)stage * Cfg::STAGE_BYTES;
-                    unsigned char* sb = sa + GM_KB_PER_STAGE * GM_SLAB;
-                    if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * nkb * (GM_SLAB + Cfg::BH_BYTES));
+                    unsigned char* s0 = smem + (size_t)stage * Cfg::STAGE_BYTES;
+                    if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
                     else mbar_arrive_remote(&full_bar[stage], 0);
-                    for (int u = 0; u < nkb; ++u) {
-                        const int k0 = (sk * GM_KB_PER_STAGE + u) * GM_KB;
-                        tma_load_2d_2sm(sa + (size_t)u * GM_SLAB, &tmA, &full_bar[stage], k0, m0, TMA_EVICT_FIRST);
-                        tma_load_2d_2sm(sb + (size_t)u * Cfg::BH_BYTES, &tmBh, &full_bar[stage], k0, n0, TMA_EVICT_LAST);
-                    }
+                    const int k0 = kb * GH_KB;
+                    tma_load_2d_2sm(s0, &tmA1, &full_bar[stage], k0, m0, TMA_EVICT_FIRST);
+                    tma_load_2d_2sm(s0 + GM_SLAB, &tmA2, &full_bar[stage], k0, m0, TMA_EVICT_FIRST);
+                    tma_load_2d_2sm(s0 + 2 * GM_SLAB, &tmB1h, &full_bar[stage], k0, n0, TMA_EVICT_LAST);
+                    tma_load_2d_2sm(s0 + 2 * GM_SLAB + Cfg::BH_BYTES, &tmB2h, &full_bar[stage], k0, n0, TMA_EVICT_LAST);
                 }
                 __syncwarp();
                 if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
@@ -281,40 +371,35 @@ gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
     } else if (warp == 1) {
         if (rank == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32(2 * GM_TILE, BN);
+            constexpr uint32_t idesc = umma_idesc_f16(2 * GM_TILE, BN);
             const uint64_t desc0 = umma_desc_sw128(smem_u32(smem));
+            const uint64_t dhi = desc0 & 0xFFFFFFFF00000000ull;
             const uint32_t lo0 = (uint32_t)desc0;
-            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+            int stage = 0; uint32_t phase = 0; uint32_t acc_phase = 0;
+            const uint32_t d_main = tmem_base, d_corr = tmem_base + (uint32_t)BN;
             for (int t = pair; t < total; t += n_pairs) {
-                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                mbar_wait(&tempty_bar[0], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                for (int sk = 0; sk < stages_per_tile; ++sk) {
-                    const int nkb = min(GM_KB_PER_STAGE, kblocks - sk * GM_KB_PER_STAGE);
+                for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     if (lane == 0) {
-                        const uint32_t a_lo = lo0 + (uint32_t)((stage * Cfg::STAGE_BYTES) >> 4);
-                        const uint32_t b_lo = a_lo + (uint32_t)((GM_KB_PER_STAGE * GM_SLAB) >> 4);
+                        const uint32_t a1 = lo0 + (uint32_t)((stage * Cfg::STAGE_BYTES) >> 4);
+                        const uint32_t a2 = a1 + (GM_SLAB >> 4), b1 = a1 + (2 * GM_SLAB >> 4), b2 = b1 + (Cfg::BH_BYTES >> 4);
 #pragma unroll
-                        for (int u = 0; u < GM_KB_PER_STAGE; ++u) {
-                            if (u < nkb) {
-#pragma unroll
-                                for (int k = 0; k < GM_KB / 8; ++k) {
-                                    const uint64_t ad = (desc0 & 0xFFFFFFFF00000000ull) | (uint64_t)(a_lo + (uint32_t)((u * GM_SLAB) >> 4) + 2 * k);
-                                    const uint64_t bd = (desc0 & 0xFFFFFFFF00000000ull) | (uint64_t)(b_lo + (uint32_t)((u * Cfg::BH_BYTES) >> 4) + 2 * k);
-                                    umma_tf32_2sm(d_tmem, ad, bd, idesc, (uint32_t)((sk | u | k) != 0));
-                                }
-                            }
+                        for (int k = 0; k < GH_KB / 16; ++k) {
+                            const uint32_t first = (uint32_t)((kb | k) != 0);
+                            umma_f16_2sm(d_main, dhi | (uint64_t)(a1 + 2 * k), dhi | (uint64_t)(b1 + 2 * k), idesc, first);
+                            umma_f16_2sm(d_corr, dhi | (uint64_t)(a1 + 2 * k), dhi | (uint64_t)(b2 + 2 * k), idesc, first);
+                            umma_f16_2sm(d_corr, dhi | (uint64_t)(a2 + 2 * k), dhi | (uint64_t)(b1 + 2 * k), idesc, 1u);
                         }
                         umma_commit_2sm(&empty_bar[stage]);
-                        if (sk == stages_per_tile - 1) umma_commit_2sm(&tfull_bar[acc]);
+                        if (kb == kblocks - 1) umma_commit_2sm(&tfull_bar[0]);
                     }
                     __syncwarp();
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
-                acc ^= 1;
-                if (acc == 0) acc_phase ^= 1;
+                acc_phase ^= 1;
             }
         }
     } else {
@@ -322,52 +407,31 @@ gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int lg = warp & 3;
         const int col_half = (warp - 2) >> 2;
         const int r_in = lg * 32 + lane;
-        int acc = 0; uint32_t acc_phase = 0;
+        uint32_t acc_phase = 0;
         for (int t = pair; t < total; t += n_pairs) {
             const int m0 = (t / n_tiles) * (2 * GM_TILE) + (int)rank * GM_TILE, n0 = (t % n_tiles) * BN;
             const int row = m0 + r_in;
-            mbar_wait(&tfull_bar[acc], acc_phase);
+            mbar_wait(&tfull_bar[0], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * BN);
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16);
 #pragma unroll 1
             for (int c0 = col_half * (BN / 2); c0 < (col_half + 1) * (BN / 2); c0 += 32) {
-                uint32_t v[32];
-                tmem_ld_x32(taddr + c0, v);
+                uint32_t v0[32], v1[32];
+                tmem_ld_x32(taddr + c0, v0);
+                tmem_ld_x32(taddr + BN + c0, v1);
                 tmem_wait_ld();
                 if (row < M) {
-                    float* crow = C + (size_t)row * N + n0 + c0;
-                    const float* rrow = residual ? residual + (size_t)row * N + n0 + c0 : nullptr;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {   // 32-byte (full-sector) vector accesses: a thread owns a row segment
-                        float o[8];
-#pragma unroll
-                        for (int t = 0; t < 8; t += 4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j + t));
-                            o[t + 0] = __uint_as_float(v[j + t + 0]) + b4.x; o[t + 1] = __uint_as_float(v[j + t + 1]) + b4.y;
-                            o[t + 2] = __uint_as_float(v[j + t + 2]) + b4.z; o[t + 3] = __uint_as_float(v[j + t + 3]) + b4.w;
-                        }
-                        if (act_gelu) {
-#pragma unroll
-                            for (int t = 0; t < 8; ++t) o[t] = gelu_erf(o[t]);
-                        }
-                        if (rrow) {
-                            float r[8];
-                            ld_global_v8(rrow + j, r);
-#pragma unroll
-                            for (int t = 0; t < 8; ++t) o[t] += r[t];
-                        }
-                        st_global_v8(crow + j, o);
-                    }
+                    const size_t off = (size_t)row * N + n0 + c0;
+                    gemm_epilogue_row32(v0, v1, bias + n0 + c0, residual ? residual + off : nullptr, act_gelu, out, off);
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (rank == 0) mbar_arrive(&tempty_bar[acc]);
-                else mbar_arrive_remote(&tempty_bar[acc], 0);
+                if (rank == 0) mbar_arrive(&tempty_bar[0]);
+                else mbar_arrive_remote(&tempty_bar[0], 0);
             }
-            acc ^= 1;
-            if (acc == 0) acc_phase ^= 1;
+            acc_phase ^= 1;
         }
     }
     tc_fence_before();
@@ -382,26 +446,27 @@ gemm2_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 // ---------------------------------------------------------------- small-M GEMM: 128 x BN tiles, split-K
 // A handful of query tokens (batch-1 latency; the per-rank slice of a batch on 8 GPUs) gives the persistent kernels
 // above 6..24 tiles for 148 SMs, each CTA streaming up to 1.5 MB of weights through a serial K loop.  This kernel
-// cuts the output into 128 x BN tiles (BN = 32 or 64) AND the K range into `splits` slices, one CTA each, so that
+// cuts the output into 128 x BN tiles (BN = 32, 64 or 128) AND the K range into `splits` slices, one CTA each, so that
 // ~148 CTAs pull the weight matrix concurrently; when M < 128 only round8(M) activation rows are staged (the other
 // MMA rows compute on stale shared memory and are never stored).  splits == 1: bias / GELU / residual epilogue
-// straight to C; splits > 1: raw fp32 partials to ws[split][M][N], summed in split order by splitk_reduce_kernel
-// (deterministic), which also applies bias / residual / LayerNorm.
-// Stages are packed: round8(M) activation rows (a_bytes) + BN weight rows per k-block, so that for a handful of
-// tokens the whole K slice of a CTA (16..24 k-blocks of ~6 KB) is in flight at once and two CTAs fit on an SM.  The
-// MMA still reads a 128-row A operand from each stage base; the bytes past a_bytes belong to later stages (or the
-// 16 KB slack after the last one) and only feed accumulator rows that are never stored.
+// straight to the outputs; splits > 1: fp32 partials (main + 2^-11 correction) to ws[split][M][N], summed in split order
+// by splitk_reduce_kernel (deterministic), which also applies bias / residual / LayerNorm and writes the split planes.
+// Stages are packed: round8(M) activation rows (a_bytes, hi then lo plane) + BN weight rows (hi, lo) per k-block, so that
+// for a handful of tokens the whole K slice of a CTA is in flight at once and two CTAs fit on an SM.  The MMA still
+// reads a 128-row A operand from each plane's base; the bytes past a_bytes belong to the following planes / stages (or
+// the 16 KB slack after the last one) and only feed accumulator rows that are never stored.
 constexpr int GSK_MAX_STAGES = 32;
 template <int BN> struct GskCfg {
-    static constexpr int B_BYTES = BN * GM_KB * 4;
+    static constexpr int B_BYTES = BN * 128;      // one plane of one weight k-block
 };
 static inline size_t gsk_smem_bytes(int n_stages, int stage_bytes) { return 2048 + (size_t)n_stages * stage_bytes + GM_SLAB; }
 
 template <int BN>
 __global__ void __launch_bounds__(GM_THREADS, 1)
-gemm_sk_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int kb_per_split,
+gemm_sk_f16s_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                    const __grid_constant__ CUtensorMap tmB1, const __grid_constant__ CUtensorMap tmB2, int M, int N, int kb_per_split,
                     int a_bytes, int n_stages, int b_evict_first, const float* __restrict__ bias, const float* __restrict__ residual,
-                    int act_gelu, float* __restrict__ C, float* __restrict__ ws)
+                    int act_gelu, GemmOut out, float* __restrict__ ws)
 {
     using Cfg = GskCfg<BN>;
     extern __shared__ unsigned char gm_smem_raw[];
@@ -411,21 +476,20 @@ gemm_sk_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint64_t* tfull_bar = empty_bar + GSK_MAX_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
     unsigned char* smem = base + 1024;
-    const int stage_bytes = a_bytes + Cfg::B_BYTES;
+    const int stage_bytes = 2 * a_bytes + 2 * Cfg::B_BYTES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BN, m0 = blockIdx.y * GM_TILE, split = blockIdx.z;
     const int kb0 = split * kb_per_split;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmA);
-        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB1); tma_prefetch_desc(&tmB2);
         for (int s = 0; s < n_stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
         mbar_init(tfull_bar, 1);
         fence_barrier_init();
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     pdl_launch_dependents();
@@ -443,28 +507,34 @@ gemm_sk_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 unsigned char* sa = smem + (size_t)stage * stage_bytes;
                 mbar_expect_tx(&full_bar[stage], tx);
-                const int k0 = (kb0 + i) * GM_KB;
-                tma_load_2d(sa, &tmA, &full_bar[stage], k0, m0, TMA_EVICT_LAST);
-                tma_load_2d(sa + a_bytes, &tmB, &full_bar[stage], k0, n0, b_evict_first ? TMA_EVICT_FIRST : TMA_EVICT_LAST);
+                const int k0 = (kb0 + i) * GH_KB;
+                const uint64_t pol = b_evict_first ? TMA_EVICT_FIRST : TMA_EVICT_LAST;
+                tma_load_2d(sa, &tmA1, &full_bar[stage], k0, m0, TMA_EVICT_LAST);
+                tma_load_2d(sa + a_bytes, &tmA2, &full_bar[stage], k0, m0, TMA_EVICT_LAST);
+                tma_load_2d(sa + 2 * a_bytes, &tmB1, &full_bar[stage], k0, n0, pol);
+                tma_load_2d(sa + 2 * a_bytes + Cfg::B_BYTES, &tmB2, &full_bar[stage], k0, n0, pol);
                 if (++stage == n_stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        constexpr uint32_t idesc = umma_idesc_tf32(GM_TILE, BN);
+        constexpr uint32_t idesc = umma_idesc_f16(GM_TILE, BN);
         const uint64_t desc0 = umma_desc_sw128(smem_u32(smem));
+        const uint64_t dhi = desc0 & 0xFFFFFFFF00000000ull;
         const uint32_t lo0 = (uint32_t)desc0;
+        const uint32_t d_main = tmem_base, d_corr = tmem_base + (uint32_t)BN;
         int stage = 0; uint32_t phase = 0;
         for (int i = 0; i < kb_per_split; ++i) {
             mbar_wait(&full_bar[stage], phase);
             tc_fence_after();
             if (lane == 0) {
-                const uint32_t a_lo = lo0 + (uint32_t)((stage * stage_bytes) >> 4);
-                const uint32_t b_lo = a_lo + (uint32_t)(a_bytes >> 4);
+                const uint32_t a1 = lo0 + (uint32_t)((stage * stage_bytes) >> 4);
+                const uint32_t a2 = a1 + (uint32_t)(a_bytes >> 4), b1 = a2 + (uint32_t)(a_bytes >> 4), b2 = b1 + (Cfg::B_BYTES >> 4);
 #pragma unroll
-                for (int k = 0; k < GM_KB / 8; ++k) {
-                    const uint64_t ad = (desc0 & 0xFFFFFFFF00000000ull) | (uint64_t)(a_lo + 2 * k);
-                    const uint64_t bd = (desc0 & 0xFFFFFFFF00000000ull) | (uint64_t)(b_lo + 2 * k);
-                    umma_tf32(tmem_base, ad, bd, idesc, (uint32_t)((i | k) != 0));
+                for (int k = 0; k < GH_KB / 16; ++k) {
+                    const uint32_t first = (uint32_t)((i | k) != 0);
+                    umma_f16(d_main, dhi | (uint64_t)(a1 + 2 * k), dhi | (uint64_t)(b1 + 2 * k), idesc, first);
+                    umma_f16(d_corr, dhi | (uint64_t)(a1 + 2 * k), dhi | (uint64_t)(b2 + 2 * k), idesc, first);
+                    umma_f16(d_corr, dhi | (uint64_t)(a2 + 2 * k), dhi | (uint64_t)(b1 + 2 * k), idesc, 1u);
                 }
                 umma_commit(&empty_bar[stage]);
                 if (i == kb_per_split - 1) umma_commit(tfull_bar);
@@ -481,41 +551,21 @@ gemm_sk_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const bool direct = gridDim.z == 1;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
-            uint32_t v[32];
-            tmem_ld_x32(taddr + c0, v);
+            uint32_t v0[32], v1[32];
+            tmem_ld_x32(taddr + c0, v0);
+            tmem_ld_x32(taddr + BN + c0, v1);
             tmem_wait_ld();
             if (row < M) {
                 if (direct) {
-                    float* crow = C + (size_t)row * N + n0 + c0;
-                    const float* rrow = residual ? residual + (size_t)row * N + n0 + c0 : nullptr;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        float o[8];
-#pragma unroll
-                        for (int t = 0; t < 8; t += 4) {
-                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + n0 + c0 + j + t));
-                            o[t + 0] = __uint_as_float(v[j + t + 0]) + b4.x; o[t + 1] = __uint_as_float(v[j + t + 1]) + b4.y;
-                            o[t + 2] = __uint_as_float(v[j + t + 2]) + b4.z; o[t + 3] = __uint_as_float(v[j + t + 3]) + b4.w;
-                        }
-                        if (act_gelu) {
-#pragma unroll
-                            for (int t = 0; t < 8; ++t) o[t] = gelu_erf(o[t]);
-                        }
-                        if (rrow) {
-                            float r[8];
-                            ld_global_v8(rrow + j, r);
-#pragma unroll
-                            for (int t = 0; t < 8; ++t) o[t] += r[t];
-                        }
-                        st_global_v8(crow + j, o);
-                    }
+                    const size_t off = (size_t)row * N + n0 + c0;
+                    gemm_epilogue_row32(v0, v1, bias + n0 + c0, residual ? residual + off : nullptr, act_gelu, out, off);
                 } else {
                     float* wrow = ws + ((size_t)split * M + row) * N + n0 + c0;
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
                         float o[8];
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) o[t] = __uint_as_float(v[j + t]);
+                        for (int t = 0; t < 8; ++t) o[t] = fmaf(__uint_as_float(v1[j + t]), GH_LO_INV, __uint_as_float(v0[j + t]));
                         st_global_v8(wrow + j, o);
                     }
                 }
@@ -526,7 +576,7 @@ gemm_sk_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
     }
 }
 
@@ -538,35 +588,56 @@ __device__ __forceinline__ float warp_sum(float v)
     return v;
 }
 
-// one warp per row: y = LayerNorm(x) * g + b   (two-pass variance like torch)
-__device__ __forceinline__ void warp_layernorm_row(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ g,
+// one warp per row: y = LayerNorm(x) * g + b   (two-pass variance like torch); a lane owns groups of 8 consecutive
+// elements (d % 8 == 0) so the fp32 row and the split fp16 planes are written with 32- / 16-byte stores
+__device__ __forceinline__ void warp_layernorm_row(const float* __restrict__ x, float* __restrict__ y, uint16_t* __restrict__ y_hi,
+                                                   uint16_t* __restrict__ y_lo, const float* __restrict__ g,
                                                    const float* __restrict__ b, int d, float eps, int lane)
 {
+    const int groups = d >> 3;
     float s = 0.f;
-    for (int i = lane; i < d; i += 32) s += x[i];
+    for (int gi = lane; gi < groups; gi += 32) {
+        const float4 a = *reinterpret_cast<const float4*>(x + gi * 8), c = *reinterpret_cast<const float4*>(x + gi * 8 + 4);
+        s += ((a.x + a.y) + (a.z + a.w)) + ((c.x + c.y) + (c.z + c.w));
+    }
     const float mean = warp_sum(s) / (float)d;
     float v = 0.f;
-    for (int i = lane; i < d; i += 32) { float t = x[i] - mean; v += t * t; }
+    for (int gi = lane; gi < groups; gi += 32) {
+        const float4 a = *reinterpret_cast<const float4*>(x + gi * 8), c = *reinterpret_cast<const float4*>(x + gi * 8 + 4);
+        const float t0 = a.x - mean, t1 = a.y - mean, t2 = a.z - mean, t3 = a.w - mean, t4 = c.x - mean, t5 = c.y - mean, t6 = c.z - mean, t7 = c.w - mean;
+        v += ((t0 * t0 + t1 * t1) + (t2 * t2 + t3 * t3)) + ((t4 * t4 + t5 * t5) + (t6 * t6 + t7 * t7));
+    }
     const float rstd = rsqrtf(warp_sum(v) / (float)d + eps);
-    for (int i = lane; i < d; i += 32) y[i] = (x[i] - mean) * rstd * g[i] + b[i];
+    for (int gi = lane; gi < groups; gi += 32) {
+        float o[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) o[t] = (x[gi * 8 + t] - mean) * rstd * g[gi * 8 + t] + b[gi * 8 + t];
+        if (y) {
+            *reinterpret_cast<float4*>(y + gi * 8) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(y + gi * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+        if (y_hi) split_store8(o, y_hi + gi * 8, y_lo + gi * 8);
+    }
 }
 
 __global__ void __launch_bounds__(256)
-layernorm_kernel(const float* __restrict__ x, float* __restrict__ y, const float* __restrict__ g, const float* __restrict__ b,
-                 int rows, int d, float eps)
+layernorm_kernel(const float* __restrict__ x, float* __restrict__ y, uint16_t* __restrict__ y_hi, uint16_t* __restrict__ y_lo,
+                 const float* __restrict__ g, const float* __restrict__ b, int rows, int d, float eps)
 {
     pdl_launch_dependents();
     pdl_wait();
     const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (r >= rows) return;
-    warp_layernorm_row(x + (size_t)r * d, y + (size_t)r * d, g, b, d, eps, lane);
+    warp_layernorm_row(x + (size_t)r * d, y ? y + (size_t)r * d : nullptr, y_hi ? y_hi + (size_t)r * d : nullptr,
+                       y_lo ? y_lo + (size_t)r * d : nullptr, g, b, d, eps, lane);
 }
 
 // embeddings: x[t] = LN(word[id] + pos[p] + type[0]); one warp per token; scratch row in shared memory
 __global__ void __launch_bounds__(256)
 embed_ln_kernel(const int32_t* __restrict__ tok, const int32_t* __restrict__ pos, const float* __restrict__ word,
                 const float* __restrict__ pemb, const float* __restrict__ temb, const float* __restrict__ g,
-                const float* __restrict__ b, float* __restrict__ x, int n_tok, int d, int vocab, float eps)
+                const float* __restrict__ b, float* __restrict__ x, uint16_t* __restrict__ x_hi, uint16_t* __restrict__ x_lo,
+                int n_tok, int d, int vocab, float eps)
 {
     extern __shared__ float e_sm[];   // [8][d]
     pdl_launch_dependents();
@@ -581,7 +652,7 @@ embed_ln_kernel(const int32_t* __restrict__ tok, const int32_t* __restrict__ pos
     const float* pr = pemb + (size_t)pos[t] * d;
     for (int i = lane; i < d; i += 32) row[i] = (wr[i] + temb[i]) + pr[i];   // torch: inputs_embeds + token_type + position
     __syncwarp();
-    warp_layernorm_row(row, x + (size_t)t * d, g, b, d, eps, lane);
+    warp_layernorm_row(row, x + (size_t)t * d, x_hi + (size_t)t * d, x_lo + (size_t)t * d, g, b, d, eps, lane);
 }
 
 // ------------------------------------------------------------------------------- attention
@@ -594,7 +665,8 @@ embed_ln_kernel(const int32_t* __restrict__ tok, const int32_t* __restrict__ pos
 constexpr int SK_MAX_SPLITS = 8;
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N, const float* __restrict__ bias, const float* residual,
-                     int act_gelu, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps, float* out)
+                     int act_gelu, const float* __restrict__ ln_g, const float* __restrict__ ln_b, float eps, float* out,
+                     uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo)
 {
     __shared__ float s_red[2][8];
     pdl_launch_dependents();
@@ -620,8 +692,17 @@ splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N, con
         }
         return s;
     };
+    auto store4 = [&](int c, const float4& o) {
+        if (out) *reinterpret_cast<float4*>(out + (size_t)row * N + c) = o;
+        if (out_hi) {
+            uint16_t h0, l0, h1, l1, h2, l2, h3, l3;
+            split_f16(o.x, h0, l0); split_f16(o.y, h1, l1); split_f16(o.z, h2, l2); split_f16(o.w, h3, l3);
+            *reinterpret_cast<uint2*>(out_hi + (size_t)row * N + c) = make_uint2((uint32_t)h0 | ((uint32_t)h1 << 16), (uint32_t)h2 | ((uint32_t)h3 << 16));
+            *reinterpret_cast<uint2*>(out_lo + (size_t)row * N + c) = make_uint2((uint32_t)l0 | ((uint32_t)l1 << 16), (uint32_t)l2 | ((uint32_t)l3 << 16));
+        }
+    };
     if (ln_g == nullptr) {
-        for (int c = tid * 4; c < N; c += 1024) *reinterpret_cast<float4*>(out + (size_t)row * N + c) = element(c);
+        for (int c = tid * 4; c < N; c += 1024) store4(c, element(c));
         return;
     }
     const int c = tid * 4;                         // N <= 1024: at most one column group per thread
@@ -648,15 +729,15 @@ splitk_reduce_kernel(const float* __restrict__ ws, int splits, int M, int N, con
         const float4 g = __ldg(reinterpret_cast<const float4*>(ln_g + c)), be = __ldg(reinterpret_cast<const float4*>(ln_b + c));
         float4 o;
         o.x = a * rstd * g.x + be.x; o.y = b * rstd * g.y + be.y; o.z = cc * rstd * g.z + be.z; o.w = dd * rstd * g.w + be.w;
-        *reinterpret_cast<float4*>(out + (size_t)row * N + c) = o;
+        store4(c, o);
     }
 }
 
 constexpr int AT_ROWS = 16;
 constexpr int AT_CHUNK = 64;
 __global__ void __launch_bounds__(256)
-attention_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ seq_off, float* __restrict__ out, int d, int heads,
-                 int max_len)
+attention_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ seq_off, uint16_t* __restrict__ out_hi,
+                 uint16_t* __restrict__ out_lo, int d, int heads, int max_len)
 {
     extern __shared__ float a_sm[];
     const int dh = d / heads;
@@ -733,9 +814,9 @@ attention_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ seq_
     for (int rr = 0; rr < 2; ++rr) {
         const int r = warp * 2 + rr;
         if (r >= nrows) break;
-        float* orow = out + (size_t)(t0 + r0 + r) * d + h * dh;
-        if (lane < dh) orow[lane] = o_acc[rr][0];
-        if (lane + 32 < dh) orow[lane + 32] = o_acc[rr][1];
+        const size_t ob = (size_t)(t0 + r0 + r) * d + h * dh;
+        if (lane < dh) split_f16(o_acc[rr][0], out_hi[ob + lane], out_lo[ob + lane]);
+        if (lane + 32 < dh) split_f16(o_acc[rr][1], out_hi[ob + lane + 32], out_lo[ob + lane + 32]);
     }
 }
 
@@ -746,7 +827,8 @@ attention_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ seq_
 constexpr int ATS_MAX = 64;
 template <int S2>
 __global__ void __launch_bounds__(128)
-attention_tiled_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ seq_off, float* __restrict__ out, int d, int heads)
+attention_tiled_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ seq_off, uint16_t* __restrict__ out_hi,
+                       uint16_t* __restrict__ out_lo, int d, int heads)
 {
     constexpr int RPT = S2 / 8;        // rows per thread
     constexpr int CPT = S2 / 16;       // score columns per thread
@@ -838,9 +920,9 @@ attention_tiled_kernel(const float* __restrict__ qkv, const int32_t* __restrict_
     for (int i = 0; i < RPT; ++i) {
         const int r = ty * RPT + i;
         if (r < len) {
-            float* orow = out + (size_t)(t0 + r) * d + h * dh + tx * cw;
+            const size_t ob = (size_t)(t0 + r) * d + h * dh + tx * cw;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if (j < cw) orow[j] = o_acc[i][j];
+            for (int j = 0; j < 4; ++j) if (j < cw) split_f16(o_acc[i][j], out_hi[ob + j], out_lo[ob + j]);
         }
     }
 }
@@ -851,7 +933,8 @@ attention_tiled_kernel(const float* __restrict__ qkv, const int32_t* __restrict_
 // register-tiled exactly like attention_tiled_kernel<64>: thread (ty, tx) owns 8 rows x 4 score columns and
 // 8 rows x (dh/16) output columns.
 __global__ void __launch_bounds__(128)
-attention_flash_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ seq_off, float* __restrict__ out, int d, int heads)
+attention_flash_kernel(const float* __restrict__ qkv, const int32_t* __restrict__ seq_off, uint16_t* __restrict__ out_hi,
+                       uint16_t* __restrict__ out_lo, int d, int heads)
 {
     constexpr int S2 = 64, RPT = 8, CPT = 4, LD = S2 + 4;
     extern __shared__ __align__(16) float af_sm[];
@@ -954,9 +1037,9 @@ attention_flash_kernel(const float* __restrict__ qkv, const int32_t* __restrict_
         const int r = r0 + ty * RPT + i;
         if (r < len) {
             const float inv = 1.f / l_run[i];
-            float* orow = out + (size_t)(t0 + r) * d + h * dh + tx * cw;
+            const size_t ob = (size_t)(t0 + r) * d + h * dh + tx * cw;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) if (j < cw) orow[j] = o_acc[i][j] * inv;
+            for (int j = 0; j < 4; ++j) if (j < cw) split_f16(o_acc[i][j] * inv, out_hi[ob + j], out_lo[ob + j]);
         }
     }
 }
@@ -1013,29 +1096,33 @@ static EncodeTiledFn emb_encode()
     }
     return fn;
 }
-static void emb_map(CUtensorMap* tm, const float* base, int rows, int cols, int box_rows = GM_TILE)
+// 2D map over one split plane [rows, cols] of fp16, box = 64 halfs (one 128-byte swizzle row) x box_rows
+static void emb_map(CUtensorMap* tm, const uint16_t* base, int rows, int cols, int box_rows = GM_TILE)
 {
     EncodeTiledFn enc = emb_encode();
     if (!enc) throw CudaError{cudaErrorUnknown, "cuTensorMapEncodeTiled unavailable", __FILE__, __LINE__};
     cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-    cuuint64_t gstride[1] = {(cuuint64_t)cols * 4};
-    cuuint32_t box[2] = {(cuuint32_t)GM_KB, (cuuint32_t)box_rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)GH_KB, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
-    if (enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    if (enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<uint16_t*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         throw CudaError{cudaErrorUnknown, "cuTensorMapEncodeTiled failed", __FILE__, __LINE__};
 }
 
-void launch_gemm_tf32(const DeviceInfo& di, const float* A, const float* B, int M, int N, int K, const float* bias,
-                      const float* residual, bool gelu, float* C, cudaStream_t st)
+// large-M GEMM on split operands: CTA pairs (256 x BN tiles) or single CTAs (128 x 128 tiles)
+void launch_gemm_f16s(const DeviceInfo& di, const SplitMat& A, const SplitMat& B, int M, int N, int K, const float* bias,
+                      const float* residual, bool gelu, float* C, uint16_t* C_hi, uint16_t* C_lo, cudaStream_t st)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        KRAG_CUDA(cudaFuncSetAttribute(gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GM_SMEM));
+        KRAG_CUDA(cudaFuncSetAttribute(gemm_f16s_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GM_SMEM));
         attr_set = true;
     }
-    CUtensorMap tmA, tmB;
-    emb_map(&tmA, A, M, K);
+    const GemmOut out{C, C_hi, C_lo};
+    CUtensorMap tmA1, tmA2, tmB1, tmB2;
+    emb_map(&tmA1, A.hi, M, K);
+    emb_map(&tmA2, A.lo, M, K);
     static int use2 = -1;
     if (use2 < 0) { const char* ev = getenv("KRAG_GEMM_2CTA"); use2 = (ev == nullptr || ev[0] != '0') ? 1 : 0; }
     // CTA pairs (256 x BN tiles) win when there are enough tiles to fill the 74 pairs; small problems (few query
@@ -1044,7 +1131,8 @@ void launch_gemm_tf32(const DeviceInfo& di, const float* A, const float* B, int 
     const int pair_tiles = ((M + 2 * GM_TILE - 1) / (2 * GM_TILE)) * (N / ((N % 256 == 0) ? 256 : 128));
     if (use2 && M > GM_TILE && pair_tiles >= di.sm_count / 4) {
         const int BN = (N % 256 == 0) ? 256 : 128;
-        emb_map(&tmB, B, N, K, BN / 2);
+        emb_map(&tmB1, B.hi, N, K, BN / 2);
+        emb_map(&tmB2, B.lo, N, K, BN / 2);
         const int total2 = ((M + 2 * GM_TILE - 1) / (2 * GM_TILE)) * (N / BN);
         const int max_pairs = di.sm_count / 2;
         const int n_pairs = total2 < max_pairs ? total2 : max_pairs;
@@ -1059,86 +1147,111 @@ void launch_gemm_tf32(const DeviceInfo& di, const float* A, const float* B, int 
         const int gelu_i = gelu ? 1 : 0;
         if (BN == 256) {
             static bool a256 = false;
-            if (!a256) { KRAG_CUDA(cudaFuncSetAttribute(gemm2_tf32_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm2Cfg<256>::SMEM)); a256 = true; }
+            if (!a256) { KRAG_CUDA(cudaFuncSetAttribute(gemm2_f16s_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm2Cfg<256>::SMEM)); a256 = true; }
             cfg.dynamicSmemBytes = Gm2Cfg<256>::SMEM;
-            KRAG_CUDA(cudaLaunchKernelEx(&cfg, gemm2_tf32_kernel<256>, tmA, tmB, M, N, K, bias, residual, gelu_i, C));
+            KRAG_CUDA(cudaLaunchKernelEx(&cfg, gemm2_f16s_kernel<256>, tmA1, tmA2, tmB1, tmB2, M, N, K, bias, residual, gelu_i, out));
         } else {
             static bool a128 = false;
-            if (!a128) { KRAG_CUDA(cudaFuncSetAttribute(gemm2_tf32_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm2Cfg<128>::SMEM)); a128 = true; }
+            if (!a128) { KRAG_CUDA(cudaFuncSetAttribute(gemm2_f16s_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gm2Cfg<128>::SMEM)); a128 = true; }
             cfg.dynamicSmemBytes = Gm2Cfg<128>::SMEM;
-            KRAG_CUDA(cudaLaunchKernelEx(&cfg, gemm2_tf32_kernel<128>, tmA, tmB, M, N, K, bias, residual, gelu_i, C));
+            KRAG_CUDA(cudaLaunchKernelEx(&cfg, gemm2_f16s_kernel<128>, tmA1, tmA2, tmB1, tmB2, M, N, K, bias, residual, gelu_i, out));
         }
         count_launch();
         return;
     }
-    emb_map(&tmB, B, N, K);
+    emb_map(&tmB1, B.hi, N, K);
+    emb_map(&tmB2, B.lo, N, K);
     const int total = ((M + GM_TILE - 1) / GM_TILE) * (N / GM_TILE);
     const int grid = total < di.sm_count ? total : di.sm_count;
-    gemm_tf32_kernel<<<grid, GM_THREADS, GM_SMEM, st>>>(tmA, tmB, M, N, K, bias, residual, gelu ? 1 : 0, C);
+    gemm_f16s_kernel<<<grid, GM_THREADS, GM_SMEM, st>>>(tmA1, tmA2, tmB1, tmB2, M, N, K, bias, residual, gelu ? 1 : 0, out);
     KRAG_CUDA(cudaGetLastError());
     count_launch();
 }
 
 
-// small-M path: 128 x BN tiles x split-K slices, ~one CTA per SM (see gemm_sk_tf32_kernel)
+// small-M path: 128 x BN tiles x split-K slices, ~one CTA per SM (see gemm_sk_f16s_kernel)
 template <int BN>
-static void launch_gemm_sk(const CUtensorMap& tmA, const CUtensorMap& tmB, int M, int N, int m_tiles, int splits, int kb_per_split, int a_rows,
-                           const float* bias, const float* residual, bool gelu, float* C, float* ws, cudaStream_t st)
+static void launch_gemm_sk(const CUtensorMap& tmA1, const CUtensorMap& tmA2, const CUtensorMap& tmB1, const CUtensorMap& tmB2, int M, int N,
+                           int m_tiles, int splits, int kb_per_split, int a_rows, const float* bias, const float* residual, bool gelu,
+                           const GemmOut& out, float* ws, cudaStream_t st)
 {
     static bool attr = false;
-    if (!attr) { KRAG_CUDA(cudaFuncSetAttribute(gemm_sk_tf32_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
-    const int a_bytes = a_rows * GM_KB * 4, stage_bytes = a_bytes + GskCfg<BN>::B_BYTES;
+    if (!attr) { KRAG_CUDA(cudaFuncSetAttribute(gemm_sk_f16s_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024)); attr = true; }
+    const int a_bytes = a_rows * 128, stage_bytes = 2 * a_bytes + 2 * GskCfg<BN>::B_BYTES;
     // a few activation rows: keep a CTA under half an SM's shared memory (two CTAs per SM, the next kernel's CTAs
     // can become resident while this one drains); full 128-row tiles take the whole SM
     const int budget = (a_rows <= 32 ? 96 : 196) * 1024;
     int n_stages = budget / stage_bytes;
     n_stages = n_stages > GSK_MAX_STAGES ? GSK_MAX_STAGES : n_stages;
     n_stages = n_stages > kb_per_split ? kb_per_split : n_stages;
-    launch_pdl(gemm_sk_tf32_kernel<BN>, dim3((unsigned)(N / BN), (unsigned)m_tiles, (unsigned)splits), dim3(GM_THREADS),
-               gsk_smem_bytes(n_stages, stage_bytes), st, tmA, tmB, M, N, kb_per_split, a_bytes, n_stages, m_tiles == 1 ? 1 : 0, bias, residual,
-               gelu ? 1 : 0, C, ws);
+    n_stages = n_stages < 1 ? 1 : n_stages;
+    launch_pdl(gemm_sk_f16s_kernel<BN>, dim3((unsigned)(N / BN), (unsigned)m_tiles, (unsigned)splits), dim3(GM_THREADS),
+               gsk_smem_bytes(n_stages, stage_bytes), st, tmA1, tmA2, tmB1, tmB2, M, N, kb_per_split, a_bytes, n_stages, m_tiles == 1 ? 1 : 0, bias,
+               residual, gelu ? 1 : 0, out, ws);
 }
 
-void launch_linear(const DeviceInfo& di, const float* A, const float* B, int M, int N, int K, const float* bias, const float* residual,
-                   bool gelu, float* C, const float* ln_g, const float* ln_b, float eps, float* Y, float* ws, size_t ws_floats,
-                   cudaStream_t st)
+// Linear layer on split operands: C = A . B^T + bias (+GELU) (+residual) -> fp32 C and / or split planes of C; with ln_g the
+// row LayerNorm of that goes to Y (fp32) and its split planes (C is then scratch).
+void launch_linear(const DeviceInfo& di, const SplitMat& A, const SplitMat& B, int M, int N, int K, const float* bias, const float* residual,
+                   bool gelu, float* C, uint16_t* C_hi, uint16_t* C_lo, const float* ln_g, const float* ln_b, float eps, float* Y,
+                   uint16_t* Y_hi, uint16_t* Y_lo, float* ws, size_t ws_floats, cudaStream_t st)
 {
     static int use_sk = -1;
     if (use_sk < 0) { const char* ev = getenv("KRAG_GEMM_SPLITK"); use_sk = (ev == nullptr || ev[0] != '0') ? 1 : 0; }
     const int m_tiles = (M + GM_TILE - 1) / GM_TILE;
     const int tiles128 = m_tiles * (N / GM_TILE);
-    if (use_sk && ws && tiles128 < di.sm_count / 2 && N % 64 == 0 && K % GM_KB == 0 && (!ln_g || N <= 1024)) {
+    if (use_sk && ws && tiles128 < di.sm_count / 2 && N % 64 == 0 && K % GH_KB == 0 && (!ln_g || N <= 1024)) {
         // long-K layers over several activation tiles (FFN2 for tens of queries): 128 x 128 tiles halve the operand
-        // re-reads through L2 (the binding resource with 4-byte operands); split-K restores the CTA count
+        // re-reads through L2 (the binding resource); split-K restores the CTA count
         static int use_wide = -1;
         if (use_wide < 0) { const char* ev = getenv("KRAG_SK_WIDE"); use_wide = (ev == nullptr || ev[0] != '0') ? 1 : 0; }
         const int BN = m_tiles == 1 ? 32 : ((use_wide && K >= 2048 && N % 128 == 0) ? 128 : 64);
-        const int ctas = m_tiles * (N / BN), kblocks = K / GM_KB;
+        const int ctas = m_tiles * (N / BN), kblocks = K / GH_KB;
         int splits = 1;
         if (ctas <= di.sm_count / 3) {              // 72 CTAs with the whole K range beat 144 + a reduce kernel
             const int want = di.sm_count / ctas < SK_MAX_SPLITS ? di.sm_count / ctas : SK_MAX_SPLITS;
-            for (int s = want; s >= 2; --s)
-                if (kblocks % s == 0 && kblocks / s >= 4 && (size_t)s * M * N <= ws_floats) { splits = s; break; }
+            for (int sp = want; sp >= 2; --sp)
+                if (kblocks % sp == 0 && kblocks / sp >= 2 && (size_t)sp * M * N <= ws_floats) { splits = sp; break; }
         }
         const int a_rows = m_tiles == 1 ? ((M + 7) / 8) * 8 : GM_TILE;
-        CUtensorMap tmA, tmB;
-        emb_map(&tmA, A, M, K, a_rows);
-        emb_map(&tmB, B, N, K, BN);
-        float* direct_out = C;
-        if (BN == 32) launch_gemm_sk<32>(tmA, tmB, M, N, m_tiles, splits, kblocks / splits, a_rows, bias, residual, gelu, direct_out, ws, st);
-        else if (BN == 128) launch_gemm_sk<128>(tmA, tmB, M, N, m_tiles, splits, kblocks / splits, a_rows, bias, residual, gelu, direct_out, ws, st);
-        else launch_gemm_sk<64>(tmA, tmB, M, N, m_tiles, splits, kblocks / splits, a_rows, bias, residual, gelu, direct_out, ws, st);
+        CUtensorMap tmA1, tmA2, tmB1, tmB2;
+        emb_map(&tmA1, A.hi, M, K, a_rows); emb_map(&tmA2, A.lo, M, K, a_rows);
+        emb_map(&tmB1, B.hi, N, K, BN); emb_map(&tmB2, B.lo, N, K, BN);
+        // splits == 1 and a LayerNorm to follow: the GEMM writes fp32 C (scratch), the LayerNorm kernel writes Y + planes
+        const GemmOut direct = ln_g ? GemmOut{C, nullptr, nullptr} : GemmOut{C, C_hi, C_lo};
+        if (BN == 32) launch_gemm_sk<32>(tmA1, tmA2, tmB1, tmB2, M, N, m_tiles, splits, kblocks / splits, a_rows, bias, residual, gelu, direct, ws, st);
+        else if (BN == 128) launch_gemm_sk<128>(tmA1, tmA2, tmB1, tmB2, M, N, m_tiles, splits, kblocks / splits, a_rows, bias, residual, gelu, direct, ws, st);
+        else launch_gemm_sk<64>(tmA1, tmA2, tmB1, tmB2, M, N, m_tiles, splits, kblocks / splits, a_rows, bias, residual, gelu, direct, ws, st);
         if (splits > 1) {
             launch_pdl(splitk_reduce_kernel, dim3((unsigned)M), dim3(256), 0, st, ws, splits, M, N, bias, residual, gelu ? 1 : 0, ln_g, ln_b, eps,
-                       ln_g ? Y : C);
+                       ln_g ? Y : C, ln_g ? Y_hi : C_hi, ln_g ? Y_lo : C_lo);
             return;
         }
     } else {
-        launch_gemm_tf32(di, A, B, M, N, K, bias, residual, gelu, C, st);
+        if (ln_g) launch_gemm_f16s(di, A, B, M, N, K, bias, residual, gelu, C, nullptr, nullptr, st);
+        else launch_gemm_f16s(di, A, B, M, N, K, bias, residual, gelu, C, C_hi, C_lo, st);
     }
     if (ln_g) {
-        launch_pdl(layernorm_kernel, dim3((unsigned)((M * 32 + 255) / 256)), dim3(256), 0, st, C, Y, ln_g, ln_b, M, N, eps);
+        launch_pdl(layernorm_kernel, dim3((unsigned)((M * 32 + 255) / 256)), dim3(256), 0, st, C, Y, Y_hi, Y_lo, ln_g, ln_b, M, N, eps);
     }
+}
+
+// test hook (krag_debug_gemm_tf32 / krag_debug_linear_ln): fp32 device operands are split here, then take the product path
+void launch_linear_f32(const DeviceInfo& di, const float* A, const float* B, int M, int N, int K, const float* bias, const float* residual,
+                       bool gelu, float* C, const float* ln_g, const float* ln_b, float eps, float* Y, float* ws, size_t ws_floats,
+                       cudaStream_t st)
+{
+    uint16_t* planes = nullptr;
+    const size_t na = (size_t)M * K, nb = (size_t)N * K;
+    KRAG_CUDA(cudaMalloc(&planes, 2 * (2 * na + 2 * nb)));
+    SplitMat As{planes, planes + na}, Bs{planes + 2 * na, planes + 2 * na + nb};
+    try {
+        launch_split_f16(A, As.hi, As.lo, (int64_t)na, st);
+        launch_split_f16(B, Bs.hi, Bs.lo, (int64_t)nb, st);
+        launch_linear(di, As, Bs, M, N, K, bias, residual, gelu, C, nullptr, nullptr, ln_g, ln_b, eps, Y, nullptr, nullptr, ws, ws_floats, st);
+        KRAG_CUDA(cudaStreamSynchronize(st));
+    } catch (...) { cudaFree(planes); throw; }
+    cudaFree(planes);
 }
 
 
@@ -1146,16 +1259,20 @@ struct Embedder {
     DeviceInfo di;
     BertConfig cfg;
     std::map<std::string, float*> t;      // HF tensor name -> device copy
-    std::vector<float*> wqkv, bqkv;       // fused per layer at finalize
+    std::vector<float*> bqkv;             // fused Q|K|V bias per layer (finalize)
+    // split fp16 planes of the GEMM weights (finalize): per layer QKV (fused), attention output, FFN1, FFN2
+    std::vector<SplitMat> s_qkv, s_o, s_f1, s_f2;
+    std::vector<uint16_t*> planes;        // owning pointers of all weight planes
     bool finalized = false;
     cudaStream_t st = nullptr;
-    cudaEvent_t done = nullptr;
+    cudaEvent_t done = nullptr, in_ev = nullptr;
     std::map<std::tuple<int, int, int>, cudaGraphExec_t> graphs;   // captured forward per (n_tok, batch, max_len)
     std::map<std::tuple<int, int, int>, int> seen;
     // workspaces, grown on demand
     int cap_tok = 0, cap_batch = 0;
     int32_t *d_tok = nullptr, *d_pos = nullptr, *d_off = nullptr;
-    float *x = nullptr, *x2 = nullptr, *qkv = nullptr, *ctx = nullptr, *ffn = nullptr, *out = nullptr;
+    float *x = nullptr, *x2 = nullptr, *qkv = nullptr, *out = nullptr;
+    uint16_t *xs = nullptr, *cs = nullptr, *fs = nullptr;   // split planes [2][T][*] of x (LayerNorm outputs), attention context, FFN1 output
     float* ws = nullptr;                  // split-K partials (small token counts)
     static constexpr size_t WS_FLOATS = (size_t)4 << 20;
 };
@@ -1163,7 +1280,7 @@ struct Embedder {
 static float* emb_get(Embedder* e, const std::string& name, int64_t n)
 {
     auto it = e->t.find(name);
-    if (it == e->t.end()) throw std::runtime_error("embedder: tensor not loaded: " + name);
+    if (it == e->t.end() || it->second == nullptr) throw std::runtime_error("embedder: tensor not loaded: " + name);
     (void)n;
     return it->second;
 }
@@ -1190,30 +1307,55 @@ void embedder_load(Embedder* e, const char* name, const float* data, int64_t n)
     e->finalized = false;
 }
 
+static SplitMat emb_split_weight(Embedder* e, const float* w, size_t n)
+{
+    uint16_t* p = nullptr;
+    KRAG_CUDA(cudaMalloc(&p, 2 * 2 * n));
+    e->planes.push_back(p);
+    SplitMat m{p, p + n};
+    launch_split_f16(w, m.hi, m.lo, (int64_t)n, e->st);
+    return m;
+}
+
 void embedder_finalize(Embedder* e)
 {
-    const int d = e->cfg.hidden;
-    for (float* p : e->wqkv) cudaFree(p);
+    const int d = e->cfg.hidden, inter = e->cfg.inter;
     for (float* p : e->bqkv) cudaFree(p);
-    e->wqkv.clear(); e->bqkv.clear();
+    for (uint16_t* p : e->planes) cudaFree(p);
+    e->bqkv.clear(); e->planes.clear(); e->s_qkv.clear(); e->s_o.clear(); e->s_f1.clear(); e->s_f2.clear();
+    for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);   // captured weight pointers are about to change
+    e->graphs.clear(); e->seen.clear();
     emb_get(e, "embeddings.word_embeddings.weight", 0); emb_get(e, "embeddings.position_embeddings.weight", 0);
     emb_get(e, "embeddings.token_type_embeddings.weight", 0); emb_get(e, "embeddings.LayerNorm.weight", 0);
     emb_get(e, "embeddings.LayerNorm.bias", 0);
+    float* wtmp = nullptr;
+    KRAG_CUDA(cudaMalloc(&wtmp, sizeof(float) * (size_t)3 * d * d));
     for (int l = 0; l < e->cfg.layers; ++l) {
-        float *w = nullptr, *b = nullptr;
-        KRAG_CUDA(cudaMalloc(&w, sizeof(float) * (size_t)3 * d * d));
+        float* b = nullptr;
         KRAG_CUDA(cudaMalloc(&b, sizeof(float) * (size_t)3 * d));
         const char* names[3] = {"attention.self.query", "attention.self.key", "attention.self.value"};
         for (int j = 0; j < 3; ++j) {
-            KRAG_CUDA(cudaMemcpy(w + (size_t)j * d * d, emb_get(e, lname(l, names[j]) + ".weight", 0), sizeof(float) * (size_t)d * d, cudaMemcpyDeviceToDevice));
-            KRAG_CUDA(cudaMemcpy(b + (size_t)j * d, emb_get(e, lname(l, names[j]) + ".bias", 0), sizeof(float) * (size_t)d, cudaMemcpyDeviceToDevice));
+            KRAG_CUDA(cudaMemcpyAsync(wtmp + (size_t)j * d * d, emb_get(e, lname(l, names[j]) + ".weight", 0), sizeof(float) * (size_t)d * d, cudaMemcpyDeviceToDevice, e->st));
+            KRAG_CUDA(cudaMemcpyAsync(b + (size_t)j * d, emb_get(e, lname(l, names[j]) + ".bias", 0), sizeof(float) * (size_t)d, cudaMemcpyDeviceToDevice, e->st));
         }
-        e->wqkv.push_back(w); e->bqkv.push_back(b);
-        for (const char* s : {"attention.output.dense.weight", "attention.output.dense.bias", "attention.output.LayerNorm.weight",
-                              "attention.output.LayerNorm.bias", "intermediate.dense.weight", "intermediate.dense.bias",
-                              "output.dense.weight", "output.dense.bias", "output.LayerNorm.weight", "output.LayerNorm.bias"})
-            emb_get(e, lname(l, s), 0);
+        e->bqkv.push_back(b);
+        e->s_qkv.push_back(emb_split_weight(e, wtmp, (size_t)3 * d * d));       // stream order: the split reads wtmp before the next layer overwrites it
+        for (const char* nm : {"attention.output.dense.bias", "attention.output.LayerNorm.weight", "attention.output.LayerNorm.bias",
+                               "intermediate.dense.bias", "output.dense.bias", "output.LayerNorm.weight", "output.LayerNorm.bias"})
+            emb_get(e, lname(l, nm), 0);
+        e->s_o.push_back(emb_split_weight(e, emb_get(e, lname(l, "attention.output.dense.weight"), 0), (size_t)d * d));
+        e->s_f1.push_back(emb_split_weight(e, emb_get(e, lname(l, "intermediate.dense.weight"), 0), (size_t)inter * d));
+        e->s_f2.push_back(emb_split_weight(e, emb_get(e, lname(l, "output.dense.weight"), 0), (size_t)d * inter));
     }
+    KRAG_CUDA(cudaStreamSynchronize(e->st));
+    cudaFree(wtmp);
+    // the fp32 copies of the GEMM weights are not read again: free them (the split planes hold the same bytes per element)
+    for (int l = 0; l < e->cfg.layers; ++l)
+        for (const char* nm : {"attention.self.query.weight", "attention.self.key.weight", "attention.self.value.weight",
+                               "attention.output.dense.weight", "intermediate.dense.weight", "output.dense.weight"}) {
+            auto it = e->t.find(lname(l, nm));
+            if (it != e->t.end() && it->second) { cudaFree(it->second); it->second = nullptr; }
+        }
     if (!e->ws) KRAG_CUDA(cudaMalloc(&e->ws, sizeof(float) * Embedder::WS_FLOATS));
     e->finalized = true;
 }
@@ -1221,12 +1363,14 @@ void embedder_finalize(Embedder* e)
 void embedder_destroy(Embedder* e)
 {
     for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);
-    for (auto& kv : e->t) cudaFree(kv.second);
-    for (float* p : e->wqkv) cudaFree(p);
+    for (auto& kv : e->t) if (kv.second) cudaFree(kv.second);
     for (float* p : e->bqkv) cudaFree(p);
-    for (void* p : {(void*)e->d_tok, (void*)e->d_pos, (void*)e->d_off, (void*)e->x, (void*)e->x2, (void*)e->qkv, (void*)e->ctx, (void*)e->ffn, (void*)e->out})
+    for (uint16_t* p : e->planes) cudaFree(p);
+    for (void* p : {(void*)e->d_tok, (void*)e->d_pos, (void*)e->d_off, (void*)e->x, (void*)e->x2, (void*)e->qkv, (void*)e->xs, (void*)e->cs, (void*)e->fs, (void*)e->out})
         if (p) cudaFree(p);
     if (e->ws) cudaFree(e->ws);
+    if (e->done) cudaEventDestroy(e->done);
+    if (e->in_ev) cudaEventDestroy(e->in_ev);
     if (e->st) cudaStreamDestroy(e->st);
     delete e;
 }
@@ -1256,14 +1400,18 @@ void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int3
         for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second);   // captured pointers are about to change
         e->graphs.clear(); e->seen.clear();
         KRAG_CUDA(cudaStreamSynchronize(st));
-        for (void* p : {(void*)e->d_tok, (void*)e->d_pos, (void*)e->d_off, (void*)e->x, (void*)e->x2, (void*)e->qkv, (void*)e->ctx, (void*)e->ffn, (void*)e->out})
+        for (void* p : {(void*)e->d_tok, (void*)e->d_pos, (void*)e->d_off, (void*)e->x, (void*)e->x2, (void*)e->qkv, (void*)e->xs, (void*)e->cs, (void*)e->fs, (void*)e->out})
             if (p) cudaFree(p);
         const size_t T = (size_t)(n_tok > e->cap_tok ? n_tok : e->cap_tok), Bc = (size_t)(batch > e->cap_batch ? batch : e->cap_batch);
         KRAG_CUDA(cudaMalloc(&e->d_tok, 4 * T)); KRAG_CUDA(cudaMalloc(&e->d_pos, 4 * T)); KRAG_CUDA(cudaMalloc(&e->d_off, 4 * (Bc + 1)));
         KRAG_CUDA(cudaMalloc(&e->x, 4 * T * d)); KRAG_CUDA(cudaMalloc(&e->x2, 4 * T * d)); KRAG_CUDA(cudaMalloc(&e->qkv, 4 * T * 3 * d));
-        KRAG_CUDA(cudaMalloc(&e->ctx, 4 * T * d)); KRAG_CUDA(cudaMalloc(&e->ffn, 4 * T * c.inter)); KRAG_CUDA(cudaMalloc(&e->out, 4 * Bc * d));
+        KRAG_CUDA(cudaMalloc(&e->xs, 2 * 2 * T * d)); KRAG_CUDA(cudaMalloc(&e->cs, 2 * 2 * T * d)); KRAG_CUDA(cudaMalloc(&e->fs, 2 * 2 * T * c.inter));
+        KRAG_CUDA(cudaMalloc(&e->out, 4 * Bc * d));
         e->cap_tok = (int)T; e->cap_batch = (int)Bc;
     }
+    // split planes: [hi plane | lo plane], each cap_tok rows
+    const SplitMat xs{e->xs, e->xs + (size_t)e->cap_tok * d}, cs{e->cs, e->cs + (size_t)e->cap_tok * d},
+                   fs{e->fs, e->fs + (size_t)e->cap_tok * c.inter};
     KRAG_CUDA(cudaMemcpyAsync(e->d_tok, tok_ids, 4 * (size_t)n_tok, cudaMemcpyHostToDevice, st));
     KRAG_CUDA(cudaMemcpyAsync(e->d_pos, pos.data(), 4 * (size_t)n_tok, cudaMemcpyHostToDevice, st));
     KRAG_CUDA(cudaMemcpyAsync(e->d_off, tok_offsets, 4 * (size_t)(batch + 1), cudaMemcpyHostToDevice, st));
@@ -1274,7 +1422,7 @@ void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int3
     launch_pdl(embed_ln_kernel, dim3((unsigned)((n_tok + 7) / 8)), dim3(256), (size_t)8 * d * 4, st, e->d_tok, e->d_pos,
                e->t["embeddings.word_embeddings.weight"], e->t["embeddings.position_embeddings.weight"],
                e->t["embeddings.token_type_embeddings.weight"], e->t["embeddings.LayerNorm.weight"], e->t["embeddings.LayerNorm.bias"], e->x,
-               n_tok, d, c.vocab, c.eps);
+               xs.hi, xs.lo, n_tok, d, c.vocab, c.eps);
     const int dh = d / c.heads;
     const size_t at_smem = sizeof(float) * ((size_t)AT_ROWS * dh + (size_t)dh * (AT_CHUNK + 1) + (size_t)AT_CHUNK * dh + (size_t)AT_ROWS * max_len);
     const size_t ats_smem32 = sizeof(float) * ((size_t)2 * 64 * (32 + 4) + (size_t)32 * 64 + (size_t)32 * (32 + 4));
@@ -1290,30 +1438,34 @@ void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int3
     static int use_flash = -1;
     if (use_flash < 0) { const char* ev = getenv("KRAG_ATTN_FLASH"); use_flash = (ev == nullptr || ev[0] != '0') ? 1 : 0; }
     for (int l = 0; l < c.layers; ++l) {
-        launch_linear(e->di, e->x, e->wqkv[(size_t)l], n_tok, 3 * d, d, e->bqkv[(size_t)l], nullptr, false, e->qkv, nullptr, nullptr, 0.f,
-                      nullptr, e->ws, Embedder::WS_FLOATS, st);
+        const size_t L = (size_t)l;
+        // QKV projection: split x -> fp32 qkv (attention is fp32 CUDA-core code)
+        launch_linear(e->di, xs, e->s_qkv[L], n_tok, 3 * d, d, e->bqkv[L], nullptr, false, e->qkv, nullptr, nullptr, nullptr, nullptr, 0.f,
+                      nullptr, nullptr, nullptr, e->ws, Embedder::WS_FLOATS, st);
         if (max_len <= 32) {
-            launch_pdl(attention_tiled_kernel<32>, dim3((unsigned)batch, (unsigned)c.heads), dim3(128), ats_smem32, st, e->qkv, e->d_off, e->ctx, d, c.heads);
+            launch_pdl(attention_tiled_kernel<32>, dim3((unsigned)batch, (unsigned)c.heads), dim3(128), ats_smem32, st, e->qkv, e->d_off, cs.hi, cs.lo, d, c.heads);
         } else if (max_len <= ATS_MAX) {
-            launch_pdl(attention_tiled_kernel<64>, dim3((unsigned)batch, (unsigned)c.heads), dim3(128), ats_smem64, st, e->qkv, e->d_off, e->ctx, d, c.heads);
+            launch_pdl(attention_tiled_kernel<64>, dim3((unsigned)batch, (unsigned)c.heads), dim3(128), ats_smem64, st, e->qkv, e->d_off, cs.hi, cs.lo, d, c.heads);
         } else {
             if (use_flash)
                 attention_flash_kernel<<<dim3((unsigned)((max_len + 63) / 64), (unsigned)c.heads, (unsigned)batch), 128, ats_smem64, st>>>(
-                    e->qkv, e->d_off, e->ctx, d, c.heads);
+                    e->qkv, e->d_off, cs.hi, cs.lo, d, c.heads);
             else
                 attention_kernel<<<dim3((unsigned)((max_len + AT_ROWS - 1) / AT_ROWS), (unsigned)c.heads, (unsigned)batch), 256, at_smem, st>>>(
-                    e->qkv, e->d_off, e->ctx, d, c.heads, max_len);
+                    e->qkv, e->d_off, cs.hi, cs.lo, d, c.heads, max_len);
             KRAG_CUDA(cudaGetLastError());
             count_launch();
         }
-        // O projection (+bias +residual) -> LayerNorm; FFN1 (+bias, GELU); FFN2 (+bias +residual) -> LayerNorm
-        launch_linear(e->di, e->ctx, e->t[lname(l, "attention.output.dense.weight")], n_tok, d, d, e->t[lname(l, "attention.output.dense.bias")],
-                      e->x, false, e->x2, e->t[lname(l, "attention.output.LayerNorm.weight")], e->t[lname(l, "attention.output.LayerNorm.bias")],
-                      c.eps, e->x, e->ws, Embedder::WS_FLOATS, st);
-        launch_linear(e->di, e->x, e->t[lname(l, "intermediate.dense.weight")], n_tok, c.inter, d, e->t[lname(l, "intermediate.dense.bias")],
-                      nullptr, true, e->ffn, nullptr, nullptr, 0.f, nullptr, e->ws, Embedder::WS_FLOATS, st);
-        launch_linear(e->di, e->ffn, e->t[lname(l, "output.dense.weight")], n_tok, d, c.inter, e->t[lname(l, "output.dense.bias")], e->x, false,
-                      e->x2, e->t[lname(l, "output.LayerNorm.weight")], e->t[lname(l, "output.LayerNorm.bias")], c.eps, e->x, e->ws,
+        // O projection (+bias +residual) -> LayerNorm -> x (fp32 residual stream) + its split planes
+        launch_linear(e->di, cs, e->s_o[L], n_tok, d, d, e->t[lname(l, "attention.output.dense.bias")], e->x, false, e->x2, nullptr, nullptr,
+                      e->t[lname(l, "attention.output.LayerNorm.weight")], e->t[lname(l, "attention.output.LayerNorm.bias")], c.eps, e->x, xs.hi, xs.lo,
+                      e->ws, Embedder::WS_FLOATS, st);
+        // FFN1 (+bias, GELU): only the split planes are written (FFN2 is the sole consumer)
+        launch_linear(e->di, xs, e->s_f1[L], n_tok, c.inter, d, e->t[lname(l, "intermediate.dense.bias")], nullptr, true, nullptr, fs.hi, fs.lo,
+                      nullptr, nullptr, 0.f, nullptr, nullptr, nullptr, e->ws, Embedder::WS_FLOATS, st);
+        // FFN2 (+bias +residual) -> LayerNorm -> x + split planes
+        launch_linear(e->di, fs, e->s_f2[L], n_tok, d, c.inter, e->t[lname(l, "output.dense.bias")], e->x, false, e->x2, nullptr, nullptr,
+                      e->t[lname(l, "output.LayerNorm.weight")], e->t[lname(l, "output.LayerNorm.bias")], c.eps, e->x, xs.hi, xs.lo, e->ws,
                       Embedder::WS_FLOATS, st);
     }
     };   // run_layers
@@ -1339,6 +1491,11 @@ void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int3
         run_layers();
     }
     if (out_dev) {
+        // the caller's buffer may still be read by work it enqueued earlier on `consumer` (the previous batch's scan): only
+        // the final writer waits for that; the forward itself overlaps with it
+        if (!e->in_ev) KRAG_CUDA(cudaEventCreateWithFlags(&e->in_ev, cudaEventDisableTiming));
+        KRAG_CUDA(cudaEventRecord(e->in_ev, consumer));
+        KRAG_CUDA(cudaStreamWaitEvent(st, e->in_ev, 0));
         cls_normalize_kernel<<<(batch * 32 + 255) / 256, 256, 0, st>>>(e->x, e->d_off, out_dev, batch, d, ld_out);
         KRAG_CUDA(cudaGetLastError());
         count_launch();

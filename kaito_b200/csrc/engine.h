@@ -110,14 +110,19 @@ void embedder_destroy(Embedder* e);
 int embedder_hidden(const Embedder* e);
 void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int32_t* tok_offsets, float* out_host,
                       float* out_dev = nullptr, int ld_out = 0, cudaStream_t consumer = nullptr);
-// C[M,N] = A[M,K] . B[N,K]^T + bias (+gelu) (+residual), fp32 in/out, TF32 tensor cores; device pointers
-// Linear layer: C = A . B^T + bias (+GELU) (+residual); with ln_g the row LayerNorm of that goes to Y (C is scratch).
+// A fp32 matrix carried as two fp16 planes: v = hi + lo * 2^-11 (see embed.cu: split operands of the K5 GEMMs)
+struct SplitMat { uint16_t* hi; uint16_t* lo; };
+void launch_split_f16(const float* in, uint16_t* hi, uint16_t* lo, int64_t n /* % 8 == 0 */, cudaStream_t st);
+// Linear layer on split operands: C = A . B^T + bias (+GELU) (+residual), fp32-accurate (three kind::f16 MMAs per step);
+// outputs: fp32 C and / or the split planes of C; with ln_g the row LayerNorm of that goes to Y / Y planes (C is scratch).
 // Picks CTA pairs / 128x128 tiles / 128xBN split-K tiles by problem size; ws = split-K workspace (may be null).
-void launch_linear(const DeviceInfo& di, const float* A, const float* B, int M, int N, int K, const float* bias, const float* residual,
-                   bool gelu, float* C, const float* ln_g, const float* ln_b, float eps, float* Y, float* ws, size_t ws_floats,
-                   cudaStream_t st);
-void launch_gemm_tf32(const DeviceInfo& di, const float* A, const float* B, int M, int N, int K, const float* bias,
-                      const float* residual, bool gelu, float* C, cudaStream_t st);
+void launch_linear(const DeviceInfo& di, const SplitMat& A, const SplitMat& B, int M, int N, int K, const float* bias, const float* residual,
+                   bool gelu, float* C, uint16_t* C_hi, uint16_t* C_lo, const float* ln_g, const float* ln_b, float eps, float* Y,
+                   uint16_t* Y_hi, uint16_t* Y_lo, float* ws, size_t ws_floats, cudaStream_t st);
+// test hook: fp32 device operands, split on the fly, then the path above
+void launch_linear_f32(const DeviceInfo& di, const float* A, const float* B, int M, int N, int K, const float* bias, const float* residual,
+                       bool gelu, float* C, const float* ln_g, const float* ln_b, float eps, float* Y, float* ws, size_t ws_floats,
+                       cudaStream_t st);
 
 // ---- synthetic data (synth.cu)
 void launch_synth_dense(float* X, int64_t n, int d, int dpad, int64_t row_base, uint64_t seed, cudaStream_t st);

@@ -1,7 +1,8 @@
-"""K5 (BERT encoder forward on tcgen05 TF32 GEMMs) against transformers.BertModel in fp32 on the CPU with
-the same seeded random weights (the real bge weights are not available offline), CLS pooling + L2 norm as
-sentence-transformers does for bge (embedding/huggingface_local_embedding.py:34-53).  Tolerances are written
-out: TF32 operands carry 10 mantissa bits, so the embeddings agree to ~1e-3, not bit-exactly."""
+"""K5 (BERT encoder forward; linear layers on tcgen05 kind::f16 with split fp16 operands = fp32-accurate products) against
+transformers.BertModel in fp32 on the CPU with the same seeded random weights (the real bge weights are not available
+offline; an opt-in test at the bottom runs the reference's own golden when a local snapshot is given), CLS pooling + L2 norm
+as sentence-transformers does for bge (embedding/huggingface_local_embedding.py:34-53).  Tolerances are written out: the
+north_star contract is 1e-4 on the returned L2^2 scores; the embeddings themselves agree to a few 1e-6."""
 import numpy as np
 import pytest
 
@@ -31,14 +32,17 @@ def test_gemm_tf32_matches_numpy(ctx, M, N, K, gelu, res):
     if res:
         ref = ref + R
     err = np.abs(got - ref)
-    assert err.max() < 2e-2 and err.mean() < 1e-3, (err.max(), err.mean())   # |a.b| ~ 1, TF32 unit roundoff 2^-11
+    print(f"gemm {M}x{N}x{K}: max {err.max():.2e} mean {err.mean():.2e}")
+    # |a.b| ~ 1: an fp32 SIMT GEMM is at ~sqrt(K) 2^-24 ~ 2e-6; the split-fp16 tensor-core product adds 2^-22 operand error
+    # and the tensor core's own accumulation rounding (TF32 operands, which this replaced, sat at 2e-2 / 1e-3)
+    assert err.max() < 5e-5 and err.mean() < 5e-6, (err.max(), err.mean())
 
 
 @pytest.mark.parametrize("M,N,K,res", [(16, 768, 3072, True), (1, 768, 768, True), (512, 384, 384, True), (300, 1024, 1024, False),
                                         (4096, 768, 768, True)])
 def test_linear_layernorm_matches_numpy(ctx, M, N, K, res):
     """GEMM + bias + residual + LayerNorm through the dispatcher (split-K reduce/LN kernel for few rows, fused epilogue +
-    LN kernel otherwise) against fp64 numpy.  Tolerance: TF32 operands (2^-11) on |a.b| ~ 1 before a unit-variance LN."""
+    LN kernel otherwise) against fp64 numpy.  Tolerance: fp32-level products on |a.b| ~ 1 before a unit-variance LN."""
     from kaito_b200 import _native
     g = np.random.default_rng(M * 7 + N + K)
     A = g.standard_normal((M, K)).astype(np.float32)
@@ -50,7 +54,8 @@ def test_linear_layernorm_matches_numpy(ctx, M, N, K, res):
     y = A.astype(np.float64) @ B.astype(np.float64).T + bias + (R if res else 0)
     ref = (y - y.mean(1, keepdims=True)) / np.sqrt(y.var(1, keepdims=True) + 1e-12) * gamma + beta
     err = np.abs(got - ref)
-    assert err.max() < 2e-2 and err.mean() < 1e-3, (err.max(), err.mean())
+    print(f"linear+ln {M}x{N}x{K}: max {err.max():.2e} mean {err.mean():.2e}")
+    assert err.max() < 5e-5 and err.mean() < 5e-6, (err.max(), err.mean())
 
 
 def _torch_reference(cfg, state, token_lists):
@@ -112,8 +117,16 @@ def test_bert_forward_matches_transformers(ctx, name, cfg, lens):
         ref = _torch_reference(cfg, state, toks)
         assert np.allclose(np.linalg.norm(got, axis=1), 1.0, atol=1e-5)
         cos = (got * ref).sum(1)
-        assert cos.min() > 0.9999, cos
-        assert np.abs(got - ref).max() < 5e-3, np.abs(got - ref).max()
+        dmax = np.abs(got - ref).max()
+        # what /retrieve returns is L2^2 between this embedding and corpus rows: north_star tolerance 1e-4 on that score
+        y = g.standard_normal((64, got.shape[1])).astype(np.float32)
+        y /= np.linalg.norm(y, axis=1, keepdims=True)
+        l2_got = ((got[:, None, :].astype(np.float64) - y[None]) ** 2).sum(-1)
+        l2_ref = ((ref[:, None, :].astype(np.float64) - y[None]) ** 2).sum(-1)
+        l2_dev = np.abs(l2_got - l2_ref).max()
+        print(f"{name}: max|d| {dmax:.2e}  1-cos {1 - cos.min():.2e}  max L2^2 deviation {l2_dev:.2e}")
+        assert l2_dev < 1e-4, l2_dev                       # the contract
+        assert dmax < 2e-5 and cos.min() > 1 - 1e-8, (dmax, cos)   # and with margin: fp32-level agreement (TF32 was 5e-3 / 1e-4)
         # batching must not change a sequence's embedding beyond fp32 summation order (packed, no padding; the GEMM tiling
         # and split-K factor follow the token count, as torch's own kernels do)
         alone = emb.embed([toks[-1]])
@@ -121,3 +134,23 @@ def test_bert_forward_matches_transformers(ctx, name, cfg, lens):
         assert np.array_equal(emb.embed([toks[-1]])[0], alone[0])          # same shape -> same bits
     finally:
         emb.destroy()
+
+
+
+@pytest.mark.skipif(not __import__("os").environ.get("KRAG_MODEL_DIR"), reason="opt-in: KRAG_MODEL_DIR=<local BAAI/bge-small-en-v1.5 snapshot>")
+def test_real_weights_reference_golden(ctx):
+    """The one numeric golden the reference's own tests hold for this path (presets/ragengine/tests/api/test_main.py:159-164):
+    after indexing "This is a test document" / updating it to "This is an updated test document", the chat query
+    "updates test query" gets source_nodes[0].score == 0.48061275482177734 (rel 1e-6) -- the squared L2 distance between the
+    bge-small-en-v1.5 embeddings of the query and of that document (faiss IndexFlatL2, faiss_store.py:44-49).  Needs the real
+    checkpoint (not available offline): point KRAG_MODEL_DIR at a snapshot holding config.json, vocab.txt and
+    model.safetensors / pytorch_model.bin."""
+    import os
+    from kaito_b200.embedding import GpuBertEmbedding
+    emb = GpuBertEmbedding.from_pretrained(ctx, os.environ["KRAG_MODEL_DIR"])
+    try:
+        q = np.asarray(emb.get_query_embedding("updates test query"), np.float64)
+        d = np.asarray(emb.get_text_embedding_batch(["This is an updated test document"])[0], np.float64)
+        assert float(((q - d) ** 2).sum()) == pytest.approx(0.48061275482177734, rel=1e-4)   # 1e-4: north_star tolerance
+    finally:
+        emb._emb.destroy()
