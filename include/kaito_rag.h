@@ -131,6 +131,11 @@ int32_t krag_index_commit_local(krag_index* idx, int64_t vocab, uint32_t* df_out
                                 int64_t* n_live_out, int64_t* total_len_out);
 int32_t krag_index_commit_global(krag_index* idx, int64_t vocab, const uint32_t* df_global /*[vocab] host*/,
                                  int64_t n_docs_global, int64_t total_len_global, int64_t ordinal_base);
+/* Global ordinal of local row r = ordinal_base + r * ordinal_stride (default base 0 / stride 1; krag_index_commit_global sets
+ * the base of a contiguous shard).  The multi-GPU service deals nodes round-robin over G shards (node o -> shard o % G, row
+ * o / G) and sets (base, stride) = (shard, G): ordinals -- and with them every tie-break -- equal the single-GPU insertion
+ * order.  Call before krag_index_commit_global / searches; no counterpart in the reference (one replica, manifests.go:81). */
+int32_t krag_index_set_ordinal_map(krag_index* idx, int64_t ordinal_base, int64_t ordinal_stride);
 int32_t krag_index_stats(krag_index* idx, krag_stats_t* out);
 /* ordinals (global) -> node ids for rows of THIS shard; KRAG_E_NOT_FOUND if out of range */
 int32_t krag_index_node_ids(krag_index* idx, int64_t n, const int64_t* ordinals, uint64_t* node_ids_out);

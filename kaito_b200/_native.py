@@ -28,7 +28,7 @@ SYMBOLS = [
     "krag_version", "krag_last_error", "krag_init", "krag_shutdown", "krag_launch_count", "krag_ctx_stream",
     "krag_index_create", "krag_index_drop", "krag_index_reserve", "krag_index_add", "krag_index_remove",
     "krag_index_commit", "krag_index_commit_local", "krag_index_commit_global", "krag_index_stats",
-    "krag_index_node_ids", "krag_index_persist", "krag_index_load", "krag_search_dense", "krag_search_bm25",
+    "krag_index_node_ids", "krag_index_set_ordinal_map", "krag_index_persist", "krag_index_load", "krag_search_dense", "krag_search_bm25",
     "krag_retrieve", "krag_dev_dense_candidates", "krag_dev_bm25_candidates", "krag_dev_merge", "krag_dev_fuse",
     "krag_synth_fill", "krag_index_read_rows", "krag_index_read_postings", "krag_tc_fallback_queries",
     "krag_debug_tc_dump", "krag_last_dense_kernel", "krag_embedder_create", "krag_embedder_load_tensor",
@@ -91,6 +91,7 @@ def load() -> C.CDLL:
     L.krag_index_commit_local.argtypes = [vp, i64, vp, C.POINTER(i64), C.POINTER(i64)]
     L.krag_index_commit_global.argtypes = [vp, i64, vp, i64, i64, i64]
     L.krag_index_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.krag_index_set_ordinal_map.argtypes = [vp, i64, i64]
     L.krag_index_node_ids.argtypes = [vp, i64, vp, vp]
     L.krag_index_persist.argtypes = [vp, C.c_char_p]
     L.krag_index_load.argtypes = [vp, C.c_char_p, C.c_char_p, C.POINTER(vp)]
@@ -337,6 +338,10 @@ class Index:
         df_global = np.ascontiguousarray(df_global, np.uint32)
         check(self._L.krag_index_commit_global(self._h, vocab, ptr(df_global), n_docs_global, total_len_global,
                                                ordinal_base))
+
+    def set_ordinal_map(self, base: int, stride: int):
+        """global ordinal of local row r = base + r * stride (round-robin shards: base = shard, stride = n_shards)"""
+        check(self._L.krag_index_set_ordinal_map(self._h, base, stride))
 
     def stats(self) -> Stats:
         s = Stats()

@@ -170,7 +170,7 @@ struct krag_index {
     bool committed = false;
     int64_t committed_rows = 0;
     int64_t vocab = 0, n_docs_global = 0, total_len_global = 0;
-    int64_t ord_base = 0;
+    int64_t ord_base = 0, ord_stride = 1;   // global ordinal of local row r = ord_base + r * ord_stride
 };
 
 namespace {
@@ -196,6 +196,8 @@ struct SlotLease {
 };
 
 const uint32_t* alive_ptr(const krag_index* ix) { return ix->has_dead ? ix->alive_d.p : nullptr; }
+OrdMap ord_map(const krag_index* ix) { return OrdMap{(uint32_t)ix->ord_base, (uint32_t)ix->ord_stride}; }
+int64_t ord_last(const krag_index* ix) { return ix->ord_base + (ix->n_rows > 0 ? (ix->n_rows - 1) * ix->ord_stride : 0); }
 
 void check_P(int P) { KRAG_REQUIRE(P >= 1 && P <= KRAG_MAX_POOL, KRAG_E_INVALID, "candidate pool must be in [1, 1024]"); }
 
@@ -209,7 +211,7 @@ void dense_candidates_dev(krag_index* ix, Slot* s, const float* d_q, int batch, 
         KRAG_CUDA(cudaMemsetAsync(d_keys, 0xFF, sizeof(uint64_t) * (size_t)batch * P, st));
         return;
     }
-    KRAG_REQUIRE(ix->ord_base + ix->n_rows <= 0xFFFFFFFFll, KRAG_E_UNSUPPORTED, "global ordinal exceeds 32 bits");
+    KRAG_REQUIRE(ord_last(ix) < 0xFFFFFFFFll, KRAG_E_UNSUPPORTED, "global ordinal exceeds 32 bits");
     s->part.reserve((int64_t)dense_scan_part_elems(c->di, P), 0, st);
     int mode = c->cfg.dense_mode;
     bool use_tc = (mode == KRAG_DENSE_TC) || (mode == KRAG_DENSE_TC_TF32) || (mode == KRAG_DENSE_TC_BF16 && dense_tc_wants(ix->n_rows, batch)) ||
@@ -218,12 +220,12 @@ void dense_candidates_dev(krag_index* ix, Slot* s, const float* d_q, int batch, 
         size_t ws = dense_tc_workspace_bytes(c->di, ix->n_rows, P);
         s->tc_ws.reserve((int64_t)ws, 0, st);
         if (launch_dense_tc(c->di, ix->X.p, ix->n_rows, ix->dpad, alive, ix->xnorm.p, ix->xn_max.p, d_q, batch, P,
-                            (uint32_t)ix->ord_base, s->tc_ws.p, ws, s->part.p, d_keys, st,
+                            ord_map(ix), s->tc_ws.p, ws, s->part.p, d_keys, st,
                             mode == KRAG_DENSE_TC_BF16 ? ix->Xh.p : nullptr, mode != KRAG_DENSE_TC_TF32))
             return;
     }
     KRAG_REQUIRE((mode != KRAG_DENSE_TC && mode != KRAG_DENSE_TC_TF32) || !dense_tc_wants(ix->n_rows, 16), KRAG_E_UNSUPPORTED, "tensor-core dense path unavailable for this index/device");
-    launch_dense_scan(c->di, ix->X.p, ix->n_rows, ix->dpad, alive, d_q, batch, P, (uint32_t)ix->ord_base,
+    launch_dense_scan(c->di, ix->X.p, ix->n_rows, ix->dpad, alive, d_q, batch, P, ord_map(ix),
                       s->part.p, d_keys, st);
 }
 
@@ -240,7 +242,7 @@ void bm25_candidates_dev(krag_index* ix, Slot* s, const uint32_t* d_terms, const
     s->part.reserve((int64_t)bm25_part_elems(ix->committed_rows, batch, P), 0, st);
     s->bm25_res.reserve((int64_t)bm25_resolve_bytes(ix->committed_rows, n_terms_total), 0, st);
     launch_bm25(ix->ctx->di, ix->post, ix->committed_rows, eligible ? eligible : alive_ptr(ix), d_terms, d_toff, n_terms_total, s->bm25_res.p, batch, P,
-                (uint32_t)ix->ord_base, s->part.p, d_keys, st);
+                ord_map(ix), s->part.p, d_keys, st);
 }
 
 // stage padded queries on the device
@@ -330,7 +332,7 @@ void commit_global_impl(krag_index* ix, int64_t vocab, const uint32_t* df_global
                         int64_t total_len_global, int64_t ord_base)
 {
     cudaStream_t st = ix->ctx->admin;
-    KRAG_REQUIRE(ord_base >= 0 && ord_base + ix->n_rows <= 0xFFFFFFFFll, KRAG_E_UNSUPPORTED, "global ordinal exceeds 32 bits");
+    KRAG_REQUIRE(ord_base >= 0 && ord_base + ix->n_rows * ix->ord_stride <= 0xFFFFFFFFll, KRAG_E_UNSUPPORTED, "global ordinal exceeds 32 bits");
     // n_docs_global == 0 is legal: every document deleted (the reference's docstore is then empty and its retriever
     // falls back to vector-only, hybrid_retriever.py:113-121); the postings come out empty and avgdl is irrelevant
     KRAG_REQUIRE(n_docs_global >= 0 && total_len_global >= 0, KRAG_E_INVALID, "n_docs_global / total_len_global must be >= 0");
@@ -597,6 +599,16 @@ int32_t krag_index_commit(krag_index* ix, int64_t vocab)
     });
 }
 
+int32_t krag_index_set_ordinal_map(krag_index* ix, int64_t ordinal_base, int64_t ordinal_stride)
+{
+    return guarded([&] {
+        KRAG_REQUIRE(ix && ordinal_base >= 0 && ordinal_stride >= 1 && ordinal_stride <= 64, KRAG_E_INVALID, "bad argument");
+        std::unique_lock<std::shared_mutex> lk(ix->mu);
+        KRAG_REQUIRE(ordinal_base + ix->n_rows * ordinal_stride <= 0xFFFFFFFFll, KRAG_E_UNSUPPORTED, "global ordinal exceeds 32 bits");
+        ix->ord_base = ordinal_base; ix->ord_stride = ordinal_stride;
+    });
+}
+
 int32_t krag_index_stats(krag_index* ix, krag_stats_t* out)
 {
     return guarded([&] {
@@ -618,8 +630,10 @@ int32_t krag_index_node_ids(krag_index* ix, int64_t n, const int64_t* ordinals, 
         KRAG_REQUIRE(ix && (n == 0 || (ordinals && out)), KRAG_E_INVALID, "null argument");
         std::shared_lock<std::shared_mutex> lk(ix->mu);
         for (int64_t i = 0; i < n; ++i) {
-            int64_t r = ordinals[i] - ix->ord_base;
-            KRAG_REQUIRE(r >= 0 && r < ix->n_rows, KRAG_E_NOT_FOUND, "ordinal is not held by this shard");
+            const int64_t off = ordinals[i] - ix->ord_base;
+            KRAG_REQUIRE(off >= 0 && off % ix->ord_stride == 0, KRAG_E_NOT_FOUND, "ordinal is not held by this shard");
+            const int64_t r = off / ix->ord_stride;
+            KRAG_REQUIRE(r < ix->n_rows, KRAG_E_NOT_FOUND, "ordinal is not held by this shard");
             out[i] = ix->node_ids[(size_t)r];
         }
     });
@@ -718,7 +732,7 @@ int32_t krag_retrieve(krag_index* ix, int32_t batch, const float* q, const uint3
             if (keyword_allow_bitmap && !pushdown) {
                 // bitmap is over local rows; fuse tests global ordinals -> shift by ord_base words is only
                 // valid when ord_base % 32 == 0; the host path is single-shard (ord_base == 0)
-                KRAG_REQUIRE(ix->ord_base == 0, KRAG_E_UNSUPPORTED, "keyword filter on host path requires ordinal_base 0");
+                KRAG_REQUIRE(ix->ord_base == 0 && ix->ord_stride == 1, KRAG_E_UNSUPPORTED, "keyword filter on host path requires ordinal_base 0, stride 1");
                 int64_t words = (ix->n_rows + 31) / 32;
                 s->allow.reserve(words, 0, st);
                 KRAG_CUDA(cudaMemcpyAsync(s->allow.p, keyword_allow_bitmap, sizeof(uint32_t) * (size_t)words, cudaMemcpyHostToDevice, st));
@@ -823,7 +837,7 @@ int32_t krag_synth_fill(krag_index* ix, int64_t n, int64_t row_base, uint64_t se
         KRAG_CUDA(cudaStreamSynchronize(st));
         ix->node_ids.resize((size_t)n);
         for (int64_t i = 0; i < n; ++i) { ix->node_ids[(size_t)i] = (uint64_t)(row_base + i); ix->id2row[(uint64_t)(row_base + i)] = i; }
-        ix->n_rows = n; ix->n_live = n; ix->ord_base = row_base; ix->committed = false;
+        ix->n_rows = n; ix->n_live = n; ix->ord_base = row_base; ix->ord_stride = 1; ix->committed = false;
     });
 }
 

@@ -14,6 +14,8 @@
 // = the algorithmic traffic), terms are applied one after another (doc ids are unique
 // inside a term, so no atomics and a fixed fp32 summation order), and the top-P select
 // runs over shared memory.
+#include <math_constants.h>
+
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -282,7 +284,7 @@ bm25_tile_kernel(const int64_t* __restrict__ post_off, const uint32_t* __restric
                  const uint32_t* __restrict__ tile_off, int64_t n_tiles_idx, int64_t vocab,
                  const uint32_t* __restrict__ q_terms, const int32_t* __restrict__ q_term_offsets,
                  const int32_t* __restrict__ q_slot, const int64_t* __restrict__ q_base, const int32_t* __restrict__ q_rare_len,
-                 int64_t n_rows, const uint32_t* __restrict__ alive, int P, int cap, uint32_t ord_base, int batch, int n_tiles, int group,
+                 int64_t n_rows, const uint32_t* __restrict__ alive, int P, int cap, OrdMap ord_base, int batch, int n_tiles, int group,
                  uint64_t* __restrict__ part /*[batch][n_groups][P]*/, unsigned long long* __restrict__ g_thr /*[batch]*/,
                  const uint32_t* __restrict__ only_flag /* != null: only queries whose flag is set */)
 {
@@ -526,10 +528,12 @@ bm25_tile_kernel(const int64_t* __restrict__ post_off, const uint32_t* __restric
 // postings) have theirs in the persistent tile index; for the others bm25_resolve_kernel builds the row per batch from
 // the term's <= 2048 document ids (binary searches out of shared memory).
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int BW_WARPS = 4;                 // warps per CTA: 4 x 16 KB accumulators, 3 CTAs per SM
+constexpr int BW_WARPS = 5;                 // warps per CTA: 5 x (16 KB accumulators + 4 KB staging), 2 CTAs per SM
 constexpr int BW_THREADS = BW_WARPS * 32;
 constexpr int BW_CHUNK = 8;                 // consecutive (sampled) sub-tiles of one query per work unit
-constexpr int BW_ROUNDS = 16;               // 32-posting rounds of a sub-tile held in registers
+constexpr int BW_STAGE_ROUNDS = 8;          // 32-posting rounds per staging buffer (double-buffered)
+constexpr int BW_STAGE_WORDS = BW_STAGE_ROUNDS * 32 * 2;           // docs[8][32] | scores[8][32]
+constexpr int BW_WARP_WORDS = BM25_SUB_DOCS + 2 * BW_STAGE_WORDS;  // per-warp shared memory, 4-byte words (20 KB)
 
 // once per batch and query-term position: posting base, boundary row, and the legacy kernel's (slot, rare length)
 __global__ void __launch_bounds__(256)
@@ -569,119 +573,131 @@ bm25_resolve_kernel(const uint32_t* __restrict__ q_terms, int n_terms, const int
 
 struct BwCtx {
     const uint32_t* post_doc; const float* post_score; float* acc; const uint32_t* alive;
-    unsigned long long* cand_q; uint32_t* cnt_q; unsigned long long thr; uint32_t t0, ord_base; int capq, lane;
+    unsigned long long* cand_q; uint32_t* cnt_q; unsigned long long thr; float thr_score;
+    uint32_t t0; OrdMap ord_base; int64_t n_rows; int capq, lane;
 };
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// rounds [u0, u0 + BW_ROUNDS) of the flattened (term, 32-posting round) sequence of one sub-tile -> registers.
-// Lane j < nt holds term j's (start, len, rounds, exclusive round prefix).
-template <bool kScores>
-__device__ __forceinline__ void bw_load_block(const BwCtx& c, int u0, int R, int64_t my_start, int my_len, int rj, int pre,
-                                              uint32_t (&d)[BW_ROUNDS], float (&sc)[BW_ROUNDS])
+// cursor over the (term, 32-posting round) sequence of one sub-tile; lane j < nt holds term j's posting range
+struct BwCursor {
+    int64_t my_start; int my_len; int nt;
+    int j, r;                 // next round to issue: term j, round r of that term
+    int R, issued;            // rounds of the sub-tile / rounds staged so far
+    uint32_t t0;
+};
+__device__ __forceinline__ void bw_cursor_reset(BwCursor& cur, int64_t my_start, int my_len, int nt, uint32_t t0)
 {
+    cur.my_start = my_start; cur.my_len = my_len; cur.nt = nt; cur.j = 0; cur.r = 0; cur.issued = 0; cur.t0 = t0;
+    int rj = (my_len + 31) >> 5;
 #pragma unroll
-    for (int u = 0; u < BW_ROUNDS; ++u) {
-        d[u] = 0xFFFFFFFFu; sc[u] = 0.f;
-        const int g = u0 + u;
-        if (g < R) {                                                      // warp-uniform
-            const unsigned m = __ballot_sync(0xffffffffu, pre <= g && g < pre + rj);   // exactly one term owns round g
-            const int j = __ffs(m) - 1;
-            const int64_t st = __shfl_sync(0xffffffffu, my_start, j);
-            const int ln = __shfl_sync(0xffffffffu, my_len, j);
-            const int pj = __shfl_sync(0xffffffffu, pre, j);
-            const int idx = (g - pj) * 32 + c.lane;
-            if (idx < ln) {
-                d[u] = __ldg(c.post_doc + st + idx);
-                if (kScores) sc[u] = __ldg(c.post_score + st + idx);
-            }
+    for (int o = 16; o > 0; o >>= 1) rj += __shfl_xor_sync(0xffffffffu, rj, o);
+    cur.R = rj;
+}
+// Stage (cp.async: the loads of all rounds are in flight together and nobody waits for them here) up to BW_STAGE_ROUNDS
+// rounds at the cursor: docs[round][lane] | scores[round][lane]; lanes past the end of a term's list get doc = ~0.
+__device__ __forceinline__ int bw_issue(const BwCtx& c, BwCursor& cur, uint32_t* buf)
+{
+    int n = 0;
+#pragma unroll 1
+    while (n < BW_STAGE_ROUNDS && cur.j < cur.nt) {
+        const int len = __shfl_sync(0xffffffffu, cur.my_len, cur.j);
+        const int base = cur.r * 32;
+        if (base >= len) { ++cur.j; cur.r = 0; continue; }               // term exhausted (or empty): next term
+        const int64_t st = __shfl_sync(0xffffffffu, cur.my_start, cur.j);
+        const int idx = base + c.lane;
+        uint32_t* dd = buf + n * 32 + c.lane;
+        if (idx < len) {
+            cp_async4(dd, c.post_doc + st + idx);
+            cp_async4(dd + BW_STAGE_ROUNDS * 32, c.post_score + st + idx);
+        } else {
+            *dd = 0xFFFFFFFFu;
         }
+        ++n; ++cur.r;
+    }
+    cur.issued += n;
+    cp_async_commit();
+    return n;
+}
+// acc[doc] += score for the staged rounds, one round after the other: rounds follow the query-term order, documents are
+// unique inside a term (no two lanes of a round collide) and a __syncwarp() separates the rounds, so every document's
+// fp32 sum is built in the oracle's order
+__device__ __forceinline__ void bw_accumulate(const BwCtx& c, const uint32_t* buf, int n)
+{
+#pragma unroll 1
+    for (int u = 0; u < n; ++u) {
+        const uint32_t d = buf[u * 32 + c.lane];
+        const uint32_t rel = d - c.t0;
+        if (d != 0xFFFFFFFFu && rel < (uint32_t)BM25_SUB_DOCS) c.acc[rel] += __uint_as_float(buf[BW_STAGE_ROUNDS * 32 + u * 32 + c.lane]);
+        __syncwarp();
     }
 }
-__device__ __forceinline__ void bw_accum_block(const BwCtx& c, int u0, int R, const uint32_t (&d)[BW_ROUNDS], const float (&sc)[BW_ROUNDS])
+// All terms of the sub-tile are in: sweep the accumulators (vectorised, conflict-free), reset what was touched and append
+// the documents that pass the query's admission threshold to its candidate list (warp-aggregated: one atomic per hit group)
+__device__ __forceinline__ void bw_claim_scan(const BwCtx& c)
 {
+    float4* acc4 = reinterpret_cast<float4*>(c.acc);
+#pragma unroll 2
+    for (int k = 0; k < BM25_SUB_DOCS / 128; ++k) {
+        const int slot = k * 32 + c.lane;
+        const float4 v = acc4[slot];
+        const bool nz = (v.x != 0.f) | (v.y != 0.f) | (v.z != 0.f) | (v.w != 0.f);     // scores are positive: touched <=> nonzero
+        if (nz) acc4[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const bool maybe = nz && ((v.x >= c.thr_score) | (v.y >= c.thr_score) | (v.z >= c.thr_score) | (v.w >= c.thr_score));
+        if (!__any_sync(0xffffffffu, maybe)) continue;
+        const float comp[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int u = 0; u < BW_ROUNDS; ++u) {
-        if (u0 + u < R) {
-            const uint32_t rel = d[u] - c.t0;
-            if (d[u] != 0xFFFFFFFFu && rel < (uint32_t)BM25_SUB_DOCS) c.acc[rel] += sc[u];
-            __syncwarp();                  // the next round may belong to the next term and touch the same document
-        }
-    }
-}
-__device__ __forceinline__ void bw_claim_block(const BwCtx& c, int u0, int R, const uint32_t (&d)[BW_ROUNDS])
-{
-#pragma unroll
-    for (int u = 0; u < BW_ROUNDS; ++u) {
-        if (u0 + u < R) {
+        for (int e = 0; e < 4; ++e) {
             bool hit = false;
             unsigned long long key = 0;
-            const uint32_t rel = d[u] - c.t0;
-            if (d[u] != 0xFFFFFFFFu && rel < (uint32_t)BM25_SUB_DOCS) {
-                const float sum = atomicExch(&c.acc[rel], 0.f);           // first claimer takes the final score
-                if (sum > 0.f && (c.alive == nullptr || bit_test(c.alive, d[u]))) {
-                    key = make_key_desc(sum, c.ord_base + d[u]);
+            if (maybe && comp[e] > 0.f && comp[e] >= c.thr_score) {
+                const uint32_t row = c.t0 + (uint32_t)(slot * 4 + e);
+                if ((int64_t)row < c.n_rows && (c.alive == nullptr || bit_test(c.alive, row))) {
+                    key = make_key_desc(comp[e], c.ord_base + row);
                     hit = key <= c.thr;
                 }
             }
             const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (m) {                                                       // one atomic per round and warp
+            if (m) {
                 const int leader = __ffs(m) - 1;
                 uint32_t base_slot = 0;
                 if (c.lane == leader) base_slot = atomicAdd(c.cnt_q, (uint32_t)__popc(m));
                 base_slot = __shfl_sync(0xffffffffu, base_slot, leader);
                 if (hit) {
-                    const uint32_t slot = base_slot + (uint32_t)__popc(m & ((1u << c.lane) - 1u));
-                    if (slot < (uint32_t)c.capq) c.cand_q[slot] = key;     // past capq: counted, dropped -> overflow flag
+                    const uint32_t at = base_slot + (uint32_t)__popc(m & ((1u << c.lane) - 1u));
+                    if (at < (uint32_t)c.capq) c.cand_q[at] = key;        // past capq: counted, dropped -> overflow flag
                 }
             }
         }
     }
+    __syncwarp();
 }
 
-// one phase (accumulate / claim) of one term chunk of one sub-tile
-template <bool kClaim>
-__device__ __forceinline__ void bw_phase(const BwCtx& c, int64_t my_start, int my_len, bool single_block_claim_from_regs,
-                                         uint32_t (&d)[BW_ROUNDS], float (&sc)[BW_ROUNDS], int& R_out)
-{
-    const int rj = (my_len + 31) >> 5;
-    int pre = rj;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, pre, o); if (c.lane >= o) pre += v; }
-    const int R = __shfl_sync(0xffffffffu, pre, 31);
-    pre -= rj;
-    R_out = R;
-    if (!kClaim) {
-        for (int u0 = 0; u0 < R; u0 += BW_ROUNDS) {
-            bw_load_block<true>(c, u0, R, my_start, my_len, rj, pre, d, sc);
-            bw_accum_block(c, u0, R, d, sc);
-        }
-    } else {
-        if (single_block_claim_from_regs) { bw_claim_block(c, 0, R, d); return; }
-        for (int u0 = 0; u0 < R; u0 += BW_ROUNDS) {
-            bw_load_block<false>(c, u0, R, my_start, my_len, rj, pre, d, sc);
-            bw_claim_block(c, u0, R, d);
-        }
-    }
-}
-
-__global__ void __launch_bounds__(BW_THREADS, 3)
+__global__ void __launch_bounds__(BW_THREADS, 2)
 bm25_warp_kernel(const uint32_t* __restrict__ post_doc, const float* __restrict__ post_score,
                  const int32_t* __restrict__ q_term_offsets, const uint32_t* const* __restrict__ q_row,
-                 const int64_t* __restrict__ q_base, int64_t n_rows, const uint32_t* __restrict__ alive, uint32_t ord_base,
+                 const int64_t* __restrict__ q_base, int64_t n_rows, const uint32_t* __restrict__ alive, OrdMap ord_base,
                  int batch, int n_s /* sub-tiles visited */, int stride /* every stride-th sub-tile */,
                  const unsigned long long* __restrict__ thr_q /* null: admit everything */, unsigned long long* __restrict__ cand,
                  uint32_t* __restrict__ cand_cnt, int capq, unsigned long long* __restrict__ unit_counter)
 {
-    extern __shared__ __align__(16) float bw_acc[];                        // [BW_WARPS][BM25_SUB_DOCS]
+    extern __shared__ __align__(16) uint32_t bw_smem[];                    // [BW_WARPS][accumulators | staging x 2]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* acc = bw_acc + (size_t)warp * BM25_SUB_DOCS;
+    uint32_t* wbase = bw_smem + (size_t)warp * BW_WARP_WORDS;
+    float* acc = reinterpret_cast<float*>(wbase);
+    uint32_t* stage = wbase + BM25_SUB_DOCS;
     for (int i = lane; i < BM25_SUB_DOCS / 4; i += 32) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncwarp();                                                          // zeroed once: the claim step resets what it touches
+    __syncwarp();                                                          // zeroed once: the claim sweep resets what was touched
 
     const int n_chunks = (n_s + BW_CHUNK - 1) / BW_CHUNK;
     const long long n_units = (long long)n_chunks * batch;
     BwCtx c;
     c.post_doc = post_doc; c.post_score = post_score; c.acc = acc; c.alive = alive; c.ord_base = ord_base; c.capq = capq; c.lane = lane;
-    uint32_t d[BW_ROUNDS]; float sc[BW_ROUNDS];
+    c.n_rows = n_rows;
     for (;;) {
         unsigned long long unit = 0;
         if (lane == 0) unit = atomicAdd(unit_counter, 1ull);               // dynamic: units differ a lot in postings
@@ -691,51 +707,77 @@ bm25_warp_kernel(const uint32_t* __restrict__ post_doc, const float* __restrict_
         const int tb = q_term_offsets[q], te = q_term_offsets[q + 1];
         if (te <= tb) continue;
         c.thr = thr_q ? thr_q[q] : KEY_PAD;
+        c.thr_score = (c.thr == KEY_PAD) ? -CUDART_INF_F : key_value_desc(c.thr);
         c.cand_q = cand + (size_t)q * capq; c.cnt_q = cand_cnt + q;
         const int s0 = ch * BW_CHUNK, ns = min(BW_CHUNK, n_s - s0);
         if (te - tb <= 32) {
-            // common case: every term of the query lives in one lane; the boundary offsets of the whole chunk are
-            // fetched at once (independent loads), then the sub-tiles run without further index reads
+            // common case: every term of the query lives in one lane; the boundary offsets of the whole chunk are fetched
+            // at once (independent loads).  Then a two-deep pipeline of staged blocks runs across the chunk's sub-tiles:
+            // while block k is accumulated, block k + 1 (same or next sub-tile) is already in flight.
+            const int nt = te - tb;
             const uint32_t* row = nullptr; int64_t base = 0;
-            if (lane < te - tb) { row = q_row[tb + lane]; base = q_base[tb + lane]; }
+            if (lane < nt) { row = q_row[tb + lane]; base = q_base[tb + lane]; }
             uint32_t olo[BW_CHUNK], ohi[BW_CHUNK];
 #pragma unroll
             for (int i = 0; i < BW_CHUNK; ++i) {
                 olo[i] = 0; ohi[i] = 0;
                 if (row != nullptr && i < ns) { const int64_t sub = (int64_t)(s0 + i) * stride; olo[i] = row[sub]; ohi[i] = row[sub + 1]; }
             }
-#pragma unroll 1
-            for (int i = 0; i < ns; ++i) {
-                uint32_t lo = 0, hi = 0;
+            BwCursor cur;
+            cur.R = 0; cur.issued = 0; cur.nt = 0; cur.j = 0; cur.r = 0; cur.my_len = 0; cur.my_start = 0; cur.t0 = 0;
+            int ii = -1;                                                   // sub-tile of the issue cursor
+            int buf = 0;
+            int nb_n = 0; uint32_t nb_t0 = 0; bool nb_last = false;        // block in flight
+            // stage the next block (advancing over empty sub-tiles); false at the end of the unit
+            auto next_block = [&](uint32_t* dst) -> bool {
+                for (;;) {
+                    if (cur.issued < cur.R) {
+                        nb_n = bw_issue(c, cur, dst);
+                        nb_t0 = cur.t0; nb_last = (cur.issued == cur.R);
+                        return true;
+                    }
+                    if (++ii >= ns) return false;
+                    uint32_t lo = 0, hi = 0;
 #pragma unroll
-                for (int k = 0; k < BW_CHUNK; ++k) if (k == i) { lo = olo[k]; hi = ohi[k]; }
-                c.t0 = (uint32_t)((int64_t)(s0 + i) * stride * BM25_SUB_DOCS);
-                const int64_t my_start = base + lo; const int my_len = (int)(hi - lo);
-                int R = 0;
-                bw_phase<false>(c, my_start, my_len, false, d, sc, R);
-                if (R == 0) continue;
+                    for (int k = 0; k < BW_CHUNK; ++k) if (k == ii) { lo = olo[k]; hi = ohi[k]; }
+                    bw_cursor_reset(cur, base + lo, (int)(hi - lo), nt, (uint32_t)((int64_t)(s0 + ii) * stride * BM25_SUB_DOCS));
+                }
+            };
+            bool have = next_block(stage);
+            while (have) {
+                const int cb_n = nb_n; const uint32_t cb_t0 = nb_t0; const bool cb_last = nb_last;
+                const uint32_t* cbuf = stage + buf * BW_STAGE_WORDS;
+                buf ^= 1;
+                have = next_block(stage + buf * BW_STAGE_WORDS);
+                if (have) cp_async_wait<1>(); else cp_async_wait<0>();
                 __syncwarp();
-                bw_phase<true>(c, my_start, my_len, R <= BW_ROUNDS, d, sc, R);
-                __syncwarp();                                              // accumulators are zero again before the next sub-tile
+                c.t0 = cb_t0;
+                bw_accumulate(c, cbuf, cb_n);
+                if (cb_last) bw_claim_scan(c);
             }
         } else {
-            // long queries: term chunks of 32; ALL chunks are accumulated (in query order) before any document is claimed
+            // long queries: term chunks of 32; ALL chunks are accumulated (in query order) before the claim sweep
             for (int i = 0; i < ns; ++i) {
                 const int64_t sub = (int64_t)(s0 + i) * stride;
                 c.t0 = (uint32_t)(sub * BM25_SUB_DOCS);
-                for (int phase = 0; phase < 2; ++phase) {
-                    for (int c0 = tb; c0 < te; c0 += 32) {
-                        int64_t my_start = 0; int my_len = 0;
-                        if (lane < te - c0) {
-                            const uint32_t* row = q_row[c0 + lane];
-                            if (row != nullptr) { const uint32_t lo = row[sub], hi = row[sub + 1]; my_start = q_base[c0 + lane] + lo; my_len = (int)(hi - lo); }
-                        }
-                        int R = 0;
-                        if (phase == 0) bw_phase<false>(c, my_start, my_len, false, d, sc, R);
-                        else bw_phase<true>(c, my_start, my_len, false, d, sc, R);
+                bool touched = false;
+                for (int c0 = tb; c0 < te; c0 += 32) {
+                    int64_t my_start = 0; int my_len = 0;
+                    if (lane < te - c0) {
+                        const uint32_t* row = q_row[c0 + lane];
+                        if (row != nullptr) { const uint32_t lo = row[sub], hi = row[sub + 1]; my_start = q_base[c0 + lane] + lo; my_len = (int)(hi - lo); }
+                    }
+                    BwCursor cur;
+                    bw_cursor_reset(cur, my_start, my_len, min(32, te - c0), c.t0);
+                    while (cur.issued < cur.R) {
+                        const int n = bw_issue(c, cur, stage);
+                        cp_async_wait<0>();
                         __syncwarp();
+                        bw_accumulate(c, stage, n);
+                        touched = true;
                     }
                 }
+                if (touched) bw_claim_scan(c);
             }
         }
     }
@@ -840,7 +882,7 @@ size_t bm25_resolve_bytes(int64_t n_rows, int n_terms_total)
 
 void launch_bm25(const DeviceInfo& di, const Postings& post, int64_t n_rows, const uint32_t* alive,
                  const uint32_t* q_terms, const int32_t* q_term_offsets, int n_terms_total, void* resolve_ws, int batch, int P,
-                 uint32_t ord_base, uint64_t* part, uint64_t* keys_out, cudaStream_t st)
+                 OrdMap ord_base, uint64_t* part, uint64_t* keys_out, cudaStream_t st)
 {
     const size_t nt = (size_t)(n_terms_total > 0 ? n_terms_total : 1);
     const int64_t n_sub = post.n_tiles;
@@ -869,7 +911,7 @@ void launch_bm25(const DeviceInfo& di, const Postings& post, int64_t n_rows, con
 
     if (!legacy_only) {
         static bool attr_set = false;
-        const size_t smem = (size_t)BW_WARPS * BM25_SUB_DOCS * 4;
+        const size_t smem = (size_t)BW_WARPS * BW_WARP_WORDS * 4;
         if (!attr_set) {
             KRAG_CUDA(cudaFuncSetAttribute(bm25_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr_set = true;
@@ -880,7 +922,7 @@ void launch_bm25(const DeviceInfo& di, const Postings& post, int64_t n_rows, con
             const int n_s = (int)((n_sub + stride - 1) / stride);
             const long long units = (long long)((n_s + BW_CHUNK - 1) / BW_CHUNK) * batch;
             const long long want = (units + BW_WARPS - 1) / BW_WARPS;
-            const long long max_grid = 3LL * di.sm_count;
+            const long long max_grid = 2LL * di.sm_count;
             const int grid = (int)(want < max_grid ? (want > 0 ? want : 1) : max_grid);
             bm25_warp_kernel<<<grid, BW_THREADS, smem, st>>>(post.doc, post.score, q_term_offsets, q_row, q_base, n_rows, alive, ord_base,
                                                              batch, n_s, stride, thr, cand, cand_cnt, L.capq, counter);

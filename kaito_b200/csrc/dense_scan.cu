@@ -25,7 +25,7 @@ constexpr int DS_TILE_ROWS = DS_WARPS * DS_ROWS_PER_WARP;  // 64 rows per CTA it
 template <int NQ>
 __global__ void __launch_bounds__(DS_THREADS, 2)
 dense_scan_kernel(const float* __restrict__ X, int64_t n_rows, int dpad, const uint32_t* __restrict__ alive,
-                  const float* __restrict__ Q, int P, int cap, int epoch_iters, uint32_t ord_base,
+                  const float* __restrict__ Q, int P, int cap, int epoch_iters, OrdMap ord_base,
                   uint64_t* __restrict__ part /*[NQ][gridDim.x][P]*/, unsigned long long* __restrict__ g_thr /*[NQ]*/)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -132,7 +132,7 @@ size_t dense_scan_part_elems(const DeviceInfo& di, int P) { return (size_t)4 * 2
 
 template <int NQ>
 static void ds_launch(const DeviceInfo& di, const float* X, int64_t n_rows, int dpad, const uint32_t* alive,
-                      const float* q, int P, uint32_t ord_base, uint64_t* part, unsigned long long* g_thr, cudaStream_t st)
+                      const float* q, int P, OrdMap ord_base, uint64_t* part, unsigned long long* g_thr, cudaStream_t st)
 {
     const int cap = ds_cap(P);
     const int epoch = (cap - P) / DS_TILE_ROWS > 0 ? (cap - P) / DS_TILE_ROWS : 1;
@@ -152,7 +152,7 @@ static void ds_launch(const DeviceInfo& di, const float* X, int64_t n_rows, int 
 }
 
 void launch_dense_scan(const DeviceInfo& di, const float* X, int64_t n_rows, int dpad, const uint32_t* alive,
-                       const float* q, int batch, int P, uint32_t ord_base, uint64_t* part, uint64_t* keys_out,
+                       const float* q, int batch, int P, OrdMap ord_base, uint64_t* part, uint64_t* keys_out,
                        cudaStream_t st)
 {
     const int grid = ds_grid(di, n_rows);

@@ -761,7 +761,7 @@ sample_threshold_kernel(const float* __restrict__ dump, int64_t S, int m, int nq
 // one 8-lane group per candidate; same arithmetic as dense_scan_kernel / oracle l2sq_row
 __global__ void __launch_bounds__(256)
 rescore_kernel(const float* __restrict__ X, int dpad, const float* __restrict__ Q, const uint32_t* __restrict__ cand_count,
-               const uint32_t* __restrict__ cand_rows, int cap, uint32_t ord_base, uint64_t* __restrict__ exact_keys)
+               const uint32_t* __restrict__ cand_rows, int cap, OrdMap ord_base, uint64_t* __restrict__ exact_keys)
 {
     extern __shared__ __align__(16) float rs_q[];   // [dpad]
     const int j = blockIdx.y, tid = threadIdx.x, lane = tid & 31, l8 = lane & 7;
@@ -905,7 +905,7 @@ static bool tc_use_2cta()
 template <int NQ>
 static void tc_pass(const DeviceInfo& di, const CUtensorMap& tmX, const CUtensorMap& tmQ, const float* X, int64_t n_rows,
                     int dpad, const float* xnorm, const uint32_t* xn_max_bits, const uint32_t* alive, const float* q,
-                    int nq, int P, uint32_t ord_base, const TcWorkspace& w, int cap, int64_t S, uint64_t* keys_out,
+                    int nq, int P, OrdMap ord_base, const TcWorkspace& w, int cap, int64_t S, uint64_t* keys_out,
                     const uint16_t* Xh, bool cvt, cudaStream_t st)
 {
     using Cfg = TcCfg<NQ>;
@@ -1043,7 +1043,7 @@ static std::atomic<int64_t> g_tc_fallback_queries{0};   // searches run concurre
 int64_t dense_tc_fallback_queries() { return g_tc_fallback_queries.load(); }
 
 bool launch_dense_tc(const DeviceInfo& di, const float* X, int64_t n_rows, int dpad, const uint32_t* alive,
-                     const float* xnorm, const uint32_t* xn_max_bits, const float* q, int batch, int P, uint32_t ord_base,
+                     const float* xnorm, const uint32_t* xn_max_bits, const float* q, int batch, int P, OrdMap ord_base,
                      void* workspace, size_t workspace_bytes, uint64_t* part, uint64_t* keys_out, cudaStream_t st,
                      const uint16_t* Xh, bool allow_cvt)
 {

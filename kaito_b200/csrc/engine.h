@@ -5,6 +5,14 @@
 
 namespace krag {
 
+// global ordinal of a local row: base + row * stride.  Contiguous shards (bench, one GPU) use stride 1; the multi-GPU
+// service deals nodes round-robin (node o -> shard o % G, row o / G), so base = shard, stride = G and ordinals -- hence
+// every tie-break -- are exactly the single-GPU insertion order.
+struct OrdMap {
+    uint32_t base, stride;
+    __host__ __device__ __forceinline__ uint32_t operator+(uint32_t row) const { return base + row * stride; }
+};
+
 struct DeviceInfo {
     int device = 0;
     int sm_count = 148;
@@ -27,7 +35,7 @@ int64_t launch_count();
 // keys_out: device [batch, P], ascending, KEY_PAD padded, ordinals already global.
 size_t dense_scan_part_elems(const DeviceInfo& di, int P);
 void launch_dense_scan(const DeviceInfo& di, const float* X, int64_t n_rows, int dpad, const uint32_t* alive,
-                       const float* q, int batch, int P, uint32_t ord_base, uint64_t* part, uint64_t* keys_out,
+                       const float* q, int batch, int P, OrdMap ord_base, uint64_t* part, uint64_t* keys_out,
                        cudaStream_t st);
 
 // ---- K2: tcgen05 TF32 candidate generation + exact fp32 rescoring (dense_tc.cu)
@@ -40,7 +48,7 @@ void launch_row_norms(const float* X, int64_t row0, int64_t n, int dpad, float* 
 // returns false when the tensor-core path cannot serve the request (caller falls back to K1 -- still GPU)
 bool launch_dense_tc(const DeviceInfo& di, const float* X, int64_t n_rows, int dpad, const uint32_t* alive,
                      const float* xnorm, const uint32_t* xn_max_bits, const float* q, int batch, int P,
-                     uint32_t ord_base, void* workspace, size_t workspace_bytes, uint64_t* part, uint64_t* keys_out,
+                     OrdMap ord_base, void* workspace, size_t workspace_bytes, uint64_t* part, uint64_t* keys_out,
                      cudaStream_t st, const uint16_t* Xh = nullptr /* optional bf16 shadow of X for the prune pass */,
                      bool allow_cvt = true /* fp32 rows rounded to bf16 on chip (kind::f16) instead of kind::tf32 */);
 void launch_f32_to_bf16(const float* in, uint16_t* out, int64_t n_elems, cudaStream_t st);
@@ -64,7 +72,7 @@ void launch_p2p_exchange_merge(uint64_t* const* d_mailboxes, uint64_t* own_mailb
 void launch_bitmap_and(uint32_t* dst, const uint32_t* other, int64_t words, cudaStream_t st);
 // append zero-score fillers to short BM25 lists (bm25s argpartition semantics)
 void launch_bm25_fill(uint64_t* keys /*[batch,P]*/, int batch, int P, const uint32_t* alive, int64_t n_rows,
-                      uint32_t ord_base, cudaStream_t st);
+                      OrdMap ord_base, cudaStream_t st);
 void launch_fuse(int batch, int P, int k, const uint64_t* dense_keys, const uint64_t* bm25_keys, double w_v, double w_t,
                  int mode, const uint32_t* allow, double* out_final, float* out_dense, float* out_sparse,
                  int32_t* out_rank, int64_t* out_ord, int32_t* out_count, cudaStream_t st);
@@ -98,7 +106,7 @@ size_t bm25_part_elems(int64_t n_rows, int batch, int P);
 size_t bm25_resolve_bytes(int64_t n_rows, int n_terms_total);   // size of launch_bm25's resolve_ws
 void launch_bm25(const DeviceInfo& di, const Postings& post, int64_t n_rows, const uint32_t* alive,
                  const uint32_t* q_terms, const int32_t* q_term_offsets, int n_terms_total, void* resolve_ws, int batch, int P,
-                 uint32_t ord_base, uint64_t* part, uint64_t* keys_out, cudaStream_t st);
+                 OrdMap ord_base, uint64_t* part, uint64_t* keys_out, cudaStream_t st);
 
 // ---- K5: BERT encoder forward (embed.cu)
 struct BertConfig;

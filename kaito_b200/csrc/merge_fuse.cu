@@ -164,7 +164,7 @@ void launch_bitmap_and(uint32_t* dst, const uint32_t* other, int64_t words, cuda
 // not already in the list (every positive-score document is in it when it is short).
 __global__ void __launch_bounds__(256)
 bm25_fill_kernel(uint64_t* __restrict__ keys, int P, const uint32_t* __restrict__ alive, int64_t n_rows,
-                 uint32_t ord_base)
+                 OrdMap ord_base)
 {
     __shared__ int s_m, s_found;
     uint64_t* k = keys + (int64_t)blockIdx.x * P;
@@ -205,7 +205,7 @@ bm25_fill_kernel(uint64_t* __restrict__ keys, int P, const uint32_t* __restrict_
     }
 }
 
-void launch_bm25_fill(uint64_t* keys, int batch, int P, const uint32_t* alive, int64_t n_rows, uint32_t ord_base,
+void launch_bm25_fill(uint64_t* keys, int batch, int P, const uint32_t* alive, int64_t n_rows, OrdMap ord_base,
                       cudaStream_t st)
 {
     bm25_fill_kernel<<<batch, 256, 0, st>>>(keys, P, alive, n_rows, ord_base);

@@ -110,6 +110,10 @@ class GpuBertEmbedding(BaseEmbeddingModel):
     def get_query_embedding(self, query: str):
         return self.get_text_embedding((self.query_instruction or "") + query)
 
+    def get_query_embedding_batch(self, queries):
+        """one K5 forward for a coalesced batch of queries (kaito_b200.batcher)"""
+        return self.get_text_embedding_batch([(self.query_instruction or "") + q for q in queries])
+
 
 class RemoteEmbeddingModel(BaseEmbeddingModel):
     """`embedding.remote` of the CRD (embedding/remote_embedding.py:24-76): POST {"inputs": text} with a bearer token to

@@ -198,23 +198,37 @@ class HybridRetriever:
         return self._state.allow_bitmap(self._metadata_filter)
 
     def retrieve(self, query: str) -> list[tuple[_Node, float]]:
+        nodes, comps = self.retrieve_batch([query])
+        self.last_components = comps[0]
+        return nodes[0]
+
+    def retrieve_batch(self, queries: list[str]):
+        """`_aretrieve` for a batch of queries that share (index, top_k, filter): ONE embedding forward and ONE engine call.
+        Returns (per query: [(node, fused score)], per query: component dicts)."""
         st = self._state
-        q = np.asarray(self._embed.get_query_embedding(query), np.float32).reshape(1, -1)
+        if hasattr(self._embed, "get_query_embedding_batch"):
+            q = np.asarray(self._embed.get_query_embedding_batch(queries), np.float32).reshape(len(queries), -1)
+        else:
+            q = np.stack([np.asarray(self._embed.get_query_embedding(x), np.float32).reshape(-1) for x in queries])
         # BM25 unavailable (empty docstore / nothing committed) -> vector-only fallback (:113-121, :216-218)
-        terms = [st.vocab.query_terms(query)] if st.committed else None
+        terms = [st.vocab.query_terms(x) for x in queries] if st.committed else None
         allow = self._allow_bitmap() if (terms is not None or self._filter_pushdown) else None
         out = st.index.retrieve(q, terms, self._max_results, cand_mult=self._candidate_multiplier,
                                 vector_weight=self._vector_weight, text_weight=self._text_weight,
                                 fusion_mode=FILTER_PUSHDOWN if (self._filter_pushdown and allow is not None) else 0,
                                 keyword_allow_bitmap=allow)
-        c = int(out["count"][0])
-        self.last_components = []
-        if "dense" in out and "sparse" in out:          # per-result L2^2 / BM25 score as computed by the fuse kernel (NaN = absent)
-            for d, s in zip(out["dense"][0, :c], out["sparse"][0, :c]):
-                hd, hs = not np.isnan(d), not np.isnan(s)
-                self.last_components.append({"dense_score": float(d) if hd else None, "sparse_score": float(s) if hs else None,
-                                             "source": "both" if hd and hs else ("dense_only" if hd else "sparse_only")})
-        return [(st.nodes[int(o)], float(s)) for o, s in zip(out["ordinal"][0, :c], out["final"][0, :c])]
+        all_nodes, all_comps = [], []
+        for b in range(len(queries)):
+            c = int(out["count"][b])
+            comps = []
+            if "dense" in out and "sparse" in out:      # per-result L2^2 / BM25 score as computed by the fuse kernel (NaN = absent)
+                for d, s in zip(out["dense"][b, :c], out["sparse"][b, :c]):
+                    hd, hs = not np.isnan(d), not np.isnan(s)
+                    comps.append({"dense_score": float(d) if hd else None, "sparse_score": float(s) if hs else None,
+                                  "source": "both" if hd and hs else ("dense_only" if hd else "sparse_only")})
+            all_nodes.append([(st.nodes[int(o)], float(s)) for o, s in zip(out["ordinal"][b, :c], out["final"][b, :c])])
+            all_comps.append(comps)
+        return all_nodes, all_comps
 
 
 class VectorStore:
@@ -325,6 +339,39 @@ class VectorStore:
         except HTTPException:
             raise
         except Exception as e:  # same envelope as base.py:972-978
+            raise HTTPException(500, f"Retrieve failed: {e}")
+
+    def retrieve_batch(self, index_name: str, queries: list[str], max_node_count: int = 5, metadata_filter: dict | None = None):
+        """retrieve() for several queries against the same index with the same top_k and filter, answered by one engine call
+        (kaito_b200.batcher coalesces concurrent /retrieve requests into this).  Returns one response dict per query; a
+        blank query yields the reference's 400 for that entry only."""
+        if index_name not in self.index_map:
+            raise HTTPException(404, f"No such index: '{index_name}' exists.")
+        bad = HTTPException(400, "Query string cannot be empty.")
+        live = [i for i, q in enumerate(queries) if q and q.strip() != ""]
+        outs: list = [bad] * len(queries)
+        if not live:
+            return outs
+        try:
+            top_k = min(max_node_count, RAG_MAX_TOP_K)
+            t0 = time.time()
+            with self._rw.reader():
+                st = self.index_map[index_name]
+                retriever = HybridRetriever(st, self.embed_model, max_results=top_k, metadata_filter=metadata_filter,
+                                            filter_pushdown=self.filter_pushdown)
+                nodes, comps = retriever.retrieve_batch([queries[i] for i in live])
+                for j, i in enumerate(live):
+                    results = [{"doc_id": n.ref_doc_id or n.node_id, "node_id": n.node_id, "text": n.text, "score": s,
+                                "metadata": n.metadata if n.metadata else None} for n, s in nodes[j]]
+                    if self.component_scores:
+                        for r, extra in zip(results, comps[j]):
+                            r.update(extra)
+                    outs[i] = {"query": queries[i], "results": results, "count": len(results)}
+            self.last_retrieve_seconds = (time.time() - t0) / len(live)
+            return outs
+        except HTTPException:
+            raise
+        except Exception as e:
             raise HTTPException(500, f"Retrieve failed: {e}")
 
     # ------------------------------------------------- /v1/chat/completions

@@ -9,7 +9,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("M,N,K,gelu,res", [(10, 128, 32, False, False), (300, 384, 384, False, True),
+@pytest.mark.parametrize("M,N,K,gelu,res", [(10, 128, 64, False, False), (300, 384, 384, False, True),
                                            (1000, 1152, 384, False, False), (257, 1536, 384, True, False),
                                            (129, 384, 1536, False, True), (4096, 768, 768, True, True),
                                            # small-M split-K path (128 x 32 tiles, M <= 128; 128 x 64 tiles above)

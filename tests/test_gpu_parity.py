@@ -374,3 +374,34 @@ def test_filter_pushdown_bit_exact(oracle, dense_mode, batch):
         ix.drop()
     finally:
         c.close()
+
+
+def test_strided_ordinal_map(ctx_scan, oracle):
+    """round-robin shards of the multi-GPU service: global ordinal = base + row * stride in every kernel that builds keys
+    (K1, K2 rescoring, K3 claim, zero fill) and back again in krag_index_node_ids"""
+    n, vocab, d, base, stride = 300_000, 3000, 64, 3, 5
+    x = oracle.synth_dense(n, d, 31)
+    off, ids, tf, dl = oracle.synth_sparse(n, vocab, 32)
+    ix = ctx_scan.create_index("strided", d)
+    try:
+        ix.add(np.arange(n, dtype=np.uint64) + 7, x, off, ids, tf, dl)
+        ix.set_ordinal_map(base, stride)
+        ix.commit(vocab)
+        assert ix.stats().ordinal_base == base
+        q = oracle.synth_queries(x, 20, 33)
+        for qq in (q[:3], q):                                   # K1 (batch < 16) and K2 (prune + exact rescoring)
+            dist, ordn = ix.search_dense(qq, 30)
+            rd, ro = oracle.dense_topk(x, qq, 30)
+            assert np.array_equal(ordn, base + stride * ro) and np.array_equal(dist, rd)
+        post = oracle.bm25_build(off, ids, tf, dl, vocab)
+        qs = oracle.synth_query_terms(vocab, 6, seed=34, rank_offset=30)
+        qs[0] = np.array([vocab - 1], np.uint32)                # short list -> zero-score fill
+        score, ordn = ix.search_bm25(qs, 30)
+        for b, qt in enumerate(qs):
+            rs, ro = oracle.bm25_query(post, qt, 30)
+            assert np.array_equal(ordn[b], np.where(ro >= 0, base + stride * ro, -1)) and np.array_equal(score[b], rs)
+        assert np.array_equal(ix.node_ids(ordn[1]), (ordn[1] - base) // stride + 7)
+        with pytest.raises(Exception):
+            ix.node_ids(np.array([base + 1], np.int64))          # not a multiple of the stride: not this shard's
+    finally:
+        ix.drop()

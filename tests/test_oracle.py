@@ -176,3 +176,45 @@ def test_doc_id_is_sha256_hex(oracle):
     assert len(h) == 64 and int(h, 16) >= 0
     import hashlib
     assert h == hashlib.sha256(b"This is a test document").hexdigest()
+
+
+# ------------------------------------------------------------------ third-party pins (present only where the wheels exist)
+GOLD_3P = os.path.join(os.path.dirname(__file__), "golden", "third_party_reference.json")
+
+
+@pytest.mark.skipif(not os.path.exists(GOLD_3P), reason="tests/golden/third_party_reference.json not generated: faiss / bm25s / "
+                    "PyStemmer are not installable offline (run oracle/gen_golden_3p.py where they are)")
+def test_third_party_golden(oracle):
+    """the oracle's restated dense L2^2, BM25 (bm25s lucene) and Snowball stems against outputs of the REAL wheels"""
+    from kaito_b200 import text as T
+    doc = json.load(open(GOLD_3P))
+    sec = doc["sections"]
+    if "pystemmer_english" in sec:
+        s = sec["pystemmer_english"]
+        assert [T.stem(w) for w in s["words"]] == s["stems"]
+    if "faiss_flat_l2" in sec:
+        for c in sec["faiss_flat_l2"]["cases"]:
+            if c["x"] is None:
+                continue
+            x, q = np.array(c["x"], np.float32), np.array(c["q"], np.float32)
+            k = min(c["k"], c["n"])
+            dist, ids = oracle.dense_topk(x, q, k)
+            want_d, want_i = np.array(c["dist"], np.float32)[:, :k], np.array(c["ids"], np.int64)[:, :k]
+            assert np.allclose(dist, want_d, atol=1e-4, rtol=0)            # north_star: scores within 1e-4 fp32
+            # ids equal wherever faiss' own ordering is unambiguous (gap to the neighbours above the fp32 noise)
+            gap = np.minimum(np.abs(np.diff(want_d, axis=1, prepend=-1)), np.abs(np.diff(want_d, axis=1, append=9)))
+            assert np.array_equal(ids[gap > 1e-5], want_i[gap > 1e-5])
+    if "bm25s_lucene" in sec:
+        b = sec["bm25s_lucene"]
+        n, vocab = len(b["corpus_token_ids"]), len(b["vocab"])
+        off, ids, tf, dl = [0], [], [], []
+        for toks in b["corpus_token_ids"]:
+            u, cnt = np.unique(np.array(toks, np.int64), return_counts=True)
+            ids += u.tolist(); tf += cnt.tolist(); off.append(len(ids)); dl.append(len(toks))
+        post = oracle.bm25_build(np.array(off, np.int64), np.array(ids, np.uint32), np.array(tf, np.uint16), np.array(dl, np.uint32), vocab)
+        for qq in b["queries"]:
+            qt = np.array([b["vocab"][t] for t in qq["query_tokens"] if t in b["vocab"]], np.uint32)
+            rs, ro = oracle.bm25_query(post, qt, n)
+            want = dict(zip(qq["doc_ids"], qq["scores"]))
+            for o, s in zip(ro, rs):
+                assert np.float32(want[int(o)]) == np.float32(s), (qq["query"], int(o))     # same fp32 score per document
