@@ -204,6 +204,10 @@ def create_app(store: vs.VectorStore, cfg: dict | None = None, llm=None) -> Fast
     emb_lat, emb_cnt = mx["rag_embedding_latency_seconds"], mx["rag_embedding_requests"]
     emb_mode = "remote" if str(cfg.get("embedding_source", "local")).lower() == "remote" else "local"   # MODE_LOCAL / MODE_REMOTE
     app.state.store, app.state.registry = store, reg
+    # request coalescer (kaito_b200/batcher.py): concurrent /retrieve calls -> one engine call per (index, top_k, filter) group
+    from .batcher import RetrieveBatcher
+    batcher = RetrieveBatcher(store) if hasattr(store, "retrieve_batch") else None
+    app.state.batcher = batcher
 
     TRACKED = ("/index", "/indexes", "/persist", "/load", "/retrieve", "/v1/chat/completions")
 
@@ -263,16 +267,35 @@ def create_app(store: vs.VectorStore, cfg: dict | None = None, llm=None) -> Fast
         return run("index", go)
 
     @app.post("/retrieve", response_model=RetrieveResponse)
-    def retrieve_from_index(request: RetrieveRequest):   # main.py:742-771
-        def go():
-            out = store.retrieve(request.index_name, request.query, request.max_node_count, request.metadata_filter)
+    async def retrieve_from_index(request: RetrieveRequest):   # main.py:742-771
+        """one query per request on the wire, as in the reference; concurrent requests are coalesced into one batched engine
+        call (the corpus is streamed once per batch, not once per request) -- the handler itself never blocks the loop"""
+        import asyncio
+        h, c = M["retrieve"]
+        t0 = time.perf_counter()
+        try:
+            if batcher is not None and batcher.enabled:
+                out = await asyncio.wrap_future(batcher.submit(request.index_name, request.query, request.max_node_count,
+                                                               request.metadata_filter))
+            else:
+                out = await asyncio.to_thread(store.retrieve, request.index_name, request.query, request.max_node_count,
+                                              request.metadata_filter)
             res_count.observe(out["count"])
             vs_lat.labels("query", "success").observe(getattr(store, "last_retrieve_seconds", 0.0))
             scores = [r["score"] for r in out["results"]]
             if scores:
                 low_score.observe(min(scores)); avg_score.observe(sum(scores) / len(scores))
+            c.labels("success").inc(); h.labels("success").observe(time.perf_counter() - t0)
             return out
-        return run("retrieve", go)
+        except vs.HTTPException as e:
+            c.labels("failure").inc(); h.labels("failure").observe(time.perf_counter() - t0)
+            raise HTTPException(status_code=e.status_code, detail=e.detail)
+        except HTTPException:
+            c.labels("failure").inc(); h.labels("failure").observe(time.perf_counter() - t0)
+            raise
+        except Exception as e:
+            c.labels("failure").inc(); h.labels("failure").observe(time.perf_counter() - t0)
+            raise HTTPException(status_code=500, detail=str(e))
 
     @app.post("/v1/chat/completions")
     def chat_completions(request: dict):   # main.py:326-353; RAG or pass-through: kaito_b200/chat.py
@@ -346,6 +369,14 @@ def resolve_model_dir(model_id: str) -> str | None:
     return None
 
 
+def _gpu_count() -> int:
+    try:
+        import torch
+        return int(torch.cuda.device_count())
+    except Exception:
+        return 1
+
+
 def main():
     """entry point of the image's `python3 main.py` shim (preset_rag.go:186): port 5000, /health probes."""
     import uvicorn
@@ -357,20 +388,40 @@ def main():
     source = cfg["embedding_source"].lower()
     if source not in ("local", "remote"):
         raise SystemExit("Invalid Embedding Type Specified (Must be Local or Remote)")          # main.py:133-141
-    engine = _native.Context(device_id=cfg["device_id"])
+    n_gpus = int(os.getenv("KRAG_NUM_GPUS", "0")) or _gpu_count()
+    ctx = _native.Context(device_id=cfg["device_id"], rank=0, world_size=max(1, n_gpus))
+    engine, workers = ctx, []
+    if n_gpus > 1:
+        # one replica per RAGEngine (manifests.go:81): every GPU of the pod belongs to this service.  Rank 0 (this process)
+        # serves HTTP and shard 0; one worker process per extra GPU holds the other shards (kaito_b200/sharded_engine.py)
+        import socket
+        import torch
+        from . import sharded_engine as se
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        workers = se.spawn_workers(n_gpus, port)
+        ctl = se.init_distributed(0, n_gpus, cfg["device_id"], port)
+        engine = se.ShardedEngine(se.native_stages_factory(ctx), torch.device("cuda", cfg["device_id"]), None, ctl)
     model_dir = resolve_model_dir(cfg["embedding_model"]) if source == "local" else None
     if source == "remote":
         from .embedding import RemoteEmbeddingModel
         embed = RemoteEmbeddingModel(cfg["remote_embedding_url"], cfg["remote_embedding_access_secret"])
     elif model_dir:
-        embed = GpuBertEmbedding.from_pretrained(engine, model_dir)          # K5: bge forward on the GPU
+        embed = GpuBertEmbedding.from_pretrained(ctx, model_dir)             # K5: bge forward on the GPU
     elif os.getenv("KRAG_ALLOW_HASHING_EMBEDDING") == "1":
         embed = HashingEmbedding(384)                                        # functional tests only, not a language model
     else:
         raise SystemExit(f"embedding model '{cfg['embedding_model']}' not found locally (no network in the pod): mount a "
                          "Hugging Face snapshot and set KRAG_MODEL_DIR, or KRAG_ALLOW_HASHING_EMBEDDING=1 for functional tests")
     app = create_app(vs.VectorStore(embed, engine), cfg)
-    uvicorn.run(app, host="0.0.0.0", port=5000)
+    try:
+        uvicorn.run(app, host="0.0.0.0", port=5000)
+    finally:
+        if workers:
+            engine.shutdown()
+            for w in workers:
+                w.wait(timeout=30)
 
 
 if __name__ == "__main__":

@@ -39,6 +39,31 @@ class NativeStages:
     def stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    # ---- mutations (the multi-GPU service: kaito_b200/sharded_engine.py)
+    def add(self, node_ids, vecs, term_offsets=None, term_ids=None, term_tf=None, doc_len=None):
+        self.index.add(node_ids, vecs, term_offsets, term_ids, term_tf, doc_len)
+
+    def remove(self, node_ids) -> int:
+        return self.index.remove(node_ids)
+
+    def set_ordinal_map(self, base: int, stride: int):
+        self.index.set_ordinal_map(base, stride)
+
+    def n_rows(self) -> int:
+        return int(self.index.stats().n_rows)
+
+    def dim_padded(self) -> int:
+        return int(self.index.stats().dim_padded)
+
+    def persist(self, path: str):
+        self.index.persist(path)
+
+    def drop(self):
+        if getattr(self, "_p2p", None) is not None:
+            self._p2p.destroy()
+            self._p2p = None
+        self.index.drop()
+
     def commit_local(self, vocab):
         return self.index.commit_local(vocab)
 
@@ -72,9 +97,9 @@ class NativeStages:
         nl, B, P = local.shape
         self._p2p.exchange_merge(nl, B, P, local.data_ptr(), merged.data_ptr(), self.stream())
 
-    def fuse(self, batch, P, k, dense_keys, bm25_keys, vw, tw, mode, out):
+    def fuse(self, batch, P, k, dense_keys, bm25_keys, vw, tw, mode, out, allow=None):
         self.ctx.dev_fuse(batch, P, k, dense_keys.data_ptr(), None if bm25_keys is None else bm25_keys.data_ptr(), vw, tw,
-                          mode, None, out["final"].data_ptr(), out["dense"].data_ptr(), out["sparse"].data_ptr(),
+                          mode, None if allow is None else allow.data_ptr(), out["final"].data_ptr(), out["dense"].data_ptr(), out["sparse"].data_ptr(),
                           out["rank"].data_ptr(), out["ordinal"].data_ptr(), out["count"].data_ptr(), self.stream())
 
 
@@ -90,9 +115,10 @@ class ShardedRetriever:
         self._p2p_state = None
 
     # ------------------------------------------------------------------ index time
-    def commit(self, vocab: int, n_local_rows: int):
+    def commit(self, vocab: int, n_local_rows: int, ordinal_base: int | None = None):
         """Global BM25 statistics: one all-reduce (df[V] + 2 scalars) and an all-gather of shard
-        sizes for the ordinal bases."""
+        sizes for the ordinal bases (contiguous shards); `ordinal_base` overrides the base for shards that carry
+        their own ordinal map (round-robin shards of the service: base = rank, stride = world)."""
         df, n_live, total_len = self.stages.commit_local(vocab)
         stats = torch.tensor([n_live, total_len], dtype=torch.int64, device=self.device)
         df_t = torch.from_numpy(df.astype(np.int64)).to(self.device)
@@ -103,7 +129,7 @@ class ShardedRetriever:
             dist.all_reduce(df_t, group=self.group)
             dist.all_reduce(sizes, group=self.group)
         n_docs, total = int(stats[0].item()), int(stats[1].item())
-        base = int(sizes[: self.rank].sum().item())
+        base = int(sizes[: self.rank].sum().item()) if ordinal_base is None else int(ordinal_base)
         self.stages.commit_global(vocab, df_t.cpu().numpy().astype(np.uint32), n_docs, total, base)
         self.hybrid = True
         return n_docs, total, base
@@ -137,7 +163,7 @@ class ShardedRetriever:
 
     def retrieve_dev(self, q: torch.Tensor, terms: torch.Tensor | None, toff: torch.Tensor | None, k: int,
                      cand_mult: float = 3.0, vector_weight: float = 0.7, text_weight: float = 0.3, mode: int = 0,
-                     toff_host: np.ndarray | None = None):
+                     toff_host: np.ndarray | None = None, allow: torch.Tensor | None = None):
         """Inputs already on this rank's device (q: [B, dim_padded] fp32 zero padded).
         Returns a dict of device tensors [B, k] (+ count [B])."""
         B = q.shape[0]
@@ -171,7 +197,10 @@ class ShardedRetriever:
             "sparse": self._tensor("sparse", (B, k), torch.float32), "rank": self._tensor("rank", (B, k), torch.int32),
             "ordinal": self._tensor("ordinal", (B, k), torch.int64), "count": self._tensor("count", (B,), torch.int32),
         }
-        self.stages.fuse(B, P, k, merged[0], merged[1] if hybrid else None, vector_weight, text_weight, mode, out)
+        if allow is not None:       # keyword-side metadata post-filter (hybrid_retriever.py:227-235): bitmap over GLOBAL ordinals
+            self.stages.fuse(B, P, k, merged[0], merged[1] if hybrid else None, vector_weight, text_weight, mode, out, allow=allow)
+        else:
+            self.stages.fuse(B, P, k, merged[0], merged[1] if hybrid else None, vector_weight, text_weight, mode, out)
         return out
 
     def embed_into(self, embedder, flat_tok: np.ndarray, tok_off: np.ndarray, q: torch.Tensor):
@@ -194,7 +223,7 @@ class ShardedRetriever:
         embedder.embed_dev(f, o, loc.data_ptr(), self.dpad, self.stages.stream())
         dist.all_gather_into_tensor(q, loc, group=self.group)
 
-    def retrieve(self, q_host: np.ndarray | None, q_terms_list, k: int, embedder=None, tokens=None, **kw):
+    def retrieve(self, q_host: np.ndarray | None, q_terms_list, k: int, embedder=None, tokens=None, allow_bitmap: np.ndarray | None = None, **kw):
         """End to end with HOST buffers: pinned H2D of the queries, the pipeline, D2H of the result.
         With `embedder` (kaito_b200._native.Embedder) and `tokens` = (flat int32 token ids, int32 offsets [B+1])
         the query vectors are produced on the GPU by the BERT forward (K5) instead of being uploaded."""
@@ -224,7 +253,14 @@ class ShardedRetriever:
             toff = self._tensor("toff", (B + 1,), torch.int32)
             terms.copy_(pin_t, non_blocking=True)
             toff.copy_(pin_o, non_blocking=True)
-        out = self.retrieve_dev(q, terms, toff, k, toff_host=offs if q_terms_list is not None else None, **kw)
+        allow = None
+        if allow_bitmap is not None:
+            ab = np.ascontiguousarray(allow_bitmap, np.uint32)
+            pin_a = self._pinned("pin_allow", (max(len(ab), 1),), torch.int32)
+            pin_a[: len(ab)] = torch.from_numpy(ab.view(np.int32))
+            allow = self._tensor("allow", (max(len(ab), 1),), torch.int32)
+            allow.copy_(pin_a, non_blocking=True)
+        out = self.retrieve_dev(q, terms, toff, k, toff_host=offs if q_terms_list is not None else None, allow=allow, **kw)
         host = {name: self._pinned("pin_out_" + name, tuple(t.shape), t.dtype) for name, t in out.items()}
         for name, t in out.items():
             host[name].copy_(t, non_blocking=True)

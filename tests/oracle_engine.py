@@ -95,3 +95,122 @@ class OracleEngine:
         if int(z["vocab"]) > 0:
             ix.commit(int(z["vocab"]))
         return ix
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# stage double for kaito_b200.sharded_engine (one shard of a round-robin sharded index), CPU + gloo
+PAD = np.uint64(0xFFFFFFFFFFFFFFFF)
+
+
+def _obits(v):
+    u = np.asarray(v, np.float32).view(np.uint32).astype(np.uint64)
+    return np.where(u & np.uint64(0x80000000), ~u & np.uint64(0xFFFFFFFF), u | np.uint64(0x80000000))
+
+
+def _from_obits(o):
+    o = o.astype(np.uint64)
+    u = np.where(o & np.uint64(0x80000000), o & np.uint64(0x7FFFFFFF), ~o & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    return u.view(np.float32)
+
+
+class OracleShardStages:
+    """what kaito_b200.sharded.NativeStages is to the CUDA library, on the CPU oracle: local candidate lists as u64 keys,
+    merge and fuse; plus the mutations the sharded engine issues"""
+
+    def __init__(self, o, name, dim):
+        self.o, self.ix = o, OracleIndex(o, name, dim)
+        self.base, self.stride, self.dim = 0, 1, dim
+
+    # mutations
+    def add(self, node_ids, vecs, term_offsets=None, term_ids=None, term_tf=None, doc_len=None):
+        self.ix.add(node_ids, vecs, term_offsets, term_ids, term_tf, doc_len)
+
+    def remove(self, node_ids):
+        return self.ix.remove(node_ids)
+
+    def set_ordinal_map(self, base, stride):
+        self.base, self.stride = base, stride
+
+    def n_rows(self):
+        return len(self.ix.ids)
+
+    def dim_padded(self):
+        return self.dim
+
+    def persist(self, path):
+        self.ix.persist(path)
+
+    def drop(self):
+        pass
+
+    def _glob(self, rows):
+        rows = np.asarray(rows, np.int64)
+        return np.where(rows >= 0, self.base + rows * self.stride, -1)
+
+    # commit
+    def commit_local(self, vocab):
+        ix, n = self.ix, len(self.ix.ids)
+        live = np.array([i not in ix.dead for i in range(n)], bool)
+        df = np.zeros(vocab, np.uint32)
+        for d in np.nonzero(live)[0]:
+            df[ix.tid[ix.off[d]:ix.off[d + 1]]] += 1
+        return df, int(live.sum()), int(ix.dl[live].astype(np.int64).sum()) if n else 0
+
+    def commit_global(self, vocab, df, n_docs, total_len, ordinal_base):
+        ix, n = self.ix, len(self.ix.ids)
+        self.base = ordinal_base
+        live = np.array([i not in ix.dead for i in range(n)], bool)
+        keep = np.repeat(live, np.diff(ix.off)) if n else np.zeros(0, bool)
+        off2 = np.concatenate([[0], np.cumsum(np.where(live, np.diff(ix.off), 0))]).astype(np.int64)
+        ix.post = self.o.bm25_build(off2, ix.tid[keep], ix.tf[keep], ix.dl, vocab, np.asarray(df, np.uint32), int(n_docs), int(total_len))
+
+    # candidate stages
+    def dense_candidates(self, q, P, out):
+        import torch
+        ix = self.ix
+        if len(ix.ids) == 0:
+            out.copy_(torch.from_numpy(np.full(tuple(out.shape), PAD, np.uint64).view(np.int64)))
+            return
+        d, o = self.o.dense_topk(ix.x, q.numpy()[:, : self.dim], P, ix._alive())
+        keys = (_obits(d) << np.uint64(32)) | self._glob(o).astype(np.uint64)
+        out.copy_(torch.from_numpy(np.where(o < 0, PAD, keys).view(np.int64)))
+
+    def bm25_candidates(self, terms, toff, batch, P, out, toff_host=None):
+        import torch
+        t, off = terms.numpy().view(np.uint32), toff.numpy()
+        for b in range(batch):
+            s, o = self.o.bm25_query(self.ix.post, t[off[b]:off[b + 1]], P, self.ix._alive())
+            keys = ((~_obits(s) & np.uint64(0xFFFFFFFF)) << np.uint64(32)) | self._glob(o).astype(np.uint64)
+            out[b].copy_(torch.from_numpy(np.where(o < 0, PAD, keys).view(np.int64)))
+
+    def merge(self, gathered, n_lists, batch, P, out):
+        import torch
+        g = gathered.numpy().view(np.uint64).reshape(n_lists, batch, P)
+        for b in range(batch):
+            out[b].copy_(torch.from_numpy(np.sort(g[:, b, :].reshape(-1))[:P].view(np.int64)))
+
+    def fuse(self, batch, P, k, dense_keys, bm25_keys, vw, tw, mode, out, allow=None):
+        import torch
+        dk = dense_keys.numpy().view(np.uint64)
+        bk = None if bm25_keys is None else bm25_keys.numpy().view(np.uint64)
+        ab = None if allow is None else allow.numpy().view(np.uint32)
+        out["count"].zero_()
+        for b in range(batch):
+            dv = dk[b] != PAD
+            dd, do = _from_obits(dk[b][dv] >> np.uint64(32)), (dk[b][dv] & np.uint64(0xFFFFFFFF)).astype(np.int64)
+            if bk is None:
+                n = min(k, len(do))
+                out["ordinal"][b, :n] = torch.from_numpy(do[:n]); out["final"][b, :n] = torch.from_numpy(dd[:n].astype(np.float64))
+                out["count"][b] = n
+                continue
+            bv = bk[b] != PAD
+            bs = _from_obits(~(bk[b][bv] >> np.uint64(32)) & np.uint64(0xFFFFFFFF))
+            bo = (bk[b][bv] & np.uint64(0xFFFFFFFF)).astype(np.int64)
+            if ab is not None:
+                keep = np.array([bool((ab[o_ >> 5] >> (o_ & 31)) & 1) for o_ in bo], bool)
+                bs, bo = bs[keep], bo[keep]
+            fin, de, sp, rk, od = self.o.fuse(dd, do, bs, bo, k, vw, tw, mode)
+            n = len(od)
+            out["final"][b, :n] = torch.from_numpy(fin); out["ordinal"][b, :n] = torch.from_numpy(od)
+            out["dense"][b, :n] = torch.from_numpy(de); out["sparse"][b, :n] = torch.from_numpy(sp)
+            out["rank"][b, :n] = torch.from_numpy(rk); out["count"][b] = n

@@ -19,12 +19,12 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _run(world):
+def _run(world, script="sharded_gpu_check.py", marker="sharded gpu check ok"):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
-           "--master-port", str(_free_port()), os.path.join(ROOT, "scripts", "sharded_gpu_check.py")]
+           "--master-port", str(_free_port()), os.path.join(ROOT, "scripts", script)]
     p = subprocess.run(cmd, cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert p.returncode == 0, p.stdout[-4000:]
-    assert f"sharded gpu check ok: world={world}" in p.stdout, p.stdout[-2000:]
+    assert f"{marker}: world={world}" in p.stdout, p.stdout[-2000:]
 
 
 @pytest.mark.parametrize("world", [1, 2, 4])
@@ -33,3 +33,13 @@ def test_sharded_retrieve_equals_single_shard_oracle(world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs, box has {torch.cuda.device_count()}")
     _run(world)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_sharded_service_equals_single_gpu_service(world):
+    """the multi-GPU SERVICE (kaito_b200.sharded_engine: round-robin shards, rank 0 = HTTP host + coalescer, workers on the other
+    GPUs) returns the single-GPU service's ids and scores -- scripts/sharded_service_check.py asserts it end to end"""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs, box has {torch.cuda.device_count()}")
+    _run(world, "sharded_service_check.py", "sharded service check ok")

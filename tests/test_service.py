@@ -168,3 +168,48 @@ def test_remote_embedding_model(oracle):
     assert r["count"] == 1
     assert np.allclose(emb.get_query_embedding("gamma delta"), local.get_text_embedding("gamma delta"))
     assert 'rag_embedding_requests_total{mode="remote",status="success"} 1.0' in c.get("/metrics").text
+
+
+def test_retrieve_requests_are_coalesced(oracle):
+    """concurrent POST /retrieve calls are answered by far fewer engine calls than requests (kaito_b200/batcher.py), each
+    request gets exactly the answer the unbatched path gives, and per-request errors stay per request"""
+    import threading
+    from tests.oracle_engine import OracleEngine
+    from kaito_b200.batcher import RetrieveBatcher
+    store = VectorStore(HashingEmbedding(64), OracleEngine(oracle))
+    docs = [{"text": f"document number {i} about topic {i % 7} and subject {i % 5}", "metadata": {"bucket": i % 3}} for i in range(60)]
+    store.index_documents("c", docs)
+    queries = [f"topic {i % 7} subject {i % 5}" for i in range(40)] + ["   "] * 2
+    want = [store.retrieve("c", q, 4) if q.strip() else None for q in queries]
+    b = RetrieveBatcher(store, max_batch=64, max_wait_s=0.05)
+    got, errs = [None] * len(queries), [None] * len(queries)
+    def go(i):
+        try:
+            got[i] = b.retrieve("c", queries[i], 4, None)
+        except Exception as e:
+            errs[i] = e
+    ts = [threading.Thread(target=go, args=(i,)) for i in range(len(queries))]
+    for t in ts: t.start()
+    for t in ts: t.join()
+    assert got[:40] == want[:40]
+    assert all(e is not None and e.status_code == 400 for e in errs[40:]) and all(e is None for e in errs[:40])
+    assert b.requests == len(queries) and b.batches <= 6 and b.max_seen >= 10, (b.batches, b.max_seen)
+    # different (top_k, filter) groups inside one window go to separate engine calls, with the right answers
+    f1, f2 = b.submit("c", queries[0], 2, None), b.submit("c", queries[0], 4, {"bucket": 1})
+    assert f1.result() == store.retrieve("c", queries[0], 2) and f2.result() == store.retrieve("c", queries[0], 4, {"bucket": 1})
+    with pytest.raises(Exception) as e:
+        b.retrieve("missing", "q", 3, None)
+    assert e.value.status_code == 404
+    b.close()
+
+
+def test_http_retrieve_goes_through_the_coalescer(oracle):
+    from tests.oracle_engine import OracleEngine
+    store = VectorStore(HashingEmbedding(64), OracleEngine(oracle))
+    app = create_app(store, dict(CFG))
+    client = TestClient(app)
+    client.post("/index", json={"index_name": "h", "documents": [{"text": f"alpha beta {i}"} for i in range(10)]})
+    r = client.post("/retrieve", json={"index_name": "h", "query": "alpha 3", "max_node_count": 3})
+    want = store.retrieve("h", "alpha 3", 3)
+    assert r.status_code == 200 and [(x["doc_id"], x["score"]) for x in r.json()["results"]] == [(x["doc_id"], x["score"]) for x in want["results"]]
+    assert app.state.batcher.requests >= 1 and app.state.batcher.batches >= 1
