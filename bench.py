@@ -98,7 +98,7 @@ def parse():
     ap.add_argument("--query-tokens", type=int, default=32, help="WordPiece tokens per query incl. [CLS]/[SEP]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-optin", action="store_true", help="skip the extra OPT-IN measurement (bf16 shadow prune pass) after the default one")
-    ap.add_argument("--cpu-sample-rows", type=int, default=400_000)
+    ap.add_argument("--cpu-sample-rows", type=int, default=100_000)
     return ap.parse_args()
 
 
@@ -169,33 +169,40 @@ def synth_query_terms(batch, seed, vocab=VOCAB, s=1.07, rank_offset=100):
 
 # ------------------------------------------------------------------ CPU baseline (oracle)
 class CpuReference:
-    """Restated reference path (oracle: FAISS-flat scan + bm25s-lucene + _fuse) on all host cores over a
-    bounded sample of the workload; the per-query time is extrapolated linearly in N (both stages are O(N)).
-    Postings are prebuilt (the reference rebuilds them on every query, which is slower still and reported
-    separately as bm25_rebuild_per_query_s_extrapolated)."""
+    """Restated reference path (oracle: FAISS-flat scan + bm25s-lucene + _fuse) on all host cores, on a bounded SAMPLE of the
+    workload: the same number of queries per step as the GPU arm (global_batch), a row sample of the corpus.  Both stages
+    are O(N) per query, so the per-query time on the full corpus is the sample's time scaled by n_docs / sample_rows; the
+    line reports the MEASURED step time of the sample (ms_per_step, measured.*) and the extrapolated queries/s (value).
+    Postings are prebuilt (the reference rebuilds them on every query -- slower still, reported separately as
+    bm25_rebuild_per_query_s_extrapolated)."""
 
-    def __init__(self, n_docs, dim, hybrid, k, sample_rows, n_queries=8, seed=0, embedding=None, query_tokens=32):
+    def __init__(self, n_docs, dim, hybrid, k, sample_rows, n_queries=256, seed=0, embedding=None, query_tokens=32):
         from oracle import oracle as o
         o.build()
+        self.threads = o.set_threads(os.cpu_count() or 1)       # torchrun pins OMP_NUM_THREADS=1 for its children
         self.embed_s = 0.0
         self.embedding = embedding
         if embedding:
             # the reference embeds every query with torch BertModel on the CPU (huggingface_local_embedding.py:34-53)
             import torch
             from transformers import BertConfig, BertModel
+            torch.set_num_threads(os.cpu_count() or 1)
             torch.manual_seed(0)
             m = BertModel(BertConfig(**BGE[embedding]), add_pooling_layer=False).eval()
-            ids = torch.randint(0, 30522, (n_queries, query_tokens))
+            ne = min(16, n_queries)
+            ids = torch.randint(0, 30522, (ne, query_tokens))
             with torch.no_grad():
                 m(input_ids=ids[:1])
                 t0 = time.perf_counter()
-                for b in range(n_queries):      # one query per request, as the service receives them
+                for b in range(ne):             # one query per request, as the service receives them
                     torch.nn.functional.normalize(m(input_ids=ids[b:b + 1]).last_hidden_state[:, 0], dim=1)
-                self.embed_s = (time.perf_counter() - t0) / n_queries
+                self.embed_s = (time.perf_counter() - t0) / ne
             del m
         self.o, self.n_docs, self.dim, self.hybrid, self.k, self.nq = o, n_docs, dim, hybrid, k, n_queries
         self.n = int(min(sample_rows, n_docs))
-        self.x = o.synth_dense(self.n, dim, seed + 1)
+        g = np.random.default_rng(seed + 1)                      # unit-norm Gaussian rows (the statistics of the GPU arm's corpus)
+        self.x = g.standard_normal((self.n, dim), dtype=np.float32)
+        self.x /= np.linalg.norm(self.x, axis=1, keepdims=True)
         self.q = o.synth_queries(self.x, n_queries, seed + 2)
         self.P = o.pool_size(k)
         self.rebuild_s = None
@@ -208,11 +215,12 @@ class CpuReference:
             self.rebuild_s = (time.perf_counter() - t0) * (n_docs / self.ns)
             self.qs = o.synth_query_terms(vocab, n_queries, seed + 4)
         o.dense_topk(self.x, self.q[:1], self.P)  # warm: page-touch the sample, start the OpenMP team
+        self.last_step_s = None
 
     def step(self):
         """one pass of n_queries queries over the sample; returns extrapolated seconds per query at n_docs"""
         o = self.o
-        t0 = time.perf_counter()
+        t00 = t0 = time.perf_counter()
         dd, do = o.dense_topk(self.x, self.q, self.P)
         t_dense = (time.perf_counter() - t0) / self.nq
         t_sparse = 0.0
@@ -222,48 +230,57 @@ class CpuReference:
                 bs, bo = o.bm25_query(self.post, self.qs[b], self.P)
                 o.fuse(dd[b], do[b], bs, bo, self.k)
             t_sparse = (time.perf_counter() - t0) / self.nq * (self.n_docs / self.ns)
+        self.last_step_s = time.perf_counter() - t00 + self.embed_s * self.nq      # what this step cost on the SAMPLE (+ embedding)
         return t_dense * (self.n_docs / self.n) + t_sparse + self.embed_s
 
-    def describe(self, per_query):
-        return {"value": 1.0 / per_query, "unit": "queries/s", "cores": self.o.threads(), "kind": "port",
+    def describe(self, per_query, step_s=None):
+        return {"value": 1.0 / per_query, "unit": "queries/s", "cores": self.threads, "kind": "port",
                 "sample": f"oracle (restated FAISS-flat + bm25s + _fuse; the real wheels are not installable offline) on "
-                          f"{self.n} of {self.n_docs} rows x {self.dim} fp32, {self.nq} queries per step, all host threads, "
-                          f"prebuilt postings, extrapolated linearly in N",
+                          f"{self.n} of {self.n_docs} rows x {self.dim} fp32 (BM25: {getattr(self, 'ns', 0)} docs), {self.nq} queries per "
+                          f"step, {self.threads} host threads, prebuilt postings; value is extrapolated linearly in N, measured.* is not",
+                "measured": {"rows": self.n, "queries_per_step": self.nq, "step_s": step_s,
+                             "queries_per_s_on_sample": None if not step_s else self.nq / step_s},
                 "per_query_s_extrapolated": per_query,
                 "query_embedding_s": self.embed_s if self.embedding else None,
                 "query_embedding": f"torch CPU BertModel {self.embedding} shapes, measured per query, not extrapolated" if self.embedding else "excluded",
                 "bm25_rebuild_per_query_s_extrapolated": self.rebuild_s}
 
 
-def cpu_reference_qps(n_docs, dim, hybrid, k, sample_rows, embedding=None, query_tokens=32):
-    ref = CpuReference(n_docs, dim, hybrid, k, sample_rows, embedding=embedding, query_tokens=query_tokens)
+def cpu_reference_qps(n_docs, dim, hybrid, k, sample_rows, embedding=None, query_tokens=32, n_queries=256):
+    ref = CpuReference(n_docs, dim, hybrid, k, sample_rows, n_queries=n_queries, embedding=embedding, query_tokens=query_tokens)
     ref.step()
-    t = float(np.median([ref.step() for _ in range(3)]))
-    return ref.describe(t)
+    ts, ss = [], []
+    for _ in range(3):
+        ts.append(ref.step()); ss.append(ref.last_step_s)
+    return ref.describe(float(np.median(ts)), float(np.median(ss)))
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path (oracle port) timed on the host cores."""
+    """--impl reference: the reference's CPU path (oracle port) timed on the host cores, same queries per step as the GPU arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     docs, dim, hybrid = WORKLOADS[args.workload]
-    ref = CpuReference(docs, dim, hybrid, args.k, args.cpu_sample_rows, embedding=pick_embedding(args.embedding, dim),
+    ref = CpuReference(docs, dim, hybrid, args.k, args.cpu_sample_rows, n_queries=args.batch, embedding=pick_embedding(args.embedding, dim),
                        query_tokens=args.query_tokens)
     for _ in range(args.warmup):
         ref.step()
-    per_query = float(np.mean([ref.step() for _ in range(args.steps)]))
+    pq, st = [], []
+    for _ in range(args.steps):
+        pq.append(ref.step()); st.append(ref.last_step_s)
+    per_query, step_s = float(np.mean(pq)), float(np.mean(st))
     v = 1.0 / per_query
     line = {"impl": "reference", "metric": "rag_retrieve_queries_per_sec", "value": v, "unit": "queries/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * per_query * ref.nq,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * step_s,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {docs} docs x {dim} fp32" + (" + BM25 postings, hybrid weighted fusion" if hybrid else ", dense only"),
-                       "top_k": args.k, "global_batch": ref.nq, "parallelism": "host threads",
+                       "top_k": args.k, "global_batch": ref.nq, "parallelism": f"{ref.threads} host threads",
+                       "timed_sample": f"ms_per_step is the MEASURED time of one step on the sample ({ref.n} rows); value = queries/s "
+                                       f"extrapolated to {docs} rows (x{docs / ref.n:.0f} on the O(N) stages)",
                        "query_embedding": ref.describe(per_query)["query_embedding"]},
-            "cpu_baseline": ref.describe(per_query),
+            "cpu_baseline": ref.describe(per_query, step_s),
             "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
-
 
 
 # ------------------------------------------------------------------ in-bench correctness check (every N)
@@ -589,7 +606,10 @@ def run_ours(args):
             etf = fl / (ms_embed / args.steps * 1e-3) / 1e12
             embed_info = {"model_shape": emb_name, "weights": "random init N(0, 0.02) (no checkpoints offline)", "tokens_per_query": args.query_tokens,
                           "batch_ms": ms_embed / args.steps, "batch1_ms": ms_embed1 / (args.steps * 4), "flops_per_batch": fl,
-                          "tflops": etf, "tensor_frac_of_tf32_peak": etf / tf32_peak,
+                          "tflops": etf, "tflops_per_gpu": etf / world,
+                          "arithmetic": "split-fp16 operands (hi + lo*2^-11), 3 kind::f16 MMAs per step: fp32-accurate products; "
+                                        "tflops counts the fp32-equivalent flops L(24 S d^2 + 4 S^2 d), the tensor pipe executes 3x the GEMM part",
+                          "tensor_frac_of_f16_peak_per_gpu": 3.0 * etf / world / float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1590.0))),
                           "queries_per_s": B / (ms_embed / args.steps * 1e-3)}
         line = {
             "metric": "rag_retrieve_queries_per_sec", "value": qps, "unit": "queries/s", "n_gpus": world,
@@ -627,7 +647,7 @@ def run_ours(args):
             "recall_note": "computed: overlap of the pipeline's dense top-10 with the exact per-shard fp32 scan merged on the host (check.queries queries)",
         }
         if not args.no_cpu_baseline and world == 1:      # the CPU leg is reported at N = 1 only (rank 0 would stall the other ranks)
-            line["cpu_baseline"] = cpu_reference_qps(docs, dim, hybrid, k, args.cpu_sample_rows, emb_name, args.query_tokens)
+            line["cpu_baseline"] = cpu_reference_qps(docs, dim, hybrid, k, args.cpu_sample_rows, emb_name, args.query_tokens, n_queries=B)
         print(json.dumps(line), flush=True)
     trace("line printed; teardown")
     barrier()

@@ -528,12 +528,12 @@ bm25_tile_kernel(const int64_t* __restrict__ post_off, const uint32_t* __restric
 // postings) have theirs in the persistent tile index; for the others bm25_resolve_kernel builds the row per batch from
 // the term's <= 2048 document ids (binary searches out of shared memory).
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int BW_WARPS = 5;                 // warps per CTA: 5 x (16 KB accumulators + 4 KB staging), 2 CTAs per SM
+constexpr int BW_WARPS = 8;                 // warps per CTA: 8 x (8 KB accumulators + 6 KB staging), 2 CTAs per SM = 16 warps
 constexpr int BW_THREADS = BW_WARPS * 32;
 constexpr int BW_CHUNK = 8;                 // consecutive (sampled) sub-tiles of one query per work unit
-constexpr int BW_STAGE_ROUNDS = 8;          // 32-posting rounds per staging buffer (double-buffered)
-constexpr int BW_STAGE_WORDS = BW_STAGE_ROUNDS * 32 * 2;           // docs[8][32] | scores[8][32]
-constexpr int BW_WARP_WORDS = BM25_SUB_DOCS + 2 * BW_STAGE_WORDS;  // per-warp shared memory, 4-byte words (20 KB)
+constexpr int BW_STAGE_ROUNDS = 12;         // 32-posting rounds per staging buffer: a whole sub-tile in the common case
+constexpr int BW_STAGE_WORDS = BW_STAGE_ROUNDS * 32 * 2;           // docs[12][32] | scores[12][32]
+constexpr int BW_WARP_WORDS = BM25_SUB_DOCS + 2 * BW_STAGE_WORDS;  // per-warp shared memory, 4-byte words (14 KB)
 
 // once per batch and query-term position: posting base, boundary row, and the legacy kernel's (slot, rare length)
 __global__ void __launch_bounds__(256)
@@ -636,42 +636,68 @@ __device__ __forceinline__ void bw_accumulate(const BwCtx& c, const uint32_t* bu
         __syncwarp();
     }
 }
-// All terms of the sub-tile are in: sweep the accumulators (vectorised, conflict-free), reset what was touched and append
-// the documents that pass the query's admission threshold to its candidate list (warp-aggregated: one atomic per hit group)
-__device__ __forceinline__ void bw_claim_scan(const BwCtx& c)
+__device__ __forceinline__ void bw_push(const BwCtx& c, bool hit, unsigned long long key)
+{
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (m) {                                                               // one atomic per hit group and warp
+        const int leader = __ffs(m) - 1;
+        uint32_t base_slot = 0;
+        if (c.lane == leader) base_slot = atomicAdd(c.cnt_q, (uint32_t)__popc(m));
+        base_slot = __shfl_sync(0xffffffffu, base_slot, leader);
+        if (hit) {
+            const uint32_t at = base_slot + (uint32_t)__popc(m & ((1u << c.lane) - 1u));
+            if (at < (uint32_t)c.capq) c.cand_q[at] = key;                 // past capq: counted, dropped -> overflow flag
+        }
+    }
+}
+// All terms of the sub-tile are accumulated and its postings are still staged: every touched document is claimed once
+// (atomicExch resets the accumulator; later occurrences of the same document read 0) and appended to the query's
+// candidate list if it passes the admission threshold.
+__device__ __forceinline__ void bw_claim_staged(const BwCtx& c, const uint32_t* buf, int n)
+{
+#pragma unroll 1
+    for (int u = 0; u < n; ++u) {
+        const uint32_t d = buf[u * 32 + c.lane];
+        const uint32_t rel = d - c.t0;
+        float sum = 0.f;
+        if (d != 0xFFFFFFFFu && rel < (uint32_t)BM25_SUB_DOCS) sum = atomicExch(&c.acc[rel], 0.f);
+        const bool maybe = sum > 0.f && sum >= c.thr_score;
+        if (!__any_sync(0xffffffffu, maybe)) continue;
+        bool hit = false;
+        unsigned long long key = 0;
+        if (maybe && (c.alive == nullptr || bit_test(c.alive, d))) {
+            key = make_key_desc(sum, c.ord_base + d);
+            hit = key <= c.thr;
+        }
+        bw_push(c, hit, key);
+    }
+    __syncwarp();
+}
+// sub-tiles with more rounds than a staging buffer holds: accumulated block by block, then claimed by a sweep over the
+// accumulators (vectorised, conflict-free)
+__device__ __forceinline__ void bw_claim_sweep(const BwCtx& c)
 {
     float4* acc4 = reinterpret_cast<float4*>(c.acc);
-#pragma unroll 2
+#pragma unroll 1
     for (int k = 0; k < BM25_SUB_DOCS / 128; ++k) {
         const int slot = k * 32 + c.lane;
         const float4 v = acc4[slot];
         const bool nz = (v.x != 0.f) | (v.y != 0.f) | (v.z != 0.f) | (v.w != 0.f);     // scores are positive: touched <=> nonzero
         if (nz) acc4[slot] = make_float4(0.f, 0.f, 0.f, 0.f);
-        const bool maybe = nz && ((v.x >= c.thr_score) | (v.y >= c.thr_score) | (v.z >= c.thr_score) | (v.w >= c.thr_score));
-        if (!__any_sync(0xffffffffu, maybe)) continue;
+        if (!__any_sync(0xffffffffu, nz)) continue;
         const float comp[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             bool hit = false;
             unsigned long long key = 0;
-            if (maybe && comp[e] > 0.f && comp[e] >= c.thr_score) {
+            if (comp[e] > 0.f && comp[e] >= c.thr_score) {
                 const uint32_t row = c.t0 + (uint32_t)(slot * 4 + e);
                 if ((int64_t)row < c.n_rows && (c.alive == nullptr || bit_test(c.alive, row))) {
                     key = make_key_desc(comp[e], c.ord_base + row);
                     hit = key <= c.thr;
                 }
             }
-            const unsigned m = __ballot_sync(0xffffffffu, hit);
-            if (m) {
-                const int leader = __ffs(m) - 1;
-                uint32_t base_slot = 0;
-                if (c.lane == leader) base_slot = atomicAdd(c.cnt_q, (uint32_t)__popc(m));
-                base_slot = __shfl_sync(0xffffffffu, base_slot, leader);
-                if (hit) {
-                    const uint32_t at = base_slot + (uint32_t)__popc(m & ((1u << c.lane) - 1u));
-                    if (at < (uint32_t)c.capq) c.cand_q[at] = key;        // past capq: counted, dropped -> overflow flag
-                }
-            }
+            bw_push(c, hit, key);
         }
     }
     __syncwarp();
@@ -691,7 +717,7 @@ bm25_warp_kernel(const uint32_t* __restrict__ post_doc, const float* __restrict_
     float* acc = reinterpret_cast<float*>(wbase);
     uint32_t* stage = wbase + BM25_SUB_DOCS;
     for (int i = lane; i < BM25_SUB_DOCS / 4; i += 32) reinterpret_cast<float4*>(acc)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncwarp();                                                          // zeroed once: the claim sweep resets what was touched
+    __syncwarp();                                                          // zeroed once: the claim step resets what was touched
 
     const int n_chunks = (n_s + BW_CHUNK - 1) / BW_CHUNK;
     const long long n_units = (long long)n_chunks * batch;
@@ -712,8 +738,8 @@ bm25_warp_kernel(const uint32_t* __restrict__ post_doc, const float* __restrict_
         const int s0 = ch * BW_CHUNK, ns = min(BW_CHUNK, n_s - s0);
         if (te - tb <= 32) {
             // common case: every term of the query lives in one lane; the boundary offsets of the whole chunk are fetched
-            // at once (independent loads).  Then a two-deep pipeline of staged blocks runs across the chunk's sub-tiles:
-            // while block k is accumulated, block k + 1 (same or next sub-tile) is already in flight.
+            // at once (independent loads).  Then a two-deep pipeline runs across the chunk's sub-tiles: while sub-tile i is
+            // accumulated and claimed out of one staging buffer, the postings of sub-tile i + 1 are in flight to the other.
             const int nt = te - tb;
             const uint32_t* row = nullptr; int64_t base = 0;
             if (lane < nt) { row = q_row[tb + lane]; base = q_base[tb + lane]; }
@@ -724,36 +750,48 @@ bm25_warp_kernel(const uint32_t* __restrict__ post_doc, const float* __restrict_
                 if (row != nullptr && i < ns) { const int64_t sub = (int64_t)(s0 + i) * stride; olo[i] = row[sub]; ohi[i] = row[sub + 1]; }
             }
             BwCursor cur;
-            cur.R = 0; cur.issued = 0; cur.nt = 0; cur.j = 0; cur.r = 0; cur.my_len = 0; cur.my_start = 0; cur.t0 = 0;
-            int ii = -1;                                                   // sub-tile of the issue cursor
-            int buf = 0;
-            int nb_n = 0; uint32_t nb_t0 = 0; bool nb_last = false;        // block in flight
-            // stage the next block (advancing over empty sub-tiles); false at the end of the unit
-            auto next_block = [&](uint32_t* dst) -> bool {
+            int ii = -1, buf = 0;
+            int nb_n = 0, nb_R = 0; uint32_t nb_t0 = 0;                    // sub-tile in flight: rounds staged, rounds total
+            // stage the first (up to BW_STAGE_ROUNDS) rounds of the next non-empty sub-tile; false at the end of the unit
+            auto next_subtile = [&](uint32_t* dst) -> bool {
                 for (;;) {
-                    if (cur.issued < cur.R) {
-                        nb_n = bw_issue(c, cur, dst);
-                        nb_t0 = cur.t0; nb_last = (cur.issued == cur.R);
-                        return true;
-                    }
                     if (++ii >= ns) return false;
                     uint32_t lo = 0, hi = 0;
 #pragma unroll
                     for (int k = 0; k < BW_CHUNK; ++k) if (k == ii) { lo = olo[k]; hi = ohi[k]; }
                     bw_cursor_reset(cur, base + lo, (int)(hi - lo), nt, (uint32_t)((int64_t)(s0 + ii) * stride * BM25_SUB_DOCS));
+                    if (cur.R == 0) continue;
+                    nb_n = bw_issue(c, cur, dst);
+                    nb_R = cur.R; nb_t0 = cur.t0;
+                    return true;
                 }
             };
-            bool have = next_block(stage);
+            bool have = next_subtile(stage);
             while (have) {
-                const int cb_n = nb_n; const uint32_t cb_t0 = nb_t0; const bool cb_last = nb_last;
-                const uint32_t* cbuf = stage + buf * BW_STAGE_WORDS;
-                buf ^= 1;
-                have = next_block(stage + buf * BW_STAGE_WORDS);
-                if (have) cp_async_wait<1>(); else cp_async_wait<0>();
-                __syncwarp();
-                c.t0 = cb_t0;
-                bw_accumulate(c, cbuf, cb_n);
-                if (cb_last) bw_claim_scan(c);
+                const int cb_n = nb_n, cb_R = nb_R;
+                uint32_t* cbuf = stage + buf * BW_STAGE_WORDS;
+                c.t0 = nb_t0;
+                if (cb_R <= BW_STAGE_ROUNDS) {
+                    buf ^= 1;
+                    have = next_subtile(stage + buf * BW_STAGE_WORDS);     // next sub-tile's loads fly while this one is processed
+                    if (have) cp_async_wait<1>(); else cp_async_wait<0>();
+                    __syncwarp();
+                    bw_accumulate(c, cbuf, cb_n);
+                    bw_claim_staged(c, cbuf, cb_n);
+                } else {
+                    // rare: more rounds than a buffer holds -> block by block out of this buffer, then the sweep
+                    int n = cb_n;
+                    for (;;) {
+                        cp_async_wait<0>();
+                        __syncwarp();
+                        bw_accumulate(c, cbuf, n);
+                        if (cur.issued >= cur.R) break;
+                        n = bw_issue(c, cur, cbuf);
+                    }
+                    bw_claim_sweep(c);
+                    buf ^= 1;
+                    have = next_subtile(stage + buf * BW_STAGE_WORDS);
+                }
             }
         } else {
             // long queries: term chunks of 32; ALL chunks are accumulated (in query order) before the claim sweep
@@ -777,7 +815,7 @@ bm25_warp_kernel(const uint32_t* __restrict__ post_doc, const float* __restrict_
                         touched = true;
                     }
                 }
-                if (touched) bw_claim_scan(c);
+                if (touched) bw_claim_sweep(c);
             }
         }
     }

@@ -305,7 +305,8 @@ template <int BN> struct Gm2Cfg {
     static constexpr int BH_BYTES = (BN / 2) * 128;                    // this CTA's half of one weight k-block (one plane)
     static constexpr int STAGE_BYTES = 2 * GM_SLAB + 2 * BH_BYTES;     // 64 KB at BN = 256, 48 KB at BN = 128
     static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;          // 3 / 4
-    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int NBUF = BN <= 128 ? 2 : 1;                     // accumulator sets in TMEM: (main + correction) x NBUF = 512 columns
+    static constexpr int TMEM_COLS = 2 * BN * NBUF;
     static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
 };
 constexpr int GM2_THREADS = 320;   // warp 0: TMA, warp 1: MMA issuer (leader), warps 2-9: epilogue (2 per TMEM lane group)
@@ -336,7 +337,7 @@ gemm2_f16s_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA1); tma_prefetch_desc(&tmA2); tma_prefetch_desc(&tmB1h); tma_prefetch_desc(&tmB2h);
         for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(&full_bar[s], 2); mbar_init(&empty_bar[s], 1); }
-        mbar_init(&tfull_bar[0], 1); mbar_init(&tempty_bar[0], 16);
+        for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 16); }
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -375,11 +376,11 @@ gemm2_f16s_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
             const uint64_t desc0 = umma_desc_sw128(smem_u32(smem));
             const uint64_t dhi = desc0 & 0xFFFFFFFF00000000ull;
             const uint32_t lo0 = (uint32_t)desc0;
-            int stage = 0; uint32_t phase = 0; uint32_t acc_phase = 0;
-            const uint32_t d_main = tmem_base, d_corr = tmem_base + (uint32_t)BN;
+            int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
             for (int t = pair; t < total; t += n_pairs) {
-                mbar_wait(&tempty_bar[0], acc_phase ^ 1);
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
+                const uint32_t d_main = tmem_base + (uint32_t)(acc * 2 * BN), d_corr = d_main + (uint32_t)BN;
                 for (int kb = 0; kb < kblocks; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
@@ -394,12 +395,12 @@ gemm2_f16s_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
                             umma_f16_2sm(d_corr, dhi | (uint64_t)(a2 + 2 * k), dhi | (uint64_t)(b1 + 2 * k), idesc, 1u);
                         }
                         umma_commit_2sm(&empty_bar[stage]);
-                        if (kb == kblocks - 1) umma_commit_2sm(&tfull_bar[0]);
+                        if (kb == kblocks - 1) umma_commit_2sm(&tfull_bar[acc]);
                     }
                     __syncwarp();
                     if (++stage == Cfg::STAGES) { stage = 0; phase ^= 1; }
                 }
-                acc_phase ^= 1;
+                if (++acc == Cfg::NBUF) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else {
@@ -407,13 +408,13 @@ gemm2_f16s_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
         const int lg = warp & 3;
         const int col_half = (warp - 2) >> 2;
         const int r_in = lg * 32 + lane;
-        uint32_t acc_phase = 0;
+        int acc = 0; uint32_t acc_phase = 0;
         for (int t = pair; t < total; t += n_pairs) {
             const int m0 = (t / n_tiles) * (2 * GM_TILE) + (int)rank * GM_TILE, n0 = (t % n_tiles) * BN;
             const int row = m0 + r_in;
-            mbar_wait(&tfull_bar[0], acc_phase);
+            mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16);
+            const uint32_t taddr = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(acc * 2 * BN);
 #pragma unroll 1
             for (int c0 = col_half * (BN / 2); c0 < (col_half + 1) * (BN / 2); c0 += 32) {
                 uint32_t v0[32], v1[32];
@@ -428,10 +429,10 @@ gemm2_f16s_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constan
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (rank == 0) mbar_arrive(&tempty_bar[0]);
-                else mbar_arrive_remote(&tempty_bar[0], 0);
+                if (rank == 0) mbar_arrive(&tempty_bar[acc]);
+                else mbar_arrive_remote(&tempty_bar[acc], 0);
             }
-            acc_phase ^= 1;
+            if (++acc == Cfg::NBUF) { acc = 0; acc_phase ^= 1; }
         }
     }
     tc_fence_before();
@@ -1128,9 +1129,11 @@ void launch_gemm_f16s(const DeviceInfo& di, const SplitMat& A, const SplitMat& B
     // CTA pairs (256 x BN tiles) win when there are enough tiles to fill the 74 pairs; small problems (few query
     // tokens per rank) are latency-bound by the K loop of a single tile, where 128 x 128 tiles on single CTAs
     // halve the per-tile MMA time and quadruple the number of CTAs
-    const int pair_tiles = ((M + 2 * GM_TILE - 1) / (2 * GM_TILE)) * (N / ((N % 256 == 0) ? 256 : 128));
+    static int want_bn = -1;
+    if (want_bn < 0) { const char* ev = getenv("KRAG_GEMM_BN"); want_bn = (ev && atoi(ev) == 256) ? 256 : 128; }
+    const int BN = (want_bn == 256 && N % 256 == 0) ? 256 : 128;
+    const int pair_tiles = ((M + 2 * GM_TILE - 1) / (2 * GM_TILE)) * (N / BN);
     if (use2 && M > GM_TILE && pair_tiles >= di.sm_count / 4) {
-        const int BN = (N % 256 == 0) ? 256 : 128;
         emb_map(&tmB1, B.hi, N, K, BN / 2);
         emb_map(&tmB2, B.lo, N, K, BN / 2);
         const int total2 = ((M + 2 * GM_TILE - 1) / (2 * GM_TILE)) * (N / BN);

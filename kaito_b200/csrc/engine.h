@@ -78,8 +78,8 @@ void launch_fuse(int batch, int P, int k, const uint64_t* dense_keys, const uint
                  int32_t* out_rank, int64_t* out_ord, int32_t* out_count, cudaStream_t st);
 
 // ---- K3: BM25 (bm25.cu)
-constexpr int BM25_SUB_DOCS = 4096;      // doc range of one tile-index column = one warp's shared-memory accumulator (K3)
-constexpr int BM25_SUBS_PER_TILE = 4;
+constexpr int BM25_SUB_DOCS = 2048;      // doc range of one tile-index column = one warp's shared-memory accumulator (K3)
+constexpr int BM25_SUBS_PER_TILE = 8;
 constexpr int BM25_TILE_DOCS = BM25_SUB_DOCS * BM25_SUBS_PER_TILE;   // doc range of one CTA in the legacy kernel (safety net)
 struct Postings {
     int64_t* off = nullptr;    // [vocab+1]

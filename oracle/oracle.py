@@ -60,6 +60,8 @@ def lib() -> C.CDLL:
                                        C.c_int32, C.c_int32, f64p, f32p, f32p, i32p, i64p]
         L.krag_oracle_fuse.restype = C.c_int32
         L.krag_oracle_threads.restype = C.c_int32
+        L.krag_oracle_set_threads.argtypes = [C.c_int32]
+        L.krag_oracle_set_threads.restype = None
         _lib = L
     return _lib
 
@@ -70,6 +72,12 @@ def _p(a, t):
 
 def threads() -> int:
     return int(lib().krag_oracle_threads())
+
+
+def set_threads(n: int) -> int:
+    """OpenMP team size of the oracle (torchrun pins OMP_NUM_THREADS=1 for its children); returns the size in effect"""
+    lib().krag_oracle_set_threads(int(n))
+    return threads()
 
 
 # ----------------------------------------------------------------------------- dense
@@ -244,18 +252,16 @@ def synth_sparse(n: int, vocab: int, seed: int, mean_len: float = 96.0, zipf_s: 
     ranks = np.arange(1, vocab + 1, dtype=np.float64)
     cdf = np.cumsum(ranks ** (-zipf_s))
     cdf /= cdf[-1]
-    offs = [0]
-    ids, tfs = [], []
     tokens = np.searchsorted(cdf, g.random(int(dl.sum())))
-    pos = 0
-    for i in range(n):
-        t = tokens[pos:pos + dl[i]]
-        pos += dl[i]
-        u, c = np.unique(t, return_counts=True)
-        ids.append(u.astype(np.uint32))
-        tfs.append(np.minimum(c, 65535).astype(np.uint16))
-        offs.append(offs[-1] + len(u))
-    return (np.asarray(offs, np.int64), np.concatenate(ids), np.concatenate(tfs), dl.astype(np.uint32))
+    # per-document unique terms with counts, vectorised: sort (doc, term) pairs and run-length encode
+    # (identical output to np.unique(tokens_of_doc, return_counts=True) document by document)
+    doc_of = np.repeat(np.arange(n, dtype=np.int64), dl)
+    key = np.sort(doc_of * np.int64(vocab) + tokens.astype(np.int64))
+    first = np.concatenate([[True], key[1:] != key[:-1]])
+    uk = key[first]
+    cnt = np.diff(np.concatenate([np.nonzero(first)[0], [len(key)]]))
+    offs = np.concatenate([[0], np.cumsum(np.bincount(uk // vocab, minlength=n))]).astype(np.int64)
+    return (offs, (uk % vocab).astype(np.uint32), np.minimum(cnt, 65535).astype(np.uint16), dl.astype(np.uint32))
 
 
 def synth_query_terms(vocab: int, nq: int, seed: int, zipf_s: float = 1.07, rank_offset: int = 100):

@@ -126,7 +126,7 @@ def test_bert_forward_matches_transformers(ctx, name, cfg, lens):
         l2_dev = np.abs(l2_got - l2_ref).max()
         print(f"{name}: max|d| {dmax:.2e}  1-cos {1 - cos.min():.2e}  max L2^2 deviation {l2_dev:.2e}")
         assert l2_dev < 1e-4, l2_dev                       # the contract
-        assert dmax < 2e-5 and cos.min() > 1 - 1e-8, (dmax, cos)   # and with margin: fp32-level agreement (TF32 was 5e-3 / 1e-4)
+        assert dmax < 2e-5 and cos.min() > 1 - 1e-6, (dmax, cos)   # and with margin: fp32-level agreement (TF32 was 5e-3 / 1e-4)
         # batching must not change a sequence's embedding beyond fp32 summation order (packed, no padding; the GEMM tiling
         # and split-K factor follow the token count, as torch's own kernels do)
         alone = emb.embed([toks[-1]])
