@@ -79,6 +79,7 @@ WORKLOADS = {
     "c3": (10_000_000, 768, True),
     "c2": (1_000_000, 768, False),
     "headline": (100_000_000, 768, True),    # BASELINE.json metric corpus: needs >= 4 GPUs in fp32 (8 recommended)
+    "c4": (100_000_000, 1024, False),        # BASELINE.json configs[3]: 100M x 1024 dense, 8 GPUs (51.2 GB fp32 per GPU)
     "tiny": (200_000, 768, True),            # functional check of the harness
 }
 

@@ -19,6 +19,7 @@ import time
 from urllib.parse import unquote
 
 from fastapi import FastAPI, HTTPException, Query, Request, Response
+from fastapi.responses import JSONResponse as _JSON
 from prometheus_client import CONTENT_TYPE_LATEST, CollectorRegistry, Counter, Gauge, Histogram, generate_latest
 from pydantic import BaseModel, Field
 
@@ -286,7 +287,12 @@ def create_app(store: vs.VectorStore, cfg: dict | None = None, llm=None) -> Fast
             if scores:
                 low_score.observe(min(scores)); avg_score.observe(sum(scores) / len(scores))
             c.labels("success").inc(); h.labels("success").observe(time.perf_counter() - t0)
-            return out
+            # models.NodeWithScore on the wire (the three optional scores serialise as null when unset) without a second
+            # pydantic pass over every result: the dicts come from our own store, the schema is fixed
+            for r in out["results"]:
+                r.setdefault("dense_score", None); r.setdefault("sparse_score", None); r.setdefault("source", None)
+                r.setdefault("metadata", None)
+            return _JSON(out)
         except vs.HTTPException as e:
             c.labels("failure").inc(); h.labels("failure").observe(time.perf_counter() - t0)
             raise HTTPException(status_code=e.status_code, detail=e.detail)

@@ -105,6 +105,19 @@ class ShardedEngine:
                 sh.vocab = cmd["vocab"]
                 sh.sr.commit(sh.vocab, sh.rows, ordinal_base=self.rank)
             return None
+        if op == "synth":
+            # load-test corpora (scripts/http_load.py): every rank generates its share of a synthetic index on the device
+            name, dim, n_total = cmd["name"], cmd["dim"], cmd["n"]
+            stages = self.factory(name, dim, None)
+            per = n_total // self.world + (1 if self.rank < n_total % self.world else 0)
+            stages.index.synth_fill(per, row_base=self.rank * (n_total // self.world + 1), seed=cmd["seed"], vocab=cmd["vocab"])
+            stages.set_ordinal_map(self.rank, self.world)
+            sh = _Shard(stages, ShardedRetriever(stages, self.device, stages.dim_padded(), self.data_group), dim)
+            sh.rows, sh.vocab = per, cmd["vocab"]
+            self.shards[name] = sh
+            if cmd["vocab"] > 0:
+                sh.sr.commit(sh.vocab, sh.rows, ordinal_base=self.rank)
+            return None
         if op == "adopt":
             old = self.shards.pop(cmd["to"], None)
             self.shards[cmd["to"]] = self.shards.pop(cmd["name"])
@@ -159,6 +172,13 @@ class ShardedEngine:
     def create_index(self, name: str, dim: int) -> "ShardedIndex":
         self._run({"op": "create", "name": name, "dim": dim})
         return ShardedIndex(self, name, dim)
+
+    def synth_index(self, name: str, dim: int, n: int, vocab: int, seed: int = 20260921) -> "ShardedIndex":
+        """load tests: a synthetic corpus of n rows generated on the devices (not on the product path)"""
+        self._run({"op": "synth", "name": name, "dim": dim, "n": int(n), "vocab": int(vocab), "seed": int(seed)})
+        ix = ShardedIndex(self, name, dim)
+        ix.n, ix.vocab = int(n), int(vocab)
+        return ix
 
     def load_index(self, name: str, path: str) -> "ShardedIndex":
         import json

@@ -48,26 +48,7 @@ def embed_text(text: str, metadata: dict | None) -> str:
     return f"{meta}\n\n{text}"
 
 
-class SentenceSplitter:
-    """Stand-in for LlamaIndex SentenceSplitter() (custom_transformer.py:32): chunk_size 1024, overlap 200,
-    counted in word tokens here (the reference counts tiktoken tokens; the BPE table is not available
-    offline).  Texts below the chunk size -- everything the reference's tests index -- stay one node."""
-
-    def __init__(self, chunk_size: int = 1024, chunk_overlap: int = 200):
-        self.chunk_size, self.chunk_overlap = chunk_size, chunk_overlap
-
-    def split(self, text: str) -> list[str]:
-        words = text.split()
-        if len(words) <= self.chunk_size:
-            return [text]
-        out, start = [], 0
-        while start < len(words):
-            end = min(len(words), start + self.chunk_size)
-            out.append(" ".join(words[start:end]))
-            if end == len(words):
-                break
-            start = end - self.chunk_overlap
-        return out
+from .splitter import CodeSplitter, SentenceSplitter   # noqa: E402  (CustomTransformer's two splitters, restated)
 
 
 class RWLock:
@@ -240,6 +221,7 @@ class VectorStore:
         self.dimension = embed_model.get_embedding_dimension()   # faiss_store.py:28
         self.index_map: dict[str, _IndexState] = {}
         self.splitter = SentenceSplitter()
+        self._code_splitters: dict[str, CodeSplitter] = {}
         self.filter_pushdown = os.getenv("KRAG_FILTER_PUSHDOWN", "0") == "1"
         self.component_scores = os.getenv("KRAG_COMPONENT_SCORES", "0") == "1"
         # many readers / one writer (aiorwlock in the reference, base.py:77-79).  The engine enforces the same
@@ -272,8 +254,8 @@ class VectorStore:
         engine accepted the whole batch, so a failure (remote embedder error, 501 for code splitting, engine error)
         leaves neither a listed-but-unretrievable document nor ordinals that a later insert would reuse."""
         for _, _, metadata in docs:                                     # validate the whole batch before any work
-            if metadata.get("split_type") == "code" and not self.code_splitter_available(metadata):
-                raise HTTPException(501, "code splitting (tree-sitter) is not available in this build")
+            if metadata.get("split_type") == "code" and not metadata.get("language"):
+                raise ValueError("Language not specified in node metadata.")      # custom_transformer.py:39-41
         node_ids, texts, offs, tids, tfs, dls, new_nodes, new_refs = [], [], [0], [], [], [], [], {}
         base = len(st.nodes)
         for doc_id, text, metadata in docs:
@@ -302,12 +284,20 @@ class VectorStore:
         self._commit(st)
         return old
 
-    def code_splitter_available(self, metadata: dict) -> bool:
-        return False
-
     def split_document(self, text: str, metadata: dict) -> list[str]:
-        """CustomTransformer.__call__ (custom_transformer.py:34-55): SentenceSplitter() unless split_type == "code"."""
-        return self.splitter.split(text)
+        """CustomTransformer.split_node (custom_transformer.py:34-49): CodeSplitter(language) for split_type == "code" (one
+        splitter per language, cached), SentenceSplitter() otherwise -- with the metadata-aware chunk budget LlamaIndex applies
+        (the "key: value" block prepended for the embedder counts against chunk_size)."""
+        if metadata.get("split_type", "default") == "code":
+            lang = metadata.get("language", "")
+            if not lang:
+                raise ValueError("Language not specified in node metadata.")
+            sp = self._code_splitters.get(lang)
+            if sp is None:
+                sp = self._code_splitters[lang] = CodeSplitter(language=lang)
+            return sp.split(text) or [text]
+        meta_str = "\n".join(f"{k}: {v}" for k, v in metadata.items()) if metadata else ""
+        return self.splitter.split(text, meta_str) or [text]
 
     def _commit(self, st: _IndexState):
         # the reference rebuilds BM25 on every query (hybrid_retriever.py:104-130); here once per mutation

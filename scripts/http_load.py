@@ -1,0 +1,178 @@
+#!/usr/bin/env python
+"""HTTP-level load test of POST /retrieve (the call a client of the RAGService makes): text queries in, JSON out, with
+WordPiece + BM25 tokenisation, the K5 forward, the coalescer and response serialisation all on the clock.
+
+    python scripts/http_load.py [--gpus G] [--docs N] [--seconds T] [--clients C] [--concurrency K]
+
+Rank 0 runs the real service app (kaito_b200.service.create_app over VectorStore) under uvicorn in this process; with
+--gpus G > 1 the engine is the ShardedEngine with G - 1 worker processes (exactly what service.main() starts).  The corpus
+is synthetic (krag_synth_fill: N x 768 unit vectors + Zipf postings) because 10M documents cannot be pushed through /index in
+a benchmark's time; the docstore is a lazy stand-in ("synthetic document <ordinal>").  Queries are strings of synthetic
+terms ("t123 t4567 ..."); the embedder has bge-base shapes with random weights and a synthetic WordPiece vocabulary.
+C client PROCESSES x K concurrent keep-alive connections each hammer the server for T seconds; the line reports completed
+requests/s, latency percentiles, and the coalescer's batch statistics."""
+import argparse
+import asyncio
+import json
+import multiprocessing as mp
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+VOCAB = 1 << 20
+
+
+def synth_queries(n, seed):
+    g = np.random.default_rng(seed)
+    s, off = 1.07, 100
+    lo, hi = float(off + 1) ** (1 - s), float(VOCAB + 1) ** (1 - s)
+    out = []
+    for _ in range(n):
+        m = int(g.integers(3, 9))
+        x = (lo + g.random(m) * (hi - lo)) ** (1.0 / (1 - s))
+        out.append(" ".join(f"t{int(v)}" for v in np.clip(x.astype(np.int64) - 1, 0, VOCAB - 1)))
+    return out
+
+
+def client_proc(port, seconds, concurrency, seed, ret):
+    import aiohttp
+
+    async def run():
+        qs = synth_queries(4096, seed)
+        lat, done, stop = [], 0, time.perf_counter() + seconds
+        conn = aiohttp.TCPConnector(limit=concurrency)
+        async with aiohttp.ClientSession(connector=conn) as sess:
+            async def worker(w):
+                nonlocal done
+                i = w
+                while time.perf_counter() < stop:
+                    body = {"index_name": "load", "query": qs[i % len(qs)], "max_node_count": 10}
+                    t0 = time.perf_counter()
+                    async with sess.post(f"http://127.0.0.1:{port}/retrieve", json=body) as r:
+                        js = await r.json()
+                        assert r.status == 200 and js["count"] == 10, (r.status, js)
+                    lat.append(time.perf_counter() - t0)
+                    done += 1
+                    i += concurrency
+            await asyncio.gather(*[worker(w) for w in range(concurrency)])
+        return done, lat
+    done, lat = asyncio.run(run())
+    ret.put((done, lat[:: max(1, len(lat) // 2000)]))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--docs", type=int, default=10_000_000)
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--seconds", type=float, default=8.0)
+    ap.add_argument("--clients", type=int, default=8)
+    ap.add_argument("--concurrency", type=int, default=64)
+    ap.add_argument("--port", type=int, default=5077)
+    a = ap.parse_args()
+
+    import torch
+    import uvicorn
+    import bench
+    from kaito_b200 import _native, sharded_engine as se, vector_store as vs
+    from kaito_b200.embedding import GpuBertEmbedding
+    from kaito_b200.service import create_app
+    from kaito_b200.text import WordPieceTokenizer
+
+    ctx = _native.Context(device_id=0, rank=0, world_size=a.gpus)
+    workers, eng = [], None
+    if a.gpus > 1:
+        import socket
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0)); mport = sk.getsockname()[1]
+        workers = se.spawn_workers(a.gpus, mport)
+        ctl = se.init_distributed(0, a.gpus, 0, mport)
+        eng = se.ShardedEngine(se.native_stages_factory(ctx), torch.device("cuda", 0), None, ctl)
+        index = eng.synth_index("load", a.dim, a.docs, VOCAB)
+    else:
+        index = ctx.create_index("load", a.dim)
+        index.synth_fill(a.docs, row_base=0, seed=20260921, vocab=VOCAB)
+        index.commit(VOCAB)
+    # embedder: bge shapes, random weights, synthetic WordPiece vocabulary ("t<id>" tokens + digit pieces)
+    name = {384: "bge-small", 768: "bge-base", 1024: "bge-large"}[a.dim]
+    cfg = dict(bench.BGE[name], max_position_embeddings=512)
+    pieces = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"] + [f"t{i}" for i in range(20000)] + ["t"] + [str(d) for d in range(10)] + \
+             [f"##{d}" for d in range(10)] + [f"##{d:02d}" for d in range(100)] + [f"##{d:03d}" for d in range(1000)]
+    pieces += [f"[unused{i}]" for i in range(cfg["vocab_size"] - len(pieces))]
+    emb = GpuBertEmbedding(ctx, WordPieceTokenizer(pieces), cfg, bench.random_bert_state(bench.BGE[name]), query_instruction=None)
+
+    class Nodes:                                   # lazy docstore of the synthetic corpus
+        def __len__(self):
+            return a.docs
+
+        def __getitem__(self, o):
+            return vs._Node(f"n{int(o)}", f"doc{int(o)}", f"synthetic document {int(o)}", None, int(o))
+
+    class Vocab:                                   # "t<id>" -> term id
+        terms = []
+
+        def __len__(self):
+            return VOCAB
+
+        def query_terms(self, text):
+            return np.array([int(w[1:]) for w in text.split() if w[:1] == "t" and w[1:].isdigit()], np.uint32)
+
+    store = vs.VectorStore(emb, eng if eng is not None else ctx)
+    st = vs._IndexState(index)
+    st.nodes, st.vocab, st.committed = Nodes(), Vocab(), True
+    store.index_map["load"] = st
+    app = create_app(store, {"persist_dir": "storage", "llm_inference_url": None})
+    srv = uvicorn.Server(uvicorn.Config(app, host="127.0.0.1", port=a.port, log_level="warning", access_log=False))
+    th = threading.Thread(target=srv.run, daemon=True)
+    th.start()
+    while not srv.started:
+        time.sleep(0.05)
+    # correctness spot check at the HTTP level: the coalesced answer equals the direct single-query engine call
+    import urllib.request
+    q0 = synth_queries(4, 1)
+    for q in q0:
+        req = urllib.request.Request(f"http://127.0.0.1:{a.port}/retrieve", json.dumps({"index_name": "load", "query": q, "max_node_count": 10}).encode(),
+                                     {"Content-Type": "application/json"})
+        got = json.loads(urllib.request.urlopen(req).read())
+        want = store.retrieve("load", q, 10)
+        assert [(r["doc_id"], r["score"]) for r in got["results"]] == [(r["doc_id"], r["score"]) for r in want["results"]]
+    b0, r0 = app.state.batcher.batches, app.state.batcher.requests
+    ret = mp.Queue()
+    procs = [mp.Process(target=client_proc, args=(a.port, a.seconds, a.concurrency, 100 + i, ret)) for i in range(a.clients)]
+    t0 = time.perf_counter()
+    for p in procs:
+        p.start()
+    outs = [ret.get() for _ in procs]
+    for p in procs:
+        p.join()
+    wall = time.perf_counter() - t0
+    done = sum(o[0] for o in outs)
+    lat = np.sort(np.concatenate([np.asarray(o[1]) for o in outs]))
+    bt = app.state.batcher
+    print(json.dumps({
+        "metric": "http_retrieve_requests_per_sec", "value": done / a.seconds, "unit": "requests/s", "n_gpus": a.gpus,
+        "config": {"workload": f"POST /retrieve, top-10, {a.docs} docs x {a.dim} fp32 + BM25 postings (synthetic), text queries of 3-8 terms",
+                   "clients": a.clients, "concurrency_per_client": a.concurrency, "seconds": a.seconds,
+                   "on_the_clock": "HTTP parse, WordPiece + BM25 tokenisation, K5 forward, coalescer, dense+BM25+fuse, JSON response"},
+        "latency_ms": {"p50": float(lat[len(lat) // 2] * 1e3), "p90": float(lat[int(len(lat) * 0.9)] * 1e3), "p99": float(lat[int(len(lat) * 0.99)] * 1e3)},
+        "coalescer": {"engine_calls": bt.batches - b0, "requests": bt.requests - r0, "mean_batch": (bt.requests - r0) / max(1, bt.batches - b0),
+                      "max_batch": bt.max_seen, "window_us": bt.max_wait_s * 1e6},
+        "wall_s": wall, "spot_check": "4 queries: HTTP answer == direct engine call (ids and fp64 scores)",
+    }), flush=True)
+    srv.should_exit = True
+    th.join(timeout=5)
+    bt.close()
+    if eng is not None:
+        eng.shutdown()
+        for w in workers:
+            w.wait(timeout=30)
+    os._exit(0)
+
+
+if __name__ == "__main__":
+    main()

@@ -162,9 +162,9 @@ def _failed_insert_leaves_no_trace(store, emb):
         store.index_documents("tx", [{"text": "beta doc about shared memory"}])
     emb.fail = False
     assert store.list_documents_in_index("tx")["total_items"] == 1           # the failed document is not listed
-    with pytest.raises(HTTPException) as e:                                   # 501 raised before any state is touched
-        store.index_documents("tx", [{"text": "delta doc"}, {"text": "def f(): pass", "metadata": {"split_type": "code", "language": "cobol"}}])
-    assert e.value.status_code == 501 and store.list_documents_in_index("tx")["total_items"] == 1
+    with pytest.raises(ValueError) as e:                                      # custom_transformer.py:39-41, raised before any state is touched
+        store.index_documents("tx", [{"text": "delta doc"}, {"text": "def f(): pass", "metadata": {"split_type": "code"}}])
+    assert "Language not specified" in str(e.value) and store.list_documents_in_index("tx")["total_items"] == 1
     b = store.index_documents("tx", [{"text": "beta doc about shared memory"}])     # the retry indexes it
     g = store.index_documents("tx", [{"text": "gamma doc about thread block clusters"}])
     assert b[0] in [x["doc_id"] for x in store.retrieve("tx", "shared memory beta", 3)["results"]]
@@ -230,3 +230,35 @@ def test_rwlock_readers_share_writers_exclude():
     wi = log.index(("w+", 0))
     assert log[wi + 1] == ("w-", 0)                                            # nothing interleaves with the writer
     assert log[:2] == [("r+", 0), ("r+", 1)] or log[0][0] == "w+"              # readers overlap each other
+
+
+def test_code_documents_are_split_by_the_code_splitter(cpu_store):
+    """split_type == "code" (custom_transformer.py:38-49): CodeSplitter(language) chunks (max_chars 1500), other documents go
+    through SentenceSplitter(); both kinds stay retrievable and keep their doc id"""
+    code = "import os\n\n\n" + "\n\n".join(f"def function_{i}(x):\n    value = x + {i}\n    return value * {i}\n" for i in range(120))
+    ids = cpu_store.index_documents("code", [{"text": code, "metadata": {"split_type": "code", "language": "python"}},
+                                             {"text": "plain prose document about retrieval"}])
+    st = cpu_store.index_map["code"]
+    code_nodes = [n for n in st.nodes if n.ref_doc_id == ids[0]]
+    assert len(code_nodes) > 3 and all(len(n.text) <= 1500 for n in code_nodes)
+    assert "".join(n.text for n in code_nodes).count("def function_") == 120          # nothing lost, nothing duplicated
+    assert [n.text for n in st.nodes if n.ref_doc_id == ids[1]] == ["plain prose document about retrieval"]
+    got = cpu_store.retrieve("code", "function_77 value", 5)
+    assert ids[0] in [r["doc_id"] for r in got["results"]]
+
+
+def test_sentence_splitter_token_budget_and_overlap():
+    from kaito_b200.splitter import SentenceSplitter, split_sentences
+    sp = SentenceSplitter(chunk_size=60, chunk_overlap=20)
+    text = " ".join(f"Sentence {i} is short." for i in range(40)) + "\n\n\n" + "A second paragraph follows. It has two sentences."
+    chunks = sp.split(text)
+    assert len(chunks) > 2 and all(sp._count(c) <= 60 for c in chunks)
+    assert "".join(split_sentences(text)) == text
+    for a, b in zip(chunks, chunks[1:]):                       # consecutive chunks of a paragraph share a tail/head of whole sentences
+        if "second paragraph" in b:
+            continue
+        tail = a.split(". ")[-1]
+        assert tail.rstrip(".") in b
+    assert sp.split("tiny") == ["tiny"]
+    with pytest.raises(ValueError):                             # metadata longer than the chunk size (LlamaIndex raises the same)
+        sp.split("text", "k: " + "v " * 200)
