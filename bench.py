@@ -187,7 +187,6 @@ class CpuReference:
             # the reference embeds every query with torch BertModel on the CPU (huggingface_local_embedding.py:34-53)
             import torch
             from transformers import BertConfig, BertModel
-            torch.set_num_threads(os.cpu_count() or 1)
             torch.manual_seed(0)
             m = BertModel(BertConfig(**BGE[embedding]), add_pooling_layer=False).eval()
             ne = min(16, n_queries)

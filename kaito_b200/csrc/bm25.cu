@@ -593,31 +593,38 @@ struct BwCursor {
 __device__ __forceinline__ void bw_cursor_reset(BwCursor& cur, int64_t my_start, int my_len, int nt, uint32_t t0)
 {
     cur.my_start = my_start; cur.my_len = my_len; cur.nt = nt; cur.j = 0; cur.r = 0; cur.issued = 0; cur.t0 = t0;
-    int rj = (my_len + 31) >> 5;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) rj += __shfl_xor_sync(0xffffffffu, rj, o);
-    cur.R = rj;
+    cur.R = (int)__reduce_add_sync(0xffffffffu, (unsigned)((my_len + 31) >> 5));     // one REDUX
 }
 // Stage (cp.async: the loads of all rounds are in flight together and nobody waits for them here) up to BW_STAGE_ROUNDS
 // rounds at the cursor: docs[round][lane] | scores[round][lane]; lanes past the end of a term's list get doc = ~0.
+// Outer loop over the terms (one pair of shuffles per term), inner loop over the 32-posting rounds of the term.
 __device__ __forceinline__ int bw_issue(const BwCtx& c, BwCursor& cur, uint32_t* buf)
 {
     int n = 0;
+    uint32_t* dd = buf + c.lane;
+    bool full = false;
 #pragma unroll 1
-    while (n < BW_STAGE_ROUNDS && cur.j < cur.nt) {
+    while (cur.j < cur.nt && !full) {
         const int len = __shfl_sync(0xffffffffu, cur.my_len, cur.j);
-        const int base = cur.r * 32;
-        if (base >= len) { ++cur.j; cur.r = 0; continue; }               // term exhausted (or empty): next term
-        const int64_t st = __shfl_sync(0xffffffffu, cur.my_start, cur.j);
-        const int idx = base + c.lane;
-        uint32_t* dd = buf + n * 32 + c.lane;
-        if (idx < len) {
-            cp_async4(dd, c.post_doc + st + idx);
-            cp_async4(dd + BW_STAGE_ROUNDS * 32, c.post_score + st + idx);
-        } else {
-            *dd = 0xFFFFFFFFu;
+        int base = cur.r * 32;
+        if (base < len) {
+            const int64_t st = __shfl_sync(0xffffffffu, cur.my_start, cur.j);
+            const uint32_t* pd = c.post_doc + st + c.lane;
+            const float* ps = c.post_score + st + c.lane;
+#pragma unroll 1
+            for (; base < len; base += 32) {
+                if (n == BW_STAGE_ROUNDS) { full = true; break; }
+                if (base + c.lane < len) {
+                    cp_async4(dd, pd + base);
+                    cp_async4(dd + BW_STAGE_ROUNDS * 32, ps + base);
+                } else {
+                    *dd = 0xFFFFFFFFu;
+                }
+                dd += 32; ++n; ++cur.r;
+            }
+            if (full) break;
         }
-        ++n; ++cur.r;
+        ++cur.j; cur.r = 0;
     }
     cur.issued += n;
     cp_async_commit();
@@ -743,12 +750,10 @@ bm25_warp_kernel(const uint32_t* __restrict__ post_doc, const float* __restrict_
             const int nt = te - tb;
             const uint32_t* row = nullptr; int64_t base = 0;
             if (lane < nt) { row = q_row[tb + lane]; base = q_base[tb + lane]; }
-            uint32_t olo[BW_CHUNK], ohi[BW_CHUNK];
-#pragma unroll
-            for (int i = 0; i < BW_CHUNK; ++i) {
-                olo[i] = 0; ohi[i] = 0;
-                if (row != nullptr && i < ns) { const int64_t sub = (int64_t)(s0 + i) * stride; olo[i] = row[sub]; ohi[i] = row[sub + 1]; }
-            }
+            // boundary offsets of the sub-tile AFTER the one being staged are fetched one step ahead (two independent loads
+            // whose latency hides under a whole sub-tile of work)
+            uint32_t nlo = 0, nhi = 0;
+            if (row != nullptr) { const int64_t sub = (int64_t)s0 * stride; nlo = row[sub]; nhi = row[sub + 1]; }
             BwCursor cur;
             int ii = -1, buf = 0;
             int nb_n = 0, nb_R = 0; uint32_t nb_t0 = 0;                    // sub-tile in flight: rounds staged, rounds total
@@ -756,9 +761,8 @@ bm25_warp_kernel(const uint32_t* __restrict__ post_doc, const float* __restrict_
             auto next_subtile = [&](uint32_t* dst) -> bool {
                 for (;;) {
                     if (++ii >= ns) return false;
-                    uint32_t lo = 0, hi = 0;
-#pragma unroll
-                    for (int k = 0; k < BW_CHUNK; ++k) if (k == ii) { lo = olo[k]; hi = ohi[k]; }
+                    const uint32_t lo = nlo, hi = nhi;
+                    if (row != nullptr && ii + 1 < ns) { const int64_t sub = (int64_t)(s0 + ii + 1) * stride; nlo = row[sub]; nhi = row[sub + 1]; }
                     bw_cursor_reset(cur, base + lo, (int)(hi - lo), nt, (uint32_t)((int64_t)(s0 + ii) * stride * BM25_SUB_DOCS));
                     if (cur.R == 0) continue;
                     nb_n = bw_issue(c, cur, dst);
