@@ -972,7 +972,10 @@ void launch_bm25(const DeviceInfo& di, const Postings& post, int64_t n_rows, con
             count_launch();
         };
         if (!complete) {
+            // sample every stride-th sub-tile: the main pass then admits ~stride * P documents per query.  Small strides cost a
+            // larger sample pass (1 / stride of the main pass) but tighten the threshold: fewer candidate pushes, shorter final select
             int stride = L.capq / (4 * P);
+            if (stride > 64) stride = 64;
             if (stride < 1) stride = 1;
             if ((int64_t)stride > n_sub) stride = (int)n_sub;
             pass(stride, nullptr, counters);                               // sample: every stride-th sub-tile, everything admitted

@@ -1479,7 +1479,7 @@ void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int3
     if (use_graph && git != e->graphs.end()) {
         KRAG_CUDA(cudaGraphLaunch(git->second, st));
         count_launch(1 + 7 * c.layers);
-    } else if (use_graph && e->seen[key]++ >= 1) {
+    } else if (use_graph && (e->seen.size() > 4096 ? (e->seen.clear(), false) : e->seen[key]++ >= 1)) {
         if (e->graphs.size() >= 64) { for (auto& kv : e->graphs) cudaGraphExecDestroy(kv.second); e->graphs.clear(); }
         cudaGraph_t g = nullptr;
         cudaGraphExec_t ex = nullptr;

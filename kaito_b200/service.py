@@ -385,9 +385,13 @@ def _gpu_count() -> int:
 
 def main():
     """entry point of the image's `python3 main.py` shim (preset_rag.go:186): port 5000, /health probes."""
+    import sys
     import uvicorn
     from . import _native
     from .embedding import GpuBertEmbedding, HashingEmbedding
+    # the event loop thread and the coalescer's dispatcher thread share the GIL; the dispatcher re-acquires it after every
+    # engine (ctypes) call, and with the default 5 ms switch interval each re-acquisition can wait that long behind a busy loop
+    sys.setswitchinterval(float(os.getenv("KRAG_GIL_SWITCH_S", "0.0002")))
     cfg = env_config()
     if cfg["vector_db_type"] not in ("faiss", "krag"):
         raise SystemExit(f"VECTOR_DB_TYPE={cfg['vector_db_type']} is not served by this image (faiss-compatible engine only)")

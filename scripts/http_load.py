@@ -84,6 +84,7 @@ def main():
     from kaito_b200.service import create_app
     from kaito_b200.text import WordPieceTokenizer
 
+    sys.setswitchinterval(float(os.getenv("KRAG_GIL_SWITCH_S", "0.0002")))     # as service.main() does
     ctx = _native.Context(device_id=0, rank=0, world_size=a.gpus)
     workers, eng = [], None
     if a.gpus > 1:
