@@ -212,21 +212,29 @@ def create_app(store: vs.VectorStore, cfg: dict | None = None, llm=None) -> Fast
 
     TRACKED = ("/index", "/indexes", "/persist", "/load", "/retrieve", "/v1/chat/completions")
 
-    @app.middleware("http")
-    async def track_requests(request: Request, call_next):   # main.py:97-128: tracked paths only; status = the handler returned
-        if not any(request.url.path.startswith(p) for p in TRACKED):
-            return await call_next(request)
-        running.inc()
-        t0 = time.perf_counter()
-        status = "failure"
-        try:
-            resp = await call_next(request)
-            status = "success"
-            return resp
-        finally:
-            running.dec()
-            e2e_lat.labels(status).observe(time.perf_counter() - t0)
-            e2e_total.labels(status).inc()
+    class TrackRequests:
+        """main.py:97-128 (in-flight gauge + end-to-end latency on the tracked paths; status = the handler returned) as a plain
+        ASGI middleware: Starlette's BaseHTTPMiddleware costs an anyio task group and two memory streams per request, which at
+        thousands of requests per second is most of the event loop's time"""
+
+        def __init__(self, inner):
+            self.inner = inner
+
+        async def __call__(self, scope, receive, send):
+            if scope["type"] != "http" or not any(scope["path"].startswith(p) for p in TRACKED):
+                return await self.inner(scope, receive, send)
+            running.inc()
+            t0 = time.perf_counter()
+            status = "failure"
+            try:
+                await self.inner(scope, receive, send)
+                status = "success"
+            finally:
+                running.dec()
+                e2e_lat.labels(status).observe(time.perf_counter() - t0)
+                e2e_total.labels(status).inc()
+
+    app.add_middleware(TrackRequests)
 
     def run(kind, fn):
         """observe latency/status like the reference's per-route try/finally blocks"""

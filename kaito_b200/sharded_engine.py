@@ -87,8 +87,14 @@ class ShardedEngine:
                 dist.gather_object(err, None, dst=0, group=self.ctl)
 
     def shutdown(self):
+        """rank 0: tell the workers to leave their loops, then tear the process groups down on this side too (the workers'
+        destroy_process_group() waits for every rank)"""
         if self.rank == 0 and self.world > 1:
             self._bcast({"op": "shutdown"})
+            try:
+                dist.destroy_process_group()
+            except Exception:
+                pass
 
     # ------------------------------------------------------------------ commands (every rank)
     def _exec(self, cmd: dict):
@@ -288,10 +294,13 @@ def worker_main():
     try:
         eng.serve()
     finally:
-        for sh in list(eng.shards.values()):
-            sh.stages.drop()
-        ctx.close()
-        dist.destroy_process_group()
+        try:
+            for sh in list(eng.shards.values()):
+                sh.stages.drop()
+            ctx.close()
+            dist.destroy_process_group()
+        finally:
+            os._exit(0)        # never linger behind a half-torn-down NCCL communicator
 
 
 def spawn_workers(world: int, master_port: int):

@@ -15,11 +15,9 @@ nvidia-smi -L | wc -l
 timeout 400 bash -c "$(declare -f tr); tr 8 bench.py --gpus 8 --steps 20 --warmup 5" > gpurun_out/r2f/c3_n8.out 2> gpurun_out/r2f/c3_n8.err; echo "c3 n8 rc=$?"; line gpurun_out/r2f/c3_n8.out c3_n8
 timeout 600 bash -c "$(declare -f tr); tr 8 bench.py --gpus 8 --workload headline --steps 5 --warmup 3 --no-optin" > gpurun_out/r2f/headline_n8.out 2> gpurun_out/r2f/headline_n8.err; echo "headline n8 rc=$?"; line gpurun_out/r2f/headline_n8.out headline_n8
 timeout 600 bash -c "$(declare -f tr); tr 8 bench.py --gpus 8 --workload c4 --steps 5 --warmup 3 --no-optin" > gpurun_out/r2f/c4_n8.out 2> gpurun_out/r2f/c4_n8.err; echo "c4 n8 rc=$?"; line gpurun_out/r2f/c4_n8.out c4_n8
-timeout 600 python -m pytest tests/test_gpu_sharded.py -x -q 2>&1 | tail -4 | tee gpurun_out/r2f/pytest_sharded.log
+timeout 600 python -m pytest tests/test_gpu_sharded.py -x -q -k "4" 2>&1 | tail -4 | tee gpurun_out/r2f/pytest_sharded.log
 timeout 400 bash -c "$(declare -f tr); tr 8 bench_index.py --chunks 131072 --seq 256" 2> gpurun_out/r2f/index_n8.err | tail -1 | tee gpurun_out/r2f/index_n8.json | cut -c1-600
 timeout 400 python scripts/http_load.py --gpus 8 --docs 10000000 --seconds 6 --clients 8 --concurrency 64 2> gpurun_out/r2f/http_n8.err | tail -1 | tee gpurun_out/r2f/http_load_n8.json | cut -c1-700
 timeout 600 bash -c "$(declare -f tr); tr 4 bench.py --gpus 4 --workload headline --steps 5 --warmup 3 --no-optin" > gpurun_out/r2f/headline_n4.out 2> gpurun_out/r2f/headline_n4.err; echo "headline n4 rc=$?"; line gpurun_out/r2f/headline_n4.out headline_n4
-timeout 300 bash -c "$(declare -f tr); tr 4 bench.py --gpus 4 --steps 20 --warmup 5 --no-optin" > gpurun_out/r2f/c3_n4.out 2> gpurun_out/r2f/c3_n4.err; line gpurun_out/r2f/c3_n4.out c3_n4
-timeout 300 bash -c "$(declare -f tr); tr 2 bench.py --gpus 2 --steps 20 --warmup 5 --no-optin" > gpurun_out/r2f/c3_n2.out 2> gpurun_out/r2f/c3_n2.err; line gpurun_out/r2f/c3_n2.out c3_n2
 tail -3 gpurun_out/r2f/*.err | cut -c1-300 | tail -40
 ls gpurun_out/r2f/

@@ -73,4 +73,5 @@ else:
 for sh in list(eng.shards.values()):
     sh.stages.drop()
 ctx.close()
-dist.destroy_process_group()
+if dist.is_initialized():
+    dist.destroy_process_group()
