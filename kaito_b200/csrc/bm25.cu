@@ -635,11 +635,23 @@ __device__ __forceinline__ int bw_issue(const BwCtx& c, BwCursor& cur, uint32_t*
 // fp32 sum is built in the oracle's order
 __device__ __forceinline__ void bw_accumulate(const BwCtx& c, const uint32_t* buf, int n)
 {
+    const uint32_t* pd = buf + c.lane;
+    const uint32_t* ps = buf + BW_STAGE_ROUNDS * 32 + c.lane;
+    int u = 0;
 #pragma unroll 1
-    for (int u = 0; u < n; ++u) {
-        const uint32_t d = buf[u * 32 + c.lane];
-        const uint32_t rel = d - c.t0;
-        if (d != 0xFFFFFFFFu && rel < (uint32_t)BM25_SUB_DOCS) c.acc[rel] += __uint_as_float(buf[BW_STAGE_ROUNDS * 32 + u * 32 + c.lane]);
+    for (; u + 1 < n; u += 2) {            // two rounds per iteration: the staged loads of the second overlap the first's RMW
+        const uint32_t d0 = pd[u * 32], d1 = pd[u * 32 + 32];
+        const float s0 = __uint_as_float(ps[u * 32]), s1 = __uint_as_float(ps[u * 32 + 32]);
+        const uint32_t r0 = d0 - c.t0, r1 = d1 - c.t0;
+        if (d0 != 0xFFFFFFFFu && r0 < (uint32_t)BM25_SUB_DOCS) c.acc[r0] += s0;
+        __syncwarp();
+        if (d1 != 0xFFFFFFFFu && r1 < (uint32_t)BM25_SUB_DOCS) c.acc[r1] += s1;
+        __syncwarp();
+    }
+    if (u < n) {
+        const uint32_t d0 = pd[u * 32];
+        const uint32_t r0 = d0 - c.t0;
+        if (d0 != 0xFFFFFFFFu && r0 < (uint32_t)BM25_SUB_DOCS) c.acc[r0] += __uint_as_float(ps[u * 32]);
         __syncwarp();
     }
 }
@@ -660,23 +672,30 @@ __device__ __forceinline__ void bw_push(const BwCtx& c, bool hit, unsigned long 
 // All terms of the sub-tile are accumulated and its postings are still staged: every touched document is claimed once
 // (atomicExch resets the accumulator; later occurrences of the same document read 0) and appended to the query's
 // candidate list if it passes the admission threshold.
+__device__ __forceinline__ void bw_claim_one(const BwCtx& c, uint32_t d, float sum)
+{
+    bool hit = false;
+    unsigned long long key = 0;
+    if (sum > 0.f && sum >= c.thr_score && (c.alive == nullptr || bit_test(c.alive, d))) {
+        key = make_key_desc(sum, c.ord_base + d);
+        hit = key <= c.thr;
+    }
+    bw_push(c, hit, key);
+}
 __device__ __forceinline__ void bw_claim_staged(const BwCtx& c, const uint32_t* buf, int n)
 {
+    const uint32_t* pd = buf + c.lane;
 #pragma unroll 1
-    for (int u = 0; u < n; ++u) {
-        const uint32_t d = buf[u * 32 + c.lane];
-        const uint32_t rel = d - c.t0;
-        float sum = 0.f;
-        if (d != 0xFFFFFFFFu && rel < (uint32_t)BM25_SUB_DOCS) sum = atomicExch(&c.acc[rel], 0.f);
-        const bool maybe = sum > 0.f && sum >= c.thr_score;
+    for (int u = 0; u < n; u += 2) {       // two rounds per iteration: both exchanges are in flight together
+        const uint32_t d0 = pd[u * 32], d1 = (u + 1 < n) ? pd[u * 32 + 32] : 0xFFFFFFFFu;
+        const uint32_t r0 = d0 - c.t0, r1 = d1 - c.t0;
+        float sum0 = 0.f, sum1 = 0.f;
+        if (d0 != 0xFFFFFFFFu && r0 < (uint32_t)BM25_SUB_DOCS) sum0 = atomicExch(&c.acc[r0], 0.f);
+        if (d1 != 0xFFFFFFFFu && r1 < (uint32_t)BM25_SUB_DOCS) sum1 = atomicExch(&c.acc[r1], 0.f);   // same document again: reads 0
+        const bool maybe = (sum0 > 0.f && sum0 >= c.thr_score) || (sum1 > 0.f && sum1 >= c.thr_score);
         if (!__any_sync(0xffffffffu, maybe)) continue;
-        bool hit = false;
-        unsigned long long key = 0;
-        if (maybe && (c.alive == nullptr || bit_test(c.alive, d))) {
-            key = make_key_desc(sum, c.ord_base + d);
-            hit = key <= c.thr;
-        }
-        bw_push(c, hit, key);
+        bw_claim_one(c, d0, sum0);
+        bw_claim_one(c, d1, sum1);
     }
     __syncwarp();
 }
@@ -884,9 +903,18 @@ static int bw_capq(int P)
     while (c < 256 * P && c < 262144) c <<= 1;
     return c;
 }
-static bool bw_legacy()
+// which query kernel serves a shard: KRAG_BM25_KERNEL = auto (default) | warp | legacy; KRAG_BM25_LEGACY=1 == legacy.
+// auto: the warp kernel's fixed passes (resolve, sample pass, two selects) cost ~0.5 ms per batch whatever the shard size,
+// the first-generation kernel has almost none but ~1.5x the per-posting cost: the curves cross near 3M rows per shard
+// (measured: 10M rows 2.2 vs 3.1 ms, 1.25M rows 0.75 vs 0.50 ms per 256-query batch).
+constexpr int64_t BW_AUTO_MIN_ROWS = 3000000;
+static bool bw_legacy(int64_t n_rows)
 {
-    return env_int("KRAG_BM25_LEGACY", 0) != 0;
+    if (env_int("KRAG_BM25_LEGACY", 0) != 0) return true;
+    const char* k = getenv("KRAG_BM25_KERNEL");
+    if (k && k[0] == 'w') return false;
+    if (k && k[0] == 'l') return true;
+    return n_rows < BW_AUTO_MIN_ROWS;
 }
 
 struct BmLayout {   // carve-up of the caller's u64 workspace (`part`)
@@ -947,7 +975,7 @@ void launch_bm25(const DeviceInfo& di, const Postings& post, int64_t n_rows, con
     uint32_t* cand_cnt = reinterpret_cast<uint32_t*>(part + L.cnt_flags);
     uint32_t* flags = cand_cnt + batch;
     unsigned long long* counters = reinterpret_cast<unsigned long long*>(part + L.counters);
-    const bool legacy_only = bw_legacy();
+    const bool legacy_only = bw_legacy(n_rows);
     const bool complete = n_rows <= (int64_t)L.capq;     // one pass without threshold cannot overflow the lists
     bool need_safety_net = legacy_only;
 

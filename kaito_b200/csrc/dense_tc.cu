@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 dense_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmQ, int64_t n_rows,
                 int kblocks, int64_t n_ltiles, int tile_stride, const float* __restrict__ xnorm,
                 const uint32_t* __restrict__ alive, const float* __restrict__ thr_g, uint32_t* __restrict__ cand_count,
-                uint32_t* __restrict__ cand_rows, int cap, float* __restrict__ dump, int64_t S)
+                uint32_t* __restrict__ cand_rows, int cap, float* __restrict__ dump, int64_t S, int dump_min)
 {
     using Cfg = TcCfg<NQ>;
     extern __shared__ unsigned char tc_smem_raw[];
@@ -182,9 +182,22 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                 tmem_ld_x32(taddr + c0, v);
                 tmem_wait_ld();
                 if (DUMP) {
+                    if (dump_min) {
+                        // threshold sampling: per query only the MINIMUM over this warp's 32 rows is kept (one REDUX per
+                        // column) -- the few smallest values of the sample, which is all the threshold needs, survive
+                        // (two of them share a 32-row group with probability ~m^2 / (2 groups)); 40x less dump traffic
+                        uint32_t mine = 0xFFFFFFFFu;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j)
-                        dump[(int64_t)(c0 + j) * S + lt * TC_TILE_M + row_in_tile] = fmaf(-2.f, __uint_as_float(v[j]), xn);
+                        for (int j = 0; j < 32; ++j) {
+                            const uint32_t mn = __reduce_min_sync(0xffffffffu, f32_ordered_bits(fmaf(-2.f, __uint_as_float(v[j]), xn)));
+                            if (lane == j) mine = mn;
+                        }
+                        dump[(int64_t)(c0 + lane) * S + lt * (TC_TILE_M / 32) + lg] = f32_from_ordered_bits(mine);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            dump[(int64_t)(c0 + j) * S + lt * TC_TILE_M + row_in_tile] = fmaf(-2.f, __uint_as_float(v[j]), xn);
+                    }
                 } else {
                     float t[32];
                     float mx = -CUDART_INF_F;
@@ -922,8 +935,11 @@ static void tc_pass(const DeviceInfo& di, const CUtensorMap& tmX, const CUtensor
     const int grid_s = (int)(s_tiles < di.sm_count ? s_tiles : di.sm_count);
     const int grid_m = (int)(n_tiles < di.sm_count ? n_tiles : di.sm_count);
     // 1. sample pass (1/64 of the tiles), dump a = |x|^2 - 2 x.q
+    // the dump holds one value per (32-row group of a sampled tile, query): S_min per query
+    const int64_t S_min = s_tiles * (TC_TILE_M / 32);
+    (void)S;
     dense_tc_kernel<NQ, true><<<grid_s, TC_THREADS, Cfg::SMEM, st>>>(tmX, tmQ, n_rows, kblocks, s_tiles, TC_SAMPLE_STRIDE, xnorm,
-                                                                     alive, nullptr, nullptr, nullptr, 0, w.dump, S);
+                                                                     alive, nullptr, nullptr, nullptr, 0, w.dump, S_min, 1);
     KRAG_CUDA(cudaGetLastError());
     count_launch();
     // 2. threshold admitting ~C rows: the m-th smallest of the sample, m = C * sample_fraction
@@ -935,19 +951,10 @@ static void tc_pass(const DeviceInfo& di, const CUtensorMap& tmX, const CUtensor
     int m = (int)((double)tc_target(P, bf16) * (double)sampled_rows / (double)n_rows + 0.5);
     if (m < 4) m = 4;
     if (m > 1024) m = 1024;
-    // two-level: 8 blocks per query keep their m smallest, a second pass takes the m-th smallest of the 8 m survivors
-    // (the survivors are parked in the exact_keys area, which is not in use before the rescoring)
-    constexpr int ST_PARTS = 4;
-    float* part_vals = reinterpret_cast<float*>(w.exact_keys);
-    if (m <= 256) {
-        sample_threshold_kernel<1024><<<dim3(NQ, ST_PARTS), ST_THREADS, 0, st>>>(w.dump, S, m, nq, nullptr, part_vals);
-        count_launch();
-        sample_threshold_kernel<1024><<<dim3(NQ, 1), ST_THREADS, 0, st>>>(part_vals, (int64_t)ST_PARTS * m, m, nq, w.thr, nullptr);
-    } else {
-        sample_threshold_kernel<2048><<<dim3(NQ, ST_PARTS), ST_THREADS, 0, st>>>(w.dump, S, m, nq, nullptr, part_vals);
-        count_launch();
-        sample_threshold_kernel<2048><<<dim3(NQ, 1), ST_THREADS, 0, st>>>(part_vals, (int64_t)ST_PARTS * m, m, nq, w.thr, nullptr);
-    }
+    // m-th smallest of the S_min group minima per query (a few thousand values: one block per query, one launch)
+    if (m > (int)S_min) m = (int)S_min;
+    if (m <= 256) sample_threshold_kernel<1024><<<dim3(NQ, 1), ST_THREADS, 0, st>>>(w.dump, S_min, m, nq, w.thr, nullptr);
+    else sample_threshold_kernel<2048><<<dim3(NQ, 1), ST_THREADS, 0, st>>>(w.dump, S_min, m, nq, w.thr, nullptr);
     KRAG_CUDA(cudaGetLastError());
     count_launch();
     KRAG_CUDA(cudaMemsetAsync(w.cand_count, 0, 256 * 4, st));
@@ -1013,7 +1020,7 @@ static void tc_pass(const DeviceInfo& di, const CUtensorMap& tmX, const CUtensor
                                          (const float*)w.thr, w.cand_count, w.cand_rows, cap));
     } else {
         dense_tc_kernel<NQ, false><<<grid_m, TC_THREADS, Cfg::SMEM, st>>>(tmX, tmQ, n_rows, kblocks, n_tiles, 1, xnorm, alive, w.thr,
-                                                                          w.cand_count, w.cand_rows, cap, nullptr, 0);
+                                                                          w.cand_count, w.cand_rows, cap, nullptr, 0, 0);
     }
     dense_timer_end(st);
     KRAG_CUDA(cudaGetLastError());
@@ -1099,7 +1106,7 @@ bool dense_tc_debug_dump(const DeviceInfo& di, const float* X, int64_t n_rows, i
     do {                                                                                                                   \
         KRAG_CUDA(cudaFuncSetAttribute(dense_tc_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TcCfg<N>::SMEM)); \
         dense_tc_kernel<N, true><<<grid, TC_THREADS, TcCfg<N>::SMEM, st>>>(tmX, tmQ, n_rows, kblocks, n_tiles, 1, xnorm, nullptr,   \
-                                                                           nullptr, nullptr, nullptr, 0, dump_out, S);     \
+                                                                           nullptr, nullptr, nullptr, 0, dump_out, S, 0);  \
     } while (0)
     if (NQ == 64) KRAG_TC_DUMP(64); else if (NQ == 128) KRAG_TC_DUMP(128); else KRAG_TC_DUMP(256);
 #undef KRAG_TC_DUMP

@@ -590,34 +590,52 @@ __device__ __forceinline__ float warp_sum(float v)
 }
 
 // one warp per row: y = LayerNorm(x) * g + b   (two-pass variance like torch); a lane owns groups of 8 consecutive
-// elements (d % 8 == 0) so the fp32 row and the split fp16 planes are written with 32- / 16-byte stores
+// elements (d % 8 == 0, d <= 1024) that it reads ONCE into registers; the fp32 row and the split fp16 planes are written
+// with 32- / 16-byte stores
+constexpr int LN_MAX_GROUPS = 4;      // 8-element groups per lane: d <= 32 * 4 * 8 = 1024
 __device__ __forceinline__ void warp_layernorm_row(const float* __restrict__ x, float* __restrict__ y, uint16_t* __restrict__ y_hi,
                                                    uint16_t* __restrict__ y_lo, const float* __restrict__ g,
                                                    const float* __restrict__ b, int d, float eps, int lane)
 {
     const int groups = d >> 3;
+    float v[LN_MAX_GROUPS][8];
     float s = 0.f;
-    for (int gi = lane; gi < groups; gi += 32) {
-        const float4 a = *reinterpret_cast<const float4*>(x + gi * 8), c = *reinterpret_cast<const float4*>(x + gi * 8 + 4);
-        s += ((a.x + a.y) + (a.z + a.w)) + ((c.x + c.y) + (c.z + c.w));
+#pragma unroll
+    for (int k = 0; k < LN_MAX_GROUPS; ++k) {
+        const int gi = lane + 32 * k;
+        if (gi < groups) {
+            const float4 a = *reinterpret_cast<const float4*>(x + gi * 8), c = *reinterpret_cast<const float4*>(x + gi * 8 + 4);
+            v[k][0] = a.x; v[k][1] = a.y; v[k][2] = a.z; v[k][3] = a.w; v[k][4] = c.x; v[k][5] = c.y; v[k][6] = c.z; v[k][7] = c.w;
+            s += ((a.x + a.y) + (a.z + a.w)) + ((c.x + c.y) + (c.z + c.w));
+        }
     }
     const float mean = warp_sum(s) / (float)d;
-    float v = 0.f;
-    for (int gi = lane; gi < groups; gi += 32) {
-        const float4 a = *reinterpret_cast<const float4*>(x + gi * 8), c = *reinterpret_cast<const float4*>(x + gi * 8 + 4);
-        const float t0 = a.x - mean, t1 = a.y - mean, t2 = a.z - mean, t3 = a.w - mean, t4 = c.x - mean, t5 = c.y - mean, t6 = c.z - mean, t7 = c.w - mean;
-        v += ((t0 * t0 + t1 * t1) + (t2 * t2 + t3 * t3)) + ((t4 * t4 + t5 * t5) + (t6 * t6 + t7 * t7));
-    }
-    const float rstd = rsqrtf(warp_sum(v) / (float)d + eps);
-    for (int gi = lane; gi < groups; gi += 32) {
-        float o[8];
+    float q = 0.f;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) o[t] = (x[gi * 8 + t] - mean) * rstd * g[gi * 8 + t] + b[gi * 8 + t];
-        if (y) {
-            *reinterpret_cast<float4*>(y + gi * 8) = make_float4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<float4*>(y + gi * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    for (int k = 0; k < LN_MAX_GROUPS; ++k) {
+        if (lane + 32 * k < groups) {
+#pragma unroll
+            for (int t = 0; t < 8; ++t) { v[k][t] -= mean; }
+            q += ((v[k][0] * v[k][0] + v[k][1] * v[k][1]) + (v[k][2] * v[k][2] + v[k][3] * v[k][3])) +
+                 ((v[k][4] * v[k][4] + v[k][5] * v[k][5]) + (v[k][6] * v[k][6] + v[k][7] * v[k][7]));
         }
-        if (y_hi) split_store8(o, y_hi + gi * 8, y_lo + gi * 8);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)d + eps);
+#pragma unroll
+    for (int k = 0; k < LN_MAX_GROUPS; ++k) {
+        const int gi = lane + 32 * k;
+        if (gi < groups) {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(g + gi * 8)), g1 = __ldg(reinterpret_cast<const float4*>(g + gi * 8 + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(b + gi * 8)), b1 = __ldg(reinterpret_cast<const float4*>(b + gi * 8 + 4));
+            float o[8];
+            o[0] = v[k][0] * rstd * g0.x + b0.x; o[1] = v[k][1] * rstd * g0.y + b0.y; o[2] = v[k][2] * rstd * g0.z + b0.z; o[3] = v[k][3] * rstd * g0.w + b0.w;
+            o[4] = v[k][4] * rstd * g1.x + b1.x; o[5] = v[k][5] * rstd * g1.y + b1.y; o[6] = v[k][6] * rstd * g1.z + b1.z; o[7] = v[k][7] * rstd * g1.w + b1.w;
+            if (y) {
+                *reinterpret_cast<float4*>(y + gi * 8) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(y + gi * 8 + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            }
+            if (y_hi) split_store8(o, y_hi + gi * 8, y_lo + gi * 8);
+        }
     }
 }
 
@@ -1201,6 +1219,7 @@ void launch_linear(const DeviceInfo& di, const SplitMat& A, const SplitMat& B, i
 {
     static int use_sk = -1;
     if (use_sk < 0) { const char* ev = getenv("KRAG_GEMM_SPLITK"); use_sk = (ev == nullptr || ev[0] != '0') ? 1 : 0; }
+    if (ln_g && N > 32 * LN_MAX_GROUPS * 8) throw std::runtime_error("launch_linear: fused LayerNorm rows hold at most 1024 elements");
     const int m_tiles = (M + GM_TILE - 1) / GM_TILE;
     const int tiles128 = m_tiles * (N / GM_TILE);
     if (use_sk && ws && tiles128 < di.sm_count / 2 && N % 64 == 0 && K % GH_KB == 0 && (!ln_g || N <= 1024)) {
@@ -1291,8 +1310,8 @@ static std::string lname(int l, const char* s) { return "encoder.layer." + std::
 
 Embedder* embedder_create(const DeviceInfo& di, const BertConfig& cfg)
 {
-    if (cfg.hidden % 128 || cfg.inter % 128 || cfg.hidden % cfg.heads || cfg.hidden / cfg.heads > 64 || (cfg.hidden / cfg.heads) % 32)
-        throw std::runtime_error("embedder: hidden/intermediate must be multiples of 128 and head_dim 32 or 64");
+    if (cfg.hidden % 128 || cfg.inter % 128 || cfg.hidden % cfg.heads || cfg.hidden / cfg.heads > 64 || (cfg.hidden / cfg.heads) % 32 || cfg.hidden > 1024)
+        throw std::runtime_error("embedder: hidden/intermediate must be multiples of 128, hidden <= 1024 and head_dim 32 or 64");
     Embedder* e = new Embedder();
     e->di = di; e->cfg = cfg;
     KRAG_CUDA(cudaStreamCreateWithFlags(&e->st, cudaStreamNonBlocking));

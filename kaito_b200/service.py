@@ -234,6 +234,22 @@ def create_app(store: vs.VectorStore, cfg: dict | None = None, llm=None) -> Fast
                 e2e_lat.labels(status).observe(time.perf_counter() - t0)
                 e2e_total.labels(status).inc()
 
+    def _observe_retrieve(status, seconds, out):
+        h, c = M["retrieve"]
+        c.labels(status).inc(); h.labels(status).observe(seconds)
+        if out is not None:
+            res_count.observe(out["count"])
+            vs_lat.labels("query", "success").observe(getattr(store, "last_retrieve_seconds", 0.0))
+            scores = [r["score"] for r in out["results"]]
+            if scores:
+                low_score.observe(min(scores)); avg_score.observe(sum(scores) / len(scores))
+
+    if batcher is not None and batcher.enabled and os.getenv("KRAG_FAST_RETRIEVE", "1") != "0":
+        # well-formed POST /retrieve requests are answered below FastAPI's routing stack (kaito_b200/fast_retrieve.py); anything
+        # else -- including every request FastAPI would reject -- still reaches the route below
+        from .fast_retrieve import FastRetrieve
+        app.add_middleware(FastRetrieve, submit=batcher.submit, observe=_observe_retrieve, max_top_k=RAG_MAX_TOP_K,
+                           http_exception_types=(vs.HTTPException, HTTPException))
     app.add_middleware(TrackRequests)
 
     def run(kind, fn):

@@ -171,6 +171,7 @@ class HybridRetriever:
         # False (reference): only the keyword list is post-filtered (:227-235).  True: the bitmap restricts the dense and
         # the BM25 scan on the GPU, so every result satisfies the filter (not the reference).
         self._filter_pushdown = filter_pushdown
+        self.want_components = True          # VectorStore turns this off unless KRAG_COMPONENT_SCORES=1 (saves 10 dicts per query)
         self.last_components: list[dict] = []
 
     def _allow_bitmap(self):
@@ -202,7 +203,7 @@ class HybridRetriever:
         for b in range(len(queries)):
             c = int(out["count"][b])
             comps = []
-            if "dense" in out and "sparse" in out:      # per-result L2^2 / BM25 score as computed by the fuse kernel (NaN = absent)
+            if self.want_components and "dense" in out and "sparse" in out:      # per-result L2^2 / BM25 score as computed by the fuse kernel (NaN = absent)
                 for d, s in zip(out["dense"][b, :c], out["sparse"][b, :c]):
                     hd, hs = not np.isnan(d), not np.isnan(s)
                     comps.append({"dense_score": float(d) if hd else None, "sparse_score": float(s) if hs else None,
@@ -349,11 +350,12 @@ class VectorStore:
                 st = self.index_map[index_name]
                 retriever = HybridRetriever(st, self.embed_model, max_results=top_k, metadata_filter=metadata_filter,
                                             filter_pushdown=self.filter_pushdown)
+                retriever.want_components = self.component_scores
                 nodes, comps = retriever.retrieve_batch([queries[i] for i in live])
                 for j, i in enumerate(live):
                     results = [{"doc_id": n.ref_doc_id or n.node_id, "node_id": n.node_id, "text": n.text, "score": s,
                                 "metadata": n.metadata if n.metadata else None} for n, s in nodes[j]]
-                    if self.component_scores:
+                    if self.component_scores and comps[j]:
                         for r, extra in zip(results, comps[j]):
                             r.update(extra)
                     outs[i] = {"query": queries[i], "results": results, "count": len(results)}

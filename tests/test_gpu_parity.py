@@ -49,6 +49,13 @@ def test_dense_tombstones_and_appends(ctx_scan, oracle):
         ix.drop()
 
 
+@pytest.fixture(params=["warp", "legacy"])
+def bm25_kernel(request, monkeypatch):
+    """both generations of K3 on the small corpora (auto picks the first-generation kernel below 3M rows per shard)"""
+    monkeypatch.setenv("KRAG_BM25_KERNEL", request.param)
+    return request.param
+
+
 def _sparse_index(ctx, oracle, n, vocab, d=32, seed=1):
     x = oracle.synth_dense(n, d, seed)
     off, ids, tf, dl = oracle.synth_sparse(n, vocab, seed + 1)
@@ -59,7 +66,7 @@ def _sparse_index(ctx, oracle, n, vocab, d=32, seed=1):
 
 
 @pytest.mark.parametrize("n,vocab", [(50, 64), (3000, 2000), (40000, 30000)])
-def test_bm25_postings_and_query_bit_exact(ctx_scan, oracle, n, vocab):
+def test_bm25_postings_and_query_bit_exact(ctx_scan, oracle, n, vocab, bm25_kernel):
     ix, x, (off, ids, tf, dl) = _sparse_index(ctx_scan, oracle, n, vocab)
     try:
         post = oracle.bm25_build(off, ids, tf, dl, vocab)
@@ -82,7 +89,7 @@ def test_bm25_postings_and_query_bit_exact(ctx_scan, oracle, n, vocab):
         ix.drop()
 
 
-def test_bm25_long_queries_dense_postings(ctx_scan, oracle):
+def test_bm25_long_queries_dense_postings(ctx_scan, oracle, bm25_kernel):
     """tiny vocabulary -> every term is frequent (thousands of postings per doc tile) and queries of
     40-70 terms span several term chunks and slab passes of the kernel's general path"""
     n, vocab = 40000, 48
@@ -101,7 +108,7 @@ def test_bm25_long_queries_dense_postings(ctx_scan, oracle):
         ix.drop()
 
 
-def test_bm25_zero_fill_and_tombstones(ctx_scan, oracle):
+def test_bm25_zero_fill_and_tombstones(ctx_scan, oracle, bm25_kernel):
     ix, x, (off, ids, tf, dl) = _sparse_index(ctx_scan, oracle, 500, 800)
     try:
         post = oracle.bm25_build(off, ids, tf, dl, 800)
@@ -139,8 +146,9 @@ def sparse_400k(ctx_scan, oracle):
     ix.drop()
 
 
-def test_bm25_warp_kernel_two_pass_bit_exact(sparse_400k, oracle):
+def test_bm25_warp_kernel_two_pass_bit_exact(sparse_400k, oracle, monkeypatch):
     ix, post, n, vocab = sparse_400k
+    monkeypatch.setenv("KRAG_BM25_KERNEL", "warp")               # auto would pick the first-generation kernel below 3M rows
     qs = oracle.synth_query_terms(vocab, 48, seed=5, rank_offset=20)
     qs[0] = np.concatenate([qs[0], qs[0]])                        # every term twice
     qs[1] = np.array([0, 1, 2, 3], np.uint32)                     # the most frequent terms: ~every document matches
@@ -156,6 +164,7 @@ def test_bm25_overflow_takes_the_exact_safety_net(sparse_400k, oracle, monkeypat
     ix, post, n, vocab = sparse_400k
     qs = oracle.synth_query_terms(vocab, 12, seed=6, rank_offset=20)
     qs[0] = np.array([vocab - 1], np.uint32)                      # a handful of matches: stays below the cap
+    monkeypatch.setenv("KRAG_BM25_KERNEL", "warp")
     monkeypatch.setenv("KRAG_BM25_CAPQ", "64")
     _bm25_batch_vs_oracle(ix, oracle, post, qs, (30,))
 
@@ -170,7 +179,7 @@ def test_bm25_legacy_kernel_still_exact(sparse_400k, oracle, monkeypatch):
 
 
 @pytest.mark.parametrize("k", [1, 10, 40, 300])
-def test_retrieve_matches_oracle_pipeline(ctx_scan, oracle, k):
+def test_retrieve_matches_oracle_pipeline(ctx_scan, oracle, k, bm25_kernel):
     n, vocab, d = 6000, 5000, 64
     ix, x, (off, ids, tf, dl) = _sparse_index(ctx_scan, oracle, n, vocab, d=d, seed=7)
     try:
@@ -376,9 +385,11 @@ def test_filter_pushdown_bit_exact(oracle, dense_mode, batch):
         c.close()
 
 
-def test_strided_ordinal_map(ctx_scan, oracle):
+@pytest.mark.parametrize("kernel", ["warp", "legacy"])
+def test_strided_ordinal_map(ctx_scan, oracle, monkeypatch, kernel):
     """round-robin shards of the multi-GPU service: global ordinal = base + row * stride in every kernel that builds keys
     (K1, K2 rescoring, K3 claim, zero fill) and back again in krag_index_node_ids"""
+    monkeypatch.setenv("KRAG_BM25_KERNEL", kernel)
     n, vocab, d, base, stride = 300_000, 3000, 64, 3, 5
     x = oracle.synth_dense(n, d, 31)
     off, ids, tf, dl = oracle.synth_sparse(n, vocab, 32)
