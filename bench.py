@@ -99,7 +99,7 @@ def parse():
     ap.add_argument("--query-tokens", type=int, default=32, help="WordPiece tokens per query incl. [CLS]/[SEP]")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-optin", action="store_true", help="skip the extra OPT-IN measurement (bf16 shadow prune pass) after the default one")
-    ap.add_argument("--cpu-sample-rows", type=int, default=100_000)
+    ap.add_argument("--cpu-sample-rows", type=int, default=40_000)
     return ap.parse_args()
 
 
@@ -208,7 +208,7 @@ class CpuReference:
         self.rebuild_s = None
         if hybrid:
             vocab = 1 << 16
-            self.ns = min(self.n, 100_000)
+            self.ns = min(self.n, 20_000)
             off, ids, tf, dl = o.synth_sparse(self.ns, vocab, seed + 3)
             t0 = time.perf_counter()
             self.post = o.bm25_build(off, ids, tf, dl, vocab)

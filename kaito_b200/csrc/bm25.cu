@@ -17,9 +17,12 @@
 #include <math_constants.h>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/block/block_scan.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <stdlib.h>
+#include <algorithm>
+#include <stdexcept>
 #include <vector>
 
 #include "engine.h"
@@ -60,17 +63,60 @@ void launch_df_histogram(const uint32_t* term_ids, const uint32_t* entry_doc, co
     count_launch();
 }
 
-__global__ void pack_sort_values_kernel(const uint32_t* __restrict__ term_ids, const uint16_t* __restrict__ term_tf,
-                                        const uint32_t* __restrict__ entry_doc, const uint32_t* __restrict__ alive,
-                                        int64_t nnz, uint32_t dead_key, uint32_t* __restrict__ keys,
-                                        uint64_t* __restrict__ vals)
+// Stable compaction of the index entries that belong to one TERM RANGE [t_lo, t_hi) of live documents: the postings are built
+// range by range (radix sort of one range at a time), so the sort's four key/value buffers hold one range, not the whole index.
+// Two passes over the raw entries: per-block counts, (exclusive scan,) ordered scatter.
+constexpr int CC_THREADS = 256;
+constexpr int CC_ITEMS = 8;                       // consecutive entries per thread: 2048 per block
+__device__ __forceinline__ bool chunk_member(const uint32_t* __restrict__ term_ids, const uint32_t* __restrict__ entry_doc,
+                                             const uint32_t* __restrict__ alive, int64_t i, uint32_t t_lo, uint32_t t_hi)
 {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x) {
-        uint32_t d = entry_doc[i];
-        bool ok = alive == nullptr || bit_test(alive, d);
-        keys[i] = ok ? term_ids[i] : dead_key;  // tombstoned docs sort past the last term
-        vals[i] = ((uint64_t)d << 16) | term_tf[i];
+    const uint32_t t = term_ids[i];
+    return t >= t_lo && t < t_hi && (alive == nullptr || bit_test(alive, entry_doc[i]));
+}
+__global__ void __launch_bounds__(CC_THREADS)
+chunk_count_kernel(const uint32_t* __restrict__ term_ids, const uint32_t* __restrict__ entry_doc,
+                   const uint32_t* __restrict__ alive, int64_t nnz, uint32_t t_lo, uint32_t t_hi, uint32_t* __restrict__ block_cnt)
+{
+    __shared__ uint32_t s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const int64_t base = ((int64_t)blockIdx.x * CC_THREADS + threadIdx.x) * CC_ITEMS;
+    uint32_t c = 0;
+#pragma unroll
+    for (int k = 0; k < CC_ITEMS; ++k)
+        if (base + k < nnz && chunk_member(term_ids, entry_doc, alive, base + k, t_lo, t_hi)) ++c;
+    c = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) block_cnt[blockIdx.x] = s_cnt;
+}
+__global__ void __launch_bounds__(CC_THREADS)
+chunk_scatter_kernel(const uint32_t* __restrict__ term_ids, const uint16_t* __restrict__ term_tf,
+                     const uint32_t* __restrict__ entry_doc, const uint32_t* __restrict__ alive, int64_t nnz, uint32_t t_lo,
+                     uint32_t t_hi, const uint32_t* __restrict__ block_off, uint32_t* __restrict__ keys,
+                     uint64_t* __restrict__ vals)
+{
+    typedef cub::BlockScan<uint32_t, CC_THREADS> Scan;
+    __shared__ typename Scan::TempStorage tmp;
+    const int64_t base = ((int64_t)blockIdx.x * CC_THREADS + threadIdx.x) * CC_ITEMS;
+    bool ok[CC_ITEMS];
+    uint32_t c = 0;
+#pragma unroll
+    for (int k = 0; k < CC_ITEMS; ++k) {
+        ok[k] = base + k < nnz && chunk_member(term_ids, entry_doc, alive, base + k, t_lo, t_hi);
+        c += ok[k] ? 1u : 0u;
     }
+    uint32_t excl;
+    Scan(tmp).ExclusiveSum(c, excl);
+    uint32_t at = block_off[blockIdx.x] + excl;          // entry order = document order: the stable sort keeps it inside a term
+#pragma unroll
+    for (int k = 0; k < CC_ITEMS; ++k)
+        if (ok[k]) {
+            keys[at] = term_ids[base + k];
+            vals[at] = ((uint64_t)entry_doc[base + k] << 16) | term_tf[base + k];
+            ++at;
+        }
 }
 
 __global__ void score_postings_kernel(const uint32_t* __restrict__ sorted_terms, const uint64_t* __restrict__ sorted_vals,
@@ -113,11 +159,13 @@ __global__ void tile_slot_kernel(const int32_t* __restrict__ flag, const int32_t
         slot[t] = flag[t] ? scan[t] : -1;
 }
 __global__ void tile_index_kernel(const uint32_t* __restrict__ sorted_terms, const uint32_t* __restrict__ post_doc,
-                                  const int64_t* __restrict__ off, const int32_t* __restrict__ slot, int64_t nnz_live,
-                                  int64_t n_tiles, uint32_t* __restrict__ tile_off)
+                                  const int64_t* __restrict__ off, const int32_t* __restrict__ slot, int64_t p_base,
+                                  int64_t p_count, int64_t n_tiles, uint32_t* __restrict__ tile_off)
 {
-    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz_live; p += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t t = sorted_terms[p];
+    // sorted_terms: the term ids of postings [p_base, p_base + p_count) (one term range of the build); post_doc: all postings
+    for (int64_t pl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; pl < p_count; pl += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = p_base + pl;
+        const uint32_t t = sorted_terms[pl];
         const int32_t sl = slot[t];
         if (sl < 0) continue;
         const int64_t b = off[t], e = off[t + 1];
@@ -152,8 +200,8 @@ struct DevScratch {
     ~DevScratch() { for (void* p : ptrs) if (p) cudaFree(p); }
 };
 
-static void build_tile_index(const uint32_t* sorted_terms, const uint32_t* post_doc, const int64_t* off, int64_t nnz_live,
-                             int64_t vocab, int64_t n_rows, Postings& out, cudaStream_t st)
+// slots of the frequent terms (df > BM25_RARE_MAX) and the (still empty) boundary table; filled range by range below
+static void prepare_tile_index(const int64_t* off, int64_t vocab, int64_t n_rows, Postings& out, cudaStream_t st)
 {
     DevScratch sc;
     int32_t* flag = sc.alloc<int32_t>((size_t)(vocab + 1));
@@ -175,15 +223,27 @@ static void build_tile_index(const uint32_t* sorted_terms, const uint32_t* post_
     int64_t n_tiles = (n_rows + BM25_SUB_DOCS - 1) / BM25_SUB_DOCS;
     if (n_tiles < 1) n_tiles = 1;
     uint32_t* tile_off = sc.alloc<uint32_t>((size_t)((int64_t)(n_slots > 0 ? n_slots : 1) * (n_tiles + 1)));
-    if (n_slots > 0) {
-        tile_index_kernel<<<148 * 8, 256, 0, st>>>(sorted_terms, post_doc, off, slot, nnz_live, n_tiles, tile_off);
-        KRAG_CUDA(cudaGetLastError());
-        count_launch();
-    }
     if (out.tile_slot) cudaFree(out.tile_slot);
     if (out.tile_off) cudaFree(out.tile_off);
     sc.keep(slot); sc.keep(tile_off);
     out.tile_slot = slot; out.tile_off = tile_off; out.n_slots = n_slots; out.n_tiles = n_tiles;
+}
+
+// postings per term range of the build: KRAG_BM25_BUILD_CHUNK, else what fits in 70 % of the free device memory at
+// 24 bytes of sort buffers per posting (+ 1 for the sort's own scratch)
+static int64_t build_chunk_cap(int64_t nnz_live)
+{
+    int64_t cap = 0;
+    if (const char* e = getenv("KRAG_BM25_BUILD_CHUNK")) cap = atoll(e);
+    if (cap <= 0) {
+        size_t free_b = 0, total_b = 0;
+        KRAG_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        cap = (int64_t)((double)free_b * 0.7 / 25.0);
+        if (cap < ((int64_t)1 << 20)) cap = (int64_t)1 << 20;
+    }
+    const int64_t hard = ((int64_t)1 << 31) - 4096;              // 32-bit block offsets / cub item counts
+    if (cap > hard) cap = hard;
+    return cap < nnz_live ? cap : nnz_live;
 }
 
 void build_postings(const uint32_t* term_ids, const uint16_t* term_tf, const uint32_t* entry_doc,
@@ -204,39 +264,73 @@ void build_postings(const uint32_t* term_ids, const uint16_t* term_tf, const uin
     void* scan_tmp = sc.alloc<unsigned char>(scan_bytes);
     cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, tmp64, off, (int)(vocab + 1), st);
     count_launch();
-    int64_t nnz_live = 0;
-    KRAG_CUDA(cudaMemcpyAsync(&nnz_live, off + vocab, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    std::vector<int64_t> h_off((size_t)(vocab + 1));
+    KRAG_CUDA(cudaMemcpyAsync(h_off.data(), off, sizeof(int64_t) * (size_t)(vocab + 1), cudaMemcpyDeviceToHost, st));
     KRAG_CUDA(cudaStreamSynchronize(st));
+    const int64_t nnz_live = h_off[(size_t)vocab];
     sc.free_now(scan_tmp); sc.free_now(tmp64); sc.free_now(df_local);
 
     uint32_t* post_doc = sc.alloc<uint32_t>((size_t)(nnz_live > 0 ? nnz_live : 1));
     float* post_score = sc.alloc<float>((size_t)(nnz_live > 0 ? nnz_live : 1));
 
-    if (nnz > 0) {
+    if (nnz > 0 && nnz_live > 0) {
+        prepare_tile_index(off, vocab, n_docs_rows, out, st);
+        // term ranges [t_lo, t_hi) of at most `cap` postings each (a single term longer than that is a range of its own)
+        const int64_t cap = build_chunk_cap(nnz_live);
+        std::vector<int64_t> cuts{0};
+        int64_t widest = 0;
+        while (cuts.back() < vocab) {
+            const int64_t t_lo = cuts.back();
+            int64_t t_hi = (int64_t)(std::upper_bound(h_off.begin() + t_lo, h_off.end(), h_off[(size_t)t_lo] + cap) - h_off.begin()) - 1;
+            if (t_hi <= t_lo) t_hi = t_lo + 1;
+            if (t_hi > vocab) t_hi = vocab;
+            cuts.push_back(t_hi);
+            widest = std::max(widest, h_off[(size_t)t_hi] - h_off[(size_t)t_lo]);
+        }
+        if (widest >= ((int64_t)1 << 31)) throw std::runtime_error("bm25 build: a single term has too many postings for one build range");
+        const int64_t n_blocks = (nnz + (int64_t)CC_THREADS * CC_ITEMS - 1) / ((int64_t)CC_THREADS * CC_ITEMS);
+        if (n_blocks >= ((int64_t)1 << 31)) throw std::runtime_error("bm25 build: too many index entries on one shard");
+        uint32_t* block_cnt = sc.alloc<uint32_t>((size_t)n_blocks);
+        uint32_t* block_off = sc.alloc<uint32_t>((size_t)n_blocks);
+        size_t bscan_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, bscan_bytes, block_cnt, block_off, (int)n_blocks, st);
+        void* bscan_tmp = sc.alloc<unsigned char>(bscan_bytes);
         // stable LSD radix sort by term id keeps documents ascending inside every term
-        uint32_t* k_in = sc.alloc<uint32_t>((size_t)nnz);
-        uint32_t* k_out = sc.alloc<uint32_t>((size_t)nnz);
-        uint64_t* v_in = sc.alloc<uint64_t>((size_t)nnz);
-        uint64_t* v_out = sc.alloc<uint64_t>((size_t)nnz);
-        pack_sort_values_kernel<<<148 * 8, 256, 0, st>>>(term_ids, term_tf, entry_doc, alive, nnz, (uint32_t)vocab,
-                                                        k_in, v_in);
-        count_launch();
+        uint32_t* k_in = sc.alloc<uint32_t>((size_t)widest);
+        uint32_t* k_out = sc.alloc<uint32_t>((size_t)widest);
+        uint64_t* v_in = sc.alloc<uint64_t>((size_t)widest);
+        uint64_t* v_out = sc.alloc<uint64_t>((size_t)widest);
         int end_bit = 1;
-        while (((int64_t)1 << end_bit) <= vocab) ++end_bit;  // keys range over [0, vocab]
+        while (((int64_t)1 << end_bit) < vocab) ++end_bit;  // keys range over [0, vocab)
         size_t sort_bytes = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, k_in, k_out, v_in, v_out, nnz, 0, end_bit, st);
+        cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, k_in, k_out, v_in, v_out, widest, 0, end_bit, st);
         void* sort_tmp = sc.alloc<unsigned char>(sort_bytes);
-        cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, k_in, k_out, v_in, v_out, nnz, 0, end_bit, st);
-        count_launch();
-        if (nnz_live > 0) {
-            score_postings_kernel<<<148 * 8, 256, 0, st>>>(k_out, v_out, doc_len, idf, avgdl, nnz_live, post_doc,
-                                                          post_score);
+        for (size_t c = 0; c + 1 < cuts.size(); ++c) {
+            const int64_t t_lo = cuts[c], t_hi = cuts[c + 1];
+            const int64_t p_base = h_off[(size_t)t_lo], m = h_off[(size_t)t_hi] - p_base;
+            if (m == 0) continue;
+            chunk_count_kernel<<<(unsigned)n_blocks, CC_THREADS, 0, st>>>(term_ids, entry_doc, alive, nnz, (uint32_t)t_lo, (uint32_t)t_hi,
+                                                                         block_cnt);
+            KRAG_CUDA(cudaGetLastError());
             count_launch();
-            build_tile_index(k_out, post_doc, off, nnz_live, vocab, n_docs_rows, out, st);
+            cub::DeviceScan::ExclusiveSum(bscan_tmp, bscan_bytes, block_cnt, block_off, (int)n_blocks, st);
+            count_launch();
+            chunk_scatter_kernel<<<(unsigned)n_blocks, CC_THREADS, 0, st>>>(term_ids, term_tf, entry_doc, alive, nnz, (uint32_t)t_lo,
+                                                                           (uint32_t)t_hi, block_off, k_in, v_in);
+            KRAG_CUDA(cudaGetLastError());
+            count_launch();
+            size_t sb = sort_bytes;
+            cub::DeviceRadixSort::SortPairs(sort_tmp, sb, k_in, k_out, v_in, v_out, m, 0, end_bit, st);
+            count_launch();
+            score_postings_kernel<<<148 * 8, 256, 0, st>>>(k_out, v_out, doc_len, idf, avgdl, m, post_doc + p_base, post_score + p_base);
+            count_launch();
+            if (out.n_slots > 0) {
+                tile_index_kernel<<<148 * 8, 256, 0, st>>>(k_out, post_doc, off, out.tile_slot, p_base, m, out.n_tiles, out.tile_off);
+                KRAG_CUDA(cudaGetLastError());
+                count_launch();
+            }
         }
         KRAG_CUDA(cudaStreamSynchronize(st));
-        sc.free_now(sort_tmp);
-        sc.free_now(k_in); sc.free_now(k_out); sc.free_now(v_in); sc.free_now(v_out);
     }
     if (nnz_live == 0 || nnz == 0) {   // no postings: every term is "rare" with an empty list
         int32_t* slot = sc.alloc<int32_t>((size_t)vocab);

@@ -126,6 +126,36 @@ def test_bm25_zero_fill_and_tombstones(ctx_scan, oracle, bm25_kernel):
         ix.drop()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("chunk", [1, 777, 50_000])
+def test_bm25_build_in_term_ranges(ctx_scan, oracle, monkeypatch, chunk, bm25_kernel):
+    """the postings build sorts one TERM RANGE at a time (KRAG_BM25_BUILD_CHUNK postings per range; by default what fits in
+    the free device memory): same postings, same tile index, same results -- also after tombstones and a re-commit"""
+    monkeypatch.setenv("KRAG_BM25_BUILD_CHUNK", str(chunk))
+    n, vocab = 40000, 3000
+    ix, x, (off, ids, tf, dl) = _sparse_index(ctx_scan, oracle, n, vocab, seed=5)
+    try:
+        post = oracle.bm25_build(off, ids, tf, dl, vocab)
+        for t in list(range(0, 60)) + list(range(vocab - 20, vocab)):
+            docs, scores, cnt = ix.read_postings(t)
+            sl = slice(post.off[t], post.off[t + 1])
+            assert cnt == post.off[t + 1] - post.off[t]
+            assert np.array_equal(docs, post.doc[sl]) and np.array_equal(scores, post.score[sl])
+        qs = oracle.synth_query_terms(vocab, 12, seed=9, rank_offset=0)      # rank_offset 0: the most frequent terms (tile index rows)
+        _bm25_batch_vs_oracle(ix, oracle, post, qs, (30, 200))
+        dead = list(range(0, n, 7))
+        ix.remove(np.array(dead, np.uint64))
+        ix.commit(vocab)                                                      # rebuild without the tombstoned documents
+        live = np.ones(n, bool); live[dead] = False
+        keep = np.repeat(live, np.diff(off))
+        off2 = np.concatenate([[0], np.cumsum(np.where(live, np.diff(off), 0))]).astype(np.int64)
+        df = np.bincount(ids[keep], minlength=vocab).astype(np.uint32)
+        post2 = oracle.bm25_build(off2, ids[keep], tf[keep], dl, vocab, df, int(live.sum()), int(dl[live].astype(np.int64).sum()))
+        _bm25_batch_vs_oracle(ix, oracle, post2, qs, (30,), oracle.alive_bitmap(n, dead))
+    finally:
+        ix.drop()
+
+
 def _bm25_batch_vs_oracle(ix, oracle, post, qs, pools, alive=None):
     for P in pools:
         score, ordn = ix.search_bm25(qs, P)
