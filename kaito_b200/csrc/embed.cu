@@ -1063,6 +1063,204 @@ attention_flash_kernel(const float* __restrict__ qkv, const int32_t* __restrict_
     }
 }
 
+// ---- tensor-core attention: mma.sync m16n8k16 on the split fp16 planes the QKV projection writes, fp32 accumulators and
+// fp32 max-subtracted softmax.  Every product is the error-compensated 3-MMA form of the GEMMs above:
+//   A . B^T = hiA.hiB + 2^-11 (hiA.loB + loA.hiB).
+// One CTA per (sequence, head, block of 16 x WARPS query rows), one warp per 16 rows (flash-style: online softmax over key
+// blocks of KB keys; probabilities go from the score accumulators straight into the A fragments of P.V).  K and V planes
+// of a key block are staged in shared memory by cp.async (STAGES = 2: the next block flies during the current one) and read
+// with ldmatrix (V transposed on the fly), rows padded by 16 bytes so the 8 x 16-byte row reads hit 8 distinct bank groups.
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr));
+}
+__device__ __forceinline__ void mma_f16(float* c, const uint32_t* a, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16_zfill(uint32_t smem_dst, const void* gsrc, bool valid)
+{
+    const int sz = valid ? 16 : 0;                        // 0 source bytes: the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint32_t& lo)
+{
+    uint16_t h0, l0, h1, l1;
+    split_f16(a, h0, l0); split_f16(b, h1, l1);
+    hi = (uint32_t)h0 | ((uint32_t)h1 << 16); lo = (uint32_t)l0 | ((uint32_t)l1 << 16);
+}
+__device__ __forceinline__ void am_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void am_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+template <int DH, int WARPS, int KB, int STAGES> struct AmCfg {
+    static constexpr int LDH = DH + 8;                                   // row stride in halfs (16 bytes of padding)
+    static constexpr int Q_HALFS = 2 * 16 * WARPS * LDH;                 // hi | lo
+    static constexpr int KV_HALFS = 2 * KB * LDH;                        // hi | lo of one operand of one stage
+    static constexpr size_t SMEM = 2 * (size_t)(Q_HALFS + 2 * STAGES * KV_HALFS);
+};
+template <int DH, int WARPS, int KB, int STAGES>
+__global__ void __launch_bounds__(WARPS * 32)
+attention_mma_kernel(const uint16_t* __restrict__ qkv_hi, const uint16_t* __restrict__ qkv_lo, const int32_t* __restrict__ seq_off,
+                     uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo, int d, int heads)
+{
+    using Cfg = AmCfg<DH, WARPS, KB, STAGES>;
+    constexpr int LDH = Cfg::LDH, QROWS = 16 * WARPS, THREADS = WARPS * 32, CH = DH / 8 /* 16-byte chunks per row */;
+    extern __shared__ __align__(16) uint16_t am_sm[];
+    uint16_t* sQ = am_sm;                                  // [2][QROWS][LDH]
+    uint16_t* sK = sQ + Cfg::Q_HALFS;                      // [STAGES][2][KB][LDH]
+    uint16_t* sV = sK + STAGES * Cfg::KV_HALFS;            // [STAGES][2][KB][LDH]
+    pdl_launch_dependents();
+    pdl_wait();
+    const int b = blockIdx.z, h = blockIdx.y;
+    const int t0 = seq_off[b], len = seq_off[b + 1] - t0;
+    const int r0 = blockIdx.x * QROWS;
+    if (r0 >= len) return;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+    const size_t ld = (size_t)3 * d;
+    // rows [row0, row0 + nrows) of one of Q | K | V (column offset `col`) of this head, both planes -> dst[2][nrows][LDH]
+    auto stage_rows = [&](uint16_t* dst, int nrows, int row0, int col) {
+        for (int i = tid; i < 2 * nrows * CH; i += THREADS) {
+            const int pl = i / (nrows * CH), rem = i % (nrows * CH), r = rem / CH, ch = rem % CH;
+            const bool valid = row0 + r < len;
+            const uint16_t* src = (pl ? qkv_lo : qkv_hi) + (valid ? (size_t)(t0 + row0 + r) * ld + col + h * DH + ch * 8 : 0);
+            cp_async16_zfill(smem_u32(dst + ((size_t)pl * nrows + r) * LDH + ch * 8), src, valid);
+        }
+    };
+    auto stage_kv = [&](int kb, int stage) {
+        stage_rows(sK + stage * Cfg::KV_HALFS, KB, kb * KB, d);
+        stage_rows(sV + stage * Cfg::KV_HALFS, KB, kb * KB, 2 * d);
+        am_commit();
+    };
+    stage_rows(sQ, QROWS, r0, 0);
+    stage_kv(0, 0);
+    const int nkb = (len + KB - 1) / KB;
+    uint32_t qh[DH / 16][4], ql[DH / 16][4];
+    float om[DH / 8][4], oc[DH / 8][4];                    // output accumulators: main and correction products
+#pragma unroll
+    for (int j = 0; j < DH / 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { om[j][e] = 0.f; oc[j][e] = 0.f; }
+    float m_run[2] = {-CUDART_INF_F, -CUDART_INF_F}, l_run[2] = {0.f, 0.f};     // rows g and g + 8 of the warp's 16
+    const float scale = rsqrtf((float)DH);
+    for (int kb = 0; kb < nkb; ++kb) {
+        const int stage = STAGES == 2 ? (kb & 1) : 0;
+        if (STAGES == 2 && kb + 1 < nkb) { stage_kv(kb + 1, (kb + 1) & 1); am_wait<1>(); } else am_wait<0>();
+        __syncthreads();
+        if (kb == 0) {
+#pragma unroll
+            for (int kk = 0; kk < DH / 16; ++kk) {
+                const uint32_t a = smem_u32(sQ + (size_t)(warp * 16 + (lane & 15)) * LDH + kk * 16 + (lane >> 4) * 8);
+                ldsm_x4(a, qh[kk][0], qh[kk][1], qh[kk][2], qh[kk][3]);
+                ldsm_x4(a + 2 * QROWS * LDH, ql[kk][0], ql[kk][1], ql[kk][2], ql[kk][3]);
+            }
+        }
+        const uint16_t* kH = sK + stage * Cfg::KV_HALFS;
+        const uint16_t* vH = sV + stage * Cfg::KV_HALFS;
+        // ---- scores: the two correction products first, scaled by 2^-11, then the main product on top (one accumulator)
+        float s[KB / 8][4];
+#pragma unroll
+        for (int j = 0; j < KB / 8; ++j) {
+            s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+            for (int k2 = 0; k2 < DH / 32; ++k2) {
+                const uint32_t a = smem_u32(kH + (size_t)(j * 8 + (lane & 7)) * LDH + k2 * 32 + (lane >> 3) * 8);
+                uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+                ldsm_x4(a, h0, h1, h2, h3);
+                ldsm_x4(a + 2 * KB * LDH, l0, l1, l2, l3);
+                mma_f16(s[j], qh[2 * k2], l0, l1); mma_f16(s[j], ql[2 * k2], h0, h1);
+                mma_f16(s[j], qh[2 * k2 + 1], l2, l3); mma_f16(s[j], ql[2 * k2 + 1], h2, h3);
+            }
+            s[j][0] *= GH_LO_INV; s[j][1] *= GH_LO_INV; s[j][2] *= GH_LO_INV; s[j][3] *= GH_LO_INV;
+#pragma unroll
+            for (int k2 = 0; k2 < DH / 32; ++k2) {
+                const uint32_t a = smem_u32(kH + (size_t)(j * 8 + (lane & 7)) * LDH + k2 * 32 + (lane >> 3) * 8);
+                uint32_t h0, h1, h2, h3;
+                ldsm_x4(a, h0, h1, h2, h3);
+                mma_f16(s[j], qh[2 * k2], h0, h1); mma_f16(s[j], qh[2 * k2 + 1], h2, h3);
+            }
+        }
+        // ---- online softmax (fp32): thread (g, t) holds columns 2t, 2t+1 of every 8-key tile for rows g (e = 0, 1) and g + 8 (e = 2, 3)
+        const int k0 = kb * KB;
+        float mx[2] = {-CUDART_INF_F, -CUDART_INF_F};
+#pragma unroll
+        for (int j = 0; j < KB / 8; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const bool in = k0 + j * 8 + 2 * t + (e & 1) < len;
+                s[j][e] = in ? s[j][e] * scale : -CUDART_INF_F;
+                mx[e >> 1] = fmaxf(mx[e >> 1], s[j][e]);
+            }
+        float corr[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+            mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+            const float m_new = fmaxf(m_run[r], mx[r]);            // finite: every key block holds at least one valid key
+            corr[r] = expf(m_run[r] - m_new);                      // exp(-inf) = 0 on the first block
+            m_run[r] = m_new;
+        }
+        float sum[2] = {0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < KB / 8; ++j)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float p = expf(s[j][e] - m_run[e >> 1]);     // masked columns: exp(-inf) = 0
+                s[j][e] = p;
+                sum[e >> 1] += p;
+            }
+        l_run[0] = l_run[0] * corr[0] + sum[0];                    // per-thread partial row sums (reduced over t at the end)
+        l_run[1] = l_run[1] * corr[1] + sum[1];
+#pragma unroll
+        for (int j = 0; j < DH / 8; ++j) {
+            om[j][0] *= corr[0]; om[j][1] *= corr[0]; om[j][2] *= corr[1]; om[j][3] *= corr[1];
+            oc[j][0] *= corr[0]; oc[j][1] *= corr[0]; oc[j][2] *= corr[1]; oc[j][3] *= corr[1];
+        }
+        // ---- out += P . V : the score accumulators of key tiles 2u, 2u+1 ARE the A fragment of 16-key step u
+#pragma unroll
+        for (int u = 0; u < KB / 16; ++u) {
+            uint32_t ph[4], pl[4];
+            split_pack2(s[2 * u][0], s[2 * u][1], ph[0], pl[0]);
+            split_pack2(s[2 * u][2], s[2 * u][3], ph[1], pl[1]);
+            split_pack2(s[2 * u + 1][0], s[2 * u + 1][1], ph[2], pl[2]);
+            split_pack2(s[2 * u + 1][2], s[2 * u + 1][3], ph[3], pl[3]);
+#pragma unroll
+            for (int jp = 0; jp < DH / 16; ++jp) {
+                const uint32_t a = smem_u32(vH + (size_t)(u * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LDH + jp * 16 + (lane >> 4) * 8);
+                uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+                ldsm_x4_trans(a, h0, h1, h2, h3);
+                ldsm_x4_trans(a + 2 * KB * LDH, l0, l1, l2, l3);
+                mma_f16(om[2 * jp], ph, h0, h1); mma_f16(oc[2 * jp], ph, l0, l1); mma_f16(oc[2 * jp], pl, h0, h1);
+                mma_f16(om[2 * jp + 1], ph, h2, h3); mma_f16(oc[2 * jp + 1], ph, l2, l3); mma_f16(oc[2 * jp + 1], pl, h2, h3);
+            }
+        }
+        __syncthreads();                                           // the stage is free again
+        if (STAGES == 1 && kb + 1 < nkb) stage_kv(kb + 1, 0);
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+        l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+    }
+    const float inv[2] = {1.f / l_run[0], 1.f / l_run[1]};
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const int row = r0 + warp * 16 + g + 8 * r;
+        if (row >= len) continue;
+        const size_t ob = (size_t)(t0 + row) * d + h * DH + 2 * t;
+#pragma unroll
+        for (int j = 0; j < DH / 8; ++j) {
+            uint32_t hi, lo;
+            split_pack2(fmaf(oc[j][2 * r], GH_LO_INV, om[j][2 * r]) * inv[r], fmaf(oc[j][2 * r + 1], GH_LO_INV, om[j][2 * r + 1]) * inv[r], hi, lo);
+            *reinterpret_cast<uint32_t*>(out_hi + ob + j * 8) = hi;
+            *reinterpret_cast<uint32_t*>(out_lo + ob + j * 8) = lo;
+        }
+    }
+}
+
 // CLS pooling + L2 normalisation (F.normalize, eps 1e-12): one warp per sequence
 __global__ void __launch_bounds__(256)
 cls_normalize_kernel(const float* __restrict__ x, const int32_t* __restrict__ seq_off, float* __restrict__ out, int batch, int d,
@@ -1099,6 +1297,29 @@ static void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t s
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     KRAG_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
     count_launch();
+}
+
+template <int DH, int WARPS, int KB, int STAGES>
+static void launch_attention_mma(const uint16_t* q_hi, const uint16_t* q_lo, const int32_t* seq_off, uint16_t* out_hi, uint16_t* out_lo, int d,
+                                 int heads, int batch, int max_len, cudaStream_t st)
+{
+    using Cfg = AmCfg<DH, WARPS, KB, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        KRAG_CUDA(cudaFuncSetAttribute(attention_mma_kernel<DH, WARPS, KB, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+        attr_set = true;
+    }
+    launch_pdl(attention_mma_kernel<DH, WARPS, KB, STAGES>, dim3((unsigned)((max_len + 16 * WARPS - 1) / (16 * WARPS)), (unsigned)heads, (unsigned)batch),
+               dim3(WARPS * 32), Cfg::SMEM, st, q_hi, q_lo, seq_off, out_hi, out_lo, d, heads);
+}
+// queries (<= 32 tokens): 2 warps, one key block; <= 64: 4 warps, one block; chunks: 4 warps, 64-key blocks, double-buffered
+template <int DH>
+static void attention_mma(const uint16_t* q_hi, const uint16_t* q_lo, const int32_t* seq_off, uint16_t* out_hi, uint16_t* out_lo, int d, int heads,
+                          int batch, int max_len, cudaStream_t st)
+{
+    if (max_len <= 32) launch_attention_mma<DH, 2, 32, 1>(q_hi, q_lo, seq_off, out_hi, out_lo, d, heads, batch, max_len, st);
+    else if (max_len <= 64) launch_attention_mma<DH, 4, 64, 1>(q_hi, q_lo, seq_off, out_hi, out_lo, d, heads, batch, max_len, st);
+    else launch_attention_mma<DH, 4, 64, 2>(q_hi, q_lo, seq_off, out_hi, out_lo, d, heads, batch, max_len, st);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -1457,11 +1678,22 @@ void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int3
         KRAG_CUDA(cudaFuncSetAttribute(attention_flash_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
         at_attr = true;
     }
+    static int use_mma = -1;
+    if (use_mma < 0) { const char* ev = getenv("KRAG_ATTN_MMA"); use_mma = (ev == nullptr || ev[0] != '0') ? 1 : 0; }
     static int use_flash = -1;
     if (use_flash < 0) { const char* ev = getenv("KRAG_ATTN_FLASH"); use_flash = (ev == nullptr || ev[0] != '0') ? 1 : 0; }
     for (int l = 0; l < c.layers; ++l) {
         const size_t L = (size_t)l;
-        // QKV projection: split x -> fp32 qkv (attention is fp32 CUDA-core code)
+        if (use_mma) {
+            // QKV projection writes the split planes only (same bytes as the fp32 matrix they replace); attention on the tensor cores
+            uint16_t* q_hi = reinterpret_cast<uint16_t*>(e->qkv);
+            uint16_t* q_lo = q_hi + (size_t)n_tok * 3 * d;
+            launch_linear(e->di, xs, e->s_qkv[L], n_tok, 3 * d, d, e->bqkv[L], nullptr, false, nullptr, q_hi, q_lo, nullptr, nullptr, 0.f,
+                          nullptr, nullptr, nullptr, e->ws, Embedder::WS_FLOATS, st);
+            if (dh == 64) attention_mma<64>(q_hi, q_lo, e->d_off, cs.hi, cs.lo, d, c.heads, batch, max_len, st);
+            else attention_mma<32>(q_hi, q_lo, e->d_off, cs.hi, cs.lo, d, c.heads, batch, max_len, st);
+        } else {
+        // KRAG_ATTN_MMA=0: fp32 qkv and the fp32 CUDA-core attention kernels
         launch_linear(e->di, xs, e->s_qkv[L], n_tok, 3 * d, d, e->bqkv[L], nullptr, false, e->qkv, nullptr, nullptr, nullptr, nullptr, 0.f,
                       nullptr, nullptr, nullptr, e->ws, Embedder::WS_FLOATS, st);
         if (max_len <= 32) {
@@ -1477,6 +1709,7 @@ void embedder_forward(Embedder* e, int batch, const int32_t* tok_ids, const int3
                     e->qkv, e->d_off, cs.hi, cs.lo, d, c.heads, max_len);
             KRAG_CUDA(cudaGetLastError());
             count_launch();
+        }
         }
         // O projection (+bias +residual) -> LayerNorm -> x (fp32 residual stream) + its split planes
         launch_linear(e->di, cs, e->s_o[L], n_tok, d, d, e->t[lname(l, "attention.output.dense.bias")], e->x, false, e->x2, nullptr, nullptr,

@@ -65,6 +65,100 @@ def client_proc(port, seconds, concurrency, seed, ret):
     ret.put((done, lat[:: max(1, len(lat) // 2000)]))
 
 
+def serve_and_load(a, app, store, check=True):
+    import uvicorn
+    srv = uvicorn.Server(uvicorn.Config(app, host="127.0.0.1", port=a.port, log_level="warning", access_log=False))
+    th = threading.Thread(target=srv.run, daemon=True)
+    th.start()
+    while not srv.started:
+        time.sleep(0.05)
+    if check:
+        # correctness spot check at the HTTP level: the coalesced answer equals the direct single-query engine call
+        import urllib.request
+        for q in synth_queries(4, 1):
+            req = urllib.request.Request(f"http://127.0.0.1:{a.port}/retrieve", json.dumps({"index_name": "load", "query": q, "max_node_count": 10}).encode(),
+                                         {"Content-Type": "application/json"})
+            got = json.loads(urllib.request.urlopen(req).read())
+            want = store.retrieve("load", q, 10)
+            assert [(r["doc_id"], r["score"]) for r in got["results"]] == [(r["doc_id"], r["score"]) for r in want["results"]]
+    bt = app.state.batcher
+    b0, r0 = bt.batches, bt.requests
+    ret = mp.Queue()
+    procs = [mp.Process(target=client_proc, args=(a.port, a.seconds, a.concurrency, 100 + i, ret)) for i in range(a.clients)]
+    t0 = time.perf_counter()
+    for p in procs:
+        p.start()
+    outs = [ret.get() for _ in procs]
+    for p in procs:
+        p.join()
+    wall = time.perf_counter() - t0
+    done = sum(o[0] for o in outs)
+    lat = np.sort(np.concatenate([np.asarray(o[1]) for o in outs]))
+    res = {"value": done / a.seconds, "unit": "requests/s",
+           "latency_ms": {"p50": float(lat[len(lat) // 2] * 1e3), "p90": float(lat[int(len(lat) * 0.9)] * 1e3), "p99": float(lat[int(len(lat) * 0.99)] * 1e3)},
+           "coalescer": {"engine_calls": bt.batches - b0, "requests": bt.requests - r0, "mean_batch": (bt.requests - r0) / max(1, bt.batches - b0),
+                         "max_batch": bt.max_seen, "window_us": bt.max_wait_s * 1e6},
+           "wall_s": wall}
+    srv.should_exit = True
+    th.join(timeout=5)
+    bt.close()
+    return res
+
+
+def host_only(a):
+    """--fake-engine: everything of the service except the GPU"""
+    from kaito_b200 import vector_store as vs
+    from kaito_b200.service import create_app
+    from kaito_b200.text import WordPieceTokenizer
+    sys.setswitchinterval(float(os.getenv("KRAG_GIL_SWITCH_S", "0.0002")))
+    pieces = ["[PAD]", "[UNK]", "[CLS]", "[SEP]", "[MASK]"] + [f"t{i}" for i in range(20000)] + ["t"] + [str(d) for d in range(10)] + \
+             [f"##{d}" for d in range(10)] + [f"##{d:02d}" for d in range(100)] + [f"##{d:03d}" for d in range(1000)]
+    tok = WordPieceTokenizer(pieces)
+
+    class Emb:
+        def get_embedding_dimension(self):
+            return a.dim
+
+        def get_query_embedding_batch(self, queries):
+            for q in queries:
+                tok.encode(q)
+            return np.zeros((len(queries), a.dim), np.float32)
+
+    class Index:
+        def retrieve(self, q, terms, k, **kw):
+            time.sleep(a.fake_engine * 1e-3)                   # releases the GIL like the ctypes call into the engine
+            B = len(q)
+            o = (np.arange(B * k, dtype=np.int64).reshape(B, k) * 7919) % a.docs
+            return {"final": np.linspace(1.0, 0.5, B * k).reshape(B, k), "ordinal": o, "count": np.full(B, k, np.int32)}
+
+    class Nodes:
+        def __len__(self):
+            return a.docs
+
+        def __getitem__(self, o):
+            return vs._Node(f"n{int(o)}", f"doc{int(o)}", f"synthetic document {int(o)}", None, int(o))
+
+    class Vocab:
+        terms = []
+
+        def __len__(self):
+            return VOCAB
+
+        def query_terms(self, text):
+            return np.array([int(w[1:]) for w in text.split() if w[:1] == "t" and w[1:].isdigit()], np.uint32)
+
+    store = vs.VectorStore(Emb(), None)
+    st = vs._IndexState(Index())
+    st.nodes, st.vocab, st.committed = Nodes(), Vocab(), True
+    store.index_map["load"] = st
+    app = create_app(store, {"persist_dir": "storage", "llm_inference_url": None})
+    res = serve_and_load(a, app, store, check=False)
+    print(json.dumps({"metric": "http_retrieve_requests_per_sec", "n_gpus": 0, **res,
+                      "config": {"workload": f"POST /retrieve, top-10, host only: engine call = sleep({a.fake_engine} ms)", "clients": a.clients,
+                                 "concurrency_per_client": a.concurrency, "seconds": a.seconds}}), flush=True)
+    os._exit(0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -74,7 +168,12 @@ def main():
     ap.add_argument("--clients", type=int, default=8)
     ap.add_argument("--concurrency", type=int, default=64)
     ap.add_argument("--port", type=int, default=5077)
+    ap.add_argument("--fake-engine", type=float, default=None, metavar="MS",
+                    help="no GPU: the engine call sleeps MS milliseconds and returns arbitrary ordinals (the real tokenisers, "
+                         "coalescer, docstore and JSON run) -- measures the ceiling of the Python host alone")
     a = ap.parse_args()
+    if a.fake_engine is not None:
+        return host_only(a)
 
     import torch
     import uvicorn
@@ -128,46 +227,14 @@ def main():
     st.nodes, st.vocab, st.committed = Nodes(), Vocab(), True
     store.index_map["load"] = st
     app = create_app(store, {"persist_dir": "storage", "llm_inference_url": None})
-    srv = uvicorn.Server(uvicorn.Config(app, host="127.0.0.1", port=a.port, log_level="warning", access_log=False))
-    th = threading.Thread(target=srv.run, daemon=True)
-    th.start()
-    while not srv.started:
-        time.sleep(0.05)
-    # correctness spot check at the HTTP level: the coalesced answer equals the direct single-query engine call
-    import urllib.request
-    q0 = synth_queries(4, 1)
-    for q in q0:
-        req = urllib.request.Request(f"http://127.0.0.1:{a.port}/retrieve", json.dumps({"index_name": "load", "query": q, "max_node_count": 10}).encode(),
-                                     {"Content-Type": "application/json"})
-        got = json.loads(urllib.request.urlopen(req).read())
-        want = store.retrieve("load", q, 10)
-        assert [(r["doc_id"], r["score"]) for r in got["results"]] == [(r["doc_id"], r["score"]) for r in want["results"]]
-    b0, r0 = app.state.batcher.batches, app.state.batcher.requests
-    ret = mp.Queue()
-    procs = [mp.Process(target=client_proc, args=(a.port, a.seconds, a.concurrency, 100 + i, ret)) for i in range(a.clients)]
-    t0 = time.perf_counter()
-    for p in procs:
-        p.start()
-    outs = [ret.get() for _ in procs]
-    for p in procs:
-        p.join()
-    wall = time.perf_counter() - t0
-    done = sum(o[0] for o in outs)
-    lat = np.sort(np.concatenate([np.asarray(o[1]) for o in outs]))
-    bt = app.state.batcher
+    res = serve_and_load(a, app, store)
     print(json.dumps({
-        "metric": "http_retrieve_requests_per_sec", "value": done / a.seconds, "unit": "requests/s", "n_gpus": a.gpus,
+        "metric": "http_retrieve_requests_per_sec", "n_gpus": a.gpus, **res,
         "config": {"workload": f"POST /retrieve, top-10, {a.docs} docs x {a.dim} fp32 + BM25 postings (synthetic), text queries of 3-8 terms",
                    "clients": a.clients, "concurrency_per_client": a.concurrency, "seconds": a.seconds,
                    "on_the_clock": "HTTP parse, WordPiece + BM25 tokenisation, K5 forward, coalescer, dense+BM25+fuse, JSON response"},
-        "latency_ms": {"p50": float(lat[len(lat) // 2] * 1e3), "p90": float(lat[int(len(lat) * 0.9)] * 1e3), "p99": float(lat[int(len(lat) * 0.99)] * 1e3)},
-        "coalescer": {"engine_calls": bt.batches - b0, "requests": bt.requests - r0, "mean_batch": (bt.requests - r0) / max(1, bt.batches - b0),
-                      "max_batch": bt.max_seen, "window_us": bt.max_wait_s * 1e6},
-        "wall_s": wall, "spot_check": "4 queries: HTTP answer == direct engine call (ids and fp64 scores)",
+        "spot_check": "4 queries: HTTP answer == direct engine call (ids and fp64 scores)",
     }), flush=True)
-    srv.should_exit = True
-    th.join(timeout=5)
-    bt.close()
     if eng is not None:
         eng.shutdown()
         for w in workers:
