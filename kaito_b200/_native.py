@@ -253,6 +253,13 @@ class Embedder:
         check(self._L.krag_embed(self._h, len(token_lists), ptr(flat), ptr(offs), ptr(out)))
         return out
 
+    def embed_flat(self, flat_tokens: np.ndarray, offsets: np.ndarray) -> np.ndarray:
+        """embed() for tokens that are already packed (int32 ids, int32 offsets [batch + 1])"""
+        flat_tokens = np.ascontiguousarray(flat_tokens, np.int32); offsets = np.ascontiguousarray(offsets, np.int32)
+        out = np.empty((len(offsets) - 1, self.hidden), np.float32)
+        check(self._L.krag_embed(self._h, len(offsets) - 1, ptr(flat_tokens), ptr(offsets), ptr(out)))
+        return out
+
     @staticmethod
     def pack(token_lists):
         offs = np.zeros(len(token_lists) + 1, np.int32)

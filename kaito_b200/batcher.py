@@ -31,6 +31,7 @@ class RetrieveBatcher:
         self.batches = 0                  # engine calls issued
         self.requests = 0                 # requests answered
         self.max_seen = 0                 # largest group sent to the engine
+        self.after_batch = None           # optional hook, called on the dispatcher thread after every window (RPC flush)
         self._t = threading.Thread(target=self._run, name="krag-retrieve-batcher", daemon=True)
         self._t.start()
 
@@ -40,8 +41,16 @@ class RetrieveBatcher:
 
     def submit(self, index_name: str, query: str, top_k: int, metadata_filter: dict | None) -> Future:
         f: Future = Future()
-        self._q.put((index_name, query, top_k, metadata_filter, f))
+        self._q.put((index_name, query, top_k, metadata_filter, f, False))
         return f
+
+    def submit_bytes(self, index_name: str, query: str, top_k: int, metadata_filter: dict | None, sink=None):
+        """like submit(), answered with (json bytes, count, fused scores) from VectorStore.retrieve_batch_bytes.
+        sink=None: returns a Future.  sink=callable: no Future is created; sink(result_or_exception) is called on the
+        dispatcher thread (the RPC server of the front-end workers passes a closure that queues the reply frame)."""
+        f = Future() if sink is None else sink
+        self._q.put((index_name, query, top_k, metadata_filter, f, True))
+        return f if sink is None else None
 
     def retrieve(self, index_name: str, query: str, top_k: int, metadata_filter: dict | None):
         """blocking convenience wrapper (sync route handlers)"""
@@ -77,20 +86,31 @@ class RetrieveBatcher:
                 batch.append(item)
             groups: dict[tuple, list] = {}
             for it in batch:
-                key = (it[0], it[2], json.dumps(it[3], sort_keys=True, default=str) if it[3] else None)
+                key = (it[0], it[2], json.dumps(it[3], sort_keys=True, default=str) if it[3] else None, it[5])
                 groups.setdefault(key, []).append(it)
-            for (index_name, top_k, _), items in groups.items():
+            for (index_name, top_k, _, as_bytes), items in groups.items():
                 self.batches += 1
                 self.requests += len(items)
                 self.max_seen = max(self.max_seen, len(items))
+                fn = self.store.retrieve_batch_bytes if as_bytes else self.store.retrieve_batch
                 try:
-                    outs = self.store.retrieve_batch(index_name, [it[1] for it in items], top_k, items[0][3])
-                    for it, out in zip(items, outs):
-                        if isinstance(out, Exception):
-                            it[4].set_exception(out)
-                        else:
-                            it[4].set_result(out)
+                    outs = fn(index_name, [it[1] for it in items], top_k, items[0][3])
                 except Exception as e:                       # the whole group failed the same way (404, engine error)
-                    for it in items:
-                        if not it[4].done():
-                            it[4].set_exception(e)
+                    outs = [e] * len(items)
+                for it, out in zip(items, outs):
+                    self._deliver(it[4], out)
+            if self.after_batch is not None:
+                self.after_batch()
+
+    @staticmethod
+    def _deliver(target, out):
+        if isinstance(target, Future):
+            if isinstance(out, Exception):
+                target.set_exception(out)
+            else:
+                target.set_result(out)
+        else:
+            try:
+                target(out)
+            except Exception:                                # a sink must not take the dispatcher down
+                pass

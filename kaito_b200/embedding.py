@@ -111,8 +111,14 @@ class GpuBertEmbedding(BaseEmbeddingModel):
         return self.get_text_embedding((self.query_instruction or "") + query)
 
     def get_query_embedding_batch(self, queries):
-        """one K5 forward for a coalesced batch of queries (kaito_b200.batcher)"""
-        return self.get_text_embedding_batch([(self.query_instruction or "") + q for q in queries])
+        """one K5 forward for a coalesced batch of queries (kaito_b200.batcher); the token ids stay packed numpy arrays from
+        the native tokeniser to the embedder's C entry point"""
+        texts = [(self.query_instruction or "") + q for q in queries]
+        if hasattr(self.tokenizer, "encode_batch_flat"):
+            flat, offs = self.tokenizer.encode_batch_flat(texts)
+            if len(flat) <= self.max_batch_tokens:
+                return self._emb.embed_flat(flat, offs)
+        return self.get_text_embedding_batch(texts)
 
 
 class RemoteEmbeddingModel(BaseEmbeddingModel):

@@ -44,11 +44,15 @@ class FastRetrieve:
         status, payload = 200, None
         try:
             out = await asyncio.wrap_future(self.submit(*req))
-            for r in out["results"]:                  # models.NodeWithScore: the optional scores serialise as null when unset
-                r.setdefault("dense_score", None); r.setdefault("sparse_score", None); r.setdefault("source", None)
-                r.setdefault("metadata", None)
-            payload = json.dumps(out, ensure_ascii=False, allow_nan=False, separators=(",", ":")).encode("utf-8")
-            self.observe("success", time.perf_counter() - t0, out)
+            if isinstance(out, tuple):                # (json bytes, count, scores) from VectorStore.retrieve_batch_bytes
+                payload = out[0]
+                self.observe("success", time.perf_counter() - t0, {"count": out[1], "results": [{"score": s} for s in out[2]]})
+            else:
+                for r in out["results"]:              # models.NodeWithScore: the optional scores serialise as null when unset
+                    r.setdefault("dense_score", None); r.setdefault("sparse_score", None); r.setdefault("source", None)
+                    r.setdefault("metadata", None)
+                payload = json.dumps(out, ensure_ascii=False, allow_nan=False, separators=(",", ":")).encode("utf-8")
+                self.observe("success", time.perf_counter() - t0, out)
         except self.exc as e:                         # vs.HTTPException / fastapi.HTTPException: {"detail": ...}
             status, payload = e.status_code, json.dumps({"detail": e.detail}).encode("utf-8")
             self.observe("failure", time.perf_counter() - t0, None)

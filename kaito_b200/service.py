@@ -244,11 +244,13 @@ def create_app(store: vs.VectorStore, cfg: dict | None = None, llm=None) -> Fast
             if scores:
                 low_score.observe(min(scores)); avg_score.observe(sum(scores) / len(scores))
 
+    app.state.observe_retrieve = _observe_retrieve        # the front-end workers' RPC server books its requests here (rpc.py)
     if batcher is not None and batcher.enabled and os.getenv("KRAG_FAST_RETRIEVE", "1") != "0":
         # well-formed POST /retrieve requests are answered below FastAPI's routing stack (kaito_b200/fast_retrieve.py); anything
         # else -- including every request FastAPI would reject -- still reaches the route below
         from .fast_retrieve import FastRetrieve
-        app.add_middleware(FastRetrieve, submit=batcher.submit, observe=_observe_retrieve, max_top_k=RAG_MAX_TOP_K,
+        app.add_middleware(FastRetrieve, submit=batcher.submit_bytes if hasattr(store, "retrieve_batch_bytes") else batcher.submit,
+                           observe=_observe_retrieve, max_top_k=RAG_MAX_TOP_K,
                            http_exception_types=(vs.HTTPException, HTTPException))
     app.add_middleware(TrackRequests)
 
@@ -449,9 +451,27 @@ def main():
         raise SystemExit(f"embedding model '{cfg['embedding_model']}' not found locally (no network in the pod): mount a "
                          "Hugging Face snapshot and set KRAG_MODEL_DIR, or KRAG_ALLOW_HASHING_EMBEDDING=1 for functional tests")
     app = create_app(vs.VectorStore(embed, engine), cfg)
+    fronts, rpc = [], None
     try:
-        uvicorn.run(app, host="0.0.0.0", port=5000)
+        n_front = int(os.getenv("KRAG_HTTP_WORKERS", "0"))
+        if n_front > 0 and app.state.batcher is not None and app.state.batcher.enabled:
+            # N front-end processes own the public port; this process keeps the engine, the coalescer and the full API on a
+            # loopback port the workers proxy to (kaito_b200/frontend.py, kaito_b200/rpc.py)
+            import tempfile
+            from . import frontend
+            from .rpc import RetrieveRpcServer
+            engine_port = int(os.getenv("KRAG_ENGINE_PORT", "5001"))
+            rpc = RetrieveRpcServer(app.state.batcher, app.state.observe_retrieve, (vs.HTTPException, HTTPException),
+                                    path=os.path.join(tempfile.gettempdir(), f"krag-rpc-{os.getpid()}.sock"))
+            fronts = frontend.spawn(n_front, "0.0.0.0", 5000, f"127.0.0.1:{engine_port}", rpc.path, None, RAG_MAX_TOP_K)
+            uvicorn.run(app, host="127.0.0.1", port=engine_port)
+        else:
+            uvicorn.run(app, host="0.0.0.0", port=5000)
     finally:
+        for p in fronts:
+            p.terminate()
+        if rpc is not None:
+            rpc.close()
         if workers:
             engine.shutdown()
             for w in workers:

@@ -357,6 +357,30 @@ class WordPieceTokenizer:
     def encode(self, text: str) -> list[int]:
         return self.encode_batch([text])[0]
 
+    def encode_batch_flat(self, texts: list[str]):
+        """(flat int32 ids, int32 offsets [n + 1]) of every text -- what the embedder's C entry point takes.  All-ASCII batches
+        (the common case for queries) never become Python lists: one native call, one masked gather."""
+        if self._nat is not None and texts and all(t.isascii() for t in texts):
+            import ctypes as C
+            raws = [t.encode("ascii") for t in texts]
+            offs = np.zeros(len(raws) + 1, np.int64)
+            np.cumsum([len(r) for r in raws], out=offs[1:])
+            ids = np.empty((len(raws), self.max_length), np.int32)
+            cnt = np.empty(len(raws), np.int32)
+            rc = _native_lib().krag_wordpiece_encode_batch(self._nat, len(raws), b"".join(raws), offs.ctypes.data_as(C.c_void_p),
+                                                           self.max_length, ids.ctypes.data_as(C.c_void_p), cnt.ctypes.data_as(C.c_void_p))
+            if rc == 0:
+                width = int(cnt.max())
+                flat = ids[:, :width][np.arange(width, dtype=np.int32)[None, :] < cnt[:, None]]
+                toff = np.zeros(len(raws) + 1, np.int32)
+                np.cumsum(cnt, out=toff[1:])
+                return np.ascontiguousarray(flat, np.int32), toff
+        lists = self.encode_batch(texts)
+        toff = np.zeros(len(lists) + 1, np.int32)
+        np.cumsum([len(t) for t in lists], out=toff[1:])
+        flat = np.fromiter((i for t in lists for i in t), np.int32, int(toff[-1]))
+        return flat, toff
+
     def encode_batch(self, texts: list[str]) -> list[list[int]]:
         """ids of every text; ASCII texts go through the native, multi-threaded encoder in one call, the rest through encode_py"""
         out: list = [None] * len(texts)

@@ -131,6 +131,24 @@ class _IndexState:
         self.ref_docs: dict[str, dict] = {}      # doc_id -> {"text", "metadata", "nodes": [ordinal]}
         self.committed = False
         self._filter_cache: dict[str, tuple[int, np.ndarray]] = {}   # filter json -> (nodes covered, allow bitmap)
+        self._frag_cache: dict[int, tuple[bytes, bytes]] = {}        # ordinal -> serialised halves of its NodeWithScore
+
+    def node_fragments(self, o: int) -> tuple[bytes, bytes]:
+        """the JSON of node `o` as a /retrieve result, minus the score: (b'{"doc_id":..,"node_id":..,"text":..,"score":',
+        b',"metadata":..,"dense_score":null,"sparse_score":null,"source":null}').  Nodes are immutable once inserted, so the
+        halves are cached; a response is then a handful of bytes joins instead of ten dicts through json.dumps."""
+        f = self._frag_cache.get(o)
+        if f is None:
+            n = self.nodes[o]
+            dumps = json.dumps
+            head = ('{"doc_id":' + dumps(n.ref_doc_id or n.node_id, ensure_ascii=False) + ',"node_id":' + dumps(n.node_id, ensure_ascii=False) +
+                    ',"text":' + dumps(n.text, ensure_ascii=False) + ',"score":').encode("utf-8")
+            tail = (',"metadata":' + dumps(n.metadata if n.metadata else None, ensure_ascii=False, allow_nan=False, separators=(",", ":")) +
+                    ',"dense_score":null,"sparse_score":null,"source":null}').encode("utf-8")
+            if len(self._frag_cache) >= 1 << 20:
+                self._frag_cache.clear()
+            f = self._frag_cache[o] = (head, tail)
+        return f
 
     def allow_bitmap(self, metadata_filter: dict) -> np.ndarray:
         """1 bit per node (ordinal order) whose metadata equals the filter on every key (hybrid_retriever.py:227-235).
@@ -188,17 +206,7 @@ class HybridRetriever:
         """`_aretrieve` for a batch of queries that share (index, top_k, filter): ONE embedding forward and ONE engine call.
         Returns (per query: [(node, fused score)], per query: component dicts)."""
         st = self._state
-        if hasattr(self._embed, "get_query_embedding_batch"):
-            q = np.asarray(self._embed.get_query_embedding_batch(queries), np.float32).reshape(len(queries), -1)
-        else:
-            q = np.stack([np.asarray(self._embed.get_query_embedding(x), np.float32).reshape(-1) for x in queries])
-        # BM25 unavailable (empty docstore / nothing committed) -> vector-only fallback (:113-121, :216-218)
-        terms = [st.vocab.query_terms(x) for x in queries] if st.committed else None
-        allow = self._allow_bitmap() if (terms is not None or self._filter_pushdown) else None
-        out = st.index.retrieve(q, terms, self._max_results, cand_mult=self._candidate_multiplier,
-                                vector_weight=self._vector_weight, text_weight=self._text_weight,
-                                fusion_mode=FILTER_PUSHDOWN if (self._filter_pushdown and allow is not None) else 0,
-                                keyword_allow_bitmap=allow)
+        out = self.retrieve_batch_raw(queries)
         all_nodes, all_comps = [], []
         for b in range(len(queries)):
             c = int(out["count"][b])
@@ -211,6 +219,22 @@ class HybridRetriever:
             all_nodes.append([(st.nodes[int(o)], float(s)) for o, s in zip(out["ordinal"][b, :c], out["final"][b, :c])])
             all_comps.append(comps)
         return all_nodes, all_comps
+
+    def retrieve_batch_raw(self, queries: list[str]) -> dict:
+        """the engine's arrays for the batch: "ordinal" [B, k] i64, "final" [B, k] f64, "count" [B] (+ "dense" / "sparse")"""
+        st = self._state
+        if hasattr(self._embed, "get_query_embedding_batch"):
+            q = np.asarray(self._embed.get_query_embedding_batch(queries), np.float32).reshape(len(queries), -1)
+        else:
+            q = np.stack([np.asarray(self._embed.get_query_embedding(x), np.float32).reshape(-1) for x in queries])
+        # BM25 unavailable (empty docstore / nothing committed) -> vector-only fallback (:113-121, :216-218)
+        terms = [st.vocab.query_terms(x) for x in queries] if st.committed else None
+        allow = self._allow_bitmap() if (terms is not None or self._filter_pushdown) else None
+        out = st.index.retrieve(q, terms, self._max_results, cand_mult=self._candidate_multiplier,
+                                vector_weight=self._vector_weight, text_weight=self._text_weight,
+                                fusion_mode=FILTER_PUSHDOWN if (self._filter_pushdown and allow is not None) else 0,
+                                keyword_allow_bitmap=allow)
+        return out
 
 
 class VectorStore:
@@ -359,6 +383,58 @@ class VectorStore:
                         for r, extra in zip(results, comps[j]):
                             r.update(extra)
                     outs[i] = {"query": queries[i], "results": results, "count": len(results)}
+            self.last_retrieve_seconds = (time.time() - t0) / len(live)
+            return outs
+        except HTTPException:
+            raise
+        except Exception as e:
+            raise HTTPException(500, f"Retrieve failed: {e}")
+
+    def retrieve_batch_bytes(self, index_name: str, queries: list[str], max_node_count: int = 5, metadata_filter: dict | None = None):
+        """retrieve_batch() with the responses already serialised: per query (json bytes, count, fused scores) or the
+        HTTPException of that entry.  The bytes parse to exactly what retrieve_batch() returns plus the null defaults of
+        models.NodeWithScore; they are assembled from cached per-node fragments (the HTTP fast path and the front-end workers
+        forward them untouched)."""
+        if self.component_scores:                       # optional per-result fields: take the dict path
+            outs = self.retrieve_batch(index_name, queries, max_node_count, metadata_filter)
+            res = []
+            for o in outs:
+                if isinstance(o, Exception):
+                    res.append(o); continue
+                for r in o["results"]:
+                    r.setdefault("dense_score", None); r.setdefault("sparse_score", None); r.setdefault("source", None)
+                res.append((json.dumps(o, ensure_ascii=False, allow_nan=False, separators=(",", ":")).encode("utf-8"), o["count"],
+                            [r["score"] for r in o["results"]]))
+            return res
+        if index_name not in self.index_map:
+            raise HTTPException(404, f"No such index: '{index_name}' exists.")
+        bad = HTTPException(400, "Query string cannot be empty.")
+        live = [i for i, q in enumerate(queries) if q and q.strip() != ""]
+        outs: list = [bad] * len(queries)
+        if not live:
+            return outs
+        try:
+            top_k = min(max_node_count, RAG_MAX_TOP_K)
+            t0 = time.time()
+            with self._rw.reader():
+                st = self.index_map[index_name]
+                retriever = HybridRetriever(st, self.embed_model, max_results=top_k, metadata_filter=metadata_filter,
+                                            filter_pushdown=self.filter_pushdown)
+                out = retriever.retrieve_batch_raw([queries[i] for i in live])
+                counts, ords, finals = out["count"].tolist(), out["ordinal"].tolist(), out["final"].tolist()
+                frag = st.node_fragments
+                for j, i in enumerate(live):
+                    c = counts[j]
+                    scores = finals[j][:c]
+                    parts = []
+                    for o, sc in zip(ords[j][:c], scores):
+                        if sc != sc or sc in (float("inf"), float("-inf")):
+                            raise ValueError("Out of range float values are not JSON compliant")
+                        head, tail = frag(o)
+                        parts.append(head + repr(sc).encode("ascii") + tail)
+                    body = b'{"query":' + json.dumps(queries[i], ensure_ascii=False).encode("utf-8") + b',"results":[' + b",".join(parts) + \
+                           b'],"count":' + str(c).encode("ascii") + b"}"
+                    outs[i] = (body, c, scores)
             self.last_retrieve_seconds = (time.time() - t0) / len(live)
             return outs
         except HTTPException:

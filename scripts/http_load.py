@@ -67,11 +67,30 @@ def client_proc(port, seconds, concurrency, seed, ret):
 
 def serve_and_load(a, app, store, check=True):
     import uvicorn
-    srv = uvicorn.Server(uvicorn.Config(app, host="127.0.0.1", port=a.port, log_level="warning", access_log=False))
+    fronts, rpc = [], None
+    engine_port = a.port + 1 if a.http_workers > 0 else a.port
+    srv = uvicorn.Server(uvicorn.Config(app, host="127.0.0.1", port=engine_port, log_level="warning", access_log=False))
     th = threading.Thread(target=srv.run, daemon=True)
     th.start()
     while not srv.started:
         time.sleep(0.05)
+    if a.http_workers > 0:                     # what service.main() does with KRAG_HTTP_WORKERS=N
+        import tempfile
+        from kaito_b200 import frontend, vector_store as vs_
+        from kaito_b200.rpc import RetrieveRpcServer
+        from kaito_b200.service import RAG_MAX_TOP_K
+        from fastapi import HTTPException as FHE
+        rpc = RetrieveRpcServer(app.state.batcher, app.state.observe_retrieve, (vs_.HTTPException, FHE),
+                                path=os.path.join(tempfile.gettempdir(), f"krag-rpc-{os.getpid()}.sock"))
+        fronts = frontend.spawn(a.http_workers, "127.0.0.1", a.port, f"127.0.0.1:{engine_port}", rpc.path, None, RAG_MAX_TOP_K)
+        import urllib.request
+        for _ in range(200):                   # wait until a worker answers (proxied /health)
+            try:
+                urllib.request.urlopen(f"http://127.0.0.1:{a.port}/health", timeout=1).read()
+                break
+            except Exception:
+                time.sleep(0.1)
+        time.sleep(1.0)                        # ... and the slower ones are listening too
     if check:
         # correctness spot check at the HTTP level: the coalesced answer equals the direct single-query engine call
         import urllib.request
@@ -99,6 +118,13 @@ def serve_and_load(a, app, store, check=True):
            "coalescer": {"engine_calls": bt.batches - b0, "requests": bt.requests - r0, "mean_batch": (bt.requests - r0) / max(1, bt.batches - b0),
                          "max_batch": bt.max_seen, "window_us": bt.max_wait_s * 1e6},
            "wall_s": wall}
+    res["http_workers"] = a.http_workers
+    for p in fronts:
+        p.terminate()
+    for p in fronts:
+        p.wait(timeout=10)
+    if rpc is not None:
+        rpc.close()
     srv.should_exit = True
     th.join(timeout=5)
     bt.close()
@@ -168,6 +194,7 @@ def main():
     ap.add_argument("--clients", type=int, default=8)
     ap.add_argument("--concurrency", type=int, default=64)
     ap.add_argument("--port", type=int, default=5077)
+    ap.add_argument("--http-workers", type=int, default=0, help="front-end worker processes on the public port (KRAG_HTTP_WORKERS)")
     ap.add_argument("--fake-engine", type=float, default=None, metavar="MS",
                     help="no GPU: the engine call sleeps MS milliseconds and returns arbitrary ordinals (the real tokenisers, "
                          "coalescer, docstore and JSON run) -- measures the ceiling of the Python host alone")

@@ -213,3 +213,54 @@ def test_http_retrieve_goes_through_the_coalescer(oracle):
     want = store.retrieve("h", "alpha 3", 3)
     assert r.status_code == 200 and [(x["doc_id"], x["score"]) for x in r.json()["results"]] == [(x["doc_id"], x["score"]) for x in want["results"]]
     assert app.state.batcher.requests >= 1 and app.state.batcher.batches >= 1
+
+
+def test_serialised_responses_equal_the_dict_path(oracle, monkeypatch):
+    """VectorStore.retrieve_batch_bytes (cached per-node JSON fragments; what the HTTP fast path and the front-end workers send)
+    parses to exactly retrieve_batch()'s dicts plus the null defaults of NodeWithScore -- unicode, metadata, blank queries, 404"""
+    import json
+    from tests.oracle_engine import OracleEngine
+    from kaito_b200.batcher import RetrieveBatcher
+    store = VectorStore(HashingEmbedding(64), OracleEngine(oracle))
+    docs = [{"text": f"dokument número {i} über thema {i % 7} \"quoted\" \\ back\nnew", "metadata": {"bucket": i % 3, "tag": f"ü{i}"}} for i in range(30)]
+    docs += [{"text": f"plain document {i} thema {i % 7}"} for i in range(10)]
+    store.index_documents("s", docs)
+    queries = [f"thema {i % 7} número" for i in range(12)] + ["  ", "ünï \"q\""]
+    for flt in (None, {"bucket": 1}):
+        want = store.retrieve_batch("s", queries, 5, flt)
+        got = store.retrieve_batch_bytes("s", queries, 5, flt)
+        for w, g in zip(want, got):
+            if isinstance(w, Exception):
+                assert isinstance(g, Exception) and g.status_code == w.status_code == 400
+                continue
+            body, count, scores = g
+            for r in w["results"]:
+                r.setdefault("dense_score", None); r.setdefault("sparse_score", None); r.setdefault("source", None)
+            assert json.loads(body) == w and count == w["count"] and scores == [r["score"] for r in w["results"]]
+    with pytest.raises(Exception) as e:
+        store.retrieve_batch_bytes("missing", ["q"], 3, None)
+    assert e.value.status_code == 404
+    # through the coalescer: futures and sinks, both kinds in one window
+    b = RetrieveBatcher(store, max_batch=64, max_wait_s=0.05)
+    sunk = []
+    f1 = b.submit("s", queries[0], 5, None)
+    f2 = b.submit_bytes("s", queries[0], 5, None)
+    assert b.submit_bytes("s", queries[1], 5, None, sink=sunk.append) is None
+    b.submit_bytes("s", "  ", 5, None, sink=sunk.append)
+    assert json.loads(f2.result()[0])["results"][0]["doc_id"] == f1.result()["results"][0]["doc_id"]
+    import time
+    t0 = time.time()
+    while len(sunk) < 2 and time.time() - t0 < 5:
+        time.sleep(0.01)
+    assert len(sunk) == 2 and json.loads(sunk[0][0])["query"] == queries[1] and sunk[1].status_code == 400
+    b.close()
+    # KRAG_COMPONENT_SCORES=1 fills the optional fields: the bytes path follows
+    monkeypatch.setenv("KRAG_COMPONENT_SCORES", "1")
+    store2 = VectorStore(HashingEmbedding(64), OracleEngine(oracle))
+    store2.index_documents("s", docs)
+    w = store2.retrieve_batch("s", queries[:2], 3, None)
+    g = store2.retrieve_batch_bytes("s", queries[:2], 3, None)
+    for o in w:
+        for r in o["results"]:
+            r.setdefault("dense_score", None); r.setdefault("sparse_score", None); r.setdefault("source", None)
+    assert [json.loads(x[0]) for x in g] == w
