@@ -13,9 +13,7 @@ j=json.loads([l for l in open('gpurun_out/r2h/bench.json') if l.startswith('{')]
 print('value',j['value'],'ms',j['ms_per_step'],'e2e',j['e2e']['value'], 'embed', j['embed']['batch_ms'], j['embed']['batch1_ms'], 'k3', j['roofline_k3']['stage_ms'], j['roofline_k3']['frac'], 'dense', j['roofline']['dense_stage_ms'], j['roofline']['kernel_ms'], j['roofline']['frac'], 'check', j['check']['fused_ids_equal'], j['check']['recall_at_10'], 'b1', j['batch1']['value'], 'fallbacks', j['config']['tc_certificate_fallback_queries'])
 PY
 nproc
-timeout 400 python scripts/http_load.py --docs 10000000 --seconds 6 --clients 8 --concurrency 64 2> gpurun_out/r2h/http_load.err | tail -1 | tee gpurun_out/r2h/http_load_n1.json | cut -c1-1100
+timeout 600 python scripts/http_load.py --docs 10000000 --seconds 6 --clients 20 --concurrency 64 --http-workers 0,4,8 2> gpurun_out/r2h/http_load.err | grep '^{' | tee gpurun_out/r2h/http_load_n1.json | cut -c1-700
 tail -3 gpurun_out/r2h/http_load.err
-timeout 400 python scripts/http_load.py --docs 10000000 --seconds 6 --clients 20 --concurrency 64 --http-workers 8 2> gpurun_out/r2h/http_load_w8.err | tail -1 | tee gpurun_out/r2h/http_load_n1_w8.json | cut -c1-1100
-tail -3 gpurun_out/r2h/http_load_w8.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/r2h/launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-optin > gpurun_out/r2h/ncu_bench.log 2>&1
 python scripts/summarize_launches.py gpurun_out/r2h/launches.csv 2>/dev/null | grep -v "synth\|df_hist\|cub::\|row_norms\|score_postings\|tile_\|pack_sort\|expand_entry\|at::" | head -28

@@ -177,11 +177,13 @@ def host_only(a):
     st = vs._IndexState(Index())
     st.nodes, st.vocab, st.committed = Nodes(), Vocab(), True
     store.index_map["load"] = st
-    app = create_app(store, {"persist_dir": "storage", "llm_inference_url": None})
-    res = serve_and_load(a, app, store, check=False)
-    print(json.dumps({"metric": "http_retrieve_requests_per_sec", "n_gpus": 0, **res,
-                      "config": {"workload": f"POST /retrieve, top-10, host only: engine call = sleep({a.fake_engine} ms)", "clients": a.clients,
-                                 "concurrency_per_client": a.concurrency, "seconds": a.seconds}}), flush=True)
+    for w in a.worker_counts:
+        a.http_workers = w
+        app = create_app(store, {"persist_dir": "storage", "llm_inference_url": None})
+        res = serve_and_load(a, app, store, check=False)
+        print(json.dumps({"metric": "http_retrieve_requests_per_sec", "n_gpus": 0, **res,
+                          "config": {"workload": f"POST /retrieve, top-10, host only: engine call = sleep({a.fake_engine} ms)", "clients": a.clients,
+                                     "concurrency_per_client": a.concurrency, "seconds": a.seconds}}), flush=True)
     os._exit(0)
 
 
@@ -194,11 +196,14 @@ def main():
     ap.add_argument("--clients", type=int, default=8)
     ap.add_argument("--concurrency", type=int, default=64)
     ap.add_argument("--port", type=int, default=5077)
-    ap.add_argument("--http-workers", type=int, default=0, help="front-end worker processes on the public port (KRAG_HTTP_WORKERS)")
+    ap.add_argument("--http-workers", default="0", help="front-end worker processes on the public port (KRAG_HTTP_WORKERS); a comma "
+                    "list runs one load test per value against the same index, one JSON line each")
     ap.add_argument("--fake-engine", type=float, default=None, metavar="MS",
                     help="no GPU: the engine call sleeps MS milliseconds and returns arbitrary ordinals (the real tokenisers, "
                          "coalescer, docstore and JSON run) -- measures the ceiling of the Python host alone")
     a = ap.parse_args()
+    a.worker_counts = [int(x) for x in str(a.http_workers).split(",")]
+    a.http_workers = a.worker_counts[0]
     if a.fake_engine is not None:
         return host_only(a)
 
@@ -253,15 +258,17 @@ def main():
     st = vs._IndexState(index)
     st.nodes, st.vocab, st.committed = Nodes(), Vocab(), True
     store.index_map["load"] = st
-    app = create_app(store, {"persist_dir": "storage", "llm_inference_url": None})
-    res = serve_and_load(a, app, store)
-    print(json.dumps({
-        "metric": "http_retrieve_requests_per_sec", "n_gpus": a.gpus, **res,
-        "config": {"workload": f"POST /retrieve, top-10, {a.docs} docs x {a.dim} fp32 + BM25 postings (synthetic), text queries of 3-8 terms",
-                   "clients": a.clients, "concurrency_per_client": a.concurrency, "seconds": a.seconds,
-                   "on_the_clock": "HTTP parse, WordPiece + BM25 tokenisation, K5 forward, coalescer, dense+BM25+fuse, JSON response"},
-        "spot_check": "4 queries: HTTP answer == direct engine call (ids and fp64 scores)",
-    }), flush=True)
+    for w in a.worker_counts:
+        a.http_workers = w
+        app = create_app(store, {"persist_dir": "storage", "llm_inference_url": None})
+        res = serve_and_load(a, app, store)
+        print(json.dumps({
+            "metric": "http_retrieve_requests_per_sec", "n_gpus": a.gpus, **res,
+            "config": {"workload": f"POST /retrieve, top-10, {a.docs} docs x {a.dim} fp32 + BM25 postings (synthetic), text queries of 3-8 terms",
+                       "clients": a.clients, "concurrency_per_client": a.concurrency, "seconds": a.seconds,
+                       "on_the_clock": "HTTP parse, WordPiece + BM25 tokenisation, K5 forward, coalescer, dense+BM25+fuse, JSON response"},
+            "spot_check": "4 queries: HTTP answer == direct engine call (ids and fp64 scores)",
+        }), flush=True)
     if eng is not None:
         eng.shutdown()
         for w in workers:
