@@ -22,7 +22,7 @@ from concurrent.futures import Future
 
 
 class RetrieveBatcher:
-    def __init__(self, store, max_batch: int | None = None, max_wait_s: float | None = None):
+    def __init__(self, store, max_batch: int | None = None, max_wait_s: float | None = None, dispatchers: int | None = None):
         self.store = store
         self.max_batch = int(os.getenv("KRAG_MAX_BATCH", "256")) if max_batch is None else max_batch
         self.max_wait_s = float(os.getenv("KRAG_BATCH_WINDOW_US", "200")) * 1e-6 if max_wait_s is None else max_wait_s
@@ -32,8 +32,13 @@ class RetrieveBatcher:
         self.requests = 0                 # requests answered
         self.max_seen = 0                 # largest group sent to the engine
         self.after_batch = None           # optional hook, called on the dispatcher thread after every window (RPC flush)
-        self._t = threading.Thread(target=self._run, name="krag-retrieve-batcher", daemon=True)
-        self._t.start()
+        # two dispatcher threads: while one batch is inside the engine call (GIL released) the other collects, tokenises and
+        # later serialises the next one, so the per-batch host work overlaps the GPU instead of adding to it
+        self._stats_mu = threading.Lock()
+        n = max(1, int(os.getenv("KRAG_BATCH_DISPATCHERS", "2")) if dispatchers is None else dispatchers)
+        self._ts = [threading.Thread(target=self._run, name=f"krag-retrieve-batcher-{i}", daemon=True) for i in range(n)]
+        for t in self._ts:
+            t.start()
 
     @property
     def enabled(self) -> bool:
@@ -58,8 +63,10 @@ class RetrieveBatcher:
 
     def close(self):
         self._stop = True
-        self._q.put(None)
-        self._t.join(timeout=5)
+        for _ in self._ts:
+            self._q.put(None)
+        for t in self._ts:
+            t.join(timeout=5)
 
     # ------------------------------------------------------------------ dispatcher
     def _run(self):
@@ -82,6 +89,7 @@ class RetrieveBatcher:
                         break
                 if item is None:
                     self._stop = True
+                    self._q.put(None)                       # the sentinel was meant for one thread: pass it on
                     break
                 batch.append(item)
             groups: dict[tuple, list] = {}
@@ -89,9 +97,10 @@ class RetrieveBatcher:
                 key = (it[0], it[2], json.dumps(it[3], sort_keys=True, default=str) if it[3] else None, it[5])
                 groups.setdefault(key, []).append(it)
             for (index_name, top_k, _, as_bytes), items in groups.items():
-                self.batches += 1
-                self.requests += len(items)
-                self.max_seen = max(self.max_seen, len(items))
+                with self._stats_mu:
+                    self.batches += 1
+                    self.requests += len(items)
+                    self.max_seen = max(self.max_seen, len(items))
                 fn = self.store.retrieve_batch_bytes if as_bytes else self.store.retrieve_batch
                 try:
                     outs = fn(index_name, [it[1] for it in items], top_k, items[0][3])

@@ -69,6 +69,8 @@ class GpuBertEmbedding(BaseEmbeddingModel):
                                      config["intermediate_size"], config["vocab_size"], config.get("max_position_embeddings", 512),
                                      config.get("type_vocab_size", 2), config.get("layer_norm_eps", 1e-12))
         self._emb.load_state_dict(state_dict)
+        import threading
+        self._mu = threading.Lock()          # one forward at a time: the embedder owns one set of activation buffers
 
     @classmethod
     def from_pretrained(cls, engine, model_dir: str, **kw):
@@ -95,10 +97,13 @@ class GpuBertEmbedding(BaseEmbeddingModel):
         out, batch, ntok = [], [], 0
         for t in token_lists:
             if batch and ntok + len(t) > self.max_batch_tokens:
-                out.append(self._emb.embed(batch)); batch, ntok = [], 0
+                with self._mu:
+                    out.append(self._emb.embed(batch))
+                batch, ntok = [], 0
             batch.append(t); ntok += len(t)
         if batch:
-            out.append(self._emb.embed(batch))
+            with self._mu:
+                out.append(self._emb.embed(batch))
         return np.concatenate(out)
 
     def get_text_embedding_batch(self, texts):
@@ -117,7 +122,8 @@ class GpuBertEmbedding(BaseEmbeddingModel):
         if hasattr(self.tokenizer, "encode_batch_flat"):
             flat, offs = self.tokenizer.encode_batch_flat(texts)
             if len(flat) <= self.max_batch_tokens:
-                return self._emb.embed_flat(flat, offs)
+                with self._mu:
+                    return self._emb.embed_flat(flat, offs)
         return self.get_text_embedding_batch(texts)
 
 

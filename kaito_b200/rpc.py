@@ -55,6 +55,7 @@ class RetrieveRpcServer:
         self.batcher, self.observe, self.exc = batcher, observe, http_exception_types
         self.path, self.port = path, port
         self._dirty: set[_Conn] = set()
+        self._mu = threading.Lock()              # sinks and flushes run on the coalescer's dispatcher threads (more than one)
         self._loop = asyncio.new_event_loop()
         self._started = threading.Event()
         self._server = None
@@ -103,24 +104,29 @@ class RetrieveRpcServer:
 
         def deliver(out):
             if isinstance(out, tuple):
-                conn.pending.append((rid, 200, out[0]))
+                reply = (rid, 200, out[0])
                 self.observe("success", time.perf_counter() - t0, {"count": out[1], "results": [{"score": s} for s in out[2]]})
             else:
                 status = getattr(out, "status_code", 500) if isinstance(out, self.exc) else 500
                 detail = getattr(out, "detail", None) if isinstance(out, self.exc) else str(out)
-                conn.pending.append((rid, status, json.dumps({"detail": detail}).encode("utf-8")))
+                reply = (rid, status, json.dumps({"detail": detail}).encode("utf-8"))
                 self.observe("failure", time.perf_counter() - t0, None)
-            self._dirty.add(conn)
+            with self._mu:
+                conn.pending.append(reply)
+                self._dirty.add(conn)
         return deliver
 
     def _flush(self):
         """after every coalescing window: one frame per connection that got replies"""
-        dirty, self._dirty = self._dirty, set()
-        for conn in dirty:
-            replies, conn.pending = conn.pending, []
-            w = conn.writer
-            if w is not None and replies:
-                self._loop.call_soon_threadsafe(self._write, w, pack_frame(replies))
+        with self._mu:
+            dirty, self._dirty = self._dirty, set()
+            out = []
+            for conn in dirty:
+                replies, conn.pending = conn.pending, []
+                if conn.writer is not None and replies:
+                    out.append((conn.writer, replies))
+        for w, replies in out:
+            self._loop.call_soon_threadsafe(self._write, w, pack_frame(replies))
 
     @staticmethod
     def _write(writer, frame):

@@ -43,6 +43,8 @@ class ShardedEngine:
         self.data_group, self.ctl = data_group, ctl_group
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.shards: dict[str, _Shard] = {}
+        import threading
+        self._cmd_mu = threading.Lock()
 
     # ------------------------------------------------------------------ control plane
     def _bcast(self, cmd: dict | None) -> dict:
@@ -53,23 +55,24 @@ class ShardedEngine:
     def _run(self, cmd: dict, ack: bool = True):
         """rank 0: broadcast `cmd`, execute it locally, collect the workers' status"""
         assert self.rank == 0
-        self._bcast(cmd)
-        err, out = None, None
-        try:
-            out = self._exec(cmd)
-        except Exception as e:           # still take part in the status gather, then raise
-            err = e
-        if ack:
-            errs = [None] * self.world
-            dist.gather_object(None if err is None else f"rank 0: {err}", errs, dst=0, group=self.ctl)
-            bad = [e for e in errs if e]
-            if err is not None:
+        with self._cmd_mu:               # one command at a time: the ranks execute the broadcast sequence in lock step
+            self._bcast(cmd)
+            err, out = None, None
+            try:
+                out = self._exec(cmd)
+            except Exception as e:           # still take part in the status gather, then raise
+                err = e
+            if ack:
+                errs = [None] * self.world
+                dist.gather_object(None if err is None else f"rank 0: {err}", errs, dst=0, group=self.ctl)
+                bad = [e for e in errs if e]
+                if err is not None:
+                    raise err
+                if bad:
+                    raise RuntimeError("; ".join(bad))
+            elif err is not None:
                 raise err
-            if bad:
-                raise RuntimeError("; ".join(bad))
-        elif err is not None:
-            raise err
-        return out
+            return out
 
     def serve(self):
         """worker loop (ranks > 0)"""
