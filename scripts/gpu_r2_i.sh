@@ -13,7 +13,7 @@ print(sys.argv[2], 'value', round(j['value'], 1), 'ms', round(j['ms_per_step'], 
       round(j['roofline']['kernel_ms'], 3), 'embed', round(j['embed']['batch_ms'], 3), 'check', j['check']['fused_ids_equal'], 'clocks', j['clocks']['sm_mhz'], j['clocks']['reasons'])
 PY
 }
-for v in main k3v2e k3v3s0 main; do
+for v in main k3v2e k3v3s0 tcold main; do
   if [ $v = main ]; then cp /tmp/krag_main.so kaito_b200/libkaito_rag.so; else cp kaito_b200/alt/libkaito_rag_$v.so kaito_b200/libkaito_rag.so; fi
   timeout 600 $B > $O/bench_$v.json 2> $O/bench_$v.err; echo "bench $v rc=$?"
   show $O/bench_$v.json $v
