@@ -626,9 +626,7 @@ constexpr int BW_WARPS = 8;                 // warps per CTA: 8 x (8 KB accumula
 constexpr int BW_THREADS = BW_WARPS * 32;
 constexpr int BW_CHUNK = 8;                 // consecutive (sampled) sub-tiles of one query per work unit
 constexpr int BW_STAGE_ROUNDS = 12;         // 32-posting rounds per staging buffer: a whole sub-tile in the common case
-constexpr int BW_STAGE_CAP = BW_STAGE_ROUNDS * 32;                  // postings per staging buffer
-constexpr int BW_STAGE_WORDS = BW_STAGE_CAP * 2;                    // docs[384] | scores[384], densely packed
-constexpr int BW_SHORT = 8;                 // lists of at most this many postings (per sub-tile) are copied by their own lane
+constexpr int BW_STAGE_WORDS = BW_STAGE_ROUNDS * 32 * 2;           // docs[12][32] | scores[12][32]
 constexpr int BW_WARP_WORDS = BM25_SUB_DOCS + 2 * BW_STAGE_WORDS;  // per-warp shared memory, 4-byte words (14 KB)
 
 // once per batch and query-term position: posting base, boundary row, and the legacy kernel's (slot, rare length)
@@ -679,102 +677,76 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// One sub-tile of one query: lane j < nt holds term j's posting range; `pre` is the exclusive prefix of the lengths, so the
-// sub-tile's postings form ONE sequence [0, T) in query-term order (term-major, documents ascending inside a term).
-struct BwSub {
-    int64_t my_start; int my_len; int pre; int T;
+// cursor over the (term, 32-posting round) sequence of one sub-tile; lane j < nt holds term j's posting range
+struct BwCursor {
+    int64_t my_start; int my_len; int nt;
+    int j, r;                 // next round to issue: term j, round r of that term
+    int R, issued;            // rounds of the sub-tile / rounds staged so far
     uint32_t t0;
 };
-__device__ __forceinline__ void bw_sub_reset(BwSub& sb, int64_t my_start, int my_len, uint32_t t0, int lane)
+__device__ __forceinline__ void bw_cursor_reset(BwCursor& cur, int64_t my_start, int my_len, int nt, uint32_t t0)
 {
-    sb.my_start = my_start; sb.my_len = my_len; sb.t0 = t0;
-    int incl = my_len;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int up = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += up;
-    }
-    sb.pre = incl - my_len;
-    sb.T = __shfl_sync(0xffffffffu, incl, 31);
+    cur.my_start = my_start; cur.my_len = my_len; cur.nt = nt; cur.j = 0; cur.r = 0; cur.issued = 0; cur.t0 = t0;
+    cur.R = (int)__reduce_add_sync(0xffffffffu, (unsigned)((my_len + 31) >> 5));     // one REDUX
 }
-// Stage (cp.async: all loads in flight together, nobody waits here) the window [w0, w0 + BW_STAGE_CAP) of the sub-tile's posting
-// sequence, DENSELY: docs[i - w0] | scores[i - w0].  Short lists (<= BW_SHORT postings in the window) are copied by their own
-// lane, all of them in parallel; longer ones by the whole warp, 32 postings per step.  Returns the postings staged.
-__device__ __forceinline__ int bw_issue(const BwCtx& c, const BwSub& sb, int w0, uint32_t* buf)
+// Stage (cp.async: the loads of all rounds are in flight together and nobody waits for them here) up to BW_STAGE_ROUNDS
+// rounds at the cursor: docs[round][lane] | scores[round][lane]; lanes past the end of a term's list get doc = ~0.
+// Outer loop over the terms (one pair of shuffles per term), inner loop over the 32-posting rounds of the term.
+__device__ __forceinline__ int bw_issue(const BwCtx& c, BwCursor& cur, uint32_t* buf)
 {
-    const int w1 = min(sb.T, w0 + BW_STAGE_CAP);
-    const int k0 = max(0, w0 - sb.pre), k1 = min(sb.my_len, w1 - sb.pre);
-    const int cnt = max(0, k1 - k0);                        // this lane's postings inside the window
-    const int p0 = sb.pre + k0 - w0;                        // ... and where they go
-    const int64_t first = sb.my_start + k0;
-    const bool is_short = cnt > 0 && cnt <= BW_SHORT;
-    const int max_short = (int)__reduce_max_sync(0xffffffffu, (unsigned)(is_short ? cnt : 0));
-    if (max_short > 0) {
-        const uint32_t* pd = c.post_doc + first;
-        const float* ps = c.post_score + first;
-        uint32_t* dd = buf + p0;
+    int n = 0;
+    uint32_t* dd = buf + c.lane;
+    bool full = false;
 #pragma unroll 1
-        for (int k = 0; k < max_short; ++k)
-            if (is_short && k < cnt) {
-                cp_async4(dd + k, pd + k);
-                cp_async4(dd + BW_STAGE_CAP + k, ps + k);
+    while (cur.j < cur.nt && !full) {
+        const int len = __shfl_sync(0xffffffffu, cur.my_len, cur.j);
+        int base = cur.r * 32;
+        if (base < len) {
+            const int64_t st = __shfl_sync(0xffffffffu, cur.my_start, cur.j);
+            const uint32_t* pd = c.post_doc + st + c.lane;
+            const float* ps = c.post_score + st + c.lane;
+#pragma unroll 1
+            for (; base < len; base += 32) {
+                if (n == BW_STAGE_ROUNDS) { full = true; break; }
+                if (base + c.lane < len) {
+                    cp_async4(dd, pd + base);
+                    cp_async4(dd + BW_STAGE_ROUNDS * 32, ps + base);
+                } else {
+                    *dd = 0xFFFFFFFFu;
+                }
+                dd += 32; ++n; ++cur.r;
             }
-    }
-    unsigned long_m = __ballot_sync(0xffffffffu, cnt > BW_SHORT);
-#pragma unroll 1
-    while (long_m) {
-        const int j = __ffs(long_m) - 1;
-        long_m &= long_m - 1;
-        const int n = __shfl_sync(0xffffffffu, cnt, j);
-        const int p = __shfl_sync(0xffffffffu, p0, j);
-        const int64_t st = __shfl_sync(0xffffffffu, first, j);
-        const uint32_t* pd = c.post_doc + st;
-        const float* ps = c.post_score + st;
-        uint32_t* dd = buf + p;
-#pragma unroll 1
-        for (int b = c.lane; b < n; b += 32) {
-            cp_async4(dd + b, pd + b);
-            cp_async4(dd + BW_STAGE_CAP + b, ps + b);
+            if (full) break;
         }
+        ++cur.j; cur.r = 0;
     }
+    cur.issued += n;
     cp_async_commit();
-    return w1 - w0;
+    return n;
 }
-// acc[doc] += score over the n staged postings, 32 per round, rounds in sequence order.  A round may hold the same document
-// more than once (different terms); those lanes add one after the other in lane = sequence order, so every document's fp32
-// sum is built in the oracle's order (query-term order).
-__device__ __forceinline__ void bw_rmw_round(const BwCtx& c, bool v, uint32_t r, float s, unsigned peers)
-{
-    const unsigned lower = peers & ((1u << c.lane) - 1u);
-    if (!__any_sync(0xffffffffu, lower != 0u)) {
-        if (v) c.acc[r] += s;
-    } else {
-        const int rank = __popc(lower);
-#pragma unroll 1
-        for (int k = 0;; ++k) {
-            if (v && rank == k) c.acc[r] += s;
-            __syncwarp();
-            if (!__any_sync(0xffffffffu, v && rank > k)) break;
-        }
-    }
-    __syncwarp();
-}
+// acc[doc] += score for the staged rounds, one round after the other: rounds follow the query-term order, documents are
+// unique inside a term (no two lanes of a round collide) and a __syncwarp() separates the rounds, so every document's
+// fp32 sum is built in the oracle's order
 __device__ __forceinline__ void bw_accumulate(const BwCtx& c, const uint32_t* buf, int n)
 {
     const uint32_t* pd = buf + c.lane;
-    const uint32_t* ps = buf + BW_STAGE_CAP + c.lane;
-    const uint32_t none = 0x80000000u | (uint32_t)c.lane;     // lanes past the end: a value no other lane holds
+    const uint32_t* ps = buf + BW_STAGE_ROUNDS * 32 + c.lane;
+    int u = 0;
 #pragma unroll 1
-    for (int b = 0; b < n; b += 64) {          // two rounds per iteration: the second round's loads and MATCH overlap the first's RMW
-        const bool v0 = b + c.lane < n, v1 = b + 32 + c.lane < n;
-        uint32_t r0 = none, r1 = none;
-        float s0 = 0.f, s1 = 0.f;
-        if (v0) { r0 = pd[b] - c.t0; s0 = __uint_as_float(ps[b]); }
-        if (v1) { r1 = pd[b + 32] - c.t0; s1 = __uint_as_float(ps[b + 32]); }
-        const unsigned m0 = __match_any_sync(0xffffffffu, r0);
-        const unsigned m1 = __match_any_sync(0xffffffffu, r1);
-        bw_rmw_round(c, v0, r0, s0, m0);
-        if (b + 32 < n) bw_rmw_round(c, v1, r1, s1, m1);
+    for (; u + 1 < n; u += 2) {            // two rounds per iteration: the staged loads of the second overlap the first's RMW
+        const uint32_t d0 = pd[u * 32], d1 = pd[u * 32 + 32];
+        const float s0 = __uint_as_float(ps[u * 32]), s1 = __uint_as_float(ps[u * 32 + 32]);
+        const uint32_t r0 = d0 - c.t0, r1 = d1 - c.t0;
+        if (d0 != 0xFFFFFFFFu && r0 < (uint32_t)BM25_SUB_DOCS) c.acc[r0] += s0;
+        __syncwarp();
+        if (d1 != 0xFFFFFFFFu && r1 < (uint32_t)BM25_SUB_DOCS) c.acc[r1] += s1;
+        __syncwarp();
+    }
+    if (u < n) {
+        const uint32_t d0 = pd[u * 32];
+        const uint32_t r0 = d0 - c.t0;
+        if (d0 != 0xFFFFFFFFu && r0 < (uint32_t)BM25_SUB_DOCS) c.acc[r0] += __uint_as_float(ps[u * 32]);
+        __syncwarp();
     }
 }
 __device__ __forceinline__ void bw_push(const BwCtx& c, bool hit, unsigned long long key)
@@ -808,12 +780,12 @@ __device__ __forceinline__ void bw_claim_staged(const BwCtx& c, const uint32_t* 
 {
     const uint32_t* pd = buf + c.lane;
 #pragma unroll 1
-    for (int b = 0; b < n; b += 64) {      // two rounds per iteration: both exchanges are in flight together
-        const bool v0 = b + c.lane < n, v1 = b + 32 + c.lane < n;
-        const uint32_t d0 = v0 ? pd[b] : 0u, d1 = v1 ? pd[b + 32] : 0u;
+    for (int u = 0; u < n; u += 2) {       // two rounds per iteration: both exchanges are in flight together
+        const uint32_t d0 = pd[u * 32], d1 = (u + 1 < n) ? pd[u * 32 + 32] : 0xFFFFFFFFu;
+        const uint32_t r0 = d0 - c.t0, r1 = d1 - c.t0;
         float sum0 = 0.f, sum1 = 0.f;
-        if (v0) sum0 = atomicExch(&c.acc[d0 - c.t0], 0.f);
-        if (v1) sum1 = atomicExch(&c.acc[d1 - c.t0], 0.f);   // same document again: reads 0
+        if (d0 != 0xFFFFFFFFu && r0 < (uint32_t)BM25_SUB_DOCS) sum0 = atomicExch(&c.acc[r0], 0.f);
+        if (d1 != 0xFFFFFFFFu && r1 < (uint32_t)BM25_SUB_DOCS) sum1 = atomicExch(&c.acc[r1], 0.f);   // same document again: reads 0
         const bool maybe = (sum0 > 0.f && sum0 >= c.thr_score) || (sum1 > 0.f && sum1 >= c.thr_score);
         if (!__any_sync(0xffffffffu, maybe)) continue;
         bw_claim_one(c, d0, sum0);
@@ -821,7 +793,7 @@ __device__ __forceinline__ void bw_claim_staged(const BwCtx& c, const uint32_t* 
     }
     __syncwarp();
 }
-// sub-tiles with more postings than a staging buffer holds: accumulated window by window, then claimed by a sweep over the
+// sub-tiles with more rounds than a staging buffer holds: accumulated block by block, then claimed by a sweep over the
 // accumulators (vectorised, conflict-free)
 __device__ __forceinline__ void bw_claim_sweep(const BwCtx& c)
 {
@@ -895,26 +867,28 @@ bm25_warp_kernel(const uint32_t* __restrict__ post_doc, const float* __restrict_
             // whose latency hides under a whole sub-tile of work)
             uint32_t nlo = 0, nhi = 0;
             if (row != nullptr) { const int64_t sub = (int64_t)s0 * stride; nlo = row[sub]; nhi = row[sub + 1]; }
-            BwSub nsb;                                                     // the sub-tile in flight
-            int ii = -1, buf = 0, nb_n = 0;
-            // stage the first window of the next non-empty sub-tile; false at the end of the unit
+            BwCursor cur;
+            int ii = -1, buf = 0;
+            int nb_n = 0, nb_R = 0; uint32_t nb_t0 = 0;                    // sub-tile in flight: rounds staged, rounds total
+            // stage the first (up to BW_STAGE_ROUNDS) rounds of the next non-empty sub-tile; false at the end of the unit
             auto next_subtile = [&](uint32_t* dst) -> bool {
                 for (;;) {
                     if (++ii >= ns) return false;
                     const uint32_t lo = nlo, hi = nhi;
                     if (row != nullptr && ii + 1 < ns) { const int64_t sub = (int64_t)(s0 + ii + 1) * stride; nlo = row[sub]; nhi = row[sub + 1]; }
-                    bw_sub_reset(nsb, base + lo, (int)(hi - lo), (uint32_t)((int64_t)(s0 + ii) * stride * BM25_SUB_DOCS), lane);
-                    if (nsb.T == 0) continue;
-                    nb_n = bw_issue(c, nsb, 0, dst);
+                    bw_cursor_reset(cur, base + lo, (int)(hi - lo), nt, (uint32_t)((int64_t)(s0 + ii) * stride * BM25_SUB_DOCS));
+                    if (cur.R == 0) continue;
+                    nb_n = bw_issue(c, cur, dst);
+                    nb_R = cur.R; nb_t0 = cur.t0;
                     return true;
                 }
             };
             bool have = next_subtile(stage);
             while (have) {
-                const int cb_n = nb_n;
+                const int cb_n = nb_n, cb_R = nb_R;
                 uint32_t* cbuf = stage + buf * BW_STAGE_WORDS;
-                c.t0 = nsb.t0;
-                if (nsb.T <= BW_STAGE_CAP) {
+                c.t0 = nb_t0;
+                if (cb_R <= BW_STAGE_ROUNDS) {
                     buf ^= 1;
                     have = next_subtile(stage + buf * BW_STAGE_WORDS);     // next sub-tile's loads fly while this one is processed
                     if (have) cp_async_wait<1>(); else cp_async_wait<0>();
@@ -922,15 +896,14 @@ bm25_warp_kernel(const uint32_t* __restrict__ post_doc, const float* __restrict_
                     bw_accumulate(c, cbuf, cb_n);
                     bw_claim_staged(c, cbuf, cb_n);
                 } else {
-                    // rare: more postings than a buffer holds -> window by window out of this buffer, then the sweep
-                    int w0 = 0, n = cb_n;
+                    // rare: more rounds than a buffer holds -> block by block out of this buffer, then the sweep
+                    int n = cb_n;
                     for (;;) {
                         cp_async_wait<0>();
                         __syncwarp();
                         bw_accumulate(c, cbuf, n);
-                        w0 += n;
-                        if (w0 >= nsb.T) break;
-                        n = bw_issue(c, nsb, w0, cbuf);
+                        if (cur.issued >= cur.R) break;
+                        n = bw_issue(c, cur, cbuf);
                     }
                     bw_claim_sweep(c);
                     buf ^= 1;
@@ -949,14 +922,13 @@ bm25_warp_kernel(const uint32_t* __restrict__ post_doc, const float* __restrict_
                         const uint32_t* row = q_row[c0 + lane];
                         if (row != nullptr) { const uint32_t lo = row[sub], hi = row[sub + 1]; my_start = q_base[c0 + lane] + lo; my_len = (int)(hi - lo); }
                     }
-                    BwSub sb;
-                    bw_sub_reset(sb, my_start, my_len, c.t0, lane);
-                    for (int w0 = 0; w0 < sb.T;) {
-                        const int n = bw_issue(c, sb, w0, stage);
+                    BwCursor cur;
+                    bw_cursor_reset(cur, my_start, my_len, min(32, te - c0), c.t0);
+                    while (cur.issued < cur.R) {
+                        const int n = bw_issue(c, cur, stage);
                         cp_async_wait<0>();
                         __syncwarp();
                         bw_accumulate(c, stage, n);
-                        w0 += n;
                         touched = true;
                     }
                 }
