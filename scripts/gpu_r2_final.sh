@@ -3,6 +3,9 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 O=gpurun_out/r2z
 mkdir -p $O
+timeout 1800 python -m pytest tests -m gpu -q 2>&1 | tail -12 | tee $O/pytest.log
+timeout 300 python -m pytest tests/test_gpu_embed.py -q -s -k "bert_forward or gemm" 2>&1 | grep -E "^(gemm|linear|small|short|bge|base|large)[^ ]*:? " | tee $O/k5_precision.log | tail -8
+for bs in "256 32" "32 32" "1 32" "128 256"; do timeout 120 python scripts/embed_probe.py bge-base $bs; done 2>&1 | tee $O/embed_probe.log
 timeout 900 python bench.py --steps 20 --warmup 5 > $O/bench.json 2> $O/bench.err; echo "bench rc=$?"
 timeout 600 python bench.py --impl reference > $O/bench_reference.json 2>/dev/null; echo "reference rc=$?"; cut -c1-260 $O/bench_reference.json
 timeout 600 python bench.py --workload c2 --steps 20 --warmup 5 --no-optin > $O/bench_c2.json 2> $O/bench_c2.err; echo "c2 rc=$?"
