@@ -45,8 +45,15 @@ def main():
                         traffic[kid] = rd[0] * UNIT_SCALE.get(rd[1], 1.0) + wr[0] * UNIT_SCALE.get(wr[1], 1.0)
             lines.append("")
     open(out_path, "w").write("\n".join(lines))
-    tj = {"_source": f"{out_path} (dram__bytes_read.sum + dram__bytes_write.sum per launch, bench.py c3, 1 GPU)", "c3": traffic}
-    json.dump(tj, open("profiles/traffic.json", "w"), indent=1)
+    # merge: kernels that are not in these reports keep the traffic of the capture they were last seen in
+    try:
+        tj = json.load(open("profiles/traffic.json"))
+    except Exception:
+        tj = {"_source": "", "c3": {}}
+    if traffic:
+        tj["c3"].update(traffic)
+        tj["_source"] = f"ids {sorted(traffic)}: {out_path}; others: " + tj.get("_source", "")[:300]
+        json.dump(tj, open("profiles/traffic.json", "w"), indent=1)
     print("\n".join(lines))
 
 
