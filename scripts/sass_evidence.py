@@ -9,7 +9,7 @@ import sys
 
 so = sys.argv[1] if len(sys.argv) > 1 else "kaito_b200/libkaito_rag.so"
 out = subprocess.run(["cuobjdump", "-sass", so], stdout=subprocess.PIPE, text=True).stdout
-pats = ["UTCHMMA", "UTMALDG", "LDTM", "UTCBAR", "LDGSTS", "SYNCS", "ATOMS", "F2FP", "MATCH", "VOTE"]
+pats = ["UTCHMMA", "UTMALDG", "LDTM", "UTCBAR", "LDGSTS", "SYNCS", "ATOMS", "F2FP", "MATCH", "VOTE", "HMMA", "LDSM"]
 cnt, n_ins, name = collections.defaultdict(collections.Counter), collections.Counter(), None
 for line in out.splitlines():
     m = re.search(r"Function : (\S+)", line)
