@@ -408,7 +408,11 @@ def run_ours(args):
     st = ix.stats()
     sr = ShardedRetriever(stages, dev, st.dim_padded)
     if hybrid:
+        free_b, total_b = torch.cuda.mem_get_info(dev)
+        trace(f"rows + raw term lists resident: {free_b / 1e9:.1f} of {total_b / 1e9:.1f} GB free before the postings build")
         sr.commit(VOCAB, n_local)
+        free_b, _ = torch.cuda.mem_get_info(dev)
+        trace(f"postings built: {free_b / 1e9:.1f} GB free")
     torch.cuda.synchronize()
     t_build = time.perf_counter() - t_build
     trace(f"index built in {t_build:.1f}s")

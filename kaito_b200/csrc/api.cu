@@ -75,6 +75,9 @@ static int32_t guarded(F&& f)
         set_error(buf);
         cudaGetLastError();
         return e.e == cudaErrorMemoryAllocation ? KRAG_E_OOM : KRAG_E_CUDA;
+    } catch (const DevOom& e) {
+        set_error(e.what());
+        return KRAG_E_OOM;
     } catch (const std::bad_alloc&) {
         set_error("host allocation failed");
         return KRAG_E_OOM;

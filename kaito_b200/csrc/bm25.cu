@@ -184,7 +184,18 @@ struct DevScratch {
     template <typename T> T* alloc(size_t n)
     {
         void* p = nullptr;
-        KRAG_CUDA(cudaMalloc(&p, sizeof(T) * (n ? n : 1)));
+        const size_t bytes = sizeof(T) * (n ? n : 1);
+        const cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaErrorMemoryAllocation) {          // say how much was asked for and what was left: the build is the memory peak
+            cudaGetLastError();
+            size_t free_b = 0, total_b = 0;
+            cudaMemGetInfo(&free_b, &total_b);
+            char msg[256];
+            snprintf(msg, sizeof msg, "bm25 index build: out of device memory (wanted %.2f GB, %.2f of %.2f GB free)", bytes / 1e9, free_b / 1e9,
+                     total_b / 1e9);
+            throw DevOom{msg};
+        }
+        KRAG_CUDA(e);
         ptrs.push_back(p);
         return static_cast<T*>(p);
     }
@@ -275,19 +286,10 @@ void build_postings(const uint32_t* term_ids, const uint16_t* term_tf, const uin
 
     if (nnz > 0 && nnz_live > 0) {
         prepare_tile_index(off, vocab, n_docs_rows, out, st);
-        // term ranges [t_lo, t_hi) of at most `cap` postings each (a single term longer than that is a range of its own)
-        const int64_t cap = build_chunk_cap(nnz_live);
-        std::vector<int64_t> cuts{0};
-        int64_t widest = 0;
-        while (cuts.back() < vocab) {
-            const int64_t t_lo = cuts.back();
-            int64_t t_hi = (int64_t)(std::upper_bound(h_off.begin() + t_lo, h_off.end(), h_off[(size_t)t_lo] + cap) - h_off.begin()) - 1;
-            if (t_hi <= t_lo) t_hi = t_lo + 1;
-            if (t_hi > vocab) t_hi = vocab;
-            cuts.push_back(t_hi);
-            widest = std::max(widest, h_off[(size_t)t_hi] - h_off[(size_t)t_lo]);
-        }
-        if (widest >= ((int64_t)1 << 31)) throw std::runtime_error("bm25 build: a single term has too many postings for one build range");
+        // term ranges [t_lo, t_hi) of at most `cap` postings each (a single term longer than that is a range of its own).  The
+        // sort buffers are sized for the widest range; if they do not fit after all (fragmentation, another context on the
+        // device), the ranges are halved until they do
+        int64_t cap = build_chunk_cap(nnz_live);
         const int64_t n_blocks = (nnz + (int64_t)CC_THREADS * CC_ITEMS - 1) / ((int64_t)CC_THREADS * CC_ITEMS);
         if (n_blocks >= ((int64_t)1 << 31)) throw std::runtime_error("bm25 build: too many index entries on one shard");
         uint32_t* block_cnt = sc.alloc<uint32_t>((size_t)n_blocks);
@@ -295,16 +297,42 @@ void build_postings(const uint32_t* term_ids, const uint16_t* term_tf, const uin
         size_t bscan_bytes = 0;
         cub::DeviceScan::ExclusiveSum(nullptr, bscan_bytes, block_cnt, block_off, (int)n_blocks, st);
         void* bscan_tmp = sc.alloc<unsigned char>(bscan_bytes);
-        // stable LSD radix sort by term id keeps documents ascending inside every term
-        uint32_t* k_in = sc.alloc<uint32_t>((size_t)widest);
-        uint32_t* k_out = sc.alloc<uint32_t>((size_t)widest);
-        uint64_t* v_in = sc.alloc<uint64_t>((size_t)widest);
-        uint64_t* v_out = sc.alloc<uint64_t>((size_t)widest);
         int end_bit = 1;
         while (((int64_t)1 << end_bit) < vocab) ++end_bit;  // keys range over [0, vocab)
+        std::vector<int64_t> cuts;
+        uint32_t *k_in = nullptr, *k_out = nullptr;
+        uint64_t *v_in = nullptr, *v_out = nullptr;
+        void* sort_tmp = nullptr;
         size_t sort_bytes = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, k_in, k_out, v_in, v_out, widest, 0, end_bit, st);
-        void* sort_tmp = sc.alloc<unsigned char>(sort_bytes);
+        for (;;) {
+            cuts.assign(1, 0);
+            int64_t widest = 0;
+            while (cuts.back() < vocab) {
+                const int64_t t_lo = cuts.back();
+                int64_t t_hi = (int64_t)(std::upper_bound(h_off.begin() + t_lo, h_off.end(), h_off[(size_t)t_lo] + cap) - h_off.begin()) - 1;
+                if (t_hi <= t_lo) t_hi = t_lo + 1;
+                if (t_hi > vocab) t_hi = vocab;
+                cuts.push_back(t_hi);
+                widest = std::max(widest, h_off[(size_t)t_hi] - h_off[(size_t)t_lo]);
+            }
+            if (widest >= ((int64_t)1 << 31)) throw std::runtime_error("bm25 build: a single term has too many postings for one build range");
+            try {
+                // stable LSD radix sort by term id keeps documents ascending inside every term
+                k_in = sc.alloc<uint32_t>((size_t)widest);
+                k_out = sc.alloc<uint32_t>((size_t)widest);
+                v_in = sc.alloc<uint64_t>((size_t)widest);
+                v_out = sc.alloc<uint64_t>((size_t)widest);
+                sort_bytes = 0;
+                cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, k_in, k_out, v_in, v_out, widest, 0, end_bit, st);
+                sort_tmp = sc.alloc<unsigned char>(sort_bytes);
+                break;
+            } catch (const DevOom&) {
+                sc.free_now(k_in); sc.free_now(k_out); sc.free_now(v_in); sc.free_now(v_out);
+                k_in = k_out = nullptr; v_in = v_out = nullptr;
+                if (cap <= ((int64_t)1 << 22) || widest > cap) throw;      // cannot get smaller: the widest range is one term
+                cap /= 2;
+            }
+        }
         for (size_t c = 0; c + 1 < cuts.size(); ++c) {
             const int64_t t_lo = cuts[c], t_hi = cuts[c + 1];
             const int64_t p_base = h_off[(size_t)t_lo], m = h_off[(size_t)t_hi] - p_base;

@@ -3,7 +3,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <stdexcept>
 namespace krag {
+
+// device allocation failure with a message that says what was asked for and what was free (KRAG_E_OOM at the C ABI)
+struct DevOom : std::runtime_error { using std::runtime_error::runtime_error; };
 
 // global ordinal of a local row: base + row * stride.  Contiguous shards (bench, one GPU) use stride 1; the multi-GPU
 // service deals nodes round-robin (node o -> shard o % G, row o / G), so base = shard, stride = G and ordinals -- hence

@@ -107,3 +107,39 @@ def test_worker_process_serves_retrieve_and_proxies_the_rest(oracle, tmp_path):
         srv.should_exit = True
         th.join(timeout=5)
         app.state.batcher.close()
+
+
+def test_rpc_client_survives_an_engine_restart(oracle, tmp_path):
+    """the worker's connection to the engine is re-established on the next request after it broke; requests in flight at the
+    time fail with ConnectionError (the worker answers 503)"""
+    import asyncio
+    from fastapi import HTTPException as FHE
+    from tests.oracle_engine import OracleEngine
+    from kaito_b200.batcher import RetrieveBatcher
+    from kaito_b200.rpc import RetrieveRpcClient
+    store = VectorStore(HashingEmbedding(64), OracleEngine(oracle))
+    store.index_documents("r", [{"text": f"alpha beta {i}"} for i in range(12)])
+    seen = []
+    path = str(tmp_path / "rpc.sock")
+
+    def start():
+        b = RetrieveBatcher(store, max_batch=16, max_wait_s=0.002)
+        return b, RetrieveRpcServer(b, lambda status, seconds, out: seen.append(status), (vs.HTTPException, FHE), path=path)
+
+    async def scenario():
+        b, srv = start()
+        cli = RetrieveRpcClient(path)
+        st, body = await cli.retrieve("r", "alpha 3", 2, None)
+        assert st == 200 and json.loads(body)["count"] == 2
+        st, body = await cli.retrieve("nope", "q", 2, None)
+        assert st == 404 and json.loads(body) == {"detail": "No such index: 'nope' exists."}
+        srv.close(); b.close()
+        await asyncio.sleep(0.1)
+        with pytest.raises((ConnectionError, OSError)):
+            await cli.retrieve("r", "alpha 3", 2, None)
+        b, srv = start()
+        st, body = await cli.retrieve("r", "alpha 4", 3, None)
+        assert st == 200 and json.loads(body)["count"] == 3
+        srv.close(); b.close()
+    asyncio.run(scenario())
+    assert seen.count("success") == 2 and seen.count("failure") == 1
