@@ -43,6 +43,7 @@ def parse_retrieve(body: bytes, max_top_k: int):
 class FrontApp:
     def __init__(self, rpc: RetrieveRpcClient, engine_http: str, max_top_k: int):
         self.rpc, self.engine_http, self.max_top_k = rpc, engine_http, max_top_k
+        self.timeout_s = float(os.getenv("KRAG_RPC_TIMEOUT_S", "300"))
         self._session = None
 
     async def __call__(self, scope, receive, send):
@@ -70,9 +71,11 @@ class FrontApp:
             req = parse_retrieve(body, self.max_top_k)
             if req is not None:
                 try:
-                    status, payload = await self.rpc.retrieve(*req)
-                except ConnectionError as e:
-                    status, payload = 503, json.dumps({"detail": str(e)}).encode("utf-8")
+                    status, payload = await asyncio.wait_for(self.rpc.retrieve(*req), timeout=self.timeout_s)
+                except (ConnectionError, OSError) as e:
+                    status, payload = 503, json.dumps({"detail": f"engine unreachable: {e}"}).encode("utf-8")
+                except asyncio.TimeoutError:
+                    status, payload = 504, json.dumps({"detail": "engine did not answer in time"}).encode("utf-8")
                 await send({"type": "http.response.start", "status": status,
                             "headers": [(b"content-type", b"application/json"), (b"content-length", str(len(payload)).encode())]})
                 await send({"type": "http.response.body", "body": payload})

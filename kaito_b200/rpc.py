@@ -55,6 +55,7 @@ class RetrieveRpcServer:
         self.batcher, self.observe, self.exc = batcher, observe, http_exception_types
         self.path, self.port = path, port
         self._dirty: set[_Conn] = set()
+        self._conns: set[_Conn] = set()          # event-loop thread only
         self._mu = threading.Lock()              # sinks and flushes run on the coalescer's dispatcher threads (more than one)
         self._loop = asyncio.new_event_loop()
         self._started = threading.Event()
@@ -83,6 +84,7 @@ class RetrieveRpcServer:
 
     async def _handle(self, reader, writer):
         conn = _Conn(writer)
+        self._conns.add(conn)
         submit = self.batcher.submit_bytes
         try:
             while True:
@@ -93,6 +95,7 @@ class RetrieveRpcServer:
             pass
         finally:
             conn.writer = None
+            self._conns.discard(conn)
             try:
                 writer.close()
             except Exception:
@@ -139,9 +142,15 @@ class RetrieveRpcServer:
         def stop():
             if self._server is not None:
                 self._server.close()
-            self._loop.stop()
+            for conn in list(self._conns):       # the workers see EOF, fail what is in flight and reconnect later
+                w, conn.writer = conn.writer, None
+                if w is not None:
+                    w.close()
+            self._loop.call_later(0.05, self._loop.stop)
         self._loop.call_soon_threadsafe(stop)
         self._t.join(timeout=5)
+        if self.batcher.after_batch == self._flush:
+            self.batcher.after_batch = None
         if self.path and os.path.exists(self.path):
             try:
                 os.unlink(self.path)
