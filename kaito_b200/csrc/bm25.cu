@@ -240,8 +240,8 @@ static void prepare_tile_index(const int64_t* off, int64_t vocab, int64_t n_rows
     out.tile_slot = slot; out.tile_off = tile_off; out.n_slots = n_slots; out.n_tiles = n_tiles;
 }
 
-// postings per term range of the build: KRAG_BM25_BUILD_CHUNK, else what fits in 70 % of the free device memory at
-// 24 bytes of sort buffers per posting (+ 1 for the sort's own scratch)
+// postings per term range of the build: KRAG_BM25_BUILD_CHUNK, else what fits in 70 % of the free device memory at 24 bytes
+// of sort buffers per posting + 12 for the alternate key/value buffers the radix sort keeps in its temporary storage
 static int64_t build_chunk_cap(int64_t nnz_live)
 {
     int64_t cap = 0;
@@ -249,7 +249,7 @@ static int64_t build_chunk_cap(int64_t nnz_live)
     if (cap <= 0) {
         size_t free_b = 0, total_b = 0;
         KRAG_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        cap = (int64_t)((double)free_b * 0.7 / 25.0);
+        cap = (int64_t)((double)free_b * 0.7 / 37.0);
         if (cap < ((int64_t)1 << 20)) cap = (int64_t)1 << 20;
     }
     const int64_t hard = ((int64_t)1 << 31) - 4096;              // 32-bit block offsets / cub item counts
