@@ -187,6 +187,11 @@ class CpuReference:
             # the reference embeds every query with torch BertModel on the CPU (huggingface_local_embedding.py:34-53)
             import torch
             from transformers import BertConfig, BertModel
+            if os.environ.get("OMP_NUM_THREADS") == "1" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+                # torchrun pins OMP_NUM_THREADS=1 for its children: give torch what it takes by default in a plain process
+                # (one thread per physical core), so the reference arm does not depend on how it was launched
+                torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))
+            self.torch_threads = torch.get_num_threads()
             torch.manual_seed(0)
             m = BertModel(BertConfig(**BGE[embedding]), add_pooling_layer=False).eval()
             ne = min(16, n_queries)
@@ -242,7 +247,7 @@ class CpuReference:
                              "queries_per_s_on_sample": None if not step_s else self.nq / step_s},
                 "per_query_s_extrapolated": per_query,
                 "query_embedding_s": self.embed_s if self.embedding else None,
-                "query_embedding": f"torch CPU BertModel {self.embedding} shapes, measured per query, not extrapolated" if self.embedding else "excluded",
+                "query_embedding": f"torch CPU BertModel {self.embedding} shapes on {getattr(self, 'torch_threads', '?')} threads, measured per query, not extrapolated" if self.embedding else "excluded",
                 "bm25_rebuild_per_query_s_extrapolated": self.rebuild_s}
 
 
