@@ -154,12 +154,29 @@ class ShardedRetriever:
             self._p2p_state = ok
         return self._p2p_state and self.stages.p2p_fits(nl, B, P)
 
-    def _tensor(self, name, shape, dtype):
-        t = self._buf.get(name)
-        if t is None or t.shape != torch.Size(shape) or t.dtype != dtype:
-            t = torch.empty(shape, dtype=dtype, device=self.device)
-            self._buf[name] = t
+    @staticmethod
+    def _numel(shape) -> int:
+        n = 1
+        for s in shape:
+            n *= int(s)
+        return n
+
+    def _storage(self, key, numel, dtype, **kw):
+        """flat buffer of at least `numel` elements, grown in powers of two: the service's batches differ in size from call to
+        call, and re-allocating (above all re-PINNING host memory: cudaHostAlloc synchronises the device and costs
+        milliseconds) on every new shape was most of a sharded /retrieve batch"""
+        t = self._buf.get(key)
+        if t is None or t.dtype != dtype or t.numel() < numel:
+            cap = 1024
+            while cap < numel:
+                cap <<= 1
+            t = torch.empty((cap,), dtype=dtype, **kw)
+            self._buf[key] = t
         return t
+
+    def _tensor(self, name, shape, dtype):
+        n = self._numel(shape)
+        return self._storage(("dev", name), n, dtype, device=self.device)[:n].view(shape)
 
     def retrieve_dev(self, q: torch.Tensor, terms: torch.Tensor | None, toff: torch.Tensor | None, k: int,
                      cand_mult: float = 3.0, vector_weight: float = 0.7, text_weight: float = 0.3, mode: int = 0,
@@ -269,11 +286,8 @@ class ShardedRetriever:
         return {name: t.numpy().copy() for name, t in host.items()}
 
     def _pinned(self, name, shape, dtype):
-        t = self._buf.get(name)
-        if t is None or t.shape != torch.Size(shape) or t.dtype != dtype:
-            t = torch.empty(shape, dtype=dtype, pin_memory=(self.device.type == "cuda"))
-            self._buf[name] = t
-        return t
+        n = self._numel(shape)
+        return self._storage(("pin", name), n, dtype, pin_memory=(self.device.type == "cuda"))[:n].view(shape)
 
     @staticmethod
     def io_bytes(B: int, dim: int, n_terms: int, k: int) -> tuple[int, int]:
