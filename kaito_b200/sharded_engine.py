@@ -45,6 +45,10 @@ class ShardedEngine:
         self.shards: dict[str, _Shard] = {}
         import threading
         self._cmd_mu = threading.Lock()
+        # the only CPU-side torch work of these processes is staging a few hundred KB per batch into pinned buffers; spread
+        # over an OpenMP team (one thread per core by default) each of those copies waits for threads the HTTP workers and
+        # clients keep descheduling -- tens of milliseconds per batch on a loaded box
+        torch.set_num_threads(1)
 
     # ------------------------------------------------------------------ control plane
     def _bcast(self, cmd: dict | None) -> dict:
