@@ -273,11 +273,12 @@ int32_t text_guard(F&& f)
     catch (const std::exception&) { return KRAG_E_INVALID; }
 }
 template <class F>
-void parallel_for(int64_t n, F&& body)
+void parallel_for(int64_t n, int64_t total_bytes, F&& body)
 {
     unsigned hw = std::thread::hardware_concurrency();
     int64_t nt = hw ? hw : 4;
-    if (nt > n / 8) nt = n / 8;          // a thread per >= 8 texts
+    if (nt > n / 8) nt = n / 8;          // a thread per >= 8 texts ...
+    if (nt > total_bytes / 32768) nt = total_bytes / 32768;   // ... and per >= 32 KB of text: a batch of queries is not worth a thread
     if (nt <= 1) { for (int64_t i = 0; i < n; ++i) body(i); return; }
     std::vector<std::thread> th;
     for (int64_t t = 0; t < nt; ++t)
@@ -328,7 +329,7 @@ int32_t krag_wordpiece_encode_batch(const krag_wordpiece* w, int64_t n, const ch
 {
     return text_guard([&] {
         if (!w || !texts || !offsets || !out_ids || !out_n || n < 0 || max_len < 2) throw std::invalid_argument("bad argument");
-        parallel_for(n, [&](int64_t i) {
+        parallel_for(n, offsets[n] - offsets[0], [&](int64_t i) {
             std::vector<int32_t> ids;
             w->encode(texts + offsets[i], offsets[i + 1] - offsets[i], max_len, ids);
             out_n[i] = (int32_t)ids.size();
