@@ -341,7 +341,7 @@ def sharded_check(ix, sr, stages, qh, qpad, terms_list, d_terms, d_toff, offs, k
         parts = [mine]
     out = sr.retrieve_dev(qpad, d_terms, d_toff, k, toff_host=offs if hybrid else None)
     torch.cuda.synchronize()
-    merged = sr._buf["merged"] if world > 1 else sr._buf["local"]
+    merged = sr.last_lists
     got_ord = out["ordinal"].cpu().numpy(); got_fin = out["final"].cpu().numpy(); got_cnt = out["count"].cpu().numpy()
     dense_keys = merged[0].cpu().numpy()
     if rank != 0:

@@ -112,6 +112,7 @@ class ShardedRetriever:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.hybrid = False
         self._buf = {}
+        self.last_lists = None
         self._p2p_state = None
 
     # ------------------------------------------------------------------ index time
@@ -209,6 +210,7 @@ class ShardedRetriever:
                 self.stages.merge(per_list[1], self.world, B, P, merged[1])
         else:
             merged = local
+        self.last_lists = merged      # [nl, B, P] u64 keys: the global candidate lists of this call (dense, then BM25)
         out = {
             "final": self._tensor("final", (B, k), torch.float64), "dense": self._tensor("dense", (B, k), torch.float32),
             "sparse": self._tensor("sparse", (B, k), torch.float32), "rank": self._tensor("rank", (B, k), torch.int32),
