@@ -75,6 +75,7 @@ class RetrieveRpcServer:
                 if os.path.exists(self.path):
                     os.unlink(self.path)
                 self._server = await asyncio.start_unix_server(self._handle, path=self.path)
+                os.chmod(self.path, 0o600)           # the workers are this process's children: nobody else talks to the engine
             else:
                 self._server = await asyncio.start_server(self._handle, host="127.0.0.1", port=self.port or 0)
                 self.port = self._server.sockets[0].getsockname()[1]

@@ -264,3 +264,57 @@ def test_serialised_responses_equal_the_dict_path(oracle, monkeypatch):
         for r in o["results"]:
             r.setdefault("dense_score", None); r.setdefault("sparse_score", None); r.setdefault("source", None)
     assert [json.loads(x[0]) for x in g] == w
+
+
+def test_coalescer_keeps_answers_apart_under_concurrency(oracle):
+    """two dispatcher threads, futures and sinks mixed, 6 submitting threads: every request gets the answer to ITS query, grouped
+    engine calls stay far below the request count, and the per-request 400s stay per request"""
+    import json
+    import threading
+    from tests.oracle_engine import OracleEngine
+    from kaito_b200.batcher import RetrieveBatcher
+    store = VectorStore(HashingEmbedding(64), OracleEngine(oracle))
+    store.index_documents("m", [{"text": f"document {i} about topic{i % 13} and subject{i % 5}"} for i in range(80)])
+    b = RetrieveBatcher(store, max_batch=32, max_wait_s=0.003, dispatchers=2)
+    n_threads, per = 6, 60
+    bad = []
+    done = threading.Semaphore(0)
+
+    def work(t):
+        pending = []
+        for i in range(per):
+            q = f"topic{(t * per + i) % 13} subject{i % 5} t{t}i{i}" if i % 17 else "   "
+            if i % 3 == 0:
+                box = []
+                b.submit_bytes("m", q, 3, None, sink=box.append)
+                pending.append((q, None, box))
+            elif i % 3 == 1:
+                pending.append((q, b.submit_bytes("m", q, 3, None), None))
+            else:
+                pending.append((q, b.submit("m", q, 3, None), None))
+        for q, fut, box in pending:
+            try:
+                if box is not None:
+                    import time
+                    t0 = time.time()
+                    while not box and time.time() - t0 < 20:
+                        time.sleep(0.001)
+                    out = box[0]
+                    if isinstance(out, Exception):
+                        raise out
+                else:
+                    out = fut.result(timeout=20)
+                body = json.loads(out[0]) if isinstance(out, tuple) else out
+                if body["query"] != q or body["count"] != len(body["results"]):
+                    bad.append((q, body["query"]))
+            except Exception as e:
+                if not (q.strip() == "" and getattr(e, "status_code", None) == 400):
+                    bad.append((q, repr(e)))
+        done.release()
+
+    ts = [threading.Thread(target=work, args=(t,)) for t in range(n_threads)]
+    for t in ts: t.start()
+    for t in ts: t.join(60)
+    assert not bad, bad[:5]
+    assert b.requests == n_threads * per and b.batches < b.requests // 3, (b.requests, b.batches)
+    b.close()
