@@ -29,7 +29,10 @@ def default_token_counter():
         enc = tiktoken.encoding_for_model("gpt-3.5-turbo")          # llama_index.core.utils.get_tokenizer()
         return lambda text: len(enc.encode(text, allowed_special="all"))
     except Exception:                                                # BPE table not cached: pre-tokeniser pieces, long words count double
-        return lambda text: sum(1 + (len(m) > 9) for m in _PRETOK.findall(text))
+        def count(text, _find=_PRETOK.findall):
+            ms = _find(text)
+            return len(ms) + sum(1 for m in ms if len(m) > 9)
+        return count
 
 
 def _split_keep_separator(text: str, sep: str) -> list[str]:

@@ -241,9 +241,13 @@ class Vocabulary:
     def doc_terms(self, text: str):
         """(unique term ids u32, tf u16, doc_len) of one node; grows the vocabulary."""
         toks = tokenize(text)
-        cnt = Counter(self.add(t) for t in toks)
-        ids = np.fromiter(cnt.keys(), np.uint32, len(cnt))
-        tf = np.fromiter((min(v, 65535) for v in cnt.values()), np.uint16, len(cnt))
+        cnt = Counter(toks)                     # C-speed counting of the strings; keys keep first-occurrence order, so new terms
+        get, add = self.ids.get, self.add       # get their ids in exactly the order a token-by-token pass would hand them out
+        known = [get(t) for t in cnt]
+        if None in known:
+            known = [add(t) if i is None else i for t, i in zip(cnt, known)]
+        ids = np.array(known, np.uint32)
+        tf = np.minimum(np.fromiter(cnt.values(), np.int64, len(cnt)), 65535).astype(np.uint16)
         return ids, tf, len(toks)
 
     def query_terms(self, text: str) -> np.ndarray:

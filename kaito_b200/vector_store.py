@@ -263,12 +263,13 @@ class VectorStore:
             if st is None:
                 st = _IndexState(self.engine.create_index(index_name, self.dimension))
                 self.index_map[index_name] = st
-            ids, fresh = [], []
+            ids, fresh, fresh_ids = [], [], set()
             for doc in documents:
                 doc_id = generate_doc_id(doc["text"])
                 ids.append(doc_id)
-                if doc_id in st.ref_docs or any(d[0] == doc_id for d in fresh):
+                if doc_id in st.ref_docs or doc_id in fresh_ids:
                     continue                                   # "already exists ... Skipping." (:123-126)
+                fresh_ids.add(doc_id)
                 fresh.append((doc_id, doc["text"], doc.get("metadata") or {}))
             if fresh:
                 self._insert(st, fresh)
