@@ -131,6 +131,28 @@ def test_dense_topk_matches_argsort(oracle):
     assert (ord3[0, 7:] == -1).all() and np.isinf(dist3[0, 7:]).all() and (ord3[0, :7] >= 0).all()
 
 
+def test_dense_topk_against_third_party_brute_force(oracle):
+    """faiss is not installable here, but two other exact L2 searches are: scikit-learn's brute-force
+    NearestNeighbors and scipy's cdist.  The oracle's top-P must be theirs -- same ids in the same order wherever the fp64
+    distances are further apart than fp32 rounding, squared distances within 2e-6."""
+    sk = pytest.importorskip("sklearn.neighbors")
+    sp = pytest.importorskip("scipy.spatial.distance")
+    for n, d, P in ((4000, 384, 30), (2500, 768, 90), (1500, 1024, 30)):
+        x = oracle.synth_dense(n, d, seed=n)
+        q = oracle.synth_queries(x, 5, seed=d)
+        dist, ordn = oracle.dense_topk(x, q, P)
+        nn = sk.NearestNeighbors(n_neighbors=P, algorithm="brute", metric="sqeuclidean").fit(x.astype(np.float64))
+        ref_d, ref_i = nn.kneighbors(q.astype(np.float64))
+        full = sp.cdist(q.astype(np.float64), x.astype(np.float64), "sqeuclidean")
+        for b in range(len(q)):
+            assert np.max(np.abs(dist[b] - ref_d[b])) < 2e-6
+            assert np.max(np.abs(dist[b] - full[b, ordn[b]])) < 2e-6
+            for j in np.nonzero(ordn[b] != ref_i[b])[0]:          # order may differ only between near-ties
+                assert abs(full[b, ordn[b, j]] - full[b, ref_i[b, j]]) < 2e-6
+            assert set(ordn[b].tolist()) == set(ref_i[b].tolist()) or \
+                np.max(np.abs(np.sort(full[b, ordn[b]]) - np.sort(full[b, ref_i[b]]))) < 2e-6
+
+
 def test_bm25_scores_match_python_restatement(oracle):
     off, ids, tf, dl = oracle.synth_sparse(300, 500, seed=3)
     post = oracle.bm25_build(off, ids, tf, dl, 500)
